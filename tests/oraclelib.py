@@ -1,0 +1,281 @@
+"""ctypes binding of oracle/liboracle.so — the CPU restatement used as the parity checker.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by the product package.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ORACLE_DIR = os.path.join(_ROOT, "oracle")
+
+NDT_OMP, FAST_GICP, FAST_VGICP = 0, 1, 2
+DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
+
+
+class Params(ctypes.Structure):
+    _fields_ = [
+        ("method", ctypes.c_int),
+        ("num_threads", ctypes.c_int),
+        ("transformation_epsilon", ctypes.c_double),
+        ("maximum_iterations", ctypes.c_int),
+        ("max_correspondence_distance", ctypes.c_double),
+        ("correspondence_randomness", ctypes.c_int),
+        ("resolution", ctypes.c_double),
+        ("neighbor_search", ctypes.c_int),
+        ("rotation_epsilon", ctypes.c_double),
+        ("lm_max_iterations", ctypes.c_int),
+        ("lm_init_lambda_factor", ctypes.c_double),
+        ("ndt_step_size", ctypes.c_double),
+        ("ndt_outlier_ratio", ctypes.c_double),
+    ]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [
+        ("T", ctypes.c_float * 16),
+        ("converged", ctypes.c_int),
+        ("iterations", ctypes.c_int),
+        ("error", ctypes.c_double),
+        ("lm_evals", ctypes.c_int),
+    ]
+
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _ORACLE_DIR], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = ctypes.CDLL(path)
+        vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+        L.orc_default_params.argtypes = [ci, ctypes.POINTER(Params)]
+        L.orc_reg_create.restype = vp
+        L.orc_reg_create.argtypes = [ctypes.POINTER(Params)]
+        L.orc_reg_destroy.argtypes = [vp]
+        L.orc_reg_set_target.argtypes = [vp, vp, ci]
+        L.orc_reg_set_source.argtypes = [vp, vp, ci]
+        L.orc_reg_align.argtypes = [vp, vp, ctypes.POINTER(Result)]
+        L.orc_reg_fitness.restype = cd
+        L.orc_reg_fitness.argtypes = [vp, cd]
+        L.orc_knn_covariances.argtypes = [vp, ci, ci, vp, vp]
+        L.orc_vgicp_voxelmap.restype = ci
+        L.orc_vgicp_voxelmap.argtypes = [vp, ci, vp, cd, vp, vp, vp, vp]
+        L.orc_reg_linearize.restype = cd
+        L.orc_reg_linearize.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.orc_reg_compute_error.restype = cd
+        L.orc_reg_compute_error.argtypes = [vp, vp]
+        L.orc_ndt_grid.restype = ci
+        L.orc_ndt_grid.argtypes = [vp, ci, cd, vp, vp, vp, vp, vp, vp]
+        L.orc_reg_ndt_derivatives.restype = cd
+        L.orc_reg_ndt_derivatives.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_distance_filter.restype = ci
+        L.orc_distance_filter.argtypes = [vp, ci, cd, cd, vp]
+        L.orc_voxelgrid.restype = ci
+        L.orc_voxelgrid.argtypes = [vp, ci, ctypes.c_float, ci, vp, vp]
+        L.orc_radius_outlier.restype = ci
+        L.orc_radius_outlier.argtypes = [vp, ci, cd, ci, vp]
+        L.orc_statistical_outlier.restype = ci
+        L.orc_statistical_outlier.argtypes = [vp, ci, ci, cd, vp, vp, ctypes.POINTER(cd)]
+        L.orc_transform_cloud.argtypes = [vp, ci, vp, vp]
+        L.orc_fitness_score.restype = cd
+        L.orc_fitness_score.argtypes = [vp, ci, vp, ci, vp, cd, ctypes.POINTER(ci)]
+        L.orc_knn.argtypes = [vp, ci, vp, ci, ci, vp, vp]
+        L.orc_set_num_threads.argtypes = [ci]
+        L.orc_get_max_threads.restype = ci
+        _lib = L
+    return _lib
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4
+    return a
+
+
+def _p(a):
+    return a.ctypes.data
+
+
+def default_params(method, **overrides):
+    p = Params()
+    lib().orc_default_params(method, ctypes.byref(p))
+    for k, v in overrides.items():
+        assert hasattr(p, k), k
+        setattr(p, k, v)
+    return p
+
+
+def colmajor(T):
+    """4x4 (row-indexed numpy) -> 16 floats column-major (Eigen::Matrix4f storage)."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T.reshape(16))
+
+
+def from_colmajor(t16):
+    return np.asarray(t16, dtype=np.float64).reshape(4, 4).T.copy()
+
+
+class Registration:
+    """Mirror of the pcl::Registration surface the reference's callers use."""
+
+    def __init__(self, params):
+        self.params = params
+        self._h = lib().orc_reg_create(ctypes.byref(params))
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_reg_destroy(self._h)
+            self._h = None
+
+    def setInputTarget(self, cloud):
+        c = _pts(cloud)
+        lib().orc_reg_set_target(self._h, _p(c), len(c))
+        self.nt = len(c)
+
+    def setInputSource(self, cloud):
+        c = _pts(cloud)
+        lib().orc_reg_set_source(self._h, _p(c), len(c))
+        self.ns = len(c)
+
+    def align(self, guess=None):
+        g = colmajor(np.eye(4) if guess is None else guess)
+        r = Result()
+        lib().orc_reg_align(self._h, _p(g), ctypes.byref(r))
+        self.result = r
+        return r
+
+    def getFinalTransformation(self):
+        return from_colmajor(list(self.result.T))
+
+    def hasConverged(self):
+        return bool(self.result.converged)
+
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max):
+        return lib().orc_reg_fitness(self._h, max_range)
+
+    # --- intermediates ---
+    def linearize(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        H = np.zeros((6, 6)); b = np.zeros(6)
+        if self.params.method == FAST_VGICP:
+            corr = np.zeros((self.ns, 3), dtype=np.int32)
+            valid = np.zeros(self.ns, dtype=np.uint8)
+            err = lib().orc_reg_linearize(self._h, _p(T), _p(H), _p(b), _p(corr), _p(valid))
+            return err, H, b, corr, valid.astype(bool)
+        corr = np.zeros(self.ns, dtype=np.int32)
+        err = lib().orc_reg_linearize(self._h, _p(T), _p(H), _p(b), _p(corr), None)
+        return err, H, b, corr, corr >= 0
+
+    def compute_error(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        return lib().orc_reg_compute_error(self._h, _p(T))
+
+    def ndt_derivatives(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        g = np.zeros(6); H = np.zeros((6, 6)); hits = np.zeros(self.ns, dtype=np.int32)
+        s = lib().orc_reg_ndt_derivatives(self._h, _p(p6), _p(g), _p(H), _p(hits))
+        return s, g, H, hits
+
+
+def knn_covariances(cloud, k=20, want_idx=False):
+    c = _pts(cloud)
+    cov = np.zeros((len(c), 6))
+    idx = np.zeros((len(c), k), dtype=np.int32) if want_idx else None
+    lib().orc_knn_covariances(_p(c), len(c), k, _p(cov), _p(idx) if want_idx else None)
+    return (cov, idx) if want_idx else cov
+
+
+def vgicp_voxelmap(cloud, cov6, resolution):
+    c = _pts(cloud)
+    cov6 = np.ascontiguousarray(cov6, dtype=np.float64)
+    n = len(c)
+    coords = np.zeros((n, 3), dtype=np.int32); npts = np.zeros(n, dtype=np.int32)
+    mean = np.zeros((n, 3)); cov = np.zeros((n, 6))
+    V = lib().orc_vgicp_voxelmap(_p(c), n, _p(cov6), resolution, _p(coords), _p(npts), _p(mean), _p(cov))
+    return coords[:V].copy(), npts[:V].copy(), mean[:V].copy(), cov[:V].copy()
+
+
+def ndt_grid(cloud, resolution):
+    c = _pts(cloud)
+    n = len(c)
+    idx = np.zeros(n, dtype=np.int32); npts = np.zeros(n, dtype=np.int32)
+    mean = np.zeros((n, 3)); icov = np.zeros((n, 9))
+    min_b = np.zeros(3, dtype=np.int32); div_b = np.zeros(3, dtype=np.int32)
+    V = lib().orc_ndt_grid(_p(c), n, resolution, _p(idx), _p(npts), _p(mean), _p(icov), _p(min_b), _p(div_b))
+    return idx[:V].copy(), npts[:V].copy(), mean[:V].copy(), icov[:V].reshape(V, 3, 3).copy(), min_b, div_b
+
+
+def distance_filter(cloud, near, far):
+    c = _pts(cloud)
+    out = np.empty_like(c)
+    m = lib().orc_distance_filter(_p(c), len(c), near, far, _p(out))
+    return out[:m].copy()
+
+
+def voxelgrid(cloud, leaf, min_points=1, want_index=False):
+    """Returns (points, overflow).  On the INT32 overflow branch PCL returns the input unchanged."""
+    c = _pts(cloud)
+    out = np.empty_like(c)
+    vidx = np.zeros(len(c), dtype=np.int32)
+    m = lib().orc_voxelgrid(_p(c), len(c), leaf, min_points, _p(out), _p(vidx))
+    if m < 0:
+        return (out.copy(), True, None) if want_index else (out.copy(), True)
+    return (out[:m].copy(), False, vidx[:m].copy()) if want_index else (out[:m].copy(), False)
+
+
+def radius_outlier(cloud, radius, min_neighbors):
+    c = _pts(cloud)
+    keep = np.zeros(len(c), dtype=np.uint8)
+    lib().orc_radius_outlier(_p(c), len(c), radius, min_neighbors, _p(keep))
+    return keep.astype(bool)
+
+
+def statistical_outlier(cloud, mean_k, stddev_mul):
+    c = _pts(cloud)
+    keep = np.zeros(len(c), dtype=np.uint8)
+    dist = np.zeros(len(c), dtype=np.float32)
+    thr = ctypes.c_double()
+    lib().orc_statistical_outlier(_p(c), len(c), mean_k, stddev_mul, _p(keep), _p(dist), ctypes.byref(thr))
+    return keep.astype(bool), dist, thr.value
+
+
+def transform_cloud(cloud, T):
+    c = _pts(cloud)
+    out = np.empty_like(c)
+    g = colmajor(T)
+    lib().orc_transform_cloud(_p(c), len(c), _p(g), _p(out))
+    return out
+
+
+def fitness_score(target, source, T, max_range=np.finfo(np.float64).max):
+    t, s = _pts(target), _pts(source)
+    g = colmajor(T)
+    nr = ctypes.c_int()
+    f = lib().orc_fitness_score(_p(t), len(t), _p(s), len(s), _p(g), max_range, ctypes.byref(nr))
+    return f, nr.value
+
+
+def knn(cloud, queries, k):
+    c, q = _pts(cloud), _pts(queries)
+    idx = np.zeros((len(q), k), dtype=np.int32); d2 = np.zeros((len(q), k), dtype=np.float32)
+    lib().orc_knn(_p(c), len(c), _p(q), len(q), k, _p(idx), _p(d2))
+    return idx, d2
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(n)
+
+
+def max_threads():
+    return lib().orc_get_max_threads()
