@@ -1,0 +1,168 @@
+/* libb2r — B200-native scan registration + prefiltering for mrg_slam's hot path.
+ *
+ * C ABI (plain pointers and sizes; no C++/torch types).  Every entry point names
+ * the reference interface it replaces (paths relative to /root/reference).
+ * All computation runs in hand-written sm_100a CUDA kernels; there is no CPU
+ * fallback: if no CUDA device is present b2r_create fails with B2R_ERR_NO_DEVICE.
+ *
+ * Conventions
+ *  - points: float32 x,y,z,intensity.  stride_bytes = 16 (packed, the KITTI layout of
+ *    python_scripts/kitti_singlerobot_processor.py:174-183; intensity at byte 12) or
+ *    32 (pcl::PointXYZI: x,y,z,1 | intensity,pad; intensity at byte 16).
+ *  - 4x4 transforms: 16 floats, COLUMN-major (Eigen::Matrix4f storage), as
+ *    pcl::Registration::align / getFinalTransformation use.
+ *  - memspace: where the caller's buffer lives (host or this handle's CUDA device).
+ *  - a handle is thread-compatible (one thread at a time); distinct handles are
+ *    independent (own CUDA stream, own workspace).
+ */
+#ifndef B2R_H_
+#define B2R_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2r_status {
+  B2R_OK = 0,
+  B2R_ERR_INVALID_ARG = 1,
+  B2R_ERR_CUDA = 2,
+  B2R_ERR_NO_DEVICE = 3,
+  B2R_ERR_CAPACITY = 4, /* a dense voxel table would exceed its cap (cloud extent / resolution) */
+  B2R_ERR_STATE = 5     /* e.g. align before set_target */
+} b2r_status;
+
+/* registration_method strings handled by select_registration_method (src/mrg_slam/registrations.cpp:46-148) */
+typedef enum b2r_method {
+  B2R_NDT_OMP = 0,   /* "NDT_OMP"    registrations.cpp:130-147 -> pclomp::NormalDistributionsTransform */
+  B2R_FAST_GICP = 1, /* "FAST_GICP"  registrations.cpp:55-63   -> fast_gicp::FastGICP ("GICP" row) */
+  B2R_FAST_VGICP = 2 /* "FAST_VGICP" registrations.cpp:76-84   -> fast_gicp::FastVGICP */
+} b2r_method;
+
+typedef enum b2r_neighbor_search { B2R_DIRECT1 = 0, B2R_DIRECT7 = 1, B2R_DIRECT27 = 2 } b2r_neighbor_search;
+typedef enum b2r_memspace { B2R_HOST = 0, B2R_DEVICE = 1 } b2r_memspace;
+
+/* The 10 reg_* ROS parameters read at registrations.cpp:34-43 plus the upstream
+ * defaults mrg_slam never overrides (parameter table). */
+typedef struct b2r_config {
+  int method;                         /* b2r_method */
+  int device;                         /* CUDA device ordinal */
+  double transformation_epsilon;      /* reg_transformation_epsilon (0.1) */
+  int maximum_iterations;             /* reg_maximum_iterations (64) */
+  double max_correspondence_distance; /* reg_max_correspondence_distance (2.0), FAST_GICP only */
+  int correspondence_randomness;      /* reg_correspondence_randomness (20): k of the covariance kNN, <= 32 */
+  double resolution;                  /* reg_resolution (1.0): VGICP voxel / NDT leaf */
+  int neighbor_search;                /* reg_nn_search_method for NDT_OMP (DIRECT7); FAST_VGICP keeps DIRECT1 */
+  double rotation_epsilon;            /* fast_gicp default 2e-3 */
+  int lm_max_iterations;              /* fast_gicp default 10 */
+  double lm_init_lambda_factor;       /* fast_gicp default 1e-9 */
+  double ndt_step_size;               /* ndt_omp default 0.1 */
+  double ndt_outlier_ratio;           /* ndt_omp default 0.55 */
+  double nn_cell_size;                /* uniform-grid cell for exact kNN / 1-NN; 0 = auto from density */
+} b2r_config;
+
+typedef struct b2r_result {
+  float T[16];    /* getFinalTransformation(), column-major */
+  int converged;  /* hasConverged() */
+  int iterations; /* nr_iterations_ as the upstream class leaves it */
+  double error;   /* last LM error (GICP/VGICP) or NDT score */
+  int evals;      /* cost-function passes over the source cloud */
+  double fitness; /* getFitnessScore(max_range) when requested by a batch call, else 0 */
+} b2r_result;
+
+typedef struct b2r_handle b2r_handle; /* one pcl::Registration object */
+typedef struct b2r_cloud b2r_cloud;   /* a device-resident point cloud + its cached search structures */
+
+/* ---- lifecycle: replaces the constructor + setter block of select_registration_method ---- */
+b2r_status b2r_default_config(int method, b2r_config* cfg);
+b2r_status b2r_create(const b2r_config* cfg, b2r_handle** out);
+void b2r_destroy(b2r_handle* h);
+const char* b2r_last_error(const b2r_handle* h);
+const char* b2r_version(void);
+
+/* ---- clouds.  A cloud may be shared by several handles' calls on the same device.  Search structures
+ * (kNN grid, covariances, voxel maps) are built lazily and cached, so promoting a source to target at a
+ * keyframe switch (scan_matching_odometry_component.cpp:332-333) reuses them. ---- */
+b2r_status b2r_cloud_create(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int memspace, b2r_cloud** out);
+void b2r_cloud_destroy(b2r_cloud* c);
+size_t b2r_cloud_size(const b2r_cloud* c);
+
+/* ---- pcl::Registration surface (apps/scan_matching_odometry_component.cpp:203,208,266,270,275;
+ *      src/mrg_slam/loop_detector.cpp:104,127,134,137,138,144) ---- */
+b2r_status b2r_set_target(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int memspace); /* setInputTarget */
+b2r_status b2r_set_source(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int memspace); /* setInputSource */
+b2r_status b2r_set_target_cloud(b2r_handle* h, b2r_cloud* c); /* setInputTarget with a retained cloud (not owned) */
+b2r_status b2r_set_source_cloud(b2r_handle* h, b2r_cloud* c);
+b2r_status b2r_align(b2r_handle* h, const float guess_colmajor[16], b2r_result* out); /* align(output, guess) */
+/* getFitnessScore(max_range): max_range is compared against the SQUARED distance, as PCL does
+ * (same code in-tree: src/mrg_slam/information_matrix_calculator.cpp:46-81). */
+b2r_status b2r_fitness(b2r_handle* h, double max_range, double* out);
+/* the `output` cloud of align(): source transformed by the final transformation (float, PCL association) */
+b2r_status b2r_transform_source(b2r_handle* h, void* out_points, size_t stride_bytes, int memspace);
+/* InformationMatrixCalculator::calc_fitness_score(cloud1, cloud2, relpose, max_range)
+ * (src/mrg_slam/information_matrix_calculator.cpp:46-81): fitness of T*source against target. */
+b2r_status b2r_fitness_pair(b2r_handle* h, b2r_cloud* target, b2r_cloud* source, const float T_colmajor[16], double max_range, double* out);
+
+/* ---- loop-closure batch: the candidate loop of LoopDetector::matching (loop_detector.cpp:126-145)
+ * for many (target, source, guess) triples at once.  If with_fitness != 0, out[i].fitness =
+ * getFitnessScore(fitness_max_range) of pair i (loop_detector.cpp:137). ---- */
+b2r_status b2r_align_batch(b2r_handle* h, b2r_cloud* const* sources, b2r_cloud* const* targets, const float* guesses_colmajor,
+                           size_t n_pairs, int with_fitness, double fitness_max_range, b2r_result* out);
+
+/* ---- prefiltering (apps/prefiltering_component.cpp:149-151).  `out` has room for n points in `memspace`,
+ * packed 16 B; *m receives the number written. ---- */
+/* distance_filter(), prefiltering_component.cpp:206-229 */
+b2r_status b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int memspace, double near_thresh,
+                               double far_thresh, void* out, size_t* m);
+/* pcl::VoxelGrid::filter, prefiltering_component.cpp:167-171 / scan_matching_odometry_component.cpp:175-179.
+ * *overflow = 1 reproduces PCL's "leaf size too small" branch: output = input unchanged. */
+b2r_status b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int memspace, float leaf, int min_points_per_voxel,
+                         void* out, size_t* m, int* overflow);
+/* pcl::RadiusOutlierRemoval::filter, prefiltering_component.cpp:195-199 */
+b2r_status b2r_radius_outlier(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int memspace, double radius, int min_neighbors,
+                              void* out, size_t* m);
+/* pcl::StatisticalOutlierRemoval::filter, prefiltering_component.cpp:190-194 */
+b2r_status b2r_statistical_outlier(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int memspace, int mean_k,
+                                   double stddev_mul, void* out, size_t* m);
+
+typedef struct b2r_prefilter_config {
+  int enable_distance_filter; double distance_near_thresh, distance_far_thresh; /* :208-216 */
+  int downsample_method;  /* 0 NONE, 1 VOXELGRID */                               /* :160-171 */
+  float downsample_resolution; int downsample_min_points_per_voxel;
+  int outlier_removal_method; /* 0 NONE, 1 STATISTICAL, 2 RADIUS */             /* :184-199 */
+  int statistical_mean_k; double statistical_stddev;
+  double radius_radius; int radius_min_neighbors;
+} b2r_prefilter_config;
+b2r_status b2r_default_prefilter_config(b2r_prefilter_config* cfg); /* values of config/mrg_slam.yaml:48-64 */
+/* cloud_callback's filter chain distance_filter -> downsample -> outlier_removal (prefiltering_component.cpp:149-151)
+ * with intermediates kept on the device. */
+b2r_status b2r_prefilter(b2r_handle* h, const b2r_prefilter_config* cfg, const void* in, size_t n, size_t stride_bytes, int memspace,
+                         void* out, size_t* m);
+
+/* ---- introspection for parity tests and benchmarks ---- */
+uint64_t b2r_kernel_launches(const b2r_handle* h); /* kernels launched by this handle so far */
+b2r_status b2r_synchronize(b2r_handle* h);
+/* which: 0 = source, 1 = target.  cov6 = xx,xy,xz,yy,yz,zz per point; knn (n*k int32, ascending distance) optional */
+b2r_status b2r_debug_covariances(b2r_handle* h, int which, double* cov6_out, int32_t* knn_out);
+/* VGICP voxel map of the target, sorted by (x,y,z) voxel coordinate; arrays sized for *V <= n_target voxels */
+b2r_status b2r_debug_voxelmap(b2r_handle* h, int32_t* coords_out, int32_t* npts_out, double* mean_out, double* cov6_out, size_t* V);
+/* linearize at pose T (4x4 row-major double): H 36 row-major, b 6, *err.  corr_out: FAST_GICP n int32 target index
+ * or -1; FAST_VGICP n*3 int32 voxel coordinates with corr_valid[n] */
+b2r_status b2r_debug_linearize(b2r_handle* h, const double* T_rowmajor, double* H, double* b, double* err, int32_t* corr_out,
+                               uint8_t* corr_valid);
+b2r_status b2r_debug_compute_error(b2r_handle* h, const double* T_lin_rowmajor, const double* T_trial_rowmajor, double* err);
+/* NDT target cells sorted by dense index; icov 9 doubles (float-rounded values) */
+b2r_status b2r_debug_ndt_grid(b2r_handle* h, int32_t* idx_out, int32_t* npts_out, double* mean_out, double* icov_out, int32_t* min_b,
+                              int32_t* div_b, size_t* V);
+b2r_status b2r_debug_ndt_derivatives(b2r_handle* h, const double* p6, double* score, double* grad6, double* hess36, int32_t* hits_out);
+/* exact kNN of `queries` in cloud c (ascending squared distance) */
+b2r_status b2r_debug_knn(b2r_handle* h, b2r_cloud* c, const float* queries_xyzi, size_t nq, int k, int32_t* idx_out, float* d2_out);
+/* per-stage device time of the last align/align_batch in milliseconds: [0] cloud prep (grid+covariances+maps),
+ * [1] optimiser loop, [2] fitness, [3] total */
+b2r_status b2r_last_timings(const b2r_handle* h, float ms_out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

@@ -1,0 +1,583 @@
+// C ABI of libb2r (include/b2r.h): handle / cloud lifecycle, the pcl::Registration surface, the loop-closure batch
+// call, the prefilter chain and introspection entry points.  All work is delegated to the CUDA modules; there is
+// no CPU code path for any computation.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <cstring>
+
+#include "internal.hpp"
+
+using namespace b2r;
+
+struct b2r_handle { Handle h; };
+struct b2r_cloud { Cloud c; };
+
+namespace {
+
+Needs needs_for(const b2r_config& cfg, bool is_target, bool want_fitness) {
+  Needs nd;
+  switch (cfg.method) {
+    case B2R_FAST_VGICP:
+      nd.cov_k = cfg.correspondence_randomness;
+      if (is_target) nd.vres = cfg.resolution;
+      break;
+    case B2R_FAST_GICP:
+      nd.cov_k = cfg.correspondence_randomness;
+      if (is_target) nd.grid = true;
+      break;
+    default:  // NDT_OMP
+      if (is_target) nd.leaf = (float)cfg.resolution;
+      break;
+  }
+  if (is_target && want_fitness) nd.grid = true;
+  return nd;
+}
+
+template <typename F>
+b2r_status guarded(b2r_handle* hh, F&& f) {
+  if (!hh) return B2R_ERR_INVALID_ARG;
+  Handle& h = hh->h;
+  try {
+    if (cudaSetDevice(h.ctx.device) != cudaSuccess) throw Error(B2R_ERR_CUDA, "cudaSetDevice failed");
+    f(h);
+    return B2R_OK;
+  } catch (const Error& e) {
+    h.last_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  } catch (const std::exception& e) {
+    h.last_error = e.what();
+    return B2R_ERR_INVALID_ARG;
+  }
+}
+
+void check_cfg(const b2r_config& cfg) {
+  if (cfg.method < B2R_NDT_OMP || cfg.method > B2R_FAST_VGICP) throw Error(B2R_ERR_INVALID_ARG, "unknown method");
+  if (cfg.resolution <= 0) throw Error(B2R_ERR_INVALID_ARG, "resolution must be > 0");
+  if (cfg.method != B2R_NDT_OMP && (cfg.correspondence_randomness < 4 || cfg.correspondence_randomness > 32))
+    throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be in [4,32]");
+}
+
+// runs the optimiser on a list of (source, target, guess) triples; clouds are prepared (batched) first
+void run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<Cloud*>& targets, const float* guesses, int with_fitness,
+               double fitness_max_range, b2r_result* out) {
+  const int np = (int)sources.size();
+  Ctx& ctx = h.ctx;
+  B2R_CUDA(cudaEventRecord(h.ev[0], ctx.stream));
+  std::vector<Cloud*> uniq;
+  std::vector<Needs> needs;
+  std::map<Cloud*, int> index;
+  auto add = [&](Cloud* c, bool is_target) {
+    if (!c) throw Error(B2R_ERR_INVALID_ARG, "null cloud");
+    if (c->n == 0) throw Error(B2R_ERR_INVALID_ARG, "empty cloud");
+    auto it = index.find(c);
+    int id;
+    if (it == index.end()) {
+      id = (int)uniq.size();
+      index[c] = id;
+      uniq.push_back(c);
+      needs.push_back(Needs());
+    } else {
+      id = it->second;
+    }
+    Needs nd = needs_for(h.cfg, is_target, with_fitness != 0);
+    Needs& cur = needs[id];
+    cur.grid = cur.grid || nd.grid;
+    cur.cov_k = std::max(cur.cov_k, nd.cov_k);
+    if (nd.vres > 0) cur.vres = nd.vres;
+    if (nd.leaf > 0) cur.leaf = nd.leaf;
+    return id;
+  };
+  std::vector<PairDesc> pairs(np);
+  std::vector<int> src_sizes(np);
+  for (int i = 0; i < np; ++i) {
+    pairs[i].src = add(sources[i], false);
+    pairs[i].tgt = add(targets[i], true);
+    src_sizes[i] = sources[i]->n;
+  }
+  clouds_prepare(ctx, h.cfg, uniq, needs);
+  std::vector<CloudView> hv(uniq.size());
+  for (size_t i = 0; i < uniq.size(); ++i) hv[i] = uniq[i]->view();
+  DBuf<CloudView> dv;
+  dv.alloc(hv.size(), ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+  B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
+  if (h.cfg.method == B2R_NDT_OMP) ndt_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
+  else lsq_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
+  B2R_CUDA(cudaEventRecord(h.ev[2], ctx.stream));
+  if (with_fitness) {
+    std::vector<float> Ts((size_t)np * 16);
+    std::vector<double> fit(np);
+    for (int i = 0; i < np; ++i) memcpy(&Ts[(size_t)i * 16], out[i].T, 64);
+    fitness_batch(ctx, dv.p, pairs, src_sizes.data(), Ts.data(), fitness_max_range, fit.data());
+    for (int i = 0; i < np; ++i) out[i].fitness = fit[i];
+  }
+  B2R_CUDA(cudaEventRecord(h.ev[3], ctx.stream));
+  B2R_CUDA(cudaEventSynchronize(h.ev[3]));
+  cudaEventElapsedTime(&h.timings[0], h.ev[0], h.ev[1]);
+  cudaEventElapsedTime(&h.timings[1], h.ev[1], h.ev[2]);
+  cudaEventElapsedTime(&h.timings[2], h.ev[2], h.ev[3]);
+  cudaEventElapsedTime(&h.timings[3], h.ev[0], h.ev[3]);
+}
+
+// two-entry view array {source, target} of the handle's current clouds, prepared for the configured method
+void prepare_current(Handle& h, DBuf<CloudView>& dv, bool want_fitness) {
+  if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set first");
+  std::vector<Cloud*> cl{h.source, h.target};
+  std::vector<Needs> nd{needs_for(h.cfg, false, false), needs_for(h.cfg, true, want_fitness)};
+  clouds_prepare(h.ctx, h.cfg, cl, nd);
+  // source == target (same object) still yields two identical views
+  CloudView hv[2] = {h.source->view(), h.target->view()};
+  dv.alloc(2, h.ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, hv, sizeof(hv), cudaMemcpyHostToDevice, h.ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2r_version(void) { return "b2r 0.1 (sm_100a)"; }
+
+b2r_status b2r_default_config(int method, b2r_config* cfg) {
+  if (!cfg) return B2R_ERR_INVALID_ARG;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->method = method;
+  cfg->device = 0;
+  cfg->transformation_epsilon = 0.1;       // config/mrg_slam.yaml:102
+  cfg->maximum_iterations = 64;            // :103
+  cfg->max_correspondence_distance = 2.0;  // :104
+  cfg->correspondence_randomness = 20;     // :107
+  cfg->resolution = 1.0;                   // :108
+  cfg->neighbor_search = method == B2R_NDT_OMP ? B2R_DIRECT7 : B2R_DIRECT1;  // :109 / fast_gicp default
+  cfg->rotation_epsilon = 2e-3;
+  cfg->lm_max_iterations = 10;
+  cfg->lm_init_lambda_factor = 1e-9;
+  cfg->ndt_step_size = 0.1;
+  cfg->ndt_outlier_ratio = 0.55;
+  cfg->nn_cell_size = 0.0;
+  return B2R_OK;
+}
+
+b2r_status b2r_create(const b2r_config* cfg, b2r_handle** out) {
+  if (!cfg || !out) return B2R_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return B2R_ERR_NO_DEVICE;  // no CPU fallback
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return B2R_ERR_INVALID_ARG;
+  b2r_handle* hh = new b2r_handle();
+  Handle& h = hh->h;
+  try {
+    check_cfg(*cfg);
+    h.cfg = *cfg;
+    h.ctx.device = cfg->device;
+    B2R_CUDA(cudaSetDevice(cfg->device));
+    B2R_CUDA(cudaStreamCreateWithFlags(&h.ctx.stream, cudaStreamNonBlocking));
+    int sms = 0;
+    B2R_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    h.ctx.num_sms = sms > 0 ? sms : 148;
+    cudaMemPool_t pool;
+    B2R_CUDA(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+    uint64_t thr = UINT64_MAX;
+    B2R_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    for (int i = 0; i < 4; ++i) B2R_CUDA(cudaEventCreate(&h.ev[i]));
+    for (int i = 0; i < 16; ++i) h.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  } catch (const Error& e) {
+    b2r_status s = e.status;
+    delete hh;
+    return s;
+  }
+  *out = hh;
+  return B2R_OK;
+}
+
+void b2r_destroy(b2r_handle* hh) {
+  if (!hh) return;
+  Handle& h = hh->h;
+  cudaSetDevice(h.ctx.device);
+  if (h.ctx.stream) cudaStreamSynchronize(h.ctx.stream);
+  h.owned_source.reset();
+  h.owned_target.reset();
+  for (int i = 0; i < 4; ++i)
+    if (h.ev[i]) cudaEventDestroy(h.ev[i]);
+  if (h.ctx.stream) { cudaStreamSynchronize(h.ctx.stream); cudaStreamDestroy(h.ctx.stream); }
+  delete hh;
+}
+
+const char* b2r_last_error(const b2r_handle* hh) { return hh ? hh->h.last_error.c_str() : "null handle"; }
+
+b2r_status b2r_cloud_create(b2r_handle* hh, const void* points, size_t n, size_t stride_bytes, int memspace, b2r_cloud** out) {
+  if (!out) return B2R_ERR_INVALID_ARG;
+  *out = nullptr;
+  return guarded(hh, [&](Handle& h) {
+    if (!points && n) throw Error(B2R_ERR_INVALID_ARG, "null points");
+    b2r_cloud* c = new b2r_cloud();
+    try {
+      cloud_upload(h.ctx, c->c, points, n, stride_bytes, memspace);
+      B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+
+void b2r_cloud_destroy(b2r_cloud* c) {
+  if (!c) return;
+  cudaSetDevice(c->c.device);
+  delete c;
+}
+size_t b2r_cloud_size(const b2r_cloud* c) { return c ? (size_t)c->c.n : 0; }
+
+b2r_status b2r_set_target(b2r_handle* hh, const void* points, size_t n, size_t stride_bytes, int memspace) {
+  return guarded(hh, [&](Handle& h) {
+    if (!points || n == 0) throw Error(B2R_ERR_INVALID_ARG, "empty target");
+    std::unique_ptr<Cloud> c(new Cloud());
+    cloud_upload(h.ctx, *c, points, n, stride_bytes, memspace);
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    h.owned_target = std::move(c);
+    h.target = h.owned_target.get();
+  });
+}
+b2r_status b2r_set_source(b2r_handle* hh, const void* points, size_t n, size_t stride_bytes, int memspace) {
+  return guarded(hh, [&](Handle& h) {
+    if (!points || n == 0) throw Error(B2R_ERR_INVALID_ARG, "empty source");
+    std::unique_ptr<Cloud> c(new Cloud());
+    cloud_upload(h.ctx, *c, points, n, stride_bytes, memspace);
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    h.owned_source = std::move(c);
+    h.source = h.owned_source.get();
+  });
+}
+b2r_status b2r_set_target_cloud(b2r_handle* hh, b2r_cloud* c) {
+  return guarded(hh, [&](Handle& h) {
+    if (!c) throw Error(B2R_ERR_INVALID_ARG, "null cloud");
+    h.target = &c->c;
+  });
+}
+b2r_status b2r_set_source_cloud(b2r_handle* hh, b2r_cloud* c) {
+  return guarded(hh, [&](Handle& h) {
+    if (!c) throw Error(B2R_ERR_INVALID_ARG, "null cloud");
+    h.source = &c->c;
+  });
+}
+
+b2r_status b2r_align(b2r_handle* hh, const float guess[16], b2r_result* out) {
+  b2r_status st = guarded(hh, [&](Handle& h) {
+    if (!guess || !out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set before align");
+    // pcl::Registration::align: converged_ = false, final_transformation_ = I before computeTransformation
+    h.converged = false;
+    for (int i = 0; i < 16; ++i) h.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    std::vector<Cloud*> s{h.source}, t{h.target};
+    run_align(h, s, t, guess, 0, 0.0, out);
+    memcpy(h.final_T, out->T, sizeof(h.final_T));
+    h.converged = out->converged != 0;
+    h.has_result = true;
+  });
+  if (st != B2R_OK && out && guess) {  // PCL style: failure leaves converged_ = false; report the guess
+    memcpy(out->T, guess, 64);
+    out->converged = 0; out->iterations = 0; out->error = 0; out->evals = 0; out->fitness = 0;
+  }
+  return st;
+}
+
+b2r_status b2r_align_batch(b2r_handle* hh, b2r_cloud* const* sources, b2r_cloud* const* targets, const float* guesses, size_t n_pairs,
+                           int with_fitness, double fitness_max_range, b2r_result* out) {
+  return guarded(hh, [&](Handle& h) {
+    if (n_pairs == 0) return;
+    if (!sources || !targets || !guesses || !out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    std::vector<Cloud*> s(n_pairs), t(n_pairs);
+    for (size_t i = 0; i < n_pairs; ++i) {
+      if (!sources[i] || !targets[i]) throw Error(B2R_ERR_INVALID_ARG, "null cloud in batch");
+      s[i] = &sources[i]->c;
+      t[i] = &targets[i]->c;
+    }
+    run_align(h, s, t, guesses, with_fitness, fitness_max_range, out);
+  });
+}
+
+b2r_status b2r_fitness(b2r_handle* hh, double max_range, double* out) {
+  return guarded(hh, [&](Handle& h) {
+    if (!out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set first");
+    std::vector<Cloud*> cl{h.source, h.target};
+    std::vector<Needs> nd(2);
+    nd[1].grid = true;
+    clouds_prepare(h.ctx, h.cfg, cl, nd);
+    CloudView hv[2] = {h.source->view(), h.target->view()};
+    DBuf<CloudView> dv;
+    dv.alloc(2, h.ctx.stream);
+    B2R_CUDA(cudaMemcpyAsync(dv.p, hv, sizeof(hv), cudaMemcpyHostToDevice, h.ctx.stream));
+    std::vector<PairDesc> pairs{PairDesc{0, 1}};
+    int ns = h.source->n;
+    fitness_batch(h.ctx, dv.p, pairs, &ns, h.final_T, max_range, out);
+  });
+}
+
+b2r_status b2r_fitness_pair(b2r_handle* hh, b2r_cloud* target, b2r_cloud* source, const float T[16], double max_range, double* out) {
+  return guarded(hh, [&](Handle& h) {
+    if (!out || !target || !source || !T) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    std::vector<Cloud*> cl{&source->c, &target->c};
+    std::vector<Needs> nd(2);
+    nd[1].grid = true;
+    clouds_prepare(h.ctx, h.cfg, cl, nd);
+    CloudView hv[2] = {source->c.view(), target->c.view()};
+    DBuf<CloudView> dv;
+    dv.alloc(2, h.ctx.stream);
+    B2R_CUDA(cudaMemcpyAsync(dv.p, hv, sizeof(hv), cudaMemcpyHostToDevice, h.ctx.stream));
+    std::vector<PairDesc> pairs{PairDesc{0, 1}};
+    int ns = source->c.n;
+    fitness_batch(h.ctx, dv.p, pairs, &ns, T, max_range, out);
+  });
+}
+
+b2r_status b2r_transform_source(b2r_handle* hh, void* out_points, size_t stride_bytes, int memspace) {
+  return guarded(hh, [&](Handle& h) {
+    if (!h.source) throw Error(B2R_ERR_STATE, "source must be set first");
+    if (!out_points) throw Error(B2R_ERR_INVALID_ARG, "null output");
+    DBuf<float4> tmp;
+    tmp.alloc(h.source->n, h.ctx.stream);
+    transform_cloud(h.ctx, h.source->pts.p, h.source->n, h.final_T, tmp.p);
+    store_points(h.ctx, tmp.p, h.source->n, out_points, stride_bytes, memspace);
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ filters
+static void finish_filter(Handle& h, DevCloud& res, void* out, size_t* m, int memspace) {
+  if (out && res.n) store_points(h.ctx, res.pts.p, res.n, out, 16, memspace);
+  B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+  if (m) *m = (size_t)res.n;
+}
+
+b2r_status b2r_distance_filter(b2r_handle* hh, const void* in, size_t n, size_t stride_bytes, int memspace, double near_thresh,
+                               double far_thresh, void* out, size_t* m) {
+  return guarded(hh, [&](Handle& h) {
+    DBuf<float4> src;
+    load_points(h.ctx, in, n, stride_bytes, memspace, src);
+    DevCloud res;
+    filter_distance(h.ctx, src.p, (int)n, near_thresh, far_thresh, res);
+    finish_filter(h, res, out, m, memspace);
+  });
+}
+
+b2r_status b2r_voxelgrid(b2r_handle* hh, const void* in, size_t n, size_t stride_bytes, int memspace, float leaf, int min_points_per_voxel,
+                         void* out, size_t* m, int* overflow) {
+  return guarded(hh, [&](Handle& h) {
+    if (!(leaf > 0)) throw Error(B2R_ERR_INVALID_ARG, "leaf must be > 0");
+    DBuf<float4> src;
+    load_points(h.ctx, in, n, stride_bytes, memspace, src);
+    DevCloud res;
+    bool ovf = false;
+    filter_voxelgrid(h.ctx, src.p, (int)n, leaf, min_points_per_voxel, res, ovf);
+    if (overflow) *overflow = ovf ? 1 : 0;
+    finish_filter(h, res, out, m, memspace);
+  });
+}
+
+b2r_status b2r_radius_outlier(b2r_handle* hh, const void* in, size_t n, size_t stride_bytes, int memspace, double radius, int min_neighbors,
+                              void* out, size_t* m) {
+  return guarded(hh, [&](Handle& h) {
+    if (!(radius > 0)) throw Error(B2R_ERR_INVALID_ARG, "radius must be > 0");
+    DBuf<float4> src;
+    load_points(h.ctx, in, n, stride_bytes, memspace, src);
+    DevCloud res;
+    filter_radius(h.ctx, h.cfg, src.p, (int)n, radius, min_neighbors, res);
+    finish_filter(h, res, out, m, memspace);
+  });
+}
+
+b2r_status b2r_statistical_outlier(b2r_handle* hh, const void* in, size_t n, size_t stride_bytes, int memspace, int mean_k, double stddev_mul,
+                                   void* out, size_t* m) {
+  return guarded(hh, [&](Handle& h) {
+    DBuf<float4> src;
+    load_points(h.ctx, in, n, stride_bytes, memspace, src);
+    DevCloud res;
+    filter_statistical(h.ctx, h.cfg, src.p, (int)n, mean_k, stddev_mul, res);
+    finish_filter(h, res, out, m, memspace);
+  });
+}
+
+b2r_status b2r_default_prefilter_config(b2r_prefilter_config* c) {
+  if (!c) return B2R_ERR_INVALID_ARG;
+  memset(c, 0, sizeof(*c));
+  c->enable_distance_filter = 1;  // config/mrg_slam.yaml:48-64
+  c->distance_near_thresh = 0.1;
+  c->distance_far_thresh = 35.0;
+  c->downsample_method = 1;
+  c->downsample_resolution = 0.1f;
+  c->downsample_min_points_per_voxel = 1;
+  c->outlier_removal_method = 2;
+  c->statistical_mean_k = 30;
+  c->statistical_stddev = 1.2;
+  c->radius_radius = 0.5;
+  c->radius_min_neighbors = 2;
+  return B2R_OK;
+}
+
+b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const void* in, size_t n, size_t stride_bytes, int memspace,
+                         void* out, size_t* m) {
+  return guarded(hh, [&](Handle& h) {
+    if (!cfg) throw Error(B2R_ERR_INVALID_ARG, "null config");
+    DevCloud cur;
+    load_points(h.ctx, in, n, stride_bytes, memspace, cur.pts);
+    cur.n = (int)n;
+    if (cfg->enable_distance_filter) {
+      DevCloud nxt;
+      filter_distance(h.ctx, cur.pts.p, cur.n, cfg->distance_near_thresh, cfg->distance_far_thresh, nxt);
+      cur = std::move(nxt);
+    }
+    if (cfg->downsample_method == 1) {
+      DevCloud nxt;
+      bool ovf = false;
+      filter_voxelgrid(h.ctx, cur.pts.p, cur.n, cfg->downsample_resolution, cfg->downsample_min_points_per_voxel, nxt, ovf);
+      cur = std::move(nxt);
+    }
+    if (cfg->outlier_removal_method == 1) {
+      DevCloud nxt;
+      filter_statistical(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->statistical_mean_k, cfg->statistical_stddev, nxt);
+      cur = std::move(nxt);
+    } else if (cfg->outlier_removal_method == 2) {
+      DevCloud nxt;
+      filter_radius(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->radius_radius, cfg->radius_min_neighbors, nxt);
+      cur = std::move(nxt);
+    }
+    finish_filter(h, cur, out, m, memspace);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ introspection
+uint64_t b2r_kernel_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.launches : 0; }
+
+b2r_status b2r_synchronize(b2r_handle* hh) {
+  return guarded(hh, [&](Handle& h) { B2R_CUDA(cudaStreamSynchronize(h.ctx.stream)); });
+}
+
+b2r_status b2r_last_timings(const b2r_handle* hh, float ms_out[4]) {
+  if (!hh || !ms_out) return B2R_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) ms_out[i] = hh->h.timings[i];
+  return B2R_OK;
+}
+
+b2r_status b2r_debug_covariances(b2r_handle* hh, int which, double* cov6_out, int32_t* knn_out) {
+  return guarded(hh, [&](Handle& h) {
+    Cloud* c = which == 0 ? h.source : h.target;
+    if (!c) throw Error(B2R_ERR_STATE, "cloud not set");
+    const int k = h.cfg.correspondence_randomness;
+    if (knn_out) {
+      debug_cov_knn(h.ctx, h.cfg, *c, k, knn_out);
+    } else {
+      std::vector<Cloud*> cl{c};
+      std::vector<Needs> nd(1);
+      nd[0].cov_k = k;
+      clouds_prepare(h.ctx, h.cfg, cl, nd);
+    }
+    if (cov6_out) {
+      B2R_CUDA(cudaMemcpyAsync(cov6_out, c->cov.p, sizeof(double) * 6 * c->n, cudaMemcpyDeviceToHost, h.ctx.stream));
+      B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    }
+  });
+}
+
+b2r_status b2r_debug_voxelmap(b2r_handle* hh, int32_t* coords_out, int32_t* npts_out, double* mean_out, double* cov6_out, size_t* V) {
+  return guarded(hh, [&](Handle& h) {
+    if (!h.target) throw Error(B2R_ERR_STATE, "target not set");
+    Cloud* c = h.target;
+    std::vector<Cloud*> cl{c};
+    std::vector<Needs> nd(1);
+    nd[0].cov_k = h.cfg.correspondence_randomness;
+    nd[0].vres = h.cfg.resolution;
+    clouds_prepare(h.ctx, h.cfg, cl, nd);
+    int nrec = 0;
+    B2R_CUDA(cudaMemcpyAsync(&nrec, c->v_nrec.p, sizeof(int), cudaMemcpyDeviceToHost, h.ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    std::vector<VoxRec> recs(nrec);
+    B2R_CUDA(cudaMemcpyAsync(recs.data(), c->vrec.p, sizeof(VoxRec) * nrec, cudaMemcpyDeviceToHost, h.ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    struct Item { int x, y, z; const VoxRec* r; };
+    std::vector<Item> items(nrec);
+    for (int i = 0; i < nrec; ++i) {
+      const int cell = recs[i].cell;
+      const int x = cell % c->vd[0], y = (cell / c->vd[0]) % c->vd[1], z = cell / (c->vd[0] * c->vd[1]);
+      items[i] = Item{x + c->vmin[0], y + c->vmin[1], z + c->vmin[2], &recs[i]};
+    }
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); });
+    for (int i = 0; i < nrec; ++i) {
+      coords_out[i * 3] = items[i].x; coords_out[i * 3 + 1] = items[i].y; coords_out[i * 3 + 2] = items[i].z;
+      npts_out[i] = items[i].r->n;
+      for (int d = 0; d < 3; ++d) mean_out[i * 3 + d] = items[i].r->mean[d];
+      for (int d = 0; d < 6; ++d) cov6_out[i * 6 + d] = items[i].r->cov[d];
+    }
+    *V = (size_t)nrec;
+  });
+}
+
+b2r_status b2r_debug_linearize(b2r_handle* hh, const double* T, double* H, double* b, double* err, int32_t* corr_out, uint8_t* corr_valid) {
+  return guarded(hh, [&](Handle& h) {
+    if (h.cfg.method == B2R_NDT_OMP) throw Error(B2R_ERR_STATE, "linearize is a GICP/VGICP entry point");
+    DBuf<CloudView> dv;
+    prepare_current(h, dv, false);
+    lsq_debug_linearize(h.ctx, h.cfg, dv.p, h.source->n, T, T, false, H, b, err, corr_out, corr_valid);
+  });
+}
+b2r_status b2r_debug_compute_error(b2r_handle* hh, const double* T_lin, const double* T_trial, double* err) {
+  return guarded(hh, [&](Handle& h) {
+    if (h.cfg.method == B2R_NDT_OMP) throw Error(B2R_ERR_STATE, "compute_error is a GICP/VGICP entry point");
+    DBuf<CloudView> dv;
+    prepare_current(h, dv, false);
+    lsq_debug_linearize(h.ctx, h.cfg, dv.p, h.source->n, T_lin, T_trial, true, nullptr, nullptr, err, nullptr, nullptr);
+  });
+}
+
+b2r_status b2r_debug_ndt_grid(b2r_handle* hh, int32_t* idx_out, int32_t* npts_out, double* mean_out, double* icov_out, int32_t* min_b,
+                              int32_t* div_b, size_t* V) {
+  return guarded(hh, [&](Handle& h) {
+    if (!h.target) throw Error(B2R_ERR_STATE, "target not set");
+    Cloud* c = h.target;
+    std::vector<Cloud*> cl{c};
+    std::vector<Needs> nd(1);
+    nd[0].leaf = (float)h.cfg.resolution;
+    clouds_prepare(h.ctx, h.cfg, cl, nd);
+    for (int d = 0; d < 3; ++d) { min_b[d] = c->min_b[d]; div_b[d] = c->div_b[d]; }
+    *V = 0;
+    if (c->ncell_ndt == 0) return;
+    int nrec = 0;
+    B2R_CUDA(cudaMemcpyAsync(&nrec, c->n_nrec.p, sizeof(int), cudaMemcpyDeviceToHost, h.ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    std::vector<NdtRec> recs(nrec);
+    B2R_CUDA(cudaMemcpyAsync(recs.data(), c->nrec.p, sizeof(NdtRec) * nrec, cudaMemcpyDeviceToHost, h.ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    std::sort(recs.begin(), recs.end(), [](const NdtRec& a, const NdtRec& b) { return a.cell < b.cell; });
+    for (int i = 0; i < nrec; ++i) {
+      idx_out[i] = recs[i].cell;
+      npts_out[i] = recs[i].n;
+      for (int d = 0; d < 3; ++d) mean_out[i * 3 + d] = recs[i].mean[d];
+      for (int d = 0; d < 9; ++d) icov_out[i * 9 + d] = recs[i].icov_d[d];
+    }
+    *V = (size_t)nrec;
+  });
+}
+
+b2r_status b2r_debug_ndt_derivatives(b2r_handle* hh, const double* p6, double* score, double* grad6, double* hess36, int32_t* hits_out) {
+  return guarded(hh, [&](Handle& h) {
+    if (h.cfg.method != B2R_NDT_OMP) throw Error(B2R_ERR_STATE, "ndt derivatives need an NDT_OMP handle");
+    DBuf<CloudView> dv;
+    prepare_current(h, dv, false);
+    ndt_debug_derivatives(h.ctx, h.cfg, dv.p, h.source->n, p6, score, grad6, hess36, hits_out);
+  });
+}
+
+b2r_status b2r_debug_knn(b2r_handle* hh, b2r_cloud* c, const float* queries, size_t nq, int k, int32_t* idx_out, float* d2_out) {
+  return guarded(hh, [&](Handle& h) {
+    if (!c || !queries || !idx_out || !d2_out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    debug_knn(h.ctx, h.cfg, c->c, queries, nq, k, idx_out, d2_out);
+  });
+}
+
+}  // extern "C"

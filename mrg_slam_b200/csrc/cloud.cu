@@ -1,0 +1,812 @@
+// Cloud-side structures: upload, bounding boxes, dense bucket grids (counting sort), exact kNN with
+// per-point covariances, VGICP Gaussian voxel maps and NDT voxel grids.
+//
+// Replaces (reference call sites -> upstream classes):
+//   A3/A5  fast_gicp setInputSource/Target + calculate_covariances   (registrations.cpp:55-63,76-84)
+//   A6     fast_gicp GaussianVoxelMap::create_voxelmap
+//   A10    pclomp::VoxelGridCovariance::filter                        (registrations.cpp:139)
+//   E13    pcl::search::KdTree (FLANN) exact kNN                      -> uniform grid, ring expansion
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <algorithm>
+
+#include "internal.hpp"
+#include "knn.cuh"
+
+namespace b2r {
+
+CloudView Cloud::view() const {
+  CloudView v;
+  memset(&v, 0, sizeof(v));
+  v.pts = pts.p; v.n = n;
+  for (int d = 0; d < 3; ++d) { v.bmin[d] = bmin[d]; v.bmax[d] = bmax[d]; }
+  v.h = h; v.inv_h = h > 0 ? 1.0f / h : 0.f;
+  for (int d = 0; d < 3; ++d) v.gd[d] = gd[d];
+  v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.spts = spts.p;
+  v.cov = cov.p;
+  v.vres = vres;
+  for (int d = 0; d < 3; ++d) { v.vmin[d] = vmin[d]; v.vd[d] = vd[d]; }
+  v.vcell = vcell; v.v_start = v_start.p; v.v_cnt = v_cnt.p; v.v_order = v_order.p; v.v_table = v_table.p; v.vrec = vrec.p;
+  v.v_nrec = v_nrec.p;
+  v.leaf = leaf; v.inv_leaf = leaf > 0 ? 1.0f / leaf : 0.f;
+  for (int d = 0; d < 3; ++d) { v.min_b[d] = min_b[d]; v.max_b[d] = max_b[d]; v.div_b[d] = div_b[d]; }
+  v.ncell_ndt = ncell_ndt; v.n_start = n_start.p; v.n_cnt = n_cnt.p; v.n_order = n_order.p; v.n_table = n_table.p; v.nrec = nrec.p;
+  v.n_nrec = n_nrec.p;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ I/O
+__global__ void repack32_kernel(const uint8_t* __restrict__ raw, int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = *reinterpret_cast<const float4*>(raw + (size_t)i * 32);
+  const float inten = *reinterpret_cast<const float*>(raw + (size_t)i * 32 + 16);
+  out[i] = make_float4(a.x, a.y, a.z, inten);
+}
+__global__ void unpack32_kernel(const float4* __restrict__ in, int n, uint8_t* __restrict__ raw) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = in[i];
+  *reinterpret_cast<float4*>(raw + (size_t)i * 32) = make_float4(p.x, p.y, p.z, 1.0f);
+  *reinterpret_cast<float4*>(raw + (size_t)i * 32 + 16) = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+
+void load_points(Ctx& ctx, const void* points, size_t n, size_t stride_bytes, int memspace, DBuf<float4>& dst) {
+  if (stride_bytes != 16 && stride_bytes != 32) throw Error(B2R_ERR_INVALID_ARG, "stride_bytes must be 16 or 32");
+  dst.alloc(n, ctx.stream);
+  if (n == 0) return;
+  cudaMemcpyKind kind = memspace == B2R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (stride_bytes == 16) {
+    B2R_CUDA(cudaMemcpyAsync(dst.p, points, n * 16, kind, ctx.stream));
+  } else {
+    DBuf<uint8_t> raw;
+    const uint8_t* src = (const uint8_t*)points;
+    if (memspace != B2R_DEVICE) {
+      raw.alloc(n * 32, ctx.stream);
+      B2R_CUDA(cudaMemcpyAsync(raw.p, points, n * 32, kind, ctx.stream));
+      src = raw.p;
+    }
+    B2R_LAUNCH(ctx, repack32_kernel, (unsigned)((n + 255) / 256), 256, 0, src, (int)n, dst.p);
+  }
+}
+
+void store_points(Ctx& ctx, const float4* src, size_t n, void* out, size_t stride_bytes, int memspace) {
+  if (stride_bytes != 16 && stride_bytes != 32) throw Error(B2R_ERR_INVALID_ARG, "stride_bytes must be 16 or 32");
+  if (n == 0) return;
+  cudaMemcpyKind kind = memspace == B2R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (stride_bytes == 16) {
+    B2R_CUDA(cudaMemcpyAsync(out, src, n * 16, kind, ctx.stream));
+  } else {
+    DBuf<uint8_t> raw;
+    uint8_t* dst = (uint8_t*)out;
+    if (memspace != B2R_DEVICE) { raw.alloc(n * 32, ctx.stream); dst = raw.p; }
+    B2R_LAUNCH(ctx, unpack32_kernel, (unsigned)((n + 255) / 256), 256, 0, src, (int)n, dst);
+    if (memspace != B2R_DEVICE) B2R_CUDA(cudaMemcpyAsync(out, raw.p, n * 32, kind, ctx.stream));
+  }
+  if (memspace != B2R_DEVICE) B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void cloud_upload(Ctx& ctx, Cloud& c, const void* points, size_t n, size_t stride_bytes, int memspace) {
+  if (n > (size_t)INT_MAX / 8) throw Error(B2R_ERR_INVALID_ARG, "cloud too large");
+  c.device = ctx.device;
+  c.n = (int)n;
+  load_points(ctx, points, n, stride_bytes, memspace, c.pts);
+  c.has_bbox = c.has_grid = false;
+  c.cov_k = 0; c.vres = 0.0; c.leaf = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ bbox
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+static inline float ordered_to_float(int i) {
+  int b = i >= 0 ? i : i ^ 0x7fffffff;
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+
+// bbox_out[cloud][6] ordered-int encoded (min x,y,z, max x,y,z); must be pre-initialised.
+__global__ void bbox_kernel(const CloudView* __restrict__ views, int* __restrict__ bbox_out) {
+  const CloudView& c = views[blockIdx.y];
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(&c.pts[i]);
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+    int* o = bbox_out + blockIdx.y * 6;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(&o[d], float_to_ordered(mn[d]));
+      atomicMax(&o[3 + d], float_to_ordered(mx[d]));
+    }
+  }
+}
+__global__ void bbox_init_kernel(int* bbox_out, int nclouds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nclouds * 6) bbox_out[i] = (i % 6) < 3 ? INT_MAX : INT_MIN;
+}
+
+// ------------------------------------------------------------------------------------------------ bucket grids
+enum { GRID_NN = 0, GRID_VGICP = 1, GRID_NDT = 2 };
+
+template <int MODE>
+__device__ __forceinline__ int cell_key(const CloudView& c, const float4& p) {
+  if (MODE == GRID_NN) {
+    int cx, cy, cz;
+    nn_cell_of(c, p.x, p.y, p.z, cx, cy, cz);
+    return (cz * c.gd[1] + cy) * c.gd[0] + cx;
+  } else if (MODE == GRID_VGICP) {
+    int x = vgicp_coord_d((double)p.x, c.vres) - c.vmin[0];
+    int y = vgicp_coord_d((double)p.y, c.vres) - c.vmin[1];
+    int z = vgicp_coord_d((double)p.z, c.vres) - c.vmin[2];
+    return (z * c.vd[1] + y) * c.vd[0] + x;
+  } else {
+    // pclomp::VoxelGridCovariance build key (float math, multiply by inverse leaf): SURVEY A.4
+    int i0 = (int)(floorf(__fmul_rn(p.x, c.inv_leaf)) - (float)c.min_b[0]);
+    int i1 = (int)(floorf(__fmul_rn(p.y, c.inv_leaf)) - (float)c.min_b[1]);
+    int i2 = (int)(floorf(__fmul_rn(p.z, c.inv_leaf)) - (float)c.min_b[2]);
+    return i0 + i1 * c.div_b[0] + i2 * c.div_b[0] * c.div_b[1];
+  }
+}
+template <int MODE>
+__device__ __forceinline__ int* grid_cnt(const CloudView& c) { return MODE == GRID_NN ? c.cell_cnt : (MODE == GRID_VGICP ? c.v_cnt : c.n_cnt); }
+template <int MODE>
+__device__ __forceinline__ int* grid_start(const CloudView& c) { return MODE == GRID_NN ? c.cell_start : (MODE == GRID_VGICP ? c.v_start : c.n_start); }
+template <int MODE>
+__device__ __forceinline__ int grid_ncell(const CloudView& c) { return MODE == GRID_NN ? c.ncell : (MODE == GRID_VGICP ? c.vcell : c.ncell_ndt); }
+
+template <int MODE>
+__global__ void grid_count_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.y];
+  int* cnt = grid_cnt<MODE>(c);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(&c.pts[i]);
+    atomicAdd(&cnt[cell_key<MODE>(c, p)], 1);
+  }
+}
+
+// One block per cloud: exclusive scan of the per-cell counts into start[0..ncell], counts reset to 0
+// (they become the scatter cursors).  For voxel grids also assigns compact record ids to occupied cells.
+template <int MODE>
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.x];
+  int* cnt = grid_cnt<MODE>(c);
+  int* start = grid_start<MODE>(c);
+  const int ncell = grid_ncell<MODE>(c);
+  int* table = MODE == GRID_VGICP ? c.v_table : (MODE == GRID_NDT ? c.n_table : nullptr);
+  constexpr int ITEMS = 8;
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < ncell; base += 1024 * ITEMS) {
+    int v[ITEMS];
+    unsigned long long tsum = 0ull;
+    const int i0 = base + threadIdx.x * ITEMS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      v[k] = (i0 + k < ncell) ? cnt[i0 + k] : 0;
+      tsum += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 32) : 0ull);  // lo: points, hi: occupied cells
+    }
+    unsigned long long incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = warp_tot[lane];
+      unsigned long long wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive offset of each warp inside the tile
+    }
+    __syncthreads();
+    unsigned long long run = carry_s + warp_tot[warp] + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      if (i0 + k < ncell) {
+        start[i0 + k] = (int)(run & 0xffffffffull);
+        if (MODE != GRID_NN) table[i0 + k] = v[k] > 0 ? (int)(run >> 32) : -1;
+        cnt[i0 + k] = 0;
+      }
+      run += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 32) : 0ull);
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;  // last thread's running total = carry after this tile
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    start[ncell] = (int)(carry_s & 0xffffffffull);
+    if (MODE == GRID_VGICP) c.v_nrec[0] = (int)(carry_s >> 32);
+    if (MODE == GRID_NDT) c.n_nrec[0] = (int)(carry_s >> 32);
+  }
+}
+
+template <int MODE>
+__global__ void grid_scatter_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.y];
+  int* cnt = grid_cnt<MODE>(c);
+  const int* start = grid_start<MODE>(c);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(&c.pts[i]);
+    int key = cell_key<MODE>(c, p);
+    int pos = start[key] + atomicAdd(&cnt[key], 1);
+    if (MODE == GRID_NN) c.spts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    else if (MODE == GRID_VGICP) c.v_order[pos] = i;
+    else c.n_order[pos] = i;
+  }
+}
+
+// in-place insertion sort of one voxel's point list (ascending original index => deterministic, index-order sums)
+__device__ __forceinline__ void sort_indices(int* a, int n) {
+  for (int i = 1; i < n; ++i) {
+    int v = a[i], j = i - 1;
+    while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+    a[j + 1] = v;
+  }
+}
+
+// VGICP: one thread per table cell; occupied cells sum their points' positions and covariances in
+// ascending point-index order (fast_gicp create_voxelmap), then divide by the count.
+__global__ void vgicp_reduce_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.y];
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < c.vcell; cell += gridDim.x * blockDim.x) {
+    const int rec = c.v_table[cell];
+    if (rec < 0) continue;
+    const int s = c.v_start[cell], e = c.v_start[cell + 1];
+    sort_indices(c.v_order + s, e - s);
+    double m0 = 0, m1 = 0, m2 = 0, cv[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = s; j < e; ++j) {
+      const int i = c.v_order[j];
+      float4 p = __ldg(&c.pts[i]);
+      m0 += (double)p.x; m1 += (double)p.y; m2 += (double)p.z;
+      const double* pc = c.cov + (size_t)i * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cv[k] += pc[k];
+    }
+    const double nn = (double)(e - s);
+    VoxRec r;
+    r.mean[0] = m0 / nn; r.mean[1] = m1 / nn; r.mean[2] = m2 / nn;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r.cov[k] = cv[k] / nn;
+    r.n = e - s;
+    r.cell = cell;
+    c.vrec[rec] = r;
+  }
+}
+
+// NDT: per-voxel mean, single-pass covariance, eigenvalue clamp and inverse (pclomp::VoxelGridCovariance)
+__global__ void ndt_reduce_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.y];
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < c.ncell_ndt; cell += gridDim.x * blockDim.x) {
+    const int rec = c.n_table[cell];
+    if (rec < 0) continue;
+    const int s = c.n_start[cell], e = c.n_start[cell + 1];
+    sort_indices(c.n_order + s, e - s);
+    double sum[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = s; j < e; ++j) {
+      float4 p = __ldg(&c.pts[c.n_order[j]]);
+      double q[3] = {(double)p.x, (double)p.y, (double)p.z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        sum[a] += q[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) cov[a * 3 + b] += q[a] * q[b];
+      }
+    }
+    NdtRec r;
+    const int npts = e - s;
+    const double nn = (double)npts;
+    double mean[3] = {sum[0] / nn, sum[1] / nn, sum[2] / nn};
+    r.mean[0] = mean[0]; r.mean[1] = mean[1]; r.mean[2] = mean[2];
+    r.n = npts;
+    r.cell = cell;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) { r.icov[a] = 0.f; r.icov_d[a] = 0.0; }
+    if (npts >= 6) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) cov[a * 3 + b] = (cov[a * 3 + b] - 2 * (sum[a] * mean[b])) / nn + mean[a] * mean[b];
+#pragma unroll
+      for (int a = 0; a < 9; ++a) cov[a] *= (nn - 1.0) / nn;
+      double S[9];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) S[a * 3 + b] = (a >= b) ? cov[a * 3 + b] : cov[b * 3 + a];
+      double ev[3], V[9];
+      sym3_eigen_dev(S, ev, V);
+      if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
+        r.n = -1;
+      } else {
+        double min_ev = 0.01 * ev[2];
+        if (ev[0] < min_ev) {
+          ev[0] = min_ev;
+          if (ev[1] < min_ev) ev[1] = min_ev;
+          // cov = V diag(ev) V^-1 (V orthonormal: inverse by cofactors as upstream does through Eigen)
+          double VL[9], Vi[9];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) VL[a * 3 + j] = V[a * 3 + j] * ev[j];
+          {
+            double c00 = V[4] * V[8] - V[5] * V[7], c01 = V[5] * V[6] - V[3] * V[8], c02 = V[3] * V[7] - V[4] * V[6];
+            double id = 1.0 / (V[0] * c00 + V[1] * c01 + V[2] * c02);
+            Vi[0] = c00 * id; Vi[1] = (V[2] * V[7] - V[1] * V[8]) * id; Vi[2] = (V[1] * V[5] - V[2] * V[4]) * id;
+            Vi[3] = c01 * id; Vi[4] = (V[0] * V[8] - V[2] * V[6]) * id; Vi[5] = (V[2] * V[3] - V[0] * V[5]) * id;
+            Vi[6] = c02 * id; Vi[7] = (V[1] * V[6] - V[0] * V[7]) * id; Vi[8] = (V[0] * V[4] - V[1] * V[3]) * id;
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) cov[a * 3 + b] = VL[a * 3 + 0] * Vi[0 * 3 + b] + VL[a * 3 + 1] * Vi[1 * 3 + b] + VL[a * 3 + 2] * Vi[2 * 3 + b];
+        }
+        double c00 = cov[4] * cov[8] - cov[5] * cov[7], c01 = cov[5] * cov[6] - cov[3] * cov[8], c02 = cov[3] * cov[7] - cov[4] * cov[6];
+        double id = 1.0 / (cov[0] * c00 + cov[1] * c01 + cov[2] * c02);
+        double ic[9];
+        ic[0] = c00 * id; ic[1] = (cov[2] * cov[7] - cov[1] * cov[8]) * id; ic[2] = (cov[1] * cov[5] - cov[2] * cov[4]) * id;
+        ic[3] = c01 * id; ic[4] = (cov[0] * cov[8] - cov[2] * cov[6]) * id; ic[5] = (cov[2] * cov[3] - cov[0] * cov[5]) * id;
+        ic[6] = c02 * id; ic[7] = (cov[1] * cov[6] - cov[0] * cov[7]) * id; ic[8] = (cov[0] * cov[4] - cov[1] * cov[3]) * id;
+        bool bad = false;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          if (isinf(ic[a])) bad = true;
+          r.icov[a] = (float)ic[a];
+          r.icov_d[a] = ic[a];
+        }
+        if (bad) r.n = -1;
+      }
+    }
+    c.nrec[rec] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kNN covariances
+// One warp per tile of 32 consecutive cell-sorted queries.  Per query: exact kNN (knn.cuh), mean/covariance of the
+// k neighbours in double, kept by lane q; afterwards every lane regularises its own covariance (PLANE:
+// singular values (1,1,1e-3), fast_gicp calculate_covariances).
+__global__ void __launch_bounds__(256) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+  const CloudView& c = views[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int base = tile * 32;
+  if (base >= c.n) return;
+  double my[6] = {0, 0, 0, 0, 0, 0};
+  int my_orig = -1;
+  const int nq = min(32, c.n - base);
+  for (int q = 0; q < nq; ++q) {
+    const float4 sp = __ldg(&c.spts[base + q]);
+    const unsigned long long key = warp_knn(c, sp.x, sp.y, sp.z, k, lane);
+    const int orig = __float_as_int(sp.w);
+    double x = 0, y = 0, z = 0;
+    const bool act = lane < k && key != ~0ull;
+    int nb_orig = -1;
+    if (act) {
+      const float4 nb = __ldg(&c.spts[(unsigned)(key & 0xffffffffull)]);
+      x = (double)nb.x; y = (double)nb.y; z = (double)nb.z;
+      nb_orig = __float_as_int(nb.w);
+    }
+    if (knn_out && lane < k) knn_out[(size_t)orig * k + lane] = nb_orig;
+    const double kk = (double)k;
+    const double mx = warp_sum(x) / kk, my_ = warp_sum(y) / kk, mz = warp_sum(z) / kk;
+    const double dx = act ? x - mx : 0.0, dy = act ? y - my_ : 0.0, dz = act ? z - mz : 0.0;
+    double cxx = warp_sum(dx * dx) / kk, cxy = warp_sum(dx * dy) / kk, cxz = warp_sum(dx * dz) / kk;
+    double cyy = warp_sum(dy * dy) / kk, cyz = warp_sum(dy * dz) / kk, czz = warp_sum(dz * dz) / kk;
+    if (lane == q) { my[0] = cxx; my[1] = cxy; my[2] = cxz; my[3] = cyy; my[4] = cyz; my[5] = czz; my_orig = orig; }
+  }
+  if (my_orig >= 0) {
+    double S[9] = {my[0], my[1], my[2], my[1], my[3], my[4], my[2], my[4], my[5]};
+    double ev[3], V[9];
+    sym3_eigen_dev(S, ev, V);
+    const double vals[3] = {1e-3, 1.0, 1.0};  // ascending eigen order: smallest = plane normal
+    double o[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double a = V[0 * 3 + j], b = V[1 * 3 + j], cc = V[2 * 3 + j];
+      o[0] += vals[j] * a * a; o[1] += vals[j] * a * b; o[2] += vals[j] * a * cc;
+      o[3] += vals[j] * b * b; o[4] += vals[j] * b * cc; o[5] += vals[j] * cc * cc;
+    }
+    double* dst = c.cov + (size_t)my_orig * 6;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) dst[t] = o[t];
+  }
+}
+
+// arbitrary queries (debug / tests): one warp per query
+__global__ void knn_query_kernel(const CloudView* __restrict__ views, const float4* __restrict__ queries, int nq, int k,
+                                 int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
+  const CloudView& c = views[0];
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const float4 p = __ldg(&queries[q]);
+  const unsigned long long key = warp_knn(c, p.x, p.y, p.z, k, lane);
+  if (lane < k) {
+    if (key != ~0ull) {
+      idx_out[(size_t)q * k + lane] = __float_as_int(c.spts[(unsigned)(key & 0xffffffffull)].w);
+      d2_out[(size_t)q * k + lane] = __uint_as_float((unsigned)(key >> 32));
+    } else {
+      idx_out[(size_t)q * k + lane] = -1;
+      d2_out[(size_t)q * k + lane] = INFINITY;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host orchestration
+static float auto_cell_size(const Cloud& c, const b2r_config& cfg) {
+  if (cfg.nn_cell_size > 0) return (float)cfg.nn_cell_size;
+  double dx = std::max(1e-3f, c.bmax[0] - c.bmin[0]), dy = std::max(1e-3f, c.bmax[1] - c.bmin[1]);
+  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 1.2; }();
+  double h = factor * std::sqrt(dx * dy / std::max(1, c.n));
+  return (float)std::min(4.0, std::max(0.05, h));
+}
+
+static void grid_dims(Cloud& c, float h) {
+  const long cap = 1l << 24;
+  for (;;) {
+    long tot = 1;
+    for (int d = 0; d < 3; ++d) {
+      c.gd[d] = (int)std::floor((c.bmax[d] - c.bmin[d]) / h) + 1;
+      tot *= c.gd[d];
+    }
+    if (tot <= cap) { c.ncell = (int)tot; c.h = h; return; }
+    h *= 1.26f;
+  }
+}
+
+static inline unsigned blocks_for(int n, int per_block, int cap) { return (unsigned)std::max(1, std::min(cap, (n + per_block - 1) / per_block)); }
+
+void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
+  std::vector<Cloud*> todo;
+  for (Cloud* c : clouds)
+    if (!c->has_bbox && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
+  if (todo.empty()) return;
+  const int nc = (int)todo.size();
+  std::vector<CloudView> hv(nc);
+  int maxn = 1;
+  for (int i = 0; i < nc; ++i) { hv[i] = todo[i]->view(); maxn = std::max(maxn, todo[i]->n); }
+  DBuf<CloudView> dv; dv.alloc(nc, ctx.stream);
+  DBuf<int> db; db.alloc((size_t)nc * 6, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * nc, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, bbox_init_kernel, (nc * 6 + 255) / 256, 256, 0, db.p, nc);
+  dim3 g(blocks_for(maxn, 256 * 8, 64), nc);
+  B2R_LAUNCH(ctx, bbox_kernel, g, 256, 0, dv.p, db.p);
+  std::vector<int> hb((size_t)nc * 6);
+  B2R_CUDA(cudaMemcpyAsync(hb.data(), db.p, sizeof(int) * nc * 6, cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int i = 0; i < nc; ++i) {
+    Cloud* c = todo[i];
+    for (int d = 0; d < 3; ++d) {
+      c->bmin[d] = c->n ? ordered_to_float(hb[i * 6 + d]) : 0.f;
+      c->bmax[d] = c->n ? ordered_to_float(hb[i * 6 + 3 + d]) : 0.f;
+    }
+    c->has_bbox = true;
+  }
+}
+
+template <int MODE>
+static void run_grid_build(Ctx& ctx, const CloudView* dviews, int nc, int maxn) {
+  dim3 g(blocks_for(maxn, 256 * 4, 4 * ctx.num_sms), nc);
+  B2R_LAUNCH(ctx, grid_count_kernel<MODE>, g, 256, 0, dviews);
+  B2R_LAUNCH(ctx, grid_scan_kernel<MODE>, nc, 1024, 0, dviews);
+  B2R_LAUNCH(ctx, grid_scatter_kernel<MODE>, g, 256, 0, dviews);
+}
+
+void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds_in, const std::vector<Needs>& needs_in) {
+  // merge duplicate clouds
+  std::vector<Cloud*> clouds;
+  std::vector<Needs> needs;
+  for (size_t i = 0; i < clouds_in.size(); ++i) {
+    Cloud* c = clouds_in[i];
+    if (c->device != ctx.device) throw Error(B2R_ERR_INVALID_ARG, "cloud lives on another device");
+    size_t j = 0;
+    for (; j < clouds.size(); ++j)
+      if (clouds[j] == c) break;
+    if (j == clouds.size()) { clouds.push_back(c); needs.push_back(Needs()); }
+    Needs& nd = needs[j];
+    const Needs& in = needs_in[i];
+    nd.grid = nd.grid || in.grid || in.cov_k > 0;
+    nd.cov_k = std::max(nd.cov_k, in.cov_k);
+    if (in.vres > 0) nd.vres = in.vres;
+    if (in.leaf > 0) nd.leaf = in.leaf;
+    if (nd.vres > 0 && nd.cov_k == 0) throw Error(B2R_ERR_STATE, "voxel map needs covariances");
+  }
+  clouds_compute_bbox(ctx, clouds);
+
+  // ---- NN grids
+  {
+    std::vector<Cloud*> todo;
+    for (size_t i = 0; i < clouds.size(); ++i)
+      if (needs[i].grid && !clouds[i]->has_grid && clouds[i]->n > 0) todo.push_back(clouds[i]);
+    if (!todo.empty()) {
+      int maxn = 1;
+      for (Cloud* c : todo) {
+        grid_dims(*c, auto_cell_size(*c, cfg));
+        c->cell_start.alloc((size_t)c->ncell + 1, ctx.stream);
+        c->cell_cnt.alloc((size_t)c->ncell, ctx.stream);
+        c->cell_cnt.zero(ctx.stream);
+        c->spts.alloc((size_t)c->n, ctx.stream);
+        maxn = std::max(maxn, c->n);
+      }
+      std::vector<CloudView> hv;
+      for (Cloud* c : todo) hv.push_back(c->view());
+      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
+      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+      run_grid_build<GRID_NN>(ctx, dv.p, (int)hv.size(), maxn);
+      B2R_CUDA(cudaStreamSynchronize(ctx.stream));  // hv must outlive the async copy
+      for (Cloud* c : todo) c->has_grid = true;
+    }
+  }
+  // ---- covariances
+  {
+    std::vector<Cloud*> todo;
+    int k = 0;
+    for (size_t i = 0; i < clouds.size(); ++i)
+      if (needs[i].cov_k > 0 && clouds[i]->cov_k != needs[i].cov_k && clouds[i]->n > 0) { todo.push_back(clouds[i]); k = needs[i].cov_k; }
+    if (!todo.empty()) {
+      if (k > 32) throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be <= 32");
+      int maxn = 1;
+      for (Cloud* c : todo) {
+        if (c->n < k) throw Error(B2R_ERR_INVALID_ARG, "cloud has fewer points than correspondence_randomness");
+        c->cov.alloc((size_t)c->n * 6, ctx.stream);
+        maxn = std::max(maxn, c->n);
+        c->vres = 0.0;  // a voxel map built from older covariances is stale
+      }
+      std::vector<CloudView> hv;
+      for (Cloud* c : todo) hv.push_back(c->view());
+      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
+      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+      dim3 g((unsigned)((maxn + 255) / 256), (unsigned)hv.size());  // 8 warps x 32 queries per block
+      B2R_LAUNCH(ctx, knn_cov_kernel, g, 256, 0, dv.p, k, (int32_t*)nullptr);
+      B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+      for (Cloud* c : todo) c->cov_k = k;
+    }
+  }
+  // ---- VGICP voxel maps
+  {
+    std::vector<Cloud*> todo;
+    for (size_t i = 0; i < clouds.size(); ++i)
+      if (needs[i].vres > 0 && clouds[i]->vres != needs[i].vres && clouds[i]->n > 0) {
+        Cloud* c = clouds[i];
+        const double res = needs[i].vres;
+        long tot = 1;
+        for (int d = 0; d < 3; ++d) {
+          c->vmin[d] = (int)std::floor((double)c->bmin[d] / res - 0.5);
+          int vmax = (int)std::floor((double)c->bmax[d] / res - 0.5);
+          c->vd[d] = vmax - c->vmin[d] + 1;
+          tot *= c->vd[d];
+        }
+        if (tot > (1l << 26)) throw Error(B2R_ERR_CAPACITY, "VGICP voxel table too large for this extent/resolution");
+        c->vcell = (int)tot;
+        c->v_start.alloc((size_t)tot + 1, ctx.stream);
+        c->v_cnt.alloc((size_t)tot, ctx.stream);
+        c->v_cnt.zero(ctx.stream);
+        c->v_table.alloc((size_t)tot, ctx.stream);
+        c->v_order.alloc((size_t)c->n, ctx.stream);
+        c->vrec.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
+        c->v_nrec.alloc(1, ctx.stream);
+        c->vres = res;
+        todo.push_back(c);
+      }
+    if (!todo.empty()) {
+      int maxn = 1, maxcell = 1;
+      std::vector<CloudView> hv;
+      for (Cloud* c : todo) { hv.push_back(c->view()); maxn = std::max(maxn, c->n); maxcell = std::max(maxcell, c->vcell); }
+      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
+      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+      run_grid_build<GRID_VGICP>(ctx, dv.p, (int)hv.size(), maxn);
+      dim3 g(blocks_for(maxcell, 128, 8 * ctx.num_sms), (unsigned)hv.size());
+      B2R_LAUNCH(ctx, vgicp_reduce_kernel, g, 128, 0, dv.p);
+      B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+  }
+  // ---- NDT grids
+  {
+    std::vector<Cloud*> todo;
+    for (size_t i = 0; i < clouds.size(); ++i)
+      if (needs[i].leaf > 0 && clouds[i]->leaf != needs[i].leaf && clouds[i]->n > 0) {
+        Cloud* c = clouds[i];
+        const float leaf = needs[i].leaf, inv_leaf = 1.0f / leaf;
+        int64_t dx = (int64_t)((c->bmax[0] - c->bmin[0]) * inv_leaf) + 1, dy = (int64_t)((c->bmax[1] - c->bmin[1]) * inv_leaf) + 1,
+                dz = (int64_t)((c->bmax[2] - c->bmin[2]) * inv_leaf) + 1;
+        c->leaf = leaf;
+        c->ndt_overflow = dx * dy * dz > (int64_t)INT32_MAX;  // PCL: warn, grid stays empty
+        long tot = 1;
+        for (int d = 0; d < 3; ++d) {
+          c->min_b[d] = (int)std::floor(c->bmin[d] * inv_leaf);
+          c->max_b[d] = (int)std::floor(c->bmax[d] * inv_leaf);
+          c->div_b[d] = c->max_b[d] - c->min_b[d] + 1;
+          tot *= c->div_b[d];
+        }
+        if (c->ndt_overflow) { c->ncell_ndt = 0; continue; }
+        if (tot > (1l << 26)) throw Error(B2R_ERR_CAPACITY, "NDT voxel table too large for this extent/resolution");
+        c->ncell_ndt = (int)tot;
+        c->n_start.alloc((size_t)tot + 1, ctx.stream);
+        c->n_cnt.alloc((size_t)tot, ctx.stream);
+        c->n_cnt.zero(ctx.stream);
+        c->n_table.alloc((size_t)tot, ctx.stream);
+        c->n_order.alloc((size_t)c->n, ctx.stream);
+        c->nrec.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
+        c->n_nrec.alloc(1, ctx.stream);
+        todo.push_back(c);
+      }
+    if (!todo.empty()) {
+      int maxn = 1, maxcell = 1;
+      std::vector<CloudView> hv;
+      for (Cloud* c : todo) { hv.push_back(c->view()); maxn = std::max(maxn, c->n); maxcell = std::max(maxcell, c->ncell_ndt); }
+      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
+      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+      run_grid_build<GRID_NDT>(ctx, dv.p, (int)hv.size(), maxn);
+      dim3 g(blocks_for(maxcell, 128, 8 * ctx.num_sms), (unsigned)hv.size());
+      B2R_LAUNCH(ctx, ndt_reduce_kernel, g, 128, 0, dv.p);
+      B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+  }
+}
+
+void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, size_t nq, int k, int32_t* idx_out, float* d2_out) {
+  if (k < 1 || k > 32) throw Error(B2R_ERR_INVALID_ARG, "k must be in [1,32]");
+  std::vector<Cloud*> cl{&c};
+  std::vector<Needs> nd(1);
+  nd[0].grid = true;
+  clouds_prepare(ctx, cfg, cl, nd);
+  CloudView hv = c.view();
+  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<float4> dq; dq.alloc(nq, ctx.stream);
+  DBuf<int32_t> di; di.alloc(nq * k, ctx.stream);
+  DBuf<float> dd; dd.alloc(nq * k, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dq.p, queries, nq * 16, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, knn_query_kernel, (unsigned)((nq + 7) / 8), 256, 0, dv.p, dq.p, (int)nq, k, di.p, dd.p);
+  B2R_CUDA(cudaMemcpyAsync(idx_out, di.p, nq * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaMemcpyAsync(d2_out, dd.p, nq * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* knn_out) {
+  std::vector<Cloud*> cl{&c};
+  std::vector<Needs> nd(1);
+  nd[0].grid = true;
+  clouds_prepare(ctx, cfg, cl, nd);
+  c.cov.alloc((size_t)c.n * 6, ctx.stream);
+  CloudView hv = c.view();
+  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<int32_t> dk; dk.alloc((size_t)c.n * k, ctx.stream);
+  B2R_LAUNCH(ctx, knn_cov_kernel, (unsigned)((c.n + 255) / 256), 256, 0, dv.p, k, dk.p);
+  B2R_CUDA(cudaMemcpyAsync(knn_out, dk.p, (size_t)c.n * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  c.cov_k = k;
+  c.vres = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ compaction
+// order-preserving stream compaction: block counts -> single-block scan -> scatter
+__global__ void compact_count_kernel(const uint8_t* __restrict__ keep, int n, int* __restrict__ block_cnt) {
+  __shared__ int wsum[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (i < n && keep[i]) ? 1 : 0;
+  int s = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ block_cnt, int nblocks, int* __restrict__ total) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? block_cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + warp_tot[warp] + incl - v;
+    if (i < nblocks) block_cnt[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void compact_scatter_kernel(const float4* __restrict__ in, const uint8_t* __restrict__ keep, int n,
+                                       const int* __restrict__ block_off, float4* __restrict__ out) {
+  __shared__ int wsum[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = (i < n && keep[i]) ? 1 : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, v);
+  if (lane == 0) wsum[warp] = __popc(bal);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += wsum[w];
+  if (v) out[block_off[blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u))] = in[i];
+}
+
+void compact_points(Ctx& ctx, const float4* in, const uint8_t* keep, int n, DevCloud& out) {
+  out.n = 0;
+  if (n == 0) return;
+  const int nb = (n + 255) / 256;
+  DBuf<int> cnt; cnt.alloc((size_t)nb + 1, ctx.stream);
+  B2R_LAUNCH(ctx, compact_count_kernel, nb, 256, 0, keep, n, cnt.p);
+  B2R_LAUNCH(ctx, compact_scan_kernel, 1, 1024, 0, cnt.p, nb, cnt.p + nb);
+  out.pts.alloc((size_t)n, ctx.stream);
+  B2R_LAUNCH(ctx, compact_scatter_kernel, nb, 256, 0, in, keep, n, cnt.p, out.pts.p);
+  int total = 0;
+  B2R_CUDA(cudaMemcpyAsync(&total, cnt.p + nb, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  out.n = total;
+}
+
+}  // namespace b2r
+
+namespace b2r {
+
+// block_off: nb + 1 ints (nb = ceil(n/256)): exclusive per-block offsets of the set flags, then the total
+void flags_block_offsets(Ctx& ctx, const uint8_t* flags, int n, int* block_off) {
+  const int nb = (n + 255) / 256;
+  B2R_LAUNCH(ctx, compact_count_kernel, nb, 256, 0, flags, n, block_off);
+  B2R_LAUNCH(ctx, compact_scan_kernel, 1, 1024, 0, block_off, nb, block_off + nb);
+}
+
+void compute_bbox(Ctx& ctx, const float4* pts, int n, float mn[3], float mx[3]) {
+  CloudView hv;
+  memset(&hv, 0, sizeof(hv));
+  hv.pts = pts;
+  hv.n = n;
+  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
+  DBuf<int> db; db.alloc(6, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, bbox_init_kernel, 1, 32, 0, db.p, 1);
+  B2R_LAUNCH(ctx, bbox_kernel, dim3(blocks_for(n, 256 * 8, 2 * ctx.num_sms), 1), 256, 0, dv.p, db.p);
+  int hb[6];
+  B2R_CUDA(cudaMemcpyAsync(hb, db.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int d = 0; d < 3; ++d) { mn[d] = ordered_to_float(hb[d]); mx[d] = ordered_to_float(hb[3 + d]); }
+}
+
+}  // namespace b2r

@@ -1,0 +1,285 @@
+// libb2r internal definitions shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b2r.h"
+
+namespace b2r {
+
+struct Error : std::runtime_error {
+  b2r_status status;
+  Error(b2r_status s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+#define B2R_CUDA(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      char _b[512];                                                                                          \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw ::b2r::Error(B2R_ERR_CUDA, _b);                                                                  \
+    }                                                                                                        \
+  } while (0)
+
+// Execution context of one handle: device, stream, launch counter.
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  int num_sms = 148;
+};
+
+#define B2R_LAUNCH(ctx, kernel, grid, block, smem, ...)            \
+  do {                                                             \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__); \
+    ++(ctx).launches;                                              \
+    B2R_CUDA(cudaGetLastError());                                  \
+  } while (0)
+
+// Stream-ordered device buffer.
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(size_t count, cudaStream_t stream) {
+    if (count <= n && p) { s = stream; return; }
+    release();
+    s = stream;
+    n = count;
+    if (count) B2R_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  void zero(cudaStream_t stream) { if (p) B2R_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), stream)); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Device-side view of a cloud and of its cached structures.  Kernels that work on many clouds take an
+// array of these and pick views[blockIdx.y].
+struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap)
+  double mean[3];
+  double cov[6];     // xx,xy,xz,yy,yz,zz
+  int n;
+  int cell;          // dense cell index inside the table (debug / export)
+};
+struct NdtRec {      // NDT leaf (pclomp::VoxelGridCovariance)
+  double mean[3];
+  float icov[9];     // inverse covariance rounded to float (updateDerivatives casts it on use)
+  int n;             // nr_points, -1 if unusable
+  int cell;
+  double icov_d[9];  // full-precision copy for export
+};
+
+struct CloudView {
+  const float4* pts;  // original order: x,y,z,intensity
+  int n;
+  float bmin[3], bmax[3];
+  // exact-NN grid (uniform, dense cell table; points copied in cell order, w = original index bits)
+  float h, inv_h;
+  int gd[3];
+  int ncell;
+  int* cell_start;  // ncell + 1
+  int* cell_cnt;    // ncell (count, then scatter cursor)
+  float4* spts;
+  // per-point covariances (original order)
+  double* cov;
+  // VGICP voxel map
+  double vres;
+  int vmin[3], vd[3];
+  int vcell;
+  int* v_start;   // vcell + 1
+  int* v_cnt;     // vcell
+  int* v_order;   // n, point indices grouped by voxel
+  int* v_table;   // vcell: record id or -1
+  VoxRec* vrec;
+  int* v_nrec;    // [1] number of records
+  // NDT grid
+  float leaf, inv_leaf;
+  int min_b[3], max_b[3], div_b[3];
+  int ncell_ndt;
+  int* n_start;
+  int* n_cnt;
+  int* n_order;
+  int* n_table;
+  NdtRec* nrec;
+  int* n_nrec;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of K doubles held per thread in v[0..K).  Result valid in thread 0..K-1 of warp 0
+// as return value for element threadIdx.x; fixed order => deterministic.  smem: K * (blockDim/32) doubles.
+template <int K>
+__device__ __forceinline__ void block_reduce_to(double* v, double* smem, double* out /*global, K values*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) smem[warp * K + k] = s;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nwarp; ++w) s += smem[w * K + k];
+    out[k] = s;
+  }
+  __syncthreads();
+}
+
+// FLANN L2_Simple squared distance: float accumulation in dimension order, no FMA contraction.
+__device__ __forceinline__ float dist2_flann(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  float r = __fmul_rn(dx, dx);
+  r = __fadd_rn(r, __fmul_rn(dy, dy));
+  r = __fadd_rn(r, __fmul_rn(dz, dz));
+  return r;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ void nn_cell_of(const CloudView& c, float x, float y, float z, int& cx, int& cy, int& cz) {
+  cx = clampi((int)floorf((x - c.bmin[0]) * c.inv_h), 0, c.gd[0] - 1);
+  cy = clampi((int)floorf((y - c.bmin[1]) * c.inv_h), 0, c.gd[1] - 1);
+  cz = clampi((int)floorf((z - c.bmin[2]) * c.inv_h), 0, c.gd[2] - 1);
+}
+// unclamped variant for queries that may lie outside the grid
+__device__ __forceinline__ void nn_cell_of_unclamped(const CloudView& c, float x, float y, float z, int& cx, int& cy, int& cz) {
+  const float big = 1.0e9f;
+  cx = (int)fminf(fmaxf(floorf((x - c.bmin[0]) * c.inv_h), -big), big);
+  cy = (int)fminf(fmaxf(floorf((y - c.bmin[1]) * c.inv_h), -big), big);
+  cz = (int)fminf(fmaxf(floorf((z - c.bmin[2]) * c.inv_h), -big), big);
+}
+
+// fast_gicp voxel_coord: floor(x / resolution - 0.5) in double
+__device__ __forceinline__ int vgicp_coord_d(double x, double res) { return (int)floor(x / res - 0.5); }
+
+// neighbour offsets: DIRECT1 {0}; DIRECT7 {0,+x,-x,+y,-y,+z,-z}; DIRECT27 full 3x3x3
+__device__ __forceinline__ void neighbor_offset(int mode, int o, int& ox, int& oy, int& oz) {
+  ox = oy = oz = 0;
+  if (mode == B2R_DIRECT7) {
+    if (o == 1) ox = 1; else if (o == 2) ox = -1; else if (o == 3) oy = 1; else if (o == 4) oy = -1; else if (o == 5) oz = 1; else if (o == 6) oz = -1;
+  } else if (mode == B2R_DIRECT27) {
+    ox = o / 9 - 1; oy = (o / 3) % 3 - 1; oz = o % 3 - 1;
+  }
+}
+
+// symmetric 3x3 helpers on 6-vectors (xx,xy,xz,yy,yz,zz)
+__device__ __forceinline__ void sym3_inverse(const double* s, double* inv) {
+  double c00 = s[3] * s[5] - s[4] * s[4];
+  double c01 = s[2] * s[4] - s[1] * s[5];
+  double c02 = s[1] * s[4] - s[2] * s[3];
+  double det = s[0] * c00 + s[1] * c01 + s[2] * c02;
+  double id = 1.0 / det;
+  inv[0] = c00 * id;
+  inv[1] = c01 * id;
+  inv[2] = c02 * id;
+  inv[3] = (s[0] * s[5] - s[2] * s[2]) * id;
+  inv[4] = (s[1] * s[2] - s[0] * s[4]) * id;
+  inv[5] = (s[0] * s[3] - s[1] * s[1]) * id;
+}
+// R S R^T for symmetric S (6) and row-major R (9) -> symmetric (6)
+__device__ __forceinline__ void rsrt(const double* R, const double* s, double* o) {
+  double A[9];  // A = R * S
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    A[r * 3 + 0] = R[r * 3 + 0] * s[0] + R[r * 3 + 1] * s[1] + R[r * 3 + 2] * s[2];
+    A[r * 3 + 1] = R[r * 3 + 0] * s[1] + R[r * 3 + 1] * s[3] + R[r * 3 + 2] * s[4];
+    A[r * 3 + 2] = R[r * 3 + 0] * s[2] + R[r * 3 + 1] * s[4] + R[r * 3 + 2] * s[5];
+  }
+  o[0] = A[0] * R[0] + A[1] * R[1] + A[2] * R[2];
+  o[1] = A[0] * R[3] + A[1] * R[4] + A[2] * R[5];
+  o[2] = A[0] * R[6] + A[1] * R[7] + A[2] * R[8];
+  o[3] = A[3] * R[3] + A[4] * R[4] + A[5] * R[5];
+  o[4] = A[3] * R[6] + A[4] * R[7] + A[5] * R[8];
+  o[5] = A[6] * R[6] + A[7] * R[7] + A[8] * R[8];
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (full 9, row-major).  evals ascending, V columns.
+__device__ inline void sym3_eigen_dev(const double* Ain, double* evals, double* V) {
+  double A[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = Ain[i];
+  double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+    double diag = A[0] * A[0] + A[4] * A[4] + A[8] * A[8];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+      double apq = A[p * 3 + q];
+      if (apq == 0.0) continue;
+      double app = A[p * 3 + p], aqq = A[q * 3 + q];
+      double theta = (aqq - app) / (2.0 * apq);
+      double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double akp = A[k * 3 + p], akq = A[k * 3 + q];
+        A[k * 3 + p] = c * akp - s * akq;
+        A[k * 3 + q] = s * akp + c * akq;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+        A[p * 3 + k] = c * apk - s * aqk;
+        A[q * 3 + k] = s * apk + c * aqk;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double qkp = Q[k * 3 + p], qkq = Q[k * 3 + q];
+        Q[k * 3 + p] = c * qkp - s * qkq;
+        Q[k * 3 + q] = s * qkp + c * qkq;
+      }
+    }
+  }
+  double d0 = A[0], d1 = A[4], d2 = A[8];
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (d1 < d0) { double t = d0; d0 = d1; d1 = t; int ti = i0; i0 = i1; i1 = ti; }
+  if (d2 < d1) { double t = d1; d1 = d2; d2 = t; int ti = i1; i1 = i2; i2 = ti; }
+  if (d1 < d0) { double t = d0; d0 = d1; d1 = t; int ti = i0; i0 = i1; i1 = ti; }
+  evals[0] = d0; evals[1] = d1; evals[2] = d2;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    V[i * 3 + 0] = Q[i * 3 + i0];
+    V[i * 3 + 1] = Q[i * 3 + i1];
+    V[i * 3 + 2] = Q[i * 3 + i2];
+  }
+}
+
+}  // namespace b2r

@@ -1,0 +1,282 @@
+// Prefiltering kernels: distance filter, VoxelGrid, radius / statistical outlier removal.
+//
+// Replaces: A19 distance_filter (apps/prefiltering_component.cpp:206-229, in-tree),
+// A16 pcl::VoxelGrid<PointXYZI>::filter (:167-171; apps/scan_matching_odometry_component.cpp:175-179),
+// A17 pcl::RadiusOutlierRemoval (:195-199), A18 pcl::StatisticalOutlierRemoval (:190-194).
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "internal.hpp"
+#include "knn.cuh"
+
+namespace b2r {
+
+void compute_bbox(Ctx& ctx, const float4* pts, int n, float mn[3], float mx[3]);  // cloud.cu
+
+// ------------------------------------------------------------------------------------------------ distance filter
+// keep iff near < |p| < far, norm in float as x^2 + (y^2 + z^2) (Eigen 3-vector reduction order), widened to double
+__global__ void distance_flag_kernel(const float4* __restrict__ in, int n, double near_t, double far_t, uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  const float s = __fadd_rn(__fmul_rn(p.x, p.x), __fadd_rn(__fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z)));
+  const double d = (double)__fsqrt_rn(s);
+  keep[i] = (d > near_t && d < far_t) ? 1 : 0;
+}
+
+void filter_distance(Ctx& ctx, const float4* in, int n, double near_t, double far_t, DevCloud& out) {
+  out.n = 0;
+  if (n == 0) return;
+  DBuf<uint8_t> keep; keep.alloc(n, ctx.stream);
+  B2R_LAUNCH(ctx, distance_flag_kernel, (n + 255) / 256, 256, 0, in, n, near_t, far_t, keep.p);
+  compact_points(ctx, in, keep.p, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------ VoxelGrid
+struct VgParams {
+  float inv_leaf;
+  int min_b[3];
+  int mul[3];
+};
+
+// key = dense voxel index (pcl::VoxelGrid: float math, floor(p*inv_leaf) - min_b), value = point index
+__global__ void vg_key_kernel(const float4* __restrict__ in, int n, VgParams prm, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  unsigned key = 0xffffffffu;  // non-finite points sort last and are dropped
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    const int i0 = (int)(floorf(__fmul_rn(p.x, prm.inv_leaf)) - (float)prm.min_b[0]);
+    const int i1 = (int)(floorf(__fmul_rn(p.y, prm.inv_leaf)) - (float)prm.min_b[1]);
+    const int i2 = (int)(floorf(__fmul_rn(p.z, prm.inv_leaf)) - (float)prm.min_b[2]);
+    key = (unsigned)(i0 * prm.mul[0] + i1 * prm.mul[1] + i2 * prm.mul[2]);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+__global__ void vg_head_kernel(const unsigned* __restrict__ keys, int n, uint8_t* __restrict__ head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned k = keys[i];
+  head[i] = (k != 0xffffffffu && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+}
+// counts per block of 256 -> (after scan) offsets; then each head writes its position
+__global__ void vg_seg_kernel(const uint8_t* __restrict__ head, int n, const int* __restrict__ block_off, int* __restrict__ seg_start) {
+  __shared__ int wsum[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = (i < n && head[i]) ? 1 : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, v);
+  if (lane == 0) wsum[warp] = __popc(bal);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += wsum[w];
+  if (v) seg_start[block_off[blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u))] = i;
+}
+// one thread per voxel: pcl::CentroidPoint<PointXYZI> — float sums in (stable-sorted = ascending point index) order,
+// divided by float(count)
+__global__ void vg_centroid_kernel(const float4* __restrict__ in, const int* __restrict__ vals, const int* __restrict__ seg_start, int nseg,
+                                   int n_valid, int min_pts, float4* __restrict__ out, uint8_t* __restrict__ keep) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const int b = seg_start[s], e = (s + 1 < nseg) ? seg_start[s + 1] : n_valid;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  for (int j = b; j < e; ++j) {
+    const float4 p = __ldg(&in[vals[j]]);
+    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+  }
+  const float cnt = (float)(e - b);
+  out[s] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
+  if (keep) keep[s] = (e - b) >= min_pts ? 1 : 0;
+}
+__global__ void count_valid_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ n_valid) {
+  // keys sorted ascending: the first 0xffffffff marks the end of the finite points
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool valid = keys[i] != 0xffffffffu;
+  const bool next_valid = (i + 1 < n) ? keys[i + 1] != 0xffffffffu : false;
+  if (valid && !next_valid) *n_valid = i + 1;
+}
+
+void flags_block_offsets(Ctx& ctx, const uint8_t* flags, int n, int* block_off);  // cloud.cu
+
+void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow) {
+  overflow = false;
+  out.n = 0;
+  if (n == 0) return;
+  float mn[3], mx[3];
+  compute_bbox(ctx, in, n, mn, mx);
+  const float inv_leaf = 1.0f / leaf;
+  const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv_leaf) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv_leaf) + 1,
+                dz = (int64_t)((mx[2] - mn[2]) * inv_leaf) + 1;
+  if (dx * dy * dz > (int64_t)INT32_MAX) {  // PCL: "Leaf size is too small ... Integer indices would overflow": output = input
+    overflow = true;
+    out.pts.alloc(n, ctx.stream);
+    B2R_CUDA(cudaMemcpyAsync(out.pts.p, in, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx.stream));
+    out.n = n;
+    return;
+  }
+  VgParams prm;
+  prm.inv_leaf = inv_leaf;
+  int div_b[3];
+  for (int d = 0; d < 3; ++d) {
+    prm.min_b[d] = (int)std::floor(mn[d] * inv_leaf);
+    div_b[d] = (int)std::floor(mx[d] * inv_leaf) - prm.min_b[d] + 1;
+  }
+  prm.mul[0] = 1; prm.mul[1] = div_b[0]; prm.mul[2] = div_b[0] * div_b[1];
+  const int64_t max_idx = (int64_t)div_b[0] * div_b[1] * div_b[2];
+  int end_bit = 1;
+  while (end_bit < 32 && ((int64_t)1 << end_bit) <= max_idx) ++end_bit;
+  end_bit = 32;  // the 0xffffffff sentinel of non-finite points needs all bits
+
+  DBuf<unsigned> k0, k1;
+  DBuf<int> v0, v1;
+  k0.alloc(n, ctx.stream); k1.alloc(n, ctx.stream); v0.alloc(n, ctx.stream); v1.alloc(n, ctx.stream);
+  const int nb = (n + 255) / 256;
+  B2R_LAUNCH(ctx, vg_key_kernel, nb, 256, 0, in, n, prm, k0.p, v0.p);
+  // stable LSD radix sort (CUB, library primitive): ascending voxel index, ties keep ascending point index
+  size_t tmp_bytes = 0;
+  B2R_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, ctx.stream));
+  DBuf<uint8_t> tmp; tmp.alloc(tmp_bytes, ctx.stream);
+  B2R_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, ctx.stream));
+  ctx.launches += 5;  // CUB onesweep: histogram + 4 digit passes
+
+  DBuf<uint8_t> head; head.alloc(n, ctx.stream);
+  DBuf<int> cnt; cnt.alloc((size_t)nb + 2, ctx.stream);
+  B2R_CUDA(cudaMemsetAsync(cnt.p + nb + 1, 0, sizeof(int), ctx.stream));
+  B2R_LAUNCH(ctx, vg_head_kernel, nb, 256, 0, k1.p, n, head.p);
+  B2R_LAUNCH(ctx, count_valid_kernel, nb, 256, 0, k1.p, n, cnt.p + nb + 1);
+  flags_block_offsets(ctx, head.p, n, cnt.p);
+  int h2[2] = {0, 0};
+  B2R_CUDA(cudaMemcpyAsync(h2, cnt.p + nb, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  const int nseg = h2[0], n_valid = h2[1];
+  if (nseg == 0) return;
+  DBuf<int> seg; seg.alloc(nseg, ctx.stream);
+  B2R_LAUNCH(ctx, vg_seg_kernel, nb, 256, 0, head.p, n, cnt.p, seg.p);
+  if (min_pts <= 1) {
+    out.pts.alloc(nseg, ctx.stream);
+    B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 127) / 128, 128, 0, in, v1.p, seg.p, nseg, n_valid, min_pts, out.pts.p, (uint8_t*)nullptr);
+    out.n = nseg;
+  } else {
+    DBuf<float4> cen; cen.alloc(nseg, ctx.stream);
+    DBuf<uint8_t> keep; keep.alloc(nseg, ctx.stream);
+    B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 127) / 128, 128, 0, in, v1.p, seg.p, nseg, n_valid, min_pts, cen.p, keep.p);
+    compact_points(ctx, cen.p, keep.p, nseg, out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ radius outlier removal
+// one thread per (cell-sorted) point: count neighbours with d2 < r2 (incl. itself), keep iff count > min_neighbors
+__global__ void radius_keep_kernel(const CloudView* __restrict__ views, float r2, int min_nb, uint8_t* __restrict__ keep) {
+  const CloudView& c = views[0];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= c.n) return;
+  const float4 p = __ldg(&c.spts[j]);
+  int k;
+  if (min_nb == 1) {
+    // PCL special case: nearestKSearch(2) and d2[1] <= r^2.  Equivalent count with a non-strict bound.
+    k = radius_count(c, p.x, p.y, p.z, nextafterf(r2, INFINITY), 1);
+  } else {
+    k = radius_count(c, p.x, p.y, p.z, r2, min_nb);
+  }
+  keep[__float_as_int(p.w)] = k > min_nb ? 1 : 0;
+}
+
+static void with_temp_cloud(Ctx& ctx, const float4* in, int n, Cloud& tmp) {
+  tmp.device = ctx.device;
+  tmp.n = n;
+  tmp.pts.alloc(n, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(tmp.pts.p, in, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx.stream));
+}
+
+void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out) {
+  out.n = 0;
+  if (n == 0) return;
+  Cloud tmp;
+  with_temp_cloud(ctx, in, n, tmp);
+  b2r_config c2 = cfg;
+  c2.nn_cell_size = radius;  // 3x3x3 cells of size >= r cover the search ball
+  std::vector<Cloud*> cl{&tmp};
+  std::vector<Needs> nd(1);
+  nd[0].grid = true;
+  clouds_prepare(ctx, c2, cl, nd);
+  CloudView hv = tmp.view();
+  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<uint8_t> keep; keep.alloc(n, ctx.stream);
+  const float r2 = (float)(radius * radius);
+  B2R_LAUNCH(ctx, radius_keep_kernel, (n + 127) / 128, 128, 0, dv.p, r2, min_nb, keep.p);
+  compact_points(ctx, in, keep.p, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------ statistical outlier removal
+// one warp per (cell-sorted) point: (mean_k+1)-NN; distances[i] = (float)(sum_{j=1..k} sqrt(d2_j) / k), double sum in
+// ascending-distance order with float sqrt, as PCL does
+__global__ void __launch_bounds__(256) sor_distance_kernel(const CloudView* __restrict__ views, int mean_k, float* __restrict__ distances) {
+  const CloudView& c = views[0];
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= c.n) return;
+  const float4 p = __ldg(&c.spts[q]);
+  const unsigned long long key = warp_knn(c, p.x, p.y, p.z, mean_k + 1, lane);
+  const float d = __fsqrt_rn(__uint_as_float((unsigned)(key >> 32)));
+  double sum = 0.0;
+  for (int j = 1; j <= mean_k; ++j) sum += (double)__shfl_sync(0xffffffffu, d, j);
+  if (lane == 0) distances[__float_as_int(p.w)] = (float)(sum / (double)mean_k);
+}
+// two-stage deterministic reduction of sum and sum of (float) squares
+__global__ void __launch_bounds__(256) sor_stats_kernel(const float* __restrict__ distances, int n, double* __restrict__ partials) {
+  __shared__ double red[2 * 8];
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float d = distances[i];
+    acc[0] += (double)d;
+    acc[1] += (double)__fmul_rn(d, d);
+  }
+  block_reduce_to<2>(acc, red, partials + blockIdx.x * 2);
+}
+__global__ void sor_threshold_kernel(const double* __restrict__ partials, int nblocks, int n, double stddev_mul, double* __restrict__ thr_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sum = 0.0, sq = 0.0;
+  for (int b = 0; b < nblocks; ++b) { sum += partials[b * 2]; sq += partials[b * 2 + 1]; }
+  const double nn = (double)n;
+  const double mean = sum / nn;
+  const double variance = (sq - sum * sum / nn) / (nn - 1.0);
+  *thr_out = mean + stddev_mul * sqrt(variance);
+}
+__global__ void sor_keep_kernel(const float* __restrict__ distances, int n, const double* __restrict__ thr, uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keep[i] = ((double)distances[i] > *thr) ? 0 : 1;
+}
+
+void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out) {
+  out.n = 0;
+  if (n == 0) return;
+  if (mean_k < 1 || mean_k > 31) throw Error(B2R_ERR_INVALID_ARG, "statistical_mean_k must be in [1,31]");
+  if (n < mean_k + 1) throw Error(B2R_ERR_INVALID_ARG, "cloud has fewer than mean_k+1 points");
+  Cloud tmp;
+  with_temp_cloud(ctx, in, n, tmp);
+  std::vector<Cloud*> cl{&tmp};
+  std::vector<Needs> nd(1);
+  nd[0].grid = true;
+  clouds_prepare(ctx, cfg, cl, nd);
+  CloudView hv = tmp.view();
+  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<float> dist; dist.alloc(n, ctx.stream);
+  B2R_LAUNCH(ctx, sor_distance_kernel, (n + 7) / 8, 256, 0, dv.p, mean_k, dist.p);
+  const int nb = std::max(1, std::min(2 * ctx.num_sms, (n + 1023) / 1024));
+  DBuf<double> part; part.alloc((size_t)nb * 2 + 1, ctx.stream);
+  B2R_LAUNCH(ctx, sor_stats_kernel, nb, 256, 0, dist.p, n, part.p);
+  B2R_LAUNCH(ctx, sor_threshold_kernel, 1, 32, 0, part.p, nb, n, stddev_mul, part.p + (size_t)nb * 2);
+  DBuf<uint8_t> keep; keep.alloc(n, ctx.stream);
+  B2R_LAUNCH(ctx, sor_keep_kernel, (n + 255) / 256, 256, 0, dist.p, n, part.p + (size_t)nb * 2, keep.p);
+  compact_points(ctx, in, keep.p, n, out);
+}
+
+}  // namespace b2r

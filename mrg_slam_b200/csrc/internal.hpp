@@ -1,0 +1,111 @@
+// libb2r host-side internals: cloud objects, handle, and the entry points of each kernel module.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2r {
+
+// Device-resident cloud with lazily built, cached search structures.
+struct Cloud {
+  int device = 0;
+  int n = 0;
+  DBuf<float4> pts;
+  bool has_bbox = false;
+  float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+  // NN grid
+  bool has_grid = false;
+  float h = 0.f;
+  int gd[3] = {0, 0, 0};
+  int ncell = 0;
+  DBuf<int> cell_start, cell_cnt;
+  DBuf<float4> spts;
+  // covariances
+  int cov_k = 0;  // k the covariances were built with (0 = none)
+  DBuf<double> cov;
+  // VGICP voxel map
+  double vres = 0.0;  // resolution the map was built with (0 = none)
+  int vmin[3] = {0, 0, 0}, vd[3] = {0, 0, 0};
+  int vcell = 0;
+  DBuf<int> v_start, v_cnt, v_order, v_table, v_nrec;
+  DBuf<VoxRec> vrec;
+  // NDT grid
+  float leaf = 0.f;  // leaf the grid was built with (0 = none)
+  int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0};
+  int ncell_ndt = 0;
+  bool ndt_overflow = false;
+  DBuf<int> n_start, n_cnt, n_order, n_table, n_nrec;
+  DBuf<NdtRec> nrec;
+
+  CloudView view() const;
+};
+
+// What a role in an alignment needs from a cloud.
+struct Needs {
+  bool grid = false;
+  int cov_k = 0;
+  double vres = 0.0;
+  float leaf = 0.f;
+};
+
+struct Handle {
+  b2r_config cfg;
+  Ctx ctx;
+  std::string last_error;
+  std::unique_ptr<Cloud> owned_source, owned_target;
+  Cloud* source = nullptr;
+  Cloud* target = nullptr;
+  // pcl::Registration state
+  float final_T[16];
+  bool converged = false;
+  bool has_result = false;
+  float timings[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// ---- cloud.cu ----
+void cloud_upload(Ctx& ctx, Cloud& c, const void* points, size_t n, size_t stride_bytes, int memspace);
+// builds whatever of `needs[i]` is missing in clouds[i]; batched launches over all clouds
+void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds, const std::vector<Needs>& needs);
+void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, size_t nq, int k, int32_t* idx_out, float* d2_out);
+void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* knn_out);
+
+// ---- lsq.cu (FAST_GICP / FAST_VGICP) ----
+struct PairDesc {
+  int src;  // index into the views array
+  int tgt;
+};
+void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
+                     const float* guesses_colmajor, b2r_result* out);
+void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, int n_src, const double* T_lin, const double* T_trial,
+                         bool trial, double* H, double* b, double* err, int32_t* corr_out, uint8_t* corr_valid);
+
+// ---- ndt.cu ----
+void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
+                     const float* guesses_colmajor, b2r_result* out);
+void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, int n_src, const double* p6, double* score,
+                           double* grad6, double* hess36, int32_t* hits_out);
+
+// ---- fitness (in lsq.cu) ----
+void fitness_batch(Ctx& ctx, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes, const float* T_colmajor,
+                   double max_range, double* out);
+void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor, float4* out);
+
+// ---- filters.cu ----
+struct DevCloud {  // packed device points + count
+  DBuf<float4> pts;
+  int n = 0;
+};
+void filter_distance(Ctx& ctx, const float4* in, int n, double near_t, double far_t, DevCloud& out);
+void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow);
+void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out);
+void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out);
+
+// shared utilities (cloud.cu)
+void compact_points(Ctx& ctx, const float4* in, const uint8_t* keep, int n, DevCloud& out);
+void load_points(Ctx& ctx, const void* points, size_t n, size_t stride_bytes, int memspace, DBuf<float4>& dst);
+void store_points(Ctx& ctx, const float4* src, size_t n, void* out, size_t stride_bytes, int memspace);
+
+}  // namespace b2r

@@ -1,0 +1,594 @@
+// FAST_GICP / FAST_VGICP: correspondence + Mahalanobis + 6x6 accumulation kernels and the on-device
+// Levenberg-Marquardt state machine; fitness score and cloud transform.
+//
+// Replaces: A7 FastVGICP::update_correspondences/linearize/compute_error, A9 FastGICP::*,
+// A8 LsqRegistration::computeTransformation/step_lm/is_converged (fast_gicp, selected at
+// src/mrg_slam/registrations.cpp:55-63,76-84), A13 pcl::Registration::getFitnessScore
+// (in-tree copy: src/mrg_slam/information_matrix_calculator.cpp:46-81), A.10 pcl::transformPointCloud.
+#include <cfloat>
+#include <cmath>
+#include <algorithm>
+
+#include "internal.hpp"
+#include "knn.cuh"
+
+namespace b2r {
+
+enum { PH_LINEARIZE = 0, PH_TRIAL = 1, PH_DONE = 2 };
+constexpr int kAcc = 28;  // Hrr(6) Hrt(9) Htt(6) b(6) err(1)
+
+struct LsqState {
+  double x0[12];  // R row-major (9), t (3)
+  double xi[12];  // trial pose
+  double dR[9], dt[3];
+  double H[36], b[6], d[6];
+  double y0, yi, lambda, nu;
+  int phase, outer, inner, converged, nr_iterations, evals, failed, pad;
+};
+
+struct LsqParams {
+  int method;  // B2R_FAST_GICP / B2R_FAST_VGICP
+  int neighbor_search;
+  double corr_thr2;  // max_correspondence_distance^2 (double compare as upstream)
+  float corr_max_d2; // search cut-off
+  double rot_eps, trans_eps;
+  int max_iterations, lm_max_iterations;
+  double lm_init_lambda_factor;
+};
+
+__device__ __forceinline__ void apply_pose(const double* x, double px, double py, double pz, double& ax, double& ay, double& az) {
+  ax = x[0] * px + x[1] * py + x[2] * pz + x[9];
+  ay = x[3] * px + x[4] * py + x[5] * pz + x[10];
+  az = x[6] * px + x[7] * py + x[8] * pz + x[11];
+}
+
+// accumulate one correspondence.  M: symmetric (6) Mahalanobis matrix; a: transformed source point; e: residual.
+__device__ __forceinline__ void accumulate(double* acc, const double* M, double ax, double ay, double az, double e0, double e1, double e2,
+                                           double w, bool lin) {
+  const double Me0 = M[0] * e0 + M[1] * e1 + M[2] * e2;
+  const double Me1 = M[1] * e0 + M[3] * e1 + M[4] * e2;
+  const double Me2 = M[2] * e0 + M[4] * e1 + M[5] * e2;
+  acc[27] += w * (e0 * Me0 + e1 * Me1 + e2 * Me2);
+  if (!lin) return;
+  // J = [S | -I], S = skew(a).  MS = M*S (columns), Hrr = S^T M S = -S*(MS), Hrt = -S^T M = S*M, Htt = M
+  const double Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
+  double MS[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    MS[r * 3 + 0] = Mf[r * 3 + 1] * az - Mf[r * 3 + 2] * ay;
+    MS[r * 3 + 1] = -Mf[r * 3 + 0] * az + Mf[r * 3 + 2] * ax;
+    MS[r * 3 + 2] = Mf[r * 3 + 0] * ay - Mf[r * 3 + 1] * ax;
+  }
+  // S*X rows: [ -az X1 + ay X2 ; az X0 - ax X2 ; -ay X0 + ax X1 ]
+  double SMS[9], SM[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    SMS[0 * 3 + j] = -az * MS[1 * 3 + j] + ay * MS[2 * 3 + j];
+    SMS[1 * 3 + j] = az * MS[0 * 3 + j] - ax * MS[2 * 3 + j];
+    SMS[2 * 3 + j] = -ay * MS[0 * 3 + j] + ax * MS[1 * 3 + j];
+    SM[0 * 3 + j] = -az * Mf[1 * 3 + j] + ay * Mf[2 * 3 + j];
+    SM[1 * 3 + j] = az * Mf[0 * 3 + j] - ax * Mf[2 * 3 + j];
+    SM[2 * 3 + j] = -ay * Mf[0 * 3 + j] + ax * Mf[1 * 3 + j];
+  }
+  acc[0] -= w * SMS[0]; acc[1] -= w * SMS[1]; acc[2] -= w * SMS[2];
+  acc[3] -= w * SMS[4]; acc[4] -= w * SMS[5]; acc[5] -= w * SMS[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[6 + t] += w * SM[t];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) acc[15 + t] += w * M[t];
+  // b = J^T M e = [S^T Me ; -Me] = [-S*Me ; -Me]
+  acc[21] -= w * (-az * Me1 + ay * Me2);
+  acc[22] -= w * (az * Me0 - ax * Me2);
+  acc[23] -= w * (-ay * Me0 + ax * Me1);
+  acc[24] -= w * Me0;
+  acc[25] -= w * Me1;
+  acc[26] -= w * Me2;
+}
+
+// grid = (chunks, pairs).  Phase LINEARIZE: correspondences + M at x0, accumulate H, b, err.
+// Phase TRIAL: err at xi with the correspondences and M of x0 (fast_gicp compute_error semantics).
+__global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+                                                        const LsqState* __restrict__ states, LsqParams prm, double* __restrict__ partials,
+                                                        int32_t* __restrict__ corr_out, uint8_t* __restrict__ corr_valid) {
+  const int pair = blockIdx.y;
+  const LsqState& st = states[pair];
+  const int phase = st.phase;
+  if (phase == PH_DONE) return;
+  const CloudView& src = views[pairs[pair].src];
+  const CloudView& tgt = views[pairs[pair].tgt];
+  __shared__ double sx0[12], sxi[12];
+  __shared__ double red[kAcc * 8];
+  if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
+  __syncthreads();
+  const bool lin = phase == PH_LINEARIZE;
+  double acc[kAcc];
+#pragma unroll
+  for (int t = 0; t < kAcc; ++t) acc[t] = 0.0;
+  float Tf[12];
+  if (prm.method == B2R_FAST_GICP) {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) Tf[t] = (float)sx0[t];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(&src.pts[i]);
+    const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+    double ax, ay, az;
+    apply_pose(sx0, px, py, pz, ax, ay, az);
+    double CA[6];
+    {
+      const double* pc = src.cov + (size_t)i * 6;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) CA[t] = __ldg(&pc[t]);
+    }
+    double RCR[6];
+    rsrt(sx0, CA, RCR);
+    if (prm.method == B2R_FAST_VGICP) {
+      const int vx = vgicp_coord_d(ax, tgt.vres), vy = vgicp_coord_d(ay, tgt.vres), vz = vgicp_coord_d(az, tgt.vres);
+      bool first = true;
+      const int noff = prm.neighbor_search == B2R_DIRECT1 ? 1 : (prm.neighbor_search == B2R_DIRECT7 ? 7 : 27);
+      for (int o = 0; o < noff; ++o) {
+        int ox, oy, oz;
+        neighbor_offset(prm.neighbor_search, o, ox, oy, oz);
+        const int cx = vx + ox - tgt.vmin[0], cy = vy + oy - tgt.vmin[1], cz = vz + oz - tgt.vmin[2];
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= tgt.vd[0] || cy >= tgt.vd[1] || cz >= tgt.vd[2]) continue;
+        const int rec = __ldg(&tgt.v_table[(cz * tgt.vd[1] + cy) * tgt.vd[0] + cx]);
+        if (rec < 0) continue;
+        const VoxRec& v = tgt.vrec[rec];
+        double S[6], M[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) S[t] = __ldg(&v.cov[t]) + RCR[t];
+        sym3_inverse(S, M);
+        const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
+        const double w = sqrt((double)__ldg(&v.n));
+        if (lin) {
+          accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
+        } else {
+          double bx, by, bz;
+          apply_pose(sxi, px, py, pz, bx, by, bz);
+          accumulate(acc, M, bx, by, bz, m0 - bx, m1 - by, m2 - bz, w, false);
+        }
+        if (corr_out && first) {
+          corr_out[(size_t)i * 3 + 0] = vx + ox; corr_out[(size_t)i * 3 + 1] = vy + oy; corr_out[(size_t)i * 3 + 2] = vz + oz;
+          corr_valid[i] = 1;
+          first = false;
+        }
+      }
+    } else {
+      // FastGICP::update_correspondences: float transform ((c0 x + c1 y) + c2 z) + c3, exact 1-NN, d2 < thr^2
+      float q[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float s = __fmul_rn(Tf[r * 3 + 0], p.x);
+        s = __fadd_rn(s, __fmul_rn(Tf[r * 3 + 1], p.y));
+        s = __fadd_rn(s, __fmul_rn(Tf[r * 3 + 2], p.z));
+        q[r] = __fadd_rn(s, Tf[9 + r]);
+      }
+      float d2;
+      const int pos = nn1_search(tgt, q[0], q[1], q[2], prm.corr_max_d2, d2);
+      const bool ok = pos >= 0 && (double)d2 < prm.corr_thr2;
+      if (corr_out) corr_out[i] = ok ? __float_as_int(tgt.spts[pos].w) : -1;
+      if (ok) {
+        const float4 tq = __ldg(&tgt.spts[pos]);
+        const double* pcb = tgt.cov + (size_t)__float_as_int(tq.w) * 6;
+        double S[6], M[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) S[t] = __ldg(&pcb[t]) + RCR[t];
+        sym3_inverse(S, M);
+        const double m0 = (double)tq.x, m1 = (double)tq.y, m2 = (double)tq.z;
+        if (lin) {
+          accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, 1.0, true);
+        } else {
+          double bx, by, bz;
+          apply_pose(sxi, px, py, pz, bx, by, bz);
+          accumulate(acc, M, bx, by, bz, m0 - bx, m1 - by, m2 - bz, 1.0, false);
+        }
+      }
+    }
+  }
+  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kAcc;
+  if (lin) {
+    block_reduce_to<kAcc>(acc, red, out);
+  } else {
+    double e[1] = {acc[27]};
+    block_reduce_to<1>(e, red, out + 27);
+  }
+}
+
+// ---- small dense math for the step kernel (one thread per pair) ----
+__device__ void ldlt6_solve_dev(const double* Ain, const double* rhs, double* x) {
+  double A[36];
+  for (int i = 0; i < 36; ++i) A[i] = Ain[i];
+  int perm[6] = {0, 1, 2, 3, 4, 5};
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[i * 6 + i]) > best) { best = fabs(A[i * 6 + i]); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) { double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
+      for (int i = 0; i < 6; ++i) { double t = A[i * 6 + k]; A[i * 6 + k] = A[i * 6 + piv]; A[i * 6 + piv] = t; }
+      int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+    }
+    const double dk = A[k * 6 + k];
+    if (dk == 0.0) continue;
+    for (int i = k + 1; i < 6; ++i) A[i * 6 + k] /= dk;
+    for (int i = k + 1; i < 6; ++i)
+      for (int j = k + 1; j <= i; ++j) {
+        A[i * 6 + j] -= A[i * 6 + k] * dk * A[j * 6 + k];
+        A[j * 6 + i] = A[i * 6 + j];
+      }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) y[i] = rhs[perm[i]];
+  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < i; ++k) y[i] -= A[i * 6 + k] * y[k];
+  for (int i = 0; i < 6; ++i) y[i] = (A[i * 6 + i] != 0.0) ? y[i] / A[i * 6 + i] : 0.0;
+  for (int i = 5; i >= 0; --i)
+    for (int k = i + 1; k < 6; ++k) y[i] -= A[k * 6 + i] * y[k];
+  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+}
+
+__device__ void so3_exp_dev(const double* om, double* R) {
+  const double theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  double imag, real;
+  if (theta_sq < 1e-10) {
+    const double theta_quad = theta_sq * theta_sq;
+    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * theta_quad;
+    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * theta_quad;
+  } else {
+    const double theta = sqrt(theta_sq), half = 0.5 * theta;
+    imag = sin(half) / theta;
+    real = cos(half);
+  }
+  const double w = real, x = imag * om[0], y = imag * om[1], z = imag * om[2];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+__device__ bool lsq_is_converged(const LsqState& s, const LsqParams& prm) {
+  double m = 0.0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) m = fmax(m, fabs(s.dR[r * 3 + c] - (r == c ? 1.0 : 0.0)) / prm.rot_eps);
+  for (int r = 0; r < 3; ++r) m = fmax(m, fabs(s.dt[r]) / prm.trans_eps);
+  return m < 1.0;
+}
+
+// d = solve(H + lambda I, -b); delta = [so3_exp(d0..2) | d3..5]; xi = delta * x0
+__device__ void lsq_propose(LsqState& s) {
+  double A[36], nb[6];
+  for (int i = 0; i < 36; ++i) A[i] = s.H[i];
+  for (int j = 0; j < 6; ++j) { A[j * 6 + j] += s.lambda; nb[j] = -s.b[j]; }
+  ldlt6_solve_dev(A, nb, s.d);
+  so3_exp_dev(s.d, s.dR);
+  s.dt[0] = s.d[3]; s.dt[1] = s.d[4]; s.dt[2] = s.d[5];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) s.xi[r * 3 + c] = s.dR[r * 3 + 0] * s.x0[0 * 3 + c] + s.dR[r * 3 + 1] * s.x0[1 * 3 + c] + s.dR[r * 3 + 2] * s.x0[2 * 3 + c];
+    s.xi[9 + r] = s.dR[r * 3 + 0] * s.x0[9] + s.dR[r * 3 + 1] * s.x0[10] + s.dR[r * 3 + 2] * s.x0[11] + s.dt[r];
+  }
+}
+
+__device__ void lsq_finish(LsqState& s, int* done_count) {
+  s.phase = PH_DONE;
+  atomicAdd(done_count, 1);
+}
+
+// One warp per pair: fixed-order sum of the chunk partials, then the LM state machine of
+// LsqRegistration::computeTransformation / step_lm advanced by one evaluation.
+__global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqParams prm, const double* __restrict__ partials, int chunks,
+                                int* __restrict__ done_count) {
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pair >= npairs) return;
+  LsqState& s = states[pair];
+  const int phase = s.phase;
+  if (phase == PH_DONE) return;
+  double v = 0.0;
+  if (lane < kAcc && (phase == PH_LINEARIZE || lane == 27)) {
+    const double* p = partials + (size_t)pair * chunks * kAcc + lane;
+    for (int c = 0; c < chunks; ++c) v += p[(size_t)c * kAcc];
+  }
+  double a[kAcc];
+#pragma unroll
+  for (int t = 0; t < kAcc; ++t) a[t] = __shfl_sync(0xffffffffu, v, t);
+  if (lane != 0) return;
+  s.evals++;
+  if (phase == PH_LINEARIZE) {
+    // unpack the symmetric system
+    const int rr[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+    for (int t = 0; t < 6; ++t) {
+      s.H[rr[t][0] * 6 + rr[t][1]] = a[t];
+      s.H[rr[t][1] * 6 + rr[t][0]] = a[t];
+      s.H[(3 + rr[t][0]) * 6 + 3 + rr[t][1]] = a[15 + t];
+      s.H[(3 + rr[t][1]) * 6 + 3 + rr[t][0]] = a[15 + t];
+    }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        s.H[r * 6 + 3 + c] = a[6 + r * 3 + c];
+        s.H[(3 + c) * 6 + r] = a[6 + r * 3 + c];
+      }
+    for (int t = 0; t < 6; ++t) s.b[t] = a[21 + t];
+    s.y0 = a[27];
+    s.nr_iterations = s.outer;
+    if (s.lambda < 0.0) {
+      double mx = 0.0;
+      for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(s.H[i * 6 + i]));
+      s.lambda = prm.lm_init_lambda_factor * mx;
+    }
+    s.nu = 2.0;
+    s.inner = 0;
+    if (prm.lm_max_iterations <= 0) {  // step_lm's loop body never runs: "lm not converged!!"
+      s.failed = 1;
+      lsq_finish(s, done_count);
+      return;
+    }
+    lsq_propose(s);
+    s.phase = PH_TRIAL;
+    return;
+  }
+  // ---- PH_TRIAL
+  s.yi = a[27];
+  double denom = 0.0;
+  for (int j = 0; j < 6; ++j) denom += s.d[j] * (s.lambda * s.d[j] - s.b[j]);
+  const double rho = (s.y0 - s.yi) / denom;
+  bool step_ok;
+  if (rho < 0) {
+    if (lsq_is_converged(s, prm)) {
+      step_ok = true;  // x0 unchanged
+    } else {
+      s.lambda = s.nu * s.lambda;
+      s.nu = 2 * s.nu;
+      s.inner++;
+      if (s.inner >= prm.lm_max_iterations) {
+        s.failed = 1;  // "lm not converged!!" -> break out of the outer loop, converged_ stays false
+        lsq_finish(s, done_count);
+        return;
+      }
+      lsq_propose(s);
+      return;  // another trial with the same H, b
+    }
+  } else {
+    for (int t = 0; t < 12; ++t) s.x0[t] = s.xi[t];
+    const double f = 1 - pow(2 * rho - 1, 3);
+    const double third = 1.0 / 3.0;
+    s.lambda = s.lambda * (third < f ? f : third);
+    step_ok = true;
+  }
+  (void)step_ok;
+  s.converged = lsq_is_converged(s, prm) ? 1 : 0;
+  s.nr_iterations = s.outer;
+  s.outer++;
+  if (s.converged || s.outer >= prm.max_iterations) {
+    lsq_finish(s, done_count);
+    return;
+  }
+  s.phase = PH_LINEARIZE;
+}
+
+__global__ void lsq_init_kernel(LsqState* __restrict__ states, int npairs, const float* __restrict__ guesses, int max_iterations,
+                                int* __restrict__ done_count) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= npairs) return;
+  LsqState& s = states[pair];
+  const float* g = guesses + (size_t)pair * 16;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) s.x0[r * 3 + c] = (double)g[c * 4 + r];
+    s.x0[9 + r] = (double)g[12 + r];
+  }
+  for (int t = 0; t < 12; ++t) s.xi[t] = s.x0[t];
+  for (int t = 0; t < 9; ++t) s.dR[t] = (t % 4 == 0) ? 1.0 : 0.0;
+  s.dt[0] = s.dt[1] = s.dt[2] = 0.0;
+  s.y0 = s.yi = 0.0;
+  s.lambda = -1.0;
+  s.nu = 2.0;
+  s.phase = PH_LINEARIZE;
+  s.outer = 0; s.inner = 0; s.converged = 0; s.nr_iterations = 0; s.evals = 0; s.failed = 0;
+  if (max_iterations <= 0) { s.phase = PH_DONE; atomicAdd(done_count, 1); }
+}
+
+static LsqParams make_params(const b2r_config& cfg) {
+  LsqParams p;
+  p.method = cfg.method;
+  p.neighbor_search = cfg.method == B2R_FAST_VGICP ? cfg.neighbor_search : B2R_DIRECT1;
+  p.corr_thr2 = cfg.max_correspondence_distance * cfg.max_correspondence_distance;
+  p.corr_max_d2 = p.corr_thr2 >= (double)FLT_MAX ? INFINITY : (float)(p.corr_thr2 * 1.0001);
+  p.rot_eps = cfg.rotation_epsilon;
+  p.trans_eps = cfg.transformation_epsilon;
+  p.max_iterations = cfg.maximum_iterations;
+  p.lm_max_iterations = cfg.lm_max_iterations;
+  p.lm_init_lambda_factor = cfg.lm_init_lambda_factor;
+  return p;
+}
+
+static int pick_chunks(const Ctx& ctx, int npairs, int maxn) {
+  int by_size = std::max(1, (maxn + 1023) / 1024);
+  int by_fill = std::max(1, (8 * ctx.num_sms + npairs - 1) / npairs);
+  return std::max(1, std::min(by_size, by_fill));
+}
+
+void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
+                     const float* guesses_colmajor, b2r_result* out) {
+  const int np = (int)pairs.size();
+  if (np == 0) return;
+  int maxn = 1;
+  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
+  const int chunks = pick_chunks(ctx, np, maxn);
+  const LsqParams prm = make_params(cfg);
+  DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
+  DBuf<LsqState> ds; ds.alloc(np, ctx.stream);
+  DBuf<float> dg; dg.alloc((size_t)np * 16, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)np * chunks * kAcc, ctx.stream);
+  DBuf<int> done; done.alloc(1, ctx.stream);
+  done.zero(ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_CUDA(cudaMemcpyAsync(dg.p, guesses_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, dg.p, cfg.maximum_iterations, done.p);
+  const dim3 ge(chunks, np);
+  const int step_blocks = (np + 3) / 4;
+  int rounds_per_check = 6;
+  int hdone = 0;
+  const long max_rounds = (long)std::max(1, cfg.maximum_iterations) * (1 + std::max(1, cfg.lm_max_iterations)) + 2;
+  long rounds = 0;
+  while (hdone < np && rounds < max_rounds) {
+    for (int r = 0; r < rounds_per_check; ++r) {
+      B2R_LAUNCH(ctx, lsq_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr, (uint8_t*)nullptr);
+      B2R_LAUNCH(ctx, lsq_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, done.p);
+    }
+    rounds += rounds_per_check;
+    B2R_CUDA(cudaMemcpyAsync(&hdone, done.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    rounds_per_check = 4;
+  }
+  std::vector<LsqState> hs(np);
+  B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(LsqState) * np, cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int i = 0; i < np; ++i) {
+    const LsqState& s = hs[i];
+    b2r_result& r = out[i];
+    for (int rr = 0; rr < 3; ++rr) {
+      for (int c = 0; c < 3; ++c) r.T[c * 4 + rr] = (float)s.x0[rr * 3 + c];
+      r.T[12 + rr] = (float)s.x0[9 + rr];
+      r.T[rr * 4 + 3] = 0.f;
+    }
+    r.T[15] = 1.f;
+    r.converged = s.converged;
+    r.iterations = s.nr_iterations;
+    r.error = s.y0;
+    r.evals = s.evals;
+    r.fitness = 0.0;
+  }
+}
+
+void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, int n_src, const double* T_lin, const double* T_trial,
+                         bool trial, double* H, double* b, double* err, int32_t* corr_out, uint8_t* corr_valid) {
+  const LsqParams prm = make_params(cfg);
+  LsqState s;
+  memset(&s, 0, sizeof(s));
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { s.x0[r * 3 + c] = T_lin[r * 4 + c]; s.xi[r * 3 + c] = T_trial[r * 4 + c]; }
+    s.x0[9 + r] = T_lin[r * 4 + 3];
+    s.xi[9 + r] = T_trial[r * 4 + 3];
+  }
+  s.phase = trial ? PH_TRIAL : PH_LINEARIZE;
+  const int chunks = pick_chunks(ctx, 1, n_src);
+  PairDesc pd{0, 1};
+  DBuf<PairDesc> dp; dp.alloc(1, ctx.stream);
+  DBuf<LsqState> ds; ds.alloc(1, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)chunks * kAcc, ctx.stream);
+  part.zero(ctx.stream);
+  DBuf<int32_t> dc;
+  DBuf<uint8_t> dvld;
+  const bool vg = cfg.method == B2R_FAST_VGICP;
+  if (corr_out) {
+    dc.alloc((size_t)n_src * (vg ? 3 : 1), ctx.stream);
+    dc.zero(ctx.stream);
+    dvld.alloc((size_t)n_src, ctx.stream);
+    dvld.zero(ctx.stream);
+  }
+  B2R_CUDA(cudaMemcpyAsync(dp.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx.stream));
+  B2R_CUDA(cudaMemcpyAsync(ds.p, &s, sizeof(s), cudaMemcpyHostToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, lsq_eval_kernel, dim3(chunks, 1), 256, 0, d_views, dp.p, ds.p, prm, part.p, corr_out ? dc.p : nullptr,
+             corr_out ? dvld.p : nullptr);
+  std::vector<double> hp((size_t)chunks * kAcc);
+  B2R_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, ctx.stream));
+  if (corr_out) {
+    B2R_CUDA(cudaMemcpyAsync(corr_out, dc.p, sizeof(int32_t) * n_src * (vg ? 3 : 1), cudaMemcpyDeviceToHost, ctx.stream));
+    if (vg && corr_valid) B2R_CUDA(cudaMemcpyAsync(corr_valid, dvld.p, n_src, cudaMemcpyDeviceToHost, ctx.stream));
+  }
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  double a[kAcc] = {0};
+  for (int c = 0; c < chunks; ++c)
+    for (int t = 0; t < kAcc; ++t) a[t] += hp[(size_t)c * kAcc + t];
+  *err = a[27];
+  if (H && !trial) {
+    const int rr[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+    for (int t = 0; t < 6; ++t) {
+      H[rr[t][0] * 6 + rr[t][1]] = H[rr[t][1] * 6 + rr[t][0]] = a[t];
+      H[(3 + rr[t][0]) * 6 + 3 + rr[t][1]] = H[(3 + rr[t][1]) * 6 + 3 + rr[t][0]] = a[15 + t];
+    }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) H[r * 6 + 3 + c] = H[(3 + c) * 6 + r] = a[6 + r * 3 + c];
+    for (int t = 0; t < 6; ++t) b[t] = a[21 + t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ transform + fitness
+// pcl::transformPointCloud, SSE association (x*c0 + y*c1) + (z*c2 + c3)  
+__device__ __forceinline__ void pcl_transform(const float* T /*col-major 16*/, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = __fadd_rn(__fadd_rn(__fmul_rn(x, T[0]), __fmul_rn(y, T[4])), __fadd_rn(__fmul_rn(z, T[8]), T[12]));
+  oy = __fadd_rn(__fadd_rn(__fmul_rn(x, T[1]), __fmul_rn(y, T[5])), __fadd_rn(__fmul_rn(z, T[9]), T[13]));
+  oz = __fadd_rn(__fadd_rn(__fmul_rn(x, T[2]), __fmul_rn(y, T[6])), __fadd_rn(__fmul_rn(z, T[10]), T[14]));
+}
+
+struct Mat16 { float m[16]; };
+
+__global__ void transform_kernel(const float4* __restrict__ in, int n, Mat16 T, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  float4 o;
+  pcl_transform(T.m, p.x, p.y, p.z, o.x, o.y, o.z);
+  o.w = p.w;
+  out[i] = o;
+}
+
+void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor, float4* out) {
+  if (n == 0) return;
+  Mat16 T;
+  memcpy(T.m, T_colmajor, sizeof(T.m));
+  B2R_LAUNCH(ctx, transform_kernel, (n + 255) / 256, 256, 0, in, n, T, out);
+}
+
+// grid = (chunks, pairs): per source point exact 1-NN squared distance into the target; sum of those <= max_range
+__global__ void __launch_bounds__(256) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+                                                       const float* __restrict__ Ts, double max_range, float max_d2,
+                                                       double* __restrict__ partials) {
+  const int pair = blockIdx.y;
+  const CloudView& src = views[pairs[pair].src];
+  const CloudView& tgt = views[pairs[pair].tgt];
+  __shared__ float T[16];
+  __shared__ double red[2 * 8];
+  if (threadIdx.x < 16) T[threadIdx.x] = Ts[(size_t)pair * 16 + threadIdx.x];
+  __syncthreads();
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(&src.pts[i]);
+    float qx, qy, qz;
+    pcl_transform(T, p.x, p.y, p.z, qx, qy, qz);
+    float d2;
+    const int pos = nn1_search(tgt, qx, qy, qz, max_d2, d2);
+    if (pos >= 0 && (double)d2 <= max_range) { acc[0] += (double)d2; acc[1] += 1.0; }
+  }
+  block_reduce_to<2>(acc, red, partials + ((size_t)pair * gridDim.x + blockIdx.x) * 2);
+}
+__global__ void fitness_finish_kernel(const double* __restrict__ partials, int npairs, int chunks, double* __restrict__ out) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= npairs) return;
+  double s = 0.0, c = 0.0;
+  for (int k = 0; k < chunks; ++k) { s += partials[((size_t)pair * chunks + k) * 2]; c += partials[((size_t)pair * chunks + k) * 2 + 1]; }
+  out[pair] = c > 0.0 ? s / c : DBL_MAX;
+}
+
+void fitness_batch(Ctx& ctx, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes, const float* T_colmajor,
+                   double max_range, double* out) {
+  const int np = (int)pairs.size();
+  if (np == 0) return;
+  int maxn = 1;
+  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
+  const int chunks = pick_chunks(ctx, np, maxn);
+  DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
+  DBuf<float> dT; dT.alloc((size_t)np * 16, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)np * chunks * 2, ctx.stream);
+  DBuf<double> dout; dout.alloc(np, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_CUDA(cudaMemcpyAsync(dT.p, T_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
+  const float max_d2 = max_range >= (double)FLT_MAX ? INFINITY : (float)(max_range * 1.0001);
+  B2R_LAUNCH(ctx, fitness_kernel, dim3(chunks, np), 256, 0, d_views, dp.p, dT.p, max_range, max_d2, part.p);
+  B2R_LAUNCH(ctx, fitness_finish_kernel, (np + 127) / 128, 128, 0, part.p, np, chunks, dout.p);
+  B2R_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * np, cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+}  // namespace b2r

@@ -1,0 +1,428 @@
+"""ctypes binding of libb2r.so (include/b2r.h) — the product's C ABI.
+
+This is the binding the tests and bench.py go through; it deliberately has no CPU path: if the shared
+library is missing, or no CUDA device is present, construction fails loudly.
+
+The `Registration` class mirrors the pcl::Registration surface that the reference's factory
+`select_registration_method()` hands out (/root/reference/src/mrg_slam/registrations.cpp:28-152) and its
+callers use (apps/scan_matching_odometry_component.cpp:203-275, src/mrg_slam/loop_detector.cpp:104-144).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libb2r.so")
+
+NDT_OMP, FAST_GICP, FAST_VGICP = 0, 1, 2
+DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
+HOST, DEVICE = 0, 1
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_STATE = range(6)
+METHOD_BY_NAME = {"NDT_OMP": NDT_OMP, "FAST_GICP": FAST_GICP, "FAST_VGICP": FAST_VGICP}
+
+
+class Config(ctypes.Structure):
+    _fields_ = [
+        ("method", ctypes.c_int),
+        ("device", ctypes.c_int),
+        ("transformation_epsilon", ctypes.c_double),
+        ("maximum_iterations", ctypes.c_int),
+        ("max_correspondence_distance", ctypes.c_double),
+        ("correspondence_randomness", ctypes.c_int),
+        ("resolution", ctypes.c_double),
+        ("neighbor_search", ctypes.c_int),
+        ("rotation_epsilon", ctypes.c_double),
+        ("lm_max_iterations", ctypes.c_int),
+        ("lm_init_lambda_factor", ctypes.c_double),
+        ("ndt_step_size", ctypes.c_double),
+        ("ndt_outlier_ratio", ctypes.c_double),
+        ("nn_cell_size", ctypes.c_double),
+    ]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [
+        ("T", ctypes.c_float * 16),
+        ("converged", ctypes.c_int),
+        ("iterations", ctypes.c_int),
+        ("error", ctypes.c_double),
+        ("evals", ctypes.c_int),
+        ("fitness", ctypes.c_double),
+    ]
+
+
+class PrefilterConfig(ctypes.Structure):
+    _fields_ = [
+        ("enable_distance_filter", ctypes.c_int),
+        ("distance_near_thresh", ctypes.c_double),
+        ("distance_far_thresh", ctypes.c_double),
+        ("downsample_method", ctypes.c_int),
+        ("downsample_resolution", ctypes.c_float),
+        ("downsample_min_points_per_voxel", ctypes.c_int),
+        ("outlier_removal_method", ctypes.c_int),
+        ("statistical_mean_k", ctypes.c_int),
+        ("statistical_stddev", ctypes.c_double),
+        ("radius_radius", ctypes.c_double),
+        ("radius_min_neighbors", ctypes.c_int),
+    ]
+
+
+# every symbol include/b2r.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "b2r_default_config", "b2r_create", "b2r_destroy", "b2r_last_error", "b2r_version",
+    "b2r_cloud_create", "b2r_cloud_destroy", "b2r_cloud_size",
+    "b2r_set_target", "b2r_set_source", "b2r_set_target_cloud", "b2r_set_source_cloud",
+    "b2r_align", "b2r_fitness", "b2r_transform_source", "b2r_fitness_pair", "b2r_align_batch",
+    "b2r_distance_filter", "b2r_voxelgrid", "b2r_radius_outlier", "b2r_statistical_outlier",
+    "b2r_default_prefilter_config", "b2r_prefilter",
+    "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_covariances", "b2r_debug_voxelmap",
+    "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
+    "b2r_debug_knn", "b2r_last_timings",
+]
+
+_lib = None
+
+
+class B2RError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"b2r status {status}: {message}")
+        self.status = status
+
+
+def load():
+    """Loads libb2r.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+    L.b2r_version.restype = ctypes.c_char_p
+    L.b2r_last_error.restype = ctypes.c_char_p
+    L.b2r_last_error.argtypes = [vp]
+    L.b2r_default_config.argtypes = [ci, ctypes.POINTER(Config)]
+    L.b2r_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
+    L.b2r_destroy.argtypes = [vp]
+    L.b2r_destroy.restype = None
+    L.b2r_cloud_create.argtypes = [vp, vp, sz, sz, ci, ctypes.POINTER(vp)]
+    L.b2r_cloud_destroy.argtypes = [vp]
+    L.b2r_cloud_destroy.restype = None
+    L.b2r_cloud_size.argtypes = [vp]
+    L.b2r_cloud_size.restype = sz
+    for name in ("b2r_set_target", "b2r_set_source"):
+        getattr(L, name).argtypes = [vp, vp, sz, sz, ci]
+    for name in ("b2r_set_target_cloud", "b2r_set_source_cloud"):
+        getattr(L, name).argtypes = [vp, vp]
+    L.b2r_align.argtypes = [vp, vp, ctypes.POINTER(Result)]
+    L.b2r_fitness.argtypes = [vp, cd, ctypes.POINTER(cd)]
+    L.b2r_transform_source.argtypes = [vp, vp, sz, ci]
+    L.b2r_fitness_pair.argtypes = [vp, vp, vp, vp, cd, ctypes.POINTER(cd)]
+    L.b2r_align_batch.argtypes = [vp, vp, vp, vp, sz, ci, cd, vp]
+    L.b2r_distance_filter.argtypes = [vp, vp, sz, sz, ci, cd, cd, vp, ctypes.POINTER(sz)]
+    L.b2r_voxelgrid.argtypes = [vp, vp, sz, sz, ci, ctypes.c_float, ci, vp, ctypes.POINTER(sz), ctypes.POINTER(ci)]
+    L.b2r_radius_outlier.argtypes = [vp, vp, sz, sz, ci, cd, ci, vp, ctypes.POINTER(sz)]
+    L.b2r_statistical_outlier.argtypes = [vp, vp, sz, sz, ci, ci, cd, vp, ctypes.POINTER(sz)]
+    L.b2r_default_prefilter_config.argtypes = [ctypes.POINTER(PrefilterConfig)]
+    L.b2r_prefilter.argtypes = [vp, ctypes.POINTER(PrefilterConfig), vp, sz, sz, ci, vp, ctypes.POINTER(sz)]
+    L.b2r_kernel_launches.argtypes = [vp]
+    L.b2r_kernel_launches.restype = ctypes.c_uint64
+    L.b2r_synchronize.argtypes = [vp]
+    L.b2r_debug_covariances.argtypes = [vp, ci, vp, vp]
+    L.b2r_debug_voxelmap.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(sz)]
+    L.b2r_debug_linearize.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cd), vp, vp]
+    L.b2r_debug_compute_error.argtypes = [vp, vp, vp, ctypes.POINTER(cd)]
+    L.b2r_debug_ndt_grid.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(sz)]
+    L.b2r_debug_ndt_derivatives.argtypes = [vp, vp, ctypes.POINTER(cd), vp, vp, vp]
+    L.b2r_debug_knn.argtypes = [vp, vp, vp, sz, ci, vp, vp]
+    L.b2r_last_timings.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def default_config(method, **overrides):
+    if isinstance(method, str):
+        method = METHOD_BY_NAME[method]
+    cfg = Config()
+    load().b2r_default_config(method, ctypes.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def colmajor(T):
+    """4x4 numpy matrix -> 16 float32, column-major (Eigen::Matrix4f storage)."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T.reshape(16))
+
+
+def from_colmajor(t16):
+    return np.asarray(t16, dtype=np.float64).reshape(4, 4).T.copy()
+
+
+def _points(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("points must be (n,4) packed or (n,8) pcl::PointXYZI float32")
+    return a
+
+
+class Cloud:
+    """A device-resident cloud (b2r_cloud) with cached search structures."""
+
+    def __init__(self, reg, points=None, device_ptr=None, n=None, stride=16):
+        self._reg = reg
+        self._lib = load()
+        h = ctypes.c_void_p()
+        if device_ptr is not None:
+            st = self._lib.b2r_cloud_create(reg._h, ctypes.c_void_p(device_ptr), n, stride, DEVICE, ctypes.byref(h))
+        else:
+            a = _points(points)
+            st = self._lib.b2r_cloud_create(reg._h, a.ctypes.data, len(a), a.shape[1] * 4, HOST, ctypes.byref(h))
+        reg._check(st)
+        self._h = h
+
+    def __len__(self):
+        return int(self._lib.b2r_cloud_size(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b2r_cloud_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Registration:
+    """pcl::Registration-shaped front end over one b2r_handle."""
+
+    def __init__(self, config):
+        self._lib = load()
+        self.config = config
+        h = ctypes.c_void_p()
+        st = self._lib.b2r_create(ctypes.byref(config), ctypes.byref(h))
+        if st != OK:
+            raise B2RError(st, "b2r_create failed (no CUDA device?)" if st == ERR_NO_DEVICE else "b2r_create failed")
+        self._h = h
+        self.result = None
+        self._src_n = 0
+        self._tgt_n = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b2r_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != OK:
+            raise B2RError(st, self._lib.b2r_last_error(self._h).decode())
+
+    # ---- pcl::Registration surface ----
+    def setInputTarget(self, cloud):
+        if isinstance(cloud, Cloud):
+            self._check(self._lib.b2r_set_target_cloud(self._h, cloud._h))
+            self._tgt_n = len(cloud)
+            self._keep_t = cloud
+        else:
+            a = _points(cloud)
+            self._check(self._lib.b2r_set_target(self._h, a.ctypes.data, len(a), a.shape[1] * 4, HOST))
+            self._tgt_n = len(a)
+
+    def setInputSource(self, cloud):
+        if isinstance(cloud, Cloud):
+            self._check(self._lib.b2r_set_source_cloud(self._h, cloud._h))
+            self._src_n = len(cloud)
+            self._keep_s = cloud
+        else:
+            a = _points(cloud)
+            self._check(self._lib.b2r_set_source(self._h, a.ctypes.data, len(a), a.shape[1] * 4, HOST))
+            self._src_n = len(a)
+
+    def align(self, guess=None):
+        g = colmajor(np.eye(4) if guess is None else guess)
+        r = Result()
+        self._check(self._lib.b2r_align(self._h, g.ctypes.data, ctypes.byref(r)))
+        self.result = r
+        return r
+
+    def getFinalTransformation(self):
+        return from_colmajor(list(self.result.T))
+
+    def hasConverged(self):
+        return bool(self.result.converged)
+
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max):
+        out = ctypes.c_double()
+        self._check(self._lib.b2r_fitness(self._h, max_range, ctypes.byref(out)))
+        return out.value
+
+    def aligned_cloud(self):
+        out = np.empty((self._src_n, 4), dtype=np.float32)
+        self._check(self._lib.b2r_transform_source(self._h, out.ctypes.data, 16, HOST))
+        return out
+
+    # ---- batch (loop closure) ----
+    def align_batch(self, sources, targets, guesses, with_fitness=False, fitness_max_range=np.finfo(np.float64).max):
+        n = len(sources)
+        assert len(targets) == n and len(guesses) == n
+        S = (ctypes.c_void_p * n)(*[c._h for c in sources])
+        T = (ctypes.c_void_p * n)(*[c._h for c in targets])
+        G = np.ascontiguousarray(np.stack([colmajor(g) for g in guesses]) if n else np.zeros((0, 16), np.float32))
+        R = (Result * n)()
+        self._check(self._lib.b2r_align_batch(self._h, S, T, G.ctypes.data, n, int(with_fitness), fitness_max_range, R))
+        return list(R)
+
+    def fitness_pair(self, target, source, T, max_range=np.finfo(np.float64).max):
+        out = ctypes.c_double()
+        g = colmajor(T)
+        self._check(self._lib.b2r_fitness_pair(self._h, target._h, source._h, g.ctypes.data, max_range, ctypes.byref(out)))
+        return out.value
+
+    # ---- filters ----
+    def _filter(self, fn, cloud, *args, extra=None):
+        a = _points(cloud)
+        out = np.empty((len(a), 4), dtype=np.float32)
+        m = ctypes.c_size_t()
+        tail = [out.ctypes.data, ctypes.byref(m)] + ([extra] if extra is not None else [])
+        self._check(fn(self._h, a.ctypes.data, len(a), a.shape[1] * 4, HOST, *args, *tail))
+        return out[: m.value].copy()
+
+    def distance_filter(self, cloud, near, far):
+        return self._filter(self._lib.b2r_distance_filter, cloud, near, far)
+
+    def voxelgrid(self, cloud, leaf, min_points=1):
+        ovf = ctypes.c_int()
+        pts = self._filter(self._lib.b2r_voxelgrid, cloud, leaf, min_points, extra=ctypes.byref(ovf))
+        return pts, bool(ovf.value)
+
+    def radius_outlier(self, cloud, radius, min_neighbors):
+        return self._filter(self._lib.b2r_radius_outlier, cloud, radius, min_neighbors)
+
+    def statistical_outlier(self, cloud, mean_k, stddev_mul):
+        return self._filter(self._lib.b2r_statistical_outlier, cloud, mean_k, stddev_mul)
+
+    def prefilter(self, cloud, cfg=None):
+        if cfg is None:
+            cfg = PrefilterConfig()
+            self._lib.b2r_default_prefilter_config(ctypes.byref(cfg))
+        a = _points(cloud)
+        out = np.empty((len(a), 4), dtype=np.float32)
+        m = ctypes.c_size_t()
+        self._check(self._lib.b2r_prefilter(self._h, ctypes.byref(cfg), a.ctypes.data, len(a), a.shape[1] * 4, HOST, out.ctypes.data,
+                                            ctypes.byref(m)))
+        return out[: m.value].copy()
+
+    # ---- introspection ----
+    def kernel_launches(self):
+        return int(self._lib.b2r_kernel_launches(self._h))
+
+    def last_timings(self):
+        t = (ctypes.c_float * 4)()
+        self._lib.b2r_last_timings(self._h, t)
+        return dict(zip(("prep_ms", "optimize_ms", "fitness_ms", "total_ms"), list(t)))
+
+    def debug_covariances(self, which, want_knn=False):
+        n = self._src_n if which == 0 else self._tgt_n
+        k = self.config.correspondence_randomness
+        cov = np.zeros((n, 6))
+        knn = np.zeros((n, k), dtype=np.int32) if want_knn else None
+        self._check(self._lib.b2r_debug_covariances(self._h, which, cov.ctypes.data, knn.ctypes.data if want_knn else None))
+        return (cov, knn) if want_knn else cov
+
+    def debug_voxelmap(self):
+        n = self._tgt_n
+        coords = np.zeros((n, 3), dtype=np.int32); npts = np.zeros(n, dtype=np.int32)
+        mean = np.zeros((n, 3)); cov = np.zeros((n, 6))
+        V = ctypes.c_size_t()
+        self._check(self._lib.b2r_debug_voxelmap(self._h, coords.ctypes.data, npts.ctypes.data, mean.ctypes.data, cov.ctypes.data, ctypes.byref(V)))
+        v = V.value
+        return coords[:v].copy(), npts[:v].copy(), mean[:v].copy(), cov[:v].copy()
+
+    def debug_linearize(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        H = np.zeros((6, 6)); b = np.zeros(6); err = ctypes.c_double()
+        n = self._src_n
+        if self.config.method == FAST_VGICP:
+            corr = np.zeros((n, 3), dtype=np.int32); valid = np.zeros(n, dtype=np.uint8)
+        else:
+            corr = np.zeros(n, dtype=np.int32); valid = np.zeros(n, dtype=np.uint8)
+        self._check(self._lib.b2r_debug_linearize(self._h, T.ctypes.data, H.ctypes.data, b.ctypes.data, ctypes.byref(err), corr.ctypes.data,
+                                                  valid.ctypes.data))
+        if self.config.method != FAST_VGICP:
+            valid = corr >= 0
+        return err.value, H, b, corr, valid.astype(bool)
+
+    def debug_compute_error(self, T_lin, T_trial):
+        a = np.ascontiguousarray(T_lin, dtype=np.float64); b = np.ascontiguousarray(T_trial, dtype=np.float64)
+        err = ctypes.c_double()
+        self._check(self._lib.b2r_debug_compute_error(self._h, a.ctypes.data, b.ctypes.data, ctypes.byref(err)))
+        return err.value
+
+    def debug_ndt_grid(self):
+        n = self._tgt_n
+        idx = np.zeros(n, dtype=np.int32); npts = np.zeros(n, dtype=np.int32)
+        mean = np.zeros((n, 3)); icov = np.zeros((n, 9))
+        min_b = np.zeros(3, dtype=np.int32); div_b = np.zeros(3, dtype=np.int32)
+        V = ctypes.c_size_t()
+        self._check(self._lib.b2r_debug_ndt_grid(self._h, idx.ctypes.data, npts.ctypes.data, mean.ctypes.data, icov.ctypes.data,
+                                                 min_b.ctypes.data, div_b.ctypes.data, ctypes.byref(V)))
+        v = V.value
+        return idx[:v].copy(), npts[:v].copy(), mean[:v].copy(), icov[:v].reshape(v, 3, 3).copy(), min_b, div_b
+
+    def debug_ndt_derivatives(self, p6):
+        p6 = np.ascontiguousarray(p6, dtype=np.float64)
+        score = ctypes.c_double(); g = np.zeros(6); H = np.zeros((6, 6)); hits = np.zeros(self._src_n, dtype=np.int32)
+        self._check(self._lib.b2r_debug_ndt_derivatives(self._h, p6.ctypes.data, ctypes.byref(score), g.ctypes.data, H.ctypes.data,
+                                                        hits.ctypes.data))
+        return score.value, g, H, hits
+
+    def debug_knn(self, cloud, queries, k):
+        q = _points(queries)
+        idx = np.zeros((len(q), k), dtype=np.int32); d2 = np.zeros((len(q), k), dtype=np.float32)
+        self._check(self._lib.b2r_debug_knn(self._h, cloud._h, q.ctypes.data, len(q), k, idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+
+def select_registration_method(params):
+    """Python mirror of select_registration_method() (/root/reference/src/mrg_slam/registrations.cpp:28-152).
+
+    `params` is a dict carrying the same ROS parameter names the reference reads at :34-43.  Method strings the
+    reference maps to classes outside this engine's scope raise; an unknown string warns and falls back to NDT
+    exactly like :117-120 does (NDT_OMP here, the engine's NDT).
+    """
+    import sys
+
+    name = params.get("registration_method", "FAST_GICP")
+    common = dict(
+        device=params.get("device", 0),
+        transformation_epsilon=params.get("reg_transformation_epsilon", 0.1),
+        maximum_iterations=params.get("reg_maximum_iterations", 64),
+    )
+    if name == "FAST_GICP":
+        cfg = default_config(FAST_GICP, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
+                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
+    elif name == "FAST_VGICP":
+        cfg = default_config(FAST_VGICP, resolution=params.get("reg_resolution", 1.0),
+                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
+    elif name in ("SMALL_GICP", "FAST_VGICP_CUDA", "ICP", "GICP", "GICP_OMP", "NDT"):
+        raise NotImplementedError(f"registration_method {name} is outside this engine's scope (see DESIGN.md)")
+    else:
+        if "NDT" not in name:
+            print(f"warning: unknown registration type({name})\n       : use NDT", file=sys.stderr)
+        nn = {"KDTREE": None, "DIRECT1": DIRECT1}.get(params.get("reg_nn_search_method", "DIRECT7"), DIRECT7)
+        if nn is None:
+            raise NotImplementedError("reg_nn_search_method KDTREE is not implemented (DIRECT1 / DIRECT7 only)")
+        cfg = default_config(NDT_OMP, resolution=params.get("reg_resolution", 1.0), neighbor_search=nn, **common)
+    return Registration(cfg)
