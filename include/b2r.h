@@ -161,6 +161,16 @@ b2r_status b2r_debug_knn(b2r_handle* h, b2r_cloud* c, const float* queries_xyzi,
 /* per-stage device time of the last align/align_batch in milliseconds: [0] cloud prep (grid+covariances+maps),
  * [1] optimiser loop, [2] fitness, [3] total */
 b2r_status b2r_last_timings(const b2r_handle* h, float ms_out[4]);
+/* CUDA events on the handle's own stream (the stream every kernel of this handle is launched on), for callers that
+ * must time a region on the device: record into slot 0..7, then read the elapsed time between two slots. */
+b2r_status b2r_event_record(b2r_handle* h, int slot);
+b2r_status b2r_event_elapsed_ms(b2r_handle* h, int slot_start, int slot_stop, float* ms);
+/* Per-kernel device timing (CUDA events around each launch of the named kernel family) for roofline reporting.
+ * kernel_id: 0 knn_cov (kNN + covariances), 1 lsq_eval (GICP/VGICP correspondence+reduction pass), 2 ndt_eval,
+ * 3 grid_build (count/scan/scatter), 4 voxel_reduce (VGICP/NDT per-voxel statistics), 5 fitness.
+ * b2r_profile_read returns the summed duration, number of launches and summed algorithmic bytes since enable. */
+b2r_status b2r_profile_enable(b2r_handle* h, int on);
+b2r_status b2r_profile_read(b2r_handle* h, int kernel_id, double* ms_sum, uint64_t* launches, double* algorithmic_bytes);
 
 #ifdef __cplusplus
 }

@@ -204,6 +204,11 @@ void b2r_destroy(b2r_handle* hh) {
   h.owned_target.reset();
   for (int i = 0; i < 4; ++i)
     if (h.ev[i]) cudaEventDestroy(h.ev[i]);
+  for (int i = 0; i < 8; ++i)
+    if (h.user_ev[i]) cudaEventDestroy(h.user_ev[i]);
+  h.ctx.prof_resolve();
+  for (cudaEvent_t e : h.ctx.ev_pool) cudaEventDestroy(e);
+  h.ctx.ev_pool.clear();
   if (h.ctx.stream) { cudaStreamSynchronize(h.ctx.stream); cudaStreamDestroy(h.ctx.stream); }
   delete hh;
 }
@@ -463,6 +468,37 @@ b2r_status b2r_last_timings(const b2r_handle* hh, float ms_out[4]) {
   if (!hh || !ms_out) return B2R_ERR_INVALID_ARG;
   for (int i = 0; i < 4; ++i) ms_out[i] = hh->h.timings[i];
   return B2R_OK;
+}
+
+b2r_status b2r_event_record(b2r_handle* hh, int slot) {
+  return guarded(hh, [&](Handle& h) {
+    if (slot < 0 || slot >= 8) throw Error(B2R_ERR_INVALID_ARG, "event slot must be in [0,8)");
+    if (!h.user_ev[slot]) B2R_CUDA(cudaEventCreate(&h.user_ev[slot]));
+    B2R_CUDA(cudaEventRecord(h.user_ev[slot], h.ctx.stream));
+  });
+}
+b2r_status b2r_event_elapsed_ms(b2r_handle* hh, int a, int b, float* ms) {
+  return guarded(hh, [&](Handle& h) {
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !ms || !h.user_ev[a] || !h.user_ev[b]) throw Error(B2R_ERR_INVALID_ARG, "bad event slots");
+    B2R_CUDA(cudaEventSynchronize(h.user_ev[b]));
+    B2R_CUDA(cudaEventElapsedTime(ms, h.user_ev[a], h.user_ev[b]));
+  });
+}
+b2r_status b2r_profile_enable(b2r_handle* hh, int on) {
+  return guarded(hh, [&](Handle& h) {
+    h.ctx.prof_resolve();
+    h.ctx.profile = on != 0;
+    for (int i = 0; i < PROF_COUNT; ++i) { h.ctx.prof_ms[i] = 0; h.ctx.prof_n[i] = 0; h.ctx.prof_bytes[i] = 0; }
+  });
+}
+b2r_status b2r_profile_read(b2r_handle* hh, int id, double* ms_sum, uint64_t* launches, double* bytes) {
+  return guarded(hh, [&](Handle& h) {
+    if (id < 0 || id >= PROF_COUNT) throw Error(B2R_ERR_INVALID_ARG, "unknown kernel id");
+    h.ctx.prof_resolve();
+    if (ms_sum) *ms_sum = h.ctx.prof_ms[id];
+    if (launches) *launches = h.ctx.prof_n[id];
+    if (bytes) *bytes = h.ctx.prof_bytes[id];
+  });
 }
 
 b2r_status b2r_debug_covariances(b2r_handle* hh, int which, double* cov6_out, int32_t* knn_out) {

@@ -29,11 +29,11 @@ CloudView Cloud::view() const {
   v.vres = vres;
   for (int d = 0; d < 3; ++d) { v.vmin[d] = vmin[d]; v.vd[d] = vd[d]; }
   v.vcell = vcell; v.v_start = v_start.p; v.v_cnt = v_cnt.p; v.v_order = v_order.p; v.v_table = v_table.p; v.vrec = vrec.p;
-  v.v_nrec = v_nrec.p;
+  v.v_nrec = v_nrec.p; v.v_reccell = v_reccell.p;
   v.leaf = leaf; v.inv_leaf = leaf > 0 ? 1.0f / leaf : 0.f;
   for (int d = 0; d < 3; ++d) { v.min_b[d] = min_b[d]; v.max_b[d] = max_b[d]; v.div_b[d] = div_b[d]; }
   v.ncell_ndt = ncell_ndt; v.n_start = n_start.p; v.n_cnt = n_cnt.p; v.n_order = n_order.p; v.n_table = n_table.p; v.nrec = nrec.p;
-  v.n_nrec = n_nrec.p;
+  v.n_nrec = n_nrec.p; v.n_reccell = n_reccell.p;
   return v;
 }
 
@@ -180,31 +180,80 @@ __global__ void grid_count_kernel(const CloudView* __restrict__ views) {
   }
 }
 
-// One block per cloud: exclusive scan of the per-cell counts into start[0..ncell], counts reset to 0
-// (they become the scatter cursors).  For voxel grids also assigns compact record ids to occupied cells.
+// Exclusive scan of the per-cell counts into start[0..ncell] in three phases (tile-local scan, scan of the tile
+// totals, apply); counts are reset to 0 (they become the scatter cursors).  For voxel grids the same pass assigns
+// compact record ids to the occupied cells (64-bit packed scan: low word points, high word occupied cells).
+constexpr int kScanItems = 8;
+constexpr int kScanTile = 1024 * kScanItems;
+
 template <int MODE>
-__global__ void __launch_bounds__(1024) grid_scan_kernel(const CloudView* __restrict__ views) {
-  const CloudView& c = views[blockIdx.x];
+__global__ void __launch_bounds__(1024) grid_scan_tile_kernel(const CloudView* __restrict__ views, unsigned long long* __restrict__ tile_tot,
+                                                              int max_tiles) {
+  const CloudView& c = views[blockIdx.y];
+  const int ncell = grid_ncell<MODE>(c);
+  const int base = blockIdx.x * kScanTile;
+  if (base >= ncell) return;
   int* cnt = grid_cnt<MODE>(c);
   int* start = grid_start<MODE>(c);
-  const int ncell = grid_ncell<MODE>(c);
   int* table = MODE == GRID_VGICP ? c.v_table : (MODE == GRID_NDT ? c.n_table : nullptr);
-  constexpr int ITEMS = 8;
+  __shared__ unsigned long long warp_tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v[kScanItems];
+  unsigned long long tsum = 0ull;
+  const int i0 = base + threadIdx.x * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (i0 + k < ncell) ? cnt[i0 + k] : 0;
+    tsum += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 32) : 0ull);
+  }
+  unsigned long long incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;
+    if (lane == 31) tile_tot[(size_t)blockIdx.y * max_tiles + blockIdx.x] = wi;
+  }
+  __syncthreads();
+  unsigned long long run = warp_tot[warp] + (incl - tsum);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (i0 + k < ncell) {
+      start[i0 + k] = (int)(run & 0xffffffffull);
+      if (MODE != GRID_NN) table[i0 + k] = v[k] > 0 ? (int)(run >> 32) : -1;
+      cnt[i0 + k] = 0;
+    }
+    run += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 32) : 0ull);
+  }
+}
+
+// one block per cloud: exclusive scan of the tile totals (in place); writes start[ncell] and the record count
+template <int MODE>
+__global__ void __launch_bounds__(1024) grid_scan_tops_kernel(const CloudView* __restrict__ views, unsigned long long* __restrict__ tile_tot,
+                                                              int max_tiles) {
+  const CloudView& c = views[blockIdx.x];
+  const int ncell = grid_ncell<MODE>(c);
+  const int ntiles = (ncell + kScanTile - 1) / kScanTile;
+  unsigned long long* tt = tile_tot + (size_t)blockIdx.x * max_tiles;
   __shared__ unsigned long long warp_tot[32];
   __shared__ unsigned long long carry_s;
   if (threadIdx.x == 0) carry_s = 0ull;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < ncell; base += 1024 * ITEMS) {
-    int v[ITEMS];
-    unsigned long long tsum = 0ull;
-    const int i0 = base + threadIdx.x * ITEMS;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      v[k] = (i0 + k < ncell) ? cnt[i0 + k] : 0;
-      tsum += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 32) : 0ull);  // lo: points, hi: occupied cells
-    }
-    unsigned long long incl = tsum;
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned long long v = i < ntiles ? tt[i] : 0ull;
+    unsigned long long incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -213,34 +262,50 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(const CloudView* __rest
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      unsigned long long w = warp_tot[lane];
-      unsigned long long wi = w;
+      unsigned long long w = warp_tot[lane], wi = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
         if (lane >= o) wi += t;
       }
-      warp_tot[lane] = wi - w;  // exclusive offset of each warp inside the tile
+      warp_tot[lane] = wi - w;
     }
     __syncthreads();
-    unsigned long long run = carry_s + warp_tot[warp] + (incl - tsum);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      if (i0 + k < ncell) {
-        start[i0 + k] = (int)(run & 0xffffffffull);
-        if (MODE != GRID_NN) table[i0 + k] = v[k] > 0 ? (int)(run >> 32) : -1;
-        cnt[i0 + k] = 0;
-      }
-      run += (unsigned long long)v[k] + (v[k] > 0 ? (1ull << 32) : 0ull);
-    }
+    const unsigned long long excl = carry_s + warp_tot[warp] + incl - v;
+    if (i < ntiles) tt[i] = excl;
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = run;  // last thread's running total = carry after this tile
+    if (threadIdx.x == 1023) carry_s = excl + v;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    start[ncell] = (int)(carry_s & 0xffffffffull);
+    grid_start<MODE>(c)[ncell] = (int)(carry_s & 0xffffffffull);
     if (MODE == GRID_VGICP) c.v_nrec[0] = (int)(carry_s >> 32);
     if (MODE == GRID_NDT) c.n_nrec[0] = (int)(carry_s >> 32);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) grid_scan_apply_kernel(const CloudView* __restrict__ views, const unsigned long long* __restrict__ tile_tot,
+                                                               int max_tiles) {
+  const CloudView& c = views[blockIdx.y];
+  const int ncell = grid_ncell<MODE>(c);
+  const int base = blockIdx.x * kScanTile;
+  if (base >= ncell) return;
+  const unsigned long long off = tile_tot[(size_t)blockIdx.y * max_tiles + blockIdx.x];
+  const int off_lo = (int)(off & 0xffffffffull), off_hi = (int)(off >> 32);
+  int* start = grid_start<MODE>(c);
+  int* table = MODE == GRID_VGICP ? c.v_table : (MODE == GRID_NDT ? c.n_table : nullptr);
+  int* reccell = MODE == GRID_VGICP ? c.v_reccell : (MODE == GRID_NDT ? c.n_reccell : nullptr);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int i = base + k * 1024 + threadIdx.x;
+    if (i < ncell) {
+      start[i] += off_lo;
+      if (MODE != GRID_NN) {
+        const int t = table[i];
+        if (t >= 0) { table[i] = t + off_hi; reccell[t + off_hi] = i; }
+      }
+    }
   }
 }
 
@@ -259,63 +324,97 @@ __global__ void grid_scatter_kernel(const CloudView* __restrict__ views) {
   }
 }
 
-// in-place insertion sort of one voxel's point list (ascending original index => deterministic, index-order sums)
-__device__ __forceinline__ void sort_indices(int* a, int n) {
-  for (int i = 1; i < n; ++i) {
-    int v = a[i], j = i - 1;
-    while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
-    a[j + 1] = v;
+__device__ __forceinline__ int warp_sort32_int(int v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      v = (lower == up) ? min(v, o) : max(v, o);
+    }
   }
+  return v;
+}
+// One warp sorts the point list [s, s+n) of a voxel ascending (the atomic scatter left it in arbitrary order), so that the
+// per-voxel sums below are evaluated in a fixed order: deterministic run to run.  Lists longer than a warp are rank-sorted
+// into the scratch half of `order` (order + n_total).  Returns the sorted list.
+__device__ __forceinline__ const int* warp_sort_segment(int* order, int n_total, int s, int n, int lane) {
+  if (n <= 32) {
+    int v = lane < n ? order[s + lane] : INT_MAX;
+    v = warp_sort32_int(v, lane);
+    if (lane < n) order[s + lane] = v;
+    __syncwarp();
+    return order + s;
+  }
+  int* dst = order + n_total + s;
+  for (int i = lane; i < n; i += 32) {
+    const int vi = order[s + i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (order[s + j] < vi) ? 1 : 0;
+    dst[rank] = vi;
+  }
+  __syncwarp();
+  return dst;
 }
 
-// VGICP: one thread per table cell; occupied cells sum their points' positions and covariances in
-// ascending point-index order (fast_gicp create_voxelmap), then divide by the count.
-__global__ void vgicp_reduce_kernel(const CloudView* __restrict__ views) {
+// VGICP: one warp per occupied voxel: sum of the points' positions and covariances (fast_gicp create_voxelmap,
+// SURVEY A.2) over the index-sorted list, lane-strided partials + fixed-order warp reduction, then divide by the count.
+__global__ void __launch_bounds__(256) vgicp_reduce_kernel(const CloudView* __restrict__ views) {
   const CloudView& c = views[blockIdx.y];
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < c.vcell; cell += gridDim.x * blockDim.x) {
-    const int rec = c.v_table[cell];
-    if (rec < 0) continue;
-    const int s = c.v_start[cell], e = c.v_start[cell + 1];
-    sort_indices(c.v_order + s, e - s);
-    double m0 = 0, m1 = 0, m2 = 0, cv[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = s; j < e; ++j) {
-      const int i = c.v_order[j];
-      float4 p = __ldg(&c.pts[i]);
-      m0 += (double)p.x; m1 += (double)p.y; m2 += (double)p.z;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nrec = c.v_nrec[0];
+  for (int rec = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rec < nrec; rec += nwarps) {
+    const int cell = c.v_reccell[rec];
+    const int s = c.v_start[cell], n = c.v_start[cell + 1] - s;
+    const int* idx = warp_sort_segment(c.v_order, c.n, s, n, lane);
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = lane; j < n; j += 32) {
+      const int i = idx[j];
+      const float4 p = __ldg(&c.pts[i]);
+      a[0] += (double)p.x; a[1] += (double)p.y; a[2] += (double)p.z;
       const double* pc = c.cov + (size_t)i * 6;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) cv[k] += pc[k];
+      for (int k = 0; k < 6; ++k) a[3 + k] += pc[k];
     }
-    const double nn = (double)(e - s);
-    VoxRec r;
-    r.mean[0] = m0 / nn; r.mean[1] = m1 / nn; r.mean[2] = m2 / nn;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) r.cov[k] = cv[k] / nn;
-    r.n = e - s;
-    r.cell = cell;
-    c.vrec[rec] = r;
+    for (int k = 0; k < 9; ++k) a[k] = warp_sum(a[k]);
+    if (lane == 0) {
+      const double nn = (double)n;
+      VoxRec r;
+      r.mean[0] = a[0] / nn; r.mean[1] = a[1] / nn; r.mean[2] = a[2] / nn;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) r.cov[k] = a[3 + k] / nn;
+      r.n = n;
+      r.cell = cell;
+      c.vrec[rec] = r;
+    }
   }
 }
 
 // NDT: per-voxel mean, single-pass covariance, eigenvalue clamp and inverse (pclomp::VoxelGridCovariance)
-__global__ void ndt_reduce_kernel(const CloudView* __restrict__ views) {
+__global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __restrict__ views) {
   const CloudView& c = views[blockIdx.y];
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < c.ncell_ndt; cell += gridDim.x * blockDim.x) {
-    const int rec = c.n_table[cell];
-    if (rec < 0) continue;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nrec = c.n_nrec[0];
+  for (int rec = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rec < nrec; rec += nwarps) {
+    const int cell = c.n_reccell[rec];
     const int s = c.n_start[cell], e = c.n_start[cell + 1];
-    sort_indices(c.n_order + s, e - s);
-    double sum[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j = s; j < e; ++j) {
-      float4 p = __ldg(&c.pts[c.n_order[j]]);
-      double q[3] = {(double)p.x, (double)p.y, (double)p.z};
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        sum[a] += q[a];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) cov[a * 3 + b] += q[a] * q[b];
-      }
+    const int* idx = warp_sort_segment(c.n_order, c.n, s, e - s, lane);
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // sum x,y,z ; sum xx,xy,xz,yy,yz,zz
+    for (int j = lane; j < e - s; j += 32) {
+      const float4 p = __ldg(&c.pts[idx[j]]);
+      const double qx = (double)p.x, qy = (double)p.y, qz = (double)p.z;
+      acc[0] += qx; acc[1] += qy; acc[2] += qz;
+      acc[3] += qx * qx; acc[4] += qx * qy; acc[5] += qx * qz; acc[6] += qy * qy; acc[7] += qy * qz; acc[8] += qz * qz;
     }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane != 0) continue;
+    double sum[3] = {acc[0], acc[1], acc[2]};
+    double cov[9] = {acc[3], acc[4], acc[5], acc[4], acc[6], acc[7], acc[5], acc[7], acc[8]};
     NdtRec r;
     const int npts = e - s;
     const double nn = (double)npts;
@@ -385,21 +484,17 @@ __global__ void ndt_reduce_kernel(const CloudView* __restrict__ views) {
 }
 
 // ------------------------------------------------------------------------------------------------ kNN covariances
-// One warp per tile of 32 consecutive cell-sorted queries.  Per query: exact kNN (knn.cuh), mean/covariance of the
-// k neighbours in double, kept by lane q; afterwards every lane regularises its own covariance (PLANE:
-// singular values (1,1,1e-3), fast_gicp calculate_covariances).
+// Kernel 1 — one warp per query, queries interleaved across the resident warps (grid-stride) so that the expensive
+// sparse-region queries spread over all SMs: exact kNN (knn.cuh), then mean / covariance of the k neighbours in double
+// by warp reductions (fast_gicp calculate_covariances).  Writes the raw covariance (6 doubles).
 __global__ void __launch_bounds__(256) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+  __shared__ KnnScratch scratch[8];
   const CloudView& c = views[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int base = tile * 32;
-  if (base >= c.n) return;
-  double my[6] = {0, 0, 0, 0, 0, 0};
-  int my_orig = -1;
-  const int nq = min(32, c.n - base);
-  for (int q = 0; q < nq; ++q) {
-    const float4 sp = __ldg(&c.spts[base + q]);
-    const unsigned long long key = warp_knn(c, sp.x, sp.y, sp.z, k, lane);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int q = blockIdx.x * (blockDim.x >> 5) + warp; q < c.n; q += nwarps) {
+    const float4 sp = __ldg(&c.spts[q]);
+    const unsigned long long key = warp_knn(c, sp.x, sp.y, sp.z, k, lane, scratch[warp]);
     const int orig = __float_as_int(sp.w);
     double x = 0, y = 0, z = 0;
     const bool act = lane < k && key != ~0ull;
@@ -411,14 +506,27 @@ __global__ void __launch_bounds__(256) knn_cov_kernel(const CloudView* __restric
     }
     if (knn_out && lane < k) knn_out[(size_t)orig * k + lane] = nb_orig;
     const double kk = (double)k;
-    const double mx = warp_sum(x) / kk, my_ = warp_sum(y) / kk, mz = warp_sum(z) / kk;
-    const double dx = act ? x - mx : 0.0, dy = act ? y - my_ : 0.0, dz = act ? z - mz : 0.0;
-    double cxx = warp_sum(dx * dx) / kk, cxy = warp_sum(dx * dy) / kk, cxz = warp_sum(dx * dz) / kk;
-    double cyy = warp_sum(dy * dy) / kk, cyz = warp_sum(dy * dz) / kk, czz = warp_sum(dz * dz) / kk;
-    if (lane == q) { my[0] = cxx; my[1] = cxy; my[2] = cxz; my[3] = cyy; my[4] = cyz; my[5] = czz; my_orig = orig; }
+    const double mx = warp_sum(x) / kk, my = warp_sum(y) / kk, mz = warp_sum(z) / kk;
+    const double dx = act ? x - mx : 0.0, dy = act ? y - my : 0.0, dz = act ? z - mz : 0.0;
+    // six products reduced together: lanes 0..5 end up owning one component each
+    double v[6] = {dx * dx, dx * dy, dx * dz, dy * dy, dy * dz, dz * dz};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) v[t] = warp_sum(v[t]) / kk;
+    if (lane == 0) {
+      double* dst = c.cov + (size_t)orig * 6;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) dst[t] = v[t];
+    }
   }
-  if (my_orig >= 0) {
-    double S[9] = {my[0], my[1], my[2], my[1], my[3], my[4], my[2], my[4], my[5]};
+}
+
+// Kernel 2 — one thread per point: PLANE regularisation, singular values replaced by (1, 1, 1e-3).
+__global__ void __launch_bounds__(128) cov_regularize_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    double* p = c.cov + (size_t)i * 6;
+    const double m0 = p[0], m1 = p[1], m2 = p[2], m3 = p[3], m4 = p[4], m5 = p[5];
+    double S[9] = {m0, m1, m2, m1, m3, m4, m2, m4, m5};
     double ev[3], V[9];
     sym3_eigen_dev(S, ev, V);
     const double vals[3] = {1e-3, 1.0, 1.0};  // ascending eigen order: smallest = plane normal
@@ -429,21 +537,21 @@ __global__ void __launch_bounds__(256) knn_cov_kernel(const CloudView* __restric
       o[0] += vals[j] * a * a; o[1] += vals[j] * a * b; o[2] += vals[j] * a * cc;
       o[3] += vals[j] * b * b; o[4] += vals[j] * b * cc; o[5] += vals[j] * cc * cc;
     }
-    double* dst = c.cov + (size_t)my_orig * 6;
 #pragma unroll
-    for (int t = 0; t < 6; ++t) dst[t] = o[t];
+    for (int t = 0; t < 6; ++t) p[t] = o[t];
   }
 }
 
 // arbitrary queries (debug / tests): one warp per query
-__global__ void knn_query_kernel(const CloudView* __restrict__ views, const float4* __restrict__ queries, int nq, int k,
-                                 int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
+__global__ void __launch_bounds__(256) knn_query_kernel(const CloudView* __restrict__ views, const float4* __restrict__ queries, int nq, int k,
+                                                         int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
+  __shared__ KnnScratch scratch[8];
   const CloudView& c = views[0];
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
   if (q >= nq) return;
   const float4 p = __ldg(&queries[q]);
-  const unsigned long long key = warp_knn(c, p.x, p.y, p.z, k, lane);
+  const unsigned long long key = warp_knn(c, p.x, p.y, p.z, k, lane, scratch[warp]);
   if (lane < k) {
     if (key != ~0ull) {
       idx_out[(size_t)q * k + lane] = __float_as_int(c.spts[(unsigned)(key & 0xffffffffull)].w);
@@ -479,6 +587,20 @@ static void grid_dims(Cloud& c, float h) {
 
 static inline unsigned blocks_for(int n, int per_block, int cap) { return (unsigned)std::max(1, std::min(cap, (n + per_block - 1) / per_block)); }
 
+// kNN covariances of a batch of clouds: search kernel (grid-stride warps, ~all SMs busy whatever the batch size) + regularisation
+static void launch_knn_cov(Ctx& ctx, const CloudView* dviews, const std::vector<Cloud*>& clouds, int k, int maxn, int32_t* knn_out) {
+  const int nc = (int)clouds.size();
+  double bytes = 0.0;  // 16 B point in + 24 B covariance out per point
+  for (Cloud* c : clouds) bytes += 40.0 * c->n;
+  // 8 queries per warp at least; enough blocks for ~8 resident blocks per SM across the batch
+  const int per_cloud = std::max(1, std::min((maxn + 63) / 64, (8 * ctx.num_sms + nc - 1) / nc));
+  {
+    ProfScope ps(ctx, PROF_KNN_COV, bytes);
+    B2R_LAUNCH(ctx, knn_cov_kernel, dim3(per_cloud, nc), 256, 0, dviews, k, knn_out);
+  }
+  B2R_LAUNCH(ctx, cov_regularize_kernel, dim3(blocks_for(maxn, 128, 4 * ctx.num_sms), nc), 128, 0, dviews);
+}
+
 void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
   std::vector<Cloud*> todo;
   for (Cloud* c : clouds)
@@ -508,10 +630,16 @@ void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
 }
 
 template <int MODE>
-static void run_grid_build(Ctx& ctx, const CloudView* dviews, int nc, int maxn) {
+static void run_grid_build(Ctx& ctx, const CloudView* dviews, int nc, int maxn, int maxcell) {
   dim3 g(blocks_for(maxn, 256 * 4, 4 * ctx.num_sms), nc);
+  const int max_tiles = (maxcell + kScanTile - 1) / kScanTile;
+  DBuf<unsigned long long> tile_tot;
+  tile_tot.alloc((size_t)nc * max_tiles, ctx.stream);
+  ProfScope ps(ctx, PROF_GRID_BUILD, 0.0);
   B2R_LAUNCH(ctx, grid_count_kernel<MODE>, g, 256, 0, dviews);
-  B2R_LAUNCH(ctx, grid_scan_kernel<MODE>, nc, 1024, 0, dviews);
+  B2R_LAUNCH(ctx, grid_scan_tile_kernel<MODE>, dim3(max_tiles, nc), 1024, 0, dviews, tile_tot.p, max_tiles);
+  B2R_LAUNCH(ctx, grid_scan_tops_kernel<MODE>, nc, 1024, 0, dviews, tile_tot.p, max_tiles);
+  B2R_LAUNCH(ctx, grid_scan_apply_kernel<MODE>, dim3(max_tiles, nc), 1024, 0, dviews, tile_tot.p, max_tiles);
   B2R_LAUNCH(ctx, grid_scatter_kernel<MODE>, g, 256, 0, dviews);
 }
 
@@ -542,9 +670,10 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     for (size_t i = 0; i < clouds.size(); ++i)
       if (needs[i].grid && !clouds[i]->has_grid && clouds[i]->n > 0) todo.push_back(clouds[i]);
     if (!todo.empty()) {
-      int maxn = 1;
+      int maxn = 1, maxcell = 1;
       for (Cloud* c : todo) {
         grid_dims(*c, auto_cell_size(*c, cfg));
+        maxcell = std::max(maxcell, c->ncell);
         c->cell_start.alloc((size_t)c->ncell + 1, ctx.stream);
         c->cell_cnt.alloc((size_t)c->ncell, ctx.stream);
         c->cell_cnt.zero(ctx.stream);
@@ -555,7 +684,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       for (Cloud* c : todo) hv.push_back(c->view());
       DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
       B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      run_grid_build<GRID_NN>(ctx, dv.p, (int)hv.size(), maxn);
+      run_grid_build<GRID_NN>(ctx, dv.p, (int)hv.size(), maxn, maxcell);
       B2R_CUDA(cudaStreamSynchronize(ctx.stream));  // hv must outlive the async copy
       for (Cloud* c : todo) c->has_grid = true;
     }
@@ -579,8 +708,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       for (Cloud* c : todo) hv.push_back(c->view());
       DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
       B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      dim3 g((unsigned)((maxn + 255) / 256), (unsigned)hv.size());  // 8 warps x 32 queries per block
-      B2R_LAUNCH(ctx, knn_cov_kernel, g, 256, 0, dv.p, k, (int32_t*)nullptr);
+      launch_knn_cov(ctx, dv.p, todo, k, maxn, nullptr);
       B2R_CUDA(cudaStreamSynchronize(ctx.stream));
       for (Cloud* c : todo) c->cov_k = k;
     }
@@ -605,7 +733,8 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
         c->v_cnt.alloc((size_t)tot, ctx.stream);
         c->v_cnt.zero(ctx.stream);
         c->v_table.alloc((size_t)tot, ctx.stream);
-        c->v_order.alloc((size_t)c->n, ctx.stream);
+        c->v_order.alloc((size_t)c->n * 2, ctx.stream);  // second half: sort scratch
+        c->v_reccell.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
         c->vrec.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
         c->v_nrec.alloc(1, ctx.stream);
         c->vres = res;
@@ -617,9 +746,12 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       for (Cloud* c : todo) { hv.push_back(c->view()); maxn = std::max(maxn, c->n); maxcell = std::max(maxcell, c->vcell); }
       DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
       B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      run_grid_build<GRID_VGICP>(ctx, dv.p, (int)hv.size(), maxn);
-      dim3 g(blocks_for(maxcell, 128, 8 * ctx.num_sms), (unsigned)hv.size());
-      B2R_LAUNCH(ctx, vgicp_reduce_kernel, g, 128, 0, dv.p);
+      run_grid_build<GRID_VGICP>(ctx, dv.p, (int)hv.size(), maxn, maxcell);
+      dim3 g(blocks_for(std::min(maxcell, maxn), 8, std::max(1, 8 * ctx.num_sms / (int)hv.size())), (unsigned)hv.size());
+      {
+        ProfScope ps(ctx, PROF_VOXEL_REDUCE, 0.0);
+        B2R_LAUNCH(ctx, vgicp_reduce_kernel, g, 256, 0, dv.p);
+      }
       B2R_CUDA(cudaStreamSynchronize(ctx.stream));
     }
   }
@@ -648,7 +780,8 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
         c->n_cnt.alloc((size_t)tot, ctx.stream);
         c->n_cnt.zero(ctx.stream);
         c->n_table.alloc((size_t)tot, ctx.stream);
-        c->n_order.alloc((size_t)c->n, ctx.stream);
+        c->n_order.alloc((size_t)c->n * 2, ctx.stream);
+        c->n_reccell.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
         c->nrec.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
         c->n_nrec.alloc(1, ctx.stream);
         todo.push_back(c);
@@ -659,9 +792,12 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       for (Cloud* c : todo) { hv.push_back(c->view()); maxn = std::max(maxn, c->n); maxcell = std::max(maxcell, c->ncell_ndt); }
       DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
       B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      run_grid_build<GRID_NDT>(ctx, dv.p, (int)hv.size(), maxn);
-      dim3 g(blocks_for(maxcell, 128, 8 * ctx.num_sms), (unsigned)hv.size());
-      B2R_LAUNCH(ctx, ndt_reduce_kernel, g, 128, 0, dv.p);
+      run_grid_build<GRID_NDT>(ctx, dv.p, (int)hv.size(), maxn, maxcell);
+      dim3 g(blocks_for(std::min(maxcell, maxn), 8, std::max(1, 8 * ctx.num_sms / (int)hv.size())), (unsigned)hv.size());
+      {
+        ProfScope ps(ctx, PROF_VOXEL_REDUCE, 0.0);
+        B2R_LAUNCH(ctx, ndt_reduce_kernel, g, 256, 0, dv.p);
+      }
       B2R_CUDA(cudaStreamSynchronize(ctx.stream));
     }
   }
@@ -696,7 +832,8 @@ void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* kn
   DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
   DBuf<int32_t> dk; dk.alloc((size_t)c.n * k, ctx.stream);
-  B2R_LAUNCH(ctx, knn_cov_kernel, (unsigned)((c.n + 255) / 256), 256, 0, dv.p, k, dk.p);
+  std::vector<Cloud*> one{&c};
+  launch_knn_cov(ctx, dv.p, one, k, c.n, dk.p);
   B2R_CUDA(cudaMemcpyAsync(knn_out, dk.p, (size_t)c.n * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
   c.cov_k = k;

@@ -27,12 +27,63 @@ struct Error : std::runtime_error {
     }                                                                                                        \
   } while (0)
 
-// Execution context of one handle: device, stream, launch counter.
+enum { PROF_KNN_COV = 0, PROF_LSQ_EVAL, PROF_NDT_EVAL, PROF_GRID_BUILD, PROF_VOXEL_REDUCE, PROF_FITNESS, PROF_COUNT };
+
+struct ProfRec {
+  int id;
+  cudaEvent_t a, b;
+  double bytes;
+};
+
+// Execution context of one handle: device, stream, launch counter, optional per-kernel event timing.
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
   int num_sms = 148;
+  bool profile = false;
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[PROF_COUNT] = {0};
+  uint64_t prof_n[PROF_COUNT] = {0};
+  double prof_bytes[PROF_COUNT] = {0};
+
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void prof_resolve() {
+    if (prof_pending.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (ProfRec& r : prof_pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { prof_ms[r.id] += ms; prof_n[r.id]++; prof_bytes[r.id] += r.bytes; }
+      ev_pool.push_back(r.a);
+      ev_pool.push_back(r.b);
+    }
+    prof_pending.clear();
+  }
+};
+
+// Brackets the launches issued during its lifetime with CUDA events on the handle's stream (only when profiling is on).
+struct ProfScope {
+  Ctx& c;
+  int id;
+  double bytes;
+  cudaEvent_t a = nullptr;
+  ProfScope(Ctx& ctx, int kernel_id, double algorithmic_bytes) : c(ctx), id(kernel_id), bytes(algorithmic_bytes) {
+    if (c.profile) { a = c.get_event(); cudaEventRecord(a, c.stream); }
+  }
+  ~ProfScope() {
+    if (a) {
+      cudaEvent_t b = c.get_event();
+      cudaEventRecord(b, c.stream);
+      c.prof_pending.push_back(ProfRec{id, a, b, bytes});
+      if (c.prof_pending.size() > 4096) c.prof_resolve();
+    }
+  }
 };
 
 #define B2R_LAUNCH(ctx, kernel, grid, block, smem, ...)            \
@@ -112,6 +163,7 @@ struct CloudView {
   int* v_table;   // vcell: record id or -1
   VoxRec* vrec;
   int* v_nrec;    // [1] number of records
+  int* v_reccell; // record id -> table cell
   // NDT grid
   float leaf, inv_leaf;
   int min_b[3], max_b[3], div_b[3];
@@ -122,6 +174,7 @@ struct CloudView {
   int* n_table;
   NdtRec* nrec;
   int* n_nrec;
+  int* n_reccell;
 };
 
 // ------------------------------------------------------------------------------------------------

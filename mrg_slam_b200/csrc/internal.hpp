@@ -29,14 +29,14 @@ struct Cloud {
   double vres = 0.0;  // resolution the map was built with (0 = none)
   int vmin[3] = {0, 0, 0}, vd[3] = {0, 0, 0};
   int vcell = 0;
-  DBuf<int> v_start, v_cnt, v_order, v_table, v_nrec;
+  DBuf<int> v_start, v_cnt, v_order, v_table, v_nrec, v_reccell;
   DBuf<VoxRec> vrec;
   // NDT grid
   float leaf = 0.f;  // leaf the grid was built with (0 = none)
   int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0};
   int ncell_ndt = 0;
   bool ndt_overflow = false;
-  DBuf<int> n_start, n_cnt, n_order, n_table, n_nrec;
+  DBuf<int> n_start, n_cnt, n_order, n_table, n_nrec, n_reccell;
   DBuf<NdtRec> nrec;
 
   CloudView view() const;
@@ -63,6 +63,7 @@ struct Handle {
   bool has_result = false;
   float timings[4] = {0, 0, 0, 0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // ---- cloud.cu ----

@@ -413,7 +413,8 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   const int np = (int)pairs.size();
   if (np == 0) return;
   int maxn = 1;
-  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
+  double total_pts = 0.0;
+  for (int i = 0; i < np; ++i) { maxn = std::max(maxn, src_sizes[i]); total_pts += src_sizes[i]; }
   const int chunks = pick_chunks(ctx, np, maxn);
   const LsqParams prm = make_params(cfg);
   DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
@@ -433,7 +434,12 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   long rounds = 0;
   while (hdone < np && rounds < max_rounds) {
     for (int r = 0; r < rounds_per_check; ++r) {
-      B2R_LAUNCH(ctx, lsq_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr, (uint8_t*)nullptr);
+      {
+        // 40 B per source point + one 64 B voxel record (VGICP) or 40 B target point+cov (GICP)
+        // per correspondence; upper bound with every point matched and every pair still active
+        ProfScope ps(ctx, PROF_LSQ_EVAL, total_pts * (cfg.method == B2R_FAST_VGICP ? 104.0 : 80.0));
+        B2R_LAUNCH(ctx, lsq_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr, (uint8_t*)nullptr);
+      }
       B2R_LAUNCH(ctx, lsq_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, done.p);
     }
     rounds += rounds_per_check;
@@ -585,7 +591,12 @@ void fitness_batch(Ctx& ctx, const CloudView* d_views, const std::vector<PairDes
   B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(dT.p, T_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
   const float max_d2 = max_range >= (double)FLT_MAX ? INFINITY : (float)(max_range * 1.0001);
-  B2R_LAUNCH(ctx, fitness_kernel, dim3(chunks, np), 256, 0, d_views, dp.p, dT.p, max_range, max_d2, part.p);
+  {
+    double pts = 0.0;  // 16 B source point + one gathered 16 B neighbour
+    for (int i = 0; i < np; ++i) pts += src_sizes[i];
+    ProfScope ps(ctx, PROF_FITNESS, 32.0 * pts);
+    B2R_LAUNCH(ctx, fitness_kernel, dim3(chunks, np), 256, 0, d_views, dp.p, dT.p, max_range, max_d2, part.p);
+  }
   B2R_LAUNCH(ctx, fitness_finish_kernel, (np + 127) / 128, 128, 0, part.p, np, chunks, dout.p);
   B2R_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * np, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));

@@ -535,7 +535,8 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   const int np = (int)pairs.size();
   if (np == 0) return;
   int maxn = 1;
-  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
+  double total_pts = 0.0;
+  for (int i = 0; i < np; ++i) { maxn = std::max(maxn, src_sizes[i]); total_pts += src_sizes[i]; }
   const int chunks = ndt_chunks(ctx, np, maxn);
   const NdtParams prm = make_ndt_params(cfg);
   std::vector<NdtState> hs(np);
@@ -556,7 +557,11 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   long rounds = 0;
   while (hdone < np && rounds < max_rounds) {
     for (int r = 0; r < rounds_per_check; ++r) {
-      B2R_LAUNCH(ctx, ndt_eval_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
+      {
+        // 16 B per source point + 64 B per voxel hit; upper bound with 7 hits (DIRECT7) per point
+        ProfScope ps(ctx, PROF_NDT_EVAL, total_pts * (16.0 + 64.0 * (cfg.neighbor_search == B2R_DIRECT1 ? 1 : 7)));
+        B2R_LAUNCH(ctx, ndt_eval_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
+      }
       B2R_LAUNCH(ctx, ndt_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, done.p);
     }
     rounds += rounds_per_check;

@@ -78,8 +78,9 @@ EXPORTED_SYMBOLS = [
     "b2r_default_prefilter_config", "b2r_prefilter",
     "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_covariances", "b2r_debug_voxelmap",
     "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
-    "b2r_debug_knn", "b2r_last_timings",
+    "b2r_debug_knn", "b2r_last_timings", "b2r_event_record", "b2r_event_elapsed_ms", "b2r_profile_enable", "b2r_profile_read",
 ]
+PROFILE_KERNELS = {"knn_cov": 0, "lsq_eval": 1, "ndt_eval": 2, "grid_build": 3, "voxel_reduce": 4, "fitness": 5}
 
 _lib = None
 
@@ -137,6 +138,10 @@ def load():
     L.b2r_debug_ndt_derivatives.argtypes = [vp, vp, ctypes.POINTER(cd), vp, vp, vp]
     L.b2r_debug_knn.argtypes = [vp, vp, vp, sz, ci, vp, vp]
     L.b2r_last_timings.argtypes = [vp, vp]
+    L.b2r_event_record.argtypes = [vp, ci]
+    L.b2r_event_elapsed_ms.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_float)]
+    L.b2r_profile_enable.argtypes = [vp, ci]
+    L.b2r_profile_read.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(cd)]
     _lib = L
     return L
 
@@ -172,12 +177,14 @@ def _points(a):
 class Cloud:
     """A device-resident cloud (b2r_cloud) with cached search structures."""
 
-    def __init__(self, reg, points=None, device_ptr=None, n=None, stride=16):
+    def __init__(self, reg, points=None, device_ptr=None, host_ptr=None, n=None, stride=16):
         self._reg = reg
         self._lib = load()
         h = ctypes.c_void_p()
         if device_ptr is not None:
             st = self._lib.b2r_cloud_create(reg._h, ctypes.c_void_p(device_ptr), n, stride, DEVICE, ctypes.byref(h))
+        elif host_ptr is not None:  # raw (e.g. pinned) host buffer
+            st = self._lib.b2r_cloud_create(reg._h, ctypes.c_void_p(host_ptr), n, stride, HOST, ctypes.byref(h))
         else:
             a = _points(points)
             st = self._lib.b2r_cloud_create(reg._h, a.ctypes.data, len(a), a.shape[1] * 4, HOST, ctypes.byref(h))
@@ -332,6 +339,25 @@ class Registration:
         t = (ctypes.c_float * 4)()
         self._lib.b2r_last_timings(self._h, t)
         return dict(zip(("prep_ms", "optimize_ms", "fitness_ms", "total_ms"), list(t)))
+
+    def event_record(self, slot):
+        self._check(self._lib.b2r_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._check(self._lib.b2r_event_elapsed_ms(self._h, a, b, ctypes.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.b2r_profile_enable(self._h, int(on)))
+
+    def profile_read(self, kernel):
+        ms, n, by = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
+        self._check(self._lib.b2r_profile_read(self._h, PROFILE_KERNELS[kernel], ctypes.byref(ms), ctypes.byref(n), ctypes.byref(by)))
+        return dict(ms=ms.value, launches=int(n.value), bytes=by.value)
+
+    def synchronize(self):
+        self._check(self._lib.b2r_synchronize(self._h))
 
     def debug_covariances(self, which, want_knn=False):
         n = self._src_n if which == 0 else self._tgt_n

@@ -667,7 +667,8 @@ struct orc_reg {
     xCx = xCx + x4[1] * xC[1];
     xCx = xCx + x4[2] * xC[2];
     float gd2 = (float)gauss_d2;
-    float e = std::exp(-gd2 * xCx * 0.5f);
+    // exp taken in double and rounded to float: models a correctly rounded expf (glibc's is, in all but rare cases)
+    float e = (float)std::exp((double)(-gd2 * xCx * 0.5f));
     float score_inc = (float)(-gauss_d1 * (double)e);
     e = gd2 * e;
     if (e > 1 || e < 0 || e != e) return 0;
@@ -1070,3 +1071,17 @@ double orc_reg_ndt_derivatives(orc_reg* r, const double* p6, double* grad6, doub
 }
 
 }  // extern "C"
+
+// ---- hooks for the oracle's own unit tests (tests/test_oracle_*.py) ----
+extern "C" {
+void orc_test_ldlt6_solve(const double* A, const double* rhs, double* x) { ldlt6_solve(A, rhs, x); }
+void orc_test_svd6_solve(const double* A, const double* rhs, double* x) { svd6_solve(A, rhs, x); }
+void orc_test_sym3_eigen(const double* A, double* evals, double* V) { sym3_eigen(A, evals, V); }
+void orc_test_m4_inverse(const double* A, double* inv) { m4_inverse(A, inv); }
+void orc_test_so3_exp(const double* omega, double* R) { so3_exp_matrix(omega, R); }
+void orc_test_euler_angles_012(const float* R_rowmajor, float* res) { euler_angles_012(R_rowmajor, res); }
+void orc_test_ndt_matrix_from_p(const double* p6, float* M_rowmajor34) { ndt_matrix_from_p(p6, M_rowmajor34); }
+double orc_test_mt_trial_value(const double* v9) {
+  return orc_reg::trialValueSelectionMT(v9[0], v9[1], v9[2], v9[3], v9[4], v9[5], v9[6], v9[7], v9[8]);
+}
+}

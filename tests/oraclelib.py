@@ -273,6 +273,68 @@ def knn(cloud, queries, k):
     return idx, d2
 
 
+def _call_test(name, *arrays):
+    fn = getattr(lib(), name)
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p] * len(arrays)
+    fn(*[a.ctypes.data for a in arrays])
+
+
+def test_ldlt6_solve(A, rhs):
+    A = np.ascontiguousarray(A, dtype=np.float64); rhs = np.ascontiguousarray(rhs, dtype=np.float64); x = np.zeros(6)
+    _call_test("orc_test_ldlt6_solve", A, rhs, x)
+    return x
+
+
+def test_svd6_solve(A, rhs):
+    A = np.ascontiguousarray(A, dtype=np.float64); rhs = np.ascontiguousarray(rhs, dtype=np.float64); x = np.zeros(6)
+    _call_test("orc_test_svd6_solve", A, rhs, x)
+    return x
+
+
+def test_sym3_eigen(A):
+    A = np.ascontiguousarray(A, dtype=np.float64); ev = np.zeros(3); V = np.zeros((3, 3))
+    _call_test("orc_test_sym3_eigen", A, ev, V)
+    return ev, V
+
+
+def test_m4_inverse(A):
+    A = np.ascontiguousarray(A, dtype=np.float64); inv = np.zeros((4, 4))
+    _call_test("orc_test_m4_inverse", A, inv)
+    return inv
+
+
+def test_so3_exp(omega):
+    w = np.ascontiguousarray(omega, dtype=np.float64); R = np.zeros((3, 3))
+    _call_test("orc_test_so3_exp", w, R)
+    return R
+
+
+def test_euler_angles_012(R):
+    R = np.ascontiguousarray(R, dtype=np.float32); res = np.zeros(3, dtype=np.float32)
+    _call_test("orc_test_euler_angles_012", R, res)
+    return res
+
+
+def test_ndt_matrix_from_p(p6):
+    p = np.ascontiguousarray(p6, dtype=np.float64); M = np.zeros((3, 4), dtype=np.float32)
+    _call_test("orc_test_ndt_matrix_from_p", p, M)
+    return M
+
+
+def test_mt_trial_value(v9):
+    v = np.ascontiguousarray(v9, dtype=np.float64)
+    fn = lib().orc_test_mt_trial_value
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_void_p]
+    return fn(v.ctypes.data)
+
+
+for _f in (test_ldlt6_solve, test_svd6_solve, test_sym3_eigen, test_m4_inverse, test_so3_exp, test_euler_angles_012,
+           test_ndt_matrix_from_p, test_mt_trial_value):
+    _f.__test__ = False  # helpers, not pytest tests
+
+
 def set_num_threads(n):
     lib().orc_set_num_threads(n)
 
