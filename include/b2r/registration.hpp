@@ -1,0 +1,224 @@
+// Header-only C++ host mirror of the pcl::Registration surface mrg_slam uses, on top of the libb2r C ABI.
+//
+// Same method names, argument meaning and error behaviour as the objects handed out by
+// mrg_slam::select_registration_method() (/root/reference/src/mrg_slam/registrations.cpp:28-152):
+//   setInputTarget / setInputSource / align / hasConverged / getFinalTransformation / getFitnessScore
+//   (+ the setters the factory calls at :49-53, :58-62, :79-83, :134-146).
+// No PCL / Eigen dependency, so it builds anywhere libb2r builds; include/b2r/pcl_adapter.hpp wraps it into a real
+// pcl::Registration<PointXYZI,PointXYZI> subclass for the ROS 2 tree.
+//
+// Error behaviour follows PCL: nothing throws on the paths the callers use; a failed call prints to stderr and leaves
+// hasConverged() == false and getFinalTransformation() == guess (callers branch only on hasConverged():
+// apps/scan_matching_odometry_component.cpp:270, src/mrg_slam/loop_detector.cpp:138).  There is no CPU fallback.
+#pragma once
+#include <array>
+#include <cfloat>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../b2r.h"
+
+namespace b2r {
+
+// Layout-compatible with pcl::PointXYZI (32 bytes: x,y,z,1 | intensity,pad).
+struct alignas(16) PointXYZI {
+  float x = 0.f, y = 0.f, z = 0.f, w = 1.f;
+  float intensity = 0.f, pad[3] = {0.f, 0.f, 0.f};
+};
+static_assert(sizeof(PointXYZI) == 32, "PointXYZI must match pcl::PointXYZI");
+
+struct PointCloud {
+  std::vector<PointXYZI> points;
+  size_t size() const { return points.size(); }
+  using Ptr = std::shared_ptr<PointCloud>;
+  using ConstPtr = std::shared_ptr<const PointCloud>;
+};
+
+using Matrix4f = std::array<float, 16>;  // column-major, like Eigen::Matrix4f
+inline Matrix4f identity4() { return Matrix4f{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; }
+
+enum class NeighborSearchMethod { KDTREE, DIRECT26, DIRECT7, DIRECT1 };  // pclomp enum names
+
+class Registration {
+ public:
+  using Ptr = std::shared_ptr<Registration>;
+
+  explicit Registration(int method, int device = 0) {
+    b2r_default_config(method, &cfg_);
+    cfg_.device = device;
+  }
+  ~Registration() { reset_handle(); }
+  Registration(const Registration&) = delete;
+  Registration& operator=(const Registration&) = delete;
+
+  // ---- setters used by the factory (applied before the first use; changing them later rebuilds the handle)
+  void setNumThreads(int) {}  // reg_num_threads: OpenMP width of the CPU libraries; meaningless on the GPU
+  void setTransformationEpsilon(double e) { cfg_.transformation_epsilon = e; dirty_ = true; }
+  void setMaximumIterations(int n) { cfg_.maximum_iterations = n; dirty_ = true; }
+  void setMaxCorrespondenceDistance(double d) { cfg_.max_correspondence_distance = d; dirty_ = true; }
+  void setCorrespondenceRandomness(int k) { cfg_.correspondence_randomness = k; dirty_ = true; }
+  void setResolution(double r) { cfg_.resolution = r; dirty_ = true; }
+  void setNeighborhoodSearchMethod(NeighborSearchMethod m) {
+    cfg_.neighbor_search = m == NeighborSearchMethod::DIRECT1 ? B2R_DIRECT1 : (m == NeighborSearchMethod::DIRECT26 ? B2R_DIRECT27 : B2R_DIRECT7);
+    if (m == NeighborSearchMethod::KDTREE) std::fprintf(stderr, "b2r: KDTREE neighbourhood search is not implemented, using DIRECT7\n");
+    dirty_ = true;
+  }
+  const b2r_config& config() const { return cfg_; }
+
+  // ---- pcl::Registration surface
+  // fast_gicp short-circuits when the same pointer is set again; so do we.  Setting as target the cloud that is the
+  // current source (keyframe switch, scan_matching_odometry_component.cpp:332-333) reuses its device structures.
+  void setInputTarget(const PointCloud::ConstPtr& cloud) {
+    if (cloud && cloud == target_ptr_) return;
+    target_ = (cloud && cloud == source_ptr_) ? source_ : upload(cloud);
+    target_ptr_ = cloud;
+  }
+  void setInputSource(const PointCloud::ConstPtr& cloud) {
+    if (cloud && cloud == source_ptr_) return;
+    source_ = (cloud && cloud == target_ptr_) ? target_ : upload(cloud);
+    source_ptr_ = cloud;
+  }
+
+  void align(PointCloud& output, const Matrix4f& guess = identity4()) {
+    converged_ = false;
+    final_ = guess;
+    nr_iterations_ = 0;
+    if (!ensure_handle() || !source_ || !target_) {
+      std::fprintf(stderr, "b2r: align() without a usable handle / source / target\n");
+      return;
+    }
+    b2r_result r;
+    if (!ok(b2r_set_target_cloud(h_, target_.get()), "set_target") || !ok(b2r_set_source_cloud(h_, source_.get()), "set_source") ||
+        !ok(b2r_align(h_, guess.data(), &r), "align"))
+      return;
+    for (int i = 0; i < 16; ++i) final_[i] = r.T[i];
+    converged_ = r.converged != 0;
+    nr_iterations_ = r.iterations;
+    last_error_value_ = r.error;
+    output.points.resize(source_ptr_->size());
+    ok(b2r_transform_source(h_, output.points.data(), sizeof(PointXYZI), B2R_HOST), "transform_source");
+  }
+
+  bool hasConverged() const { return converged_; }
+  Matrix4f getFinalTransformation() const { return final_; }
+  int getNumberOfIterations() const { return nr_iterations_; }
+  double getFitnessScore(double max_range = DBL_MAX) {
+    double out = DBL_MAX;
+    if (!ensure_handle() || !source_ || !target_) return out;
+    ok(b2r_fitness(h_, max_range, &out), "fitness");
+    return out;
+  }
+  const std::string& lastError() const { return last_error_; }
+  b2r_handle* handle() { return ensure_handle() ? h_ : nullptr; }
+
+ private:
+  using CloudHandle = std::shared_ptr<b2r_cloud>;
+
+  bool ok(b2r_status s, const char* what) {
+    if (s == B2R_OK) return true;
+    last_error_ = std::string(what) + ": " + (h_ ? b2r_last_error(h_) : "no handle");
+    std::fprintf(stderr, "b2r: %s failed (status %d): %s\n", what, (int)s, h_ ? b2r_last_error(h_) : "no handle");
+    return false;
+  }
+  bool ensure_handle() {
+    if (h_ && !dirty_) return true;
+    if (h_) {
+      // parameters changed: device clouds survive (they are not owned by the handle), the handle is rebuilt
+      b2r_destroy(h_);
+      h_ = nullptr;
+    }
+    b2r_status s = b2r_create(&cfg_, &h_);
+    dirty_ = false;
+    if (s != B2R_OK) {
+      h_ = nullptr;
+      last_error_ = s == B2R_ERR_NO_DEVICE ? "no CUDA device (libb2r has no CPU fallback)" : "b2r_create failed";
+      std::fprintf(stderr, "b2r: %s\n", last_error_.c_str());
+      return false;
+    }
+    return true;
+  }
+  void reset_handle() {
+    source_.reset();
+    target_.reset();
+    if (h_) b2r_destroy(h_);
+    h_ = nullptr;
+  }
+  CloudHandle upload(const PointCloud::ConstPtr& cloud) {
+    if (!cloud || cloud->size() == 0 || !ensure_handle()) return nullptr;
+    b2r_cloud* c = nullptr;
+    if (!ok(b2r_cloud_create(h_, cloud->points.data(), cloud->size(), sizeof(PointXYZI), B2R_HOST, &c), "cloud_create")) return nullptr;
+    return CloudHandle(c, [](b2r_cloud* p) { b2r_cloud_destroy(p); });
+  }
+
+  b2r_config cfg_;
+  b2r_handle* h_ = nullptr;
+  bool dirty_ = true;
+  PointCloud::ConstPtr source_ptr_, target_ptr_;
+  CloudHandle source_, target_;
+  Matrix4f final_ = identity4();
+  bool converged_ = false;
+  int nr_iterations_ = 0;
+  double last_error_value_ = 0.0;
+  std::string last_error_;
+};
+
+// The ten ROS parameters select_registration_method() reads (registrations.cpp:34-43), with the code defaults of
+// apps/scan_matching_odometry_component.cpp:122-132.
+struct RegistrationParams {
+  std::string registration_method = "FAST_GICP";
+  int reg_num_threads = 0;
+  double reg_transformation_epsilon = 0.1;
+  int reg_maximum_iterations = 64;
+  double reg_max_correspondence_distance = 2.0;
+  int reg_max_optimizer_iterations = 20;
+  bool reg_use_reciprocal_correspondences = false;
+  int reg_correspondence_randomness = 20;
+  double reg_resolution = 1.0;
+  std::string reg_nn_search_method = "DIRECT7";
+  int device = 0;
+};
+
+// Mirror of mrg_slam::select_registration_method (registrations.cpp:46-148) for the methods this engine covers.
+// Method strings that map to classes outside the engine return nullptr (the reference's trailing `return nullptr`),
+// unknown strings warn and fall back to NDT exactly like :117-120 (NDT_OMP, the engine's NDT).
+inline Registration::Ptr select_registration_method(const RegistrationParams& p) {
+  const std::string& m = p.registration_method;
+  if (m == "FAST_GICP") {
+    auto r = std::make_shared<Registration>(B2R_FAST_GICP, p.device);
+    r->setNumThreads(p.reg_num_threads);
+    r->setTransformationEpsilon(p.reg_transformation_epsilon);
+    r->setMaximumIterations(p.reg_maximum_iterations);
+    r->setMaxCorrespondenceDistance(p.reg_max_correspondence_distance);
+    r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
+    return r;
+  }
+  if (m == "FAST_VGICP") {
+    auto r = std::make_shared<Registration>(B2R_FAST_VGICP, p.device);
+    r->setNumThreads(p.reg_num_threads);
+    r->setResolution(p.reg_resolution);
+    r->setTransformationEpsilon(p.reg_transformation_epsilon);
+    r->setMaximumIterations(p.reg_maximum_iterations);
+    r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
+    return r;
+  }
+  if (m == "SMALL_GICP" || m == "FAST_VGICP_CUDA" || m == "ICP" || m.find("GICP") != std::string::npos || m == "NDT") {
+    std::fprintf(stderr, "b2r: registration_method %s is outside this engine's scope\n", m.c_str());
+    return nullptr;
+  }
+  if (m.find("NDT") == std::string::npos) {
+    std::fprintf(stderr, "warning: unknown registration type(%s)\n       : use NDT\n", m.c_str());
+  }
+  auto r = std::make_shared<Registration>(B2R_NDT_OMP, p.device);
+  if (p.reg_num_threads > 0) r->setNumThreads(p.reg_num_threads);
+  r->setTransformationEpsilon(p.reg_transformation_epsilon);
+  r->setMaximumIterations(p.reg_maximum_iterations);
+  r->setResolution(p.reg_resolution);
+  if (p.reg_nn_search_method == "KDTREE") r->setNeighborhoodSearchMethod(NeighborSearchMethod::KDTREE);
+  else if (p.reg_nn_search_method == "DIRECT1") r->setNeighborhoodSearchMethod(NeighborSearchMethod::DIRECT1);
+  else r->setNeighborhoodSearchMethod(NeighborSearchMethod::DIRECT7);
+  return r;
+}
+
+}  // namespace b2r
