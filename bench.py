@@ -220,10 +220,7 @@ def run_b2r(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step(bufs, on_device):
-        if on_device:
-            cl = [B.Cloud(reg, device_ptr=b.data_ptr(), n=b.shape[0]) for b in bufs]
-        else:
-            cl = [B.Cloud(reg, host_ptr=b.data_ptr(), n=b.shape[0]) for b in bufs]
+        cl = B.create_clouds(reg, [b.data_ptr() for b in bufs], [b.shape[0] for b in bufs], B.DEVICE if on_device else B.HOST)
         res = reg.align_batch(cl[1:], cl[:-1], guesses)
         for c in cl:
             c.close()

@@ -85,6 +85,9 @@ const char* b2r_version(void);
  * (kNN grid, covariances, voxel maps) are built lazily and cached, so promoting a source to target at a
  * keyframe switch (scan_matching_odometry_component.cpp:332-333) reuses them. ---- */
 b2r_status b2r_cloud_create(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int memspace, b2r_cloud** out);
+/* same for `count` clouds with a single device synchronisation at the end (loop-closure batches, graph loading) */
+b2r_status b2r_cloud_create_batch(b2r_handle* h, const void* const* points, const size_t* n, size_t count, size_t stride_bytes, int memspace,
+                                  b2r_cloud** out);
 void b2r_cloud_destroy(b2r_cloud* c);
 size_t b2r_cloud_size(const b2r_cloud* c);
 

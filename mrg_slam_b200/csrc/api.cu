@@ -232,6 +232,25 @@ b2r_status b2r_cloud_create(b2r_handle* hh, const void* points, size_t n, size_t
   });
 }
 
+b2r_status b2r_cloud_create_batch(b2r_handle* hh, const void* const* points, const size_t* n, size_t count, size_t stride_bytes, int memspace,
+                                  b2r_cloud** out) {
+  if (!out || (count && (!points || !n))) return B2R_ERR_INVALID_ARG;
+  for (size_t i = 0; i < count; ++i) out[i] = nullptr;
+  return guarded(hh, [&](Handle& h) {
+    try {
+      for (size_t i = 0; i < count; ++i) {
+        if (!points[i] && n[i]) throw Error(B2R_ERR_INVALID_ARG, "null points");
+        out[i] = new b2r_cloud();
+        cloud_upload(h.ctx, out[i]->c, points[i], n[i], stride_bytes, memspace);
+      }
+      B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    } catch (...) {
+      for (size_t i = 0; i < count; ++i) { delete out[i]; out[i] = nullptr; }
+      throw;
+    }
+  });
+}
+
 void b2r_cloud_destroy(b2r_cloud* c) {
   if (!c) return;
   cudaSetDevice(c->c.device);

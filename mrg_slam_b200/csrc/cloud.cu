@@ -324,6 +324,22 @@ __global__ void grid_scatter_kernel(const CloudView* __restrict__ views) {
   }
 }
 
+// NN grid: the atomic scatter leaves the points of a cell in arbitrary order; sort each cell by original index so that the
+// cell-sorted copy (and with it every tie-break by position in the searches) is identical from run to run.
+__global__ void grid_cellsort_kernel(const CloudView* __restrict__ views) {
+  const CloudView& c = views[blockIdx.y];
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < c.ncell; cell += gridDim.x * blockDim.x) {
+    const int s = c.cell_start[cell], e = c.cell_start[cell + 1];
+    for (int i = s + 1; i < e; ++i) {
+      const float4 v = c.spts[i];
+      const int key = __float_as_int(v.w);
+      int j = i - 1;
+      while (j >= s && __float_as_int(c.spts[j].w) > key) { c.spts[j + 1] = c.spts[j]; --j; }
+      c.spts[j + 1] = v;
+    }
+  }
+}
+
 __device__ __forceinline__ int warp_sort32_int(int v, int lane) {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
@@ -641,6 +657,7 @@ static void run_grid_build(Ctx& ctx, const CloudView* dviews, int nc, int maxn, 
   B2R_LAUNCH(ctx, grid_scan_tops_kernel<MODE>, nc, 1024, 0, dviews, tile_tot.p, max_tiles);
   B2R_LAUNCH(ctx, grid_scan_apply_kernel<MODE>, dim3(max_tiles, nc), 1024, 0, dviews, tile_tot.p, max_tiles);
   B2R_LAUNCH(ctx, grid_scatter_kernel<MODE>, g, 256, 0, dviews);
+  if (MODE == GRID_NN) B2R_LAUNCH(ctx, grid_cellsort_kernel, dim3(blocks_for(maxcell, 256, 8 * ctx.num_sms), nc), 256, 0, dviews);
 }
 
 void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds_in, const std::vector<Needs>& needs_in) {

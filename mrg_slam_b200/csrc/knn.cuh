@@ -29,9 +29,8 @@ __device__ __forceinline__ unsigned long long warp_sort32(unsigned long long v, 
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
       const unsigned long long o = __shfl_xor_sync(B2R_FULL, v, j);
-      const bool up = (lane & k) == 0;
-      const bool lower = (lane & j) == 0;
-      v = (lower == up) ? u64min(v, o) : u64max(v, o);
+      const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+      v = ((v > o) == keep_min) ? o : v;  // one 64-bit compare per exchange
     }
   }
   return v;
@@ -43,7 +42,7 @@ __device__ __forceinline__ unsigned long long warp_merge32(unsigned long long li
 #pragma unroll
   for (int j = 16; j > 0; j >>= 1) {
     const unsigned long long o = __shfl_xor_sync(B2R_FULL, m, j);
-    m = ((lane & j) == 0) ? u64min(m, o) : u64max(m, o);
+    m = ((m > o) == ((lane & j) == 0)) ? o : m;
   }
   return m;
 }

@@ -71,7 +71,7 @@ class PrefilterConfig(ctypes.Structure):
 # every symbol include/b2r.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "b2r_default_config", "b2r_create", "b2r_destroy", "b2r_last_error", "b2r_version",
-    "b2r_cloud_create", "b2r_cloud_destroy", "b2r_cloud_size",
+    "b2r_cloud_create", "b2r_cloud_create_batch", "b2r_cloud_destroy", "b2r_cloud_size",
     "b2r_set_target", "b2r_set_source", "b2r_set_target_cloud", "b2r_set_source_cloud",
     "b2r_align", "b2r_fitness", "b2r_transform_source", "b2r_fitness_pair", "b2r_align_batch",
     "b2r_distance_filter", "b2r_voxelgrid", "b2r_radius_outlier", "b2r_statistical_outlier",
@@ -108,6 +108,7 @@ def load():
     L.b2r_destroy.argtypes = [vp]
     L.b2r_destroy.restype = None
     L.b2r_cloud_create.argtypes = [vp, vp, sz, sz, ci, ctypes.POINTER(vp)]
+    L.b2r_cloud_create_batch.argtypes = [vp, vp, vp, sz, sz, ci, vp]
     L.b2r_cloud_destroy.argtypes = [vp]
     L.b2r_cloud_destroy.restype = None
     L.b2r_cloud_size.argtypes = [vp]
@@ -204,6 +205,21 @@ class Cloud:
             self.close()
         except Exception:
             pass
+
+
+def create_clouds(reg, pointers, sizes, memspace, stride=16):
+    """b2r_cloud_create_batch over raw buffers (device or host pointers): one synchronisation for the whole batch."""
+    n = len(pointers)
+    P = (ctypes.c_void_p * n)(*pointers)
+    N = (ctypes.c_size_t * n)(*sizes)
+    H = (ctypes.c_void_p * n)()
+    reg._check(load().b2r_cloud_create_batch(reg._h, P, N, n, stride, memspace, H))
+    out = []
+    for i in range(n):
+        c = Cloud.__new__(Cloud)
+        c._reg, c._lib, c._h = reg, load(), ctypes.c_void_p(H[i])
+        out.append(c)
+    return out
 
 
 class Registration:
