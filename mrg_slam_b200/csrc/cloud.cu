@@ -500,81 +500,142 @@ __global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ kNN covariances
-// Kernel 1 — one warp per query, queries interleaved across the resident warps (grid-stride) so that the expensive
-// sparse-region queries spread over all SMs: exact kNN (knn.cuh), then mean / covariance of the k neighbours in double
-// by warp reductions (fast_gicp calculate_covariances).  Writes the raw covariance (6 doubles).
-__global__ void __launch_bounds__(256) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
-  __shared__ KnnScratch scratch[8];
-  const CloudView& c = views[blockIdx.y];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
-  for (int q = blockIdx.x * (blockDim.x >> 5) + warp; q < c.n; q += nwarps) {
-    const float4 sp = __ldg(&c.spts[q]);
-    const unsigned long long key = warp_knn(c, sp.x, sp.y, sp.z, k, lane, scratch[warp]);
-    const int orig = __float_as_int(sp.w);
-    double x = 0, y = 0, z = 0;
-    const bool act = lane < k && key != ~0ull;
-    int nb_orig = -1;
-    if (act) {
-      const float4 nb = __ldg(&c.spts[(unsigned)(key & 0xffffffffull)]);
-      x = (double)nb.x; y = (double)nb.y; z = (double)nb.z;
-      nb_orig = __float_as_int(nb.w);
-    }
-    if (knn_out && lane < k) knn_out[(size_t)orig * k + lane] = nb_orig;
-    const double kk = (double)k;
-    const double mx = warp_sum(x) / kk, my = warp_sum(y) / kk, mz = warp_sum(z) / kk;
-    const double dx = act ? x - mx : 0.0, dy = act ? y - my : 0.0, dz = act ? z - mz : 0.0;
-    // six products reduced together: lanes 0..5 end up owning one component each
-    double v[6] = {dx * dx, dx * dy, dx * dz, dy * dy, dy * dz, dz * dz};
-#pragma unroll
-    for (int t = 0; t < 6; ++t) v[t] = warp_sum(v[t]) / kk;
-    if (lane == 0) {
-      double* dst = c.cov + (size_t)orig * 6;
-#pragma unroll
-      for (int t = 0; t < 6; ++t) dst[t] = v[t];
+// fast_gicp calculate_covariances in one kernel, one thread per (cell-sorted) point:
+//   pass 1  exact k-th nearest squared distance dk (knn.cuh, K floats in registers);
+//   pass 2  the same cells again, accumulating sum(d) and sum(d d^T) of d = p - query in double over the points with
+//           d2 <= dk (the k nearest; ties beyond k are resolved towards the lower position on a rare slow path);
+//   then    covariance = E[d d^T] - E[d] E[d]^T (shift-invariant, so identical to the centred sum of the reference up
+//           to rounding ~1e-15), symmetric 3x3 Jacobi eigen-decomposition, PLANE regularisation (1, 1, 1e-3).
+struct CovAccum {
+  double s[9];
+  int cnt;
+};
+struct CovVisitor {
+  const CloudView& c;
+  float qx, qy, qz, dk;
+  bool ties;  // accept d2 == dk as well as d2 < dk
+  int k;
+  int32_t* knn_row;
+  CovAccum a;
+  __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
+  __device__ __forceinline__ void add(const float4& p) {
+    const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;
+    a.s[0] += dx; a.s[1] += dy; a.s[2] += dz;
+    a.s[3] += dx * dx; a.s[4] += dx * dy; a.s[5] += dx * dz; a.s[6] += dy * dy; a.s[7] += dy * dz; a.s[8] += dz * dz;
+    if (knn_row && a.cnt < k) knn_row[a.cnt] = __float_as_int(p.w);
+    ++a.cnt;
+  }
+  __device__ __forceinline__ void run(int s, int e) {
+    for (int j = s; j < e; ++j) {
+      const float4 p = __ldg(&c.spts[j]);
+      const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+      if (d2 < dk || (ties && d2 == dk)) add(p);
     }
   }
-}
-
-// Kernel 2 — one thread per point: PLANE regularisation, singular values replaced by (1, 1, 1e-3).
-__global__ void __launch_bounds__(128) cov_regularize_kernel(const CloudView* __restrict__ views) {
-  const CloudView& c = views[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
-    double* p = c.cov + (size_t)i * 6;
-    const double m0 = p[0], m1 = p[1], m2 = p[2], m3 = p[3], m4 = p[4], m5 = p[5];
-    double S[9] = {m0, m1, m2, m1, m3, m4, m2, m4, m5};
-    double ev[3], V[9];
-    sym3_eigen_dev(S, ev, V);
-    const double vals[3] = {1e-3, 1.0, 1.0};  // ascending eigen order: smallest = plane normal
-    double o[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double a = V[0 * 3 + j], b = V[1 * 3 + j], cc = V[2 * 3 + j];
-      o[0] += vals[j] * a * a; o[1] += vals[j] * a * b; o[2] += vals[j] * a * cc;
-      o[3] += vals[j] * b * b; o[4] += vals[j] * b * cc; o[5] += vals[j] * cc * cc;
+};
+// lowest position > after whose distance equals dk exactly
+struct TieVisitor {
+  const CloudView& c;
+  float qx, qy, qz, dk;
+  int after, found;
+  __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
+  __device__ __forceinline__ void run(int s, int e) {
+    for (int j = max(s, after + 1); j < e; ++j) {
+      if (j >= found) break;
+      const float4 p = __ldg(&c.spts[j]);
+      if (dist2_flann(qx, qy, qz, p.x, p.y, p.z) == dk) found = j;
     }
-#pragma unroll
-    for (int t = 0; t < 6; ++t) p[t] = o[t];
   }
+};
+// more than k points within dk (exact ties at the k-th distance): strictly closer ones, then ties by ascending position.
+// Rare; everything goes in and out by value so that the caller's accumulators stay in registers.
+__device__ __noinline__ CovAccum cov_accumulate_ties(const CloudView* cp, float qx, float qy, float qz, int r, float dk, int k,
+                                                     int32_t* knn_row) {
+  const CloudView& c = *cp;
+  const QueryCell q = query_cell(c, qx, qy, qz);
+  CovVisitor v{c, qx, qy, qz, dk, false, k, knn_row, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
+  visit_ring<false>(c, q, r, false, v);
+  int last = -1;
+  while (v.a.cnt < k) {
+    TieVisitor tv{c, qx, qy, qz, dk, last, INT_MAX};
+    visit_ring<false>(c, q, r, false, tv);
+    if (tv.found == INT_MAX) break;
+    v.add(__ldg(&c.spts[tv.found]));
+    last = tv.found;
+  }
+  return v.a;
 }
 
-// arbitrary queries (debug / tests): one warp per query
-__global__ void __launch_bounds__(256) knn_query_kernel(const CloudView* __restrict__ views, const float4* __restrict__ queries, int nq, int k,
-                                                         int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
-  __shared__ KnnScratch scratch[8];
+template <int K>
+__global__ void __launch_bounds__(128) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+  const CloudView& c = views[blockIdx.y];
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= c.n) return;
+  const float4 sp = __ldg(&c.spts[qi]);
+  const int orig = __float_as_int(sp.w);
+  const QueryCell q = query_cell(c, sp.x, sp.y, sp.z);
+  float dk;
+  int r;
+  {
+    TopkVisitor<K> tv(c, sp.x, sp.y, sp.z);
+    r = knn_topk<K>(c, q, k, tv);
+    dk = topk_kth<K>(tv.d, k);
+  }
+  CovVisitor v{c, sp.x, sp.y, sp.z, dk, true, k, knn_out ? knn_out + (size_t)orig * k : nullptr, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
+  visit_ring<false>(c, q, r, false, v);
+  if (v.a.cnt > k) v.a = cov_accumulate_ties(&c, sp.x, sp.y, sp.z, r, dk, k, v.knn_row);
+  const double kk = (double)k;
+  const double mx = v.a.s[0] / kk, my = v.a.s[1] / kk, mz = v.a.s[2] / kk;
+  const double m0 = v.a.s[3] / kk - mx * mx, m1 = v.a.s[4] / kk - mx * my, m2 = v.a.s[5] / kk - mx * mz;
+  const double m3 = v.a.s[6] / kk - my * my, m4 = v.a.s[7] / kk - my * mz, m5 = v.a.s[8] / kk - mz * mz;
+  // PLANE regularisation: singular values replaced by (1, 1, 1e-3), smallest = plane normal
+  double S[9] = {m0, m1, m2, m1, m3, m4, m2, m4, m5};
+  double ev[3], V[9];
+  sym3_eigen_dev(S, ev, V);
+  const double vals[3] = {1e-3, 1.0, 1.0};
+  double o[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double a = V[0 * 3 + j], b = V[1 * 3 + j], cc = V[2 * 3 + j];
+    o[0] += vals[j] * a * a; o[1] += vals[j] * a * b; o[2] += vals[j] * a * cc;
+    o[3] += vals[j] * b * b; o[4] += vals[j] * b * cc; o[5] += vals[j] * cc * cc;
+  }
+  double* dst = c.cov + (size_t)orig * 6;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) dst[t] = o[t];
+}
+
+// arbitrary queries (debug / tests): one thread per query, neighbours as (distance, position) keys
+__global__ void __launch_bounds__(64) knn_query_kernel(const CloudView* __restrict__ views, const float4* __restrict__ queries, int nq, int k,
+                                                        int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
   const CloudView& c = views[0];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (q >= nq) return;
-  const float4 p = __ldg(&queries[q]);
-  const unsigned long long key = warp_knn(c, p.x, p.y, p.z, k, lane, scratch[warp]);
-  if (lane < k) {
-    if (key != ~0ull) {
-      idx_out[(size_t)q * k + lane] = __float_as_int(c.spts[(unsigned)(key & 0xffffffffull)].w);
-      d2_out[(size_t)q * k + lane] = __uint_as_float((unsigned)(key >> 32));
-    } else {
-      idx_out[(size_t)q * k + lane] = -1;
-      d2_out[(size_t)q * k + lane] = INFINITY;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const float4 p = __ldg(&queries[qi]);
+  const QueryCell q = query_cell(c, p.x, p.y, p.z);
+  TopkKeyVisitor<32> v(c, p.x, p.y, p.z);
+  int r = cells_outside(c, q.cx, q.cy, q.cz) + 1;
+  visit_ring<false>(c, q, r, false, v);
+  for (;;) {
+    unsigned long long kth = v.d[31];
+#pragma unroll
+    for (int i = 30; i >= 0; --i) kth = (i >= k - 1) ? v.d[i] : kth;
+    if (kth != ~0ull && __uint_as_float((unsigned)(kth >> 32)) <= ring_safe_d2(r, c.h)) break;
+    if (ring_covers_grid(c, q.cx, q.cy, q.cz, r)) break;
+    ++r;
+    visit_ring<false>(c, q, r, true, v);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i < k) {
+      const unsigned long long key = v.d[i];
+      if (key != ~0ull) {
+        idx_out[(size_t)qi * k + i] = __float_as_int(c.spts[(unsigned)(key & 0xffffffffull)].w);
+        d2_out[(size_t)qi * k + i] = __uint_as_float((unsigned)(key >> 32));
+      } else {
+        idx_out[(size_t)qi * k + i] = -1;
+        d2_out[(size_t)qi * k + i] = INFINITY;
+      }
     }
   }
 }
@@ -583,7 +644,7 @@ __global__ void __launch_bounds__(256) knn_query_kernel(const CloudView* __restr
 static float auto_cell_size(const Cloud& c, const b2r_config& cfg) {
   if (cfg.nn_cell_size > 0) return (float)cfg.nn_cell_size;
   double dx = std::max(1e-3f, c.bmax[0] - c.bmin[0]), dy = std::max(1e-3f, c.bmax[1] - c.bmin[1]);
-  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 1.2; }();
+  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 2.0; }();
   double h = factor * std::sqrt(dx * dy / std::max(1, c.n));
   return (float)std::min(4.0, std::max(0.05, h));
 }
@@ -603,18 +664,18 @@ static void grid_dims(Cloud& c, float h) {
 
 static inline unsigned blocks_for(int n, int per_block, int cap) { return (unsigned)std::max(1, std::min(cap, (n + per_block - 1) / per_block)); }
 
-// kNN covariances of a batch of clouds: search kernel (grid-stride warps, ~all SMs busy whatever the batch size) + regularisation
+// kNN covariances of a batch of clouds: one launch, one thread per point, clouds on grid.y
 static void launch_knn_cov(Ctx& ctx, const CloudView* dviews, const std::vector<Cloud*>& clouds, int k, int maxn, int32_t* knn_out) {
   const int nc = (int)clouds.size();
   double bytes = 0.0;  // 16 B point in + 24 B covariance out per point
   for (Cloud* c : clouds) bytes += 40.0 * c->n;
-  // 8 queries per warp at least; enough blocks for ~8 resident blocks per SM across the batch
-  const int per_cloud = std::max(1, std::min((maxn + 63) / 64, (8 * ctx.num_sms + nc - 1) / nc));
-  {
-    ProfScope ps(ctx, PROF_KNN_COV, bytes);
-    B2R_LAUNCH(ctx, knn_cov_kernel, dim3(per_cloud, nc), 256, 0, dviews, k, knn_out);
-  }
-  B2R_LAUNCH(ctx, cov_regularize_kernel, dim3(blocks_for(maxn, 128, 4 * ctx.num_sms), nc), 128, 0, dviews);
+  const dim3 grid((unsigned)((maxn + 127) / 128), (unsigned)nc);
+  ProfScope ps(ctx, PROF_KNN_COV, bytes);
+  if (k <= 8) B2R_LAUNCH(ctx, knn_cov_kernel<8>, grid, 128, 0, dviews, k, knn_out);
+  else if (k <= 16) B2R_LAUNCH(ctx, knn_cov_kernel<16>, grid, 128, 0, dviews, k, knn_out);
+  else if (k <= 20) B2R_LAUNCH(ctx, knn_cov_kernel<20>, grid, 128, 0, dviews, k, knn_out);
+  else if (k <= 24) B2R_LAUNCH(ctx, knn_cov_kernel<24>, grid, 128, 0, dviews, k, knn_out);
+  else B2R_LAUNCH(ctx, knn_cov_kernel<32>, grid, 128, 0, dviews, k, knn_out);
 }
 
 void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
@@ -833,7 +894,7 @@ void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, 
   DBuf<int32_t> di; di.alloc(nq * k, ctx.stream);
   DBuf<float> dd; dd.alloc(nq * k, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dq.p, queries, nq * 16, cudaMemcpyHostToDevice, ctx.stream));
-  B2R_LAUNCH(ctx, knn_query_kernel, (unsigned)((nq + 7) / 8), 256, 0, dv.p, dq.p, (int)nq, k, di.p, dd.p);
+  B2R_LAUNCH(ctx, knn_query_kernel, (unsigned)((nq + 63) / 64), 64, 0, dv.p, dq.p, (int)nq, k, di.p, dd.p);
   B2R_CUDA(cudaMemcpyAsync(idx_out, di.p, nq * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(d2_out, dd.p, nq * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));

@@ -321,18 +321,21 @@ __device__ inline void sym3_eigen_dev(const double* Ain, double* evals, double* 
       }
     }
   }
+  // ascending eigenvalues; columns swapped with compile-time indices (a permutation array would be indexed
+  // dynamically and push Q into local memory)
   double d0 = A[0], d1 = A[4], d2 = A[8];
-  int i0 = 0, i1 = 1, i2 = 2;
-  if (d1 < d0) { double t = d0; d0 = d1; d1 = t; int ti = i0; i0 = i1; i1 = ti; }
-  if (d2 < d1) { double t = d1; d1 = d2; d2 = t; int ti = i1; i1 = i2; i2 = ti; }
-  if (d1 < d0) { double t = d0; d0 = d1; d1 = t; int ti = i0; i0 = i1; i1 = ti; }
+#define B2R_EIG_CSWAP(da, db, ca, cb)                                   \
+  if (db < da) {                                                        \
+    double t = da; da = db; db = t;                                     \
+    _Pragma("unroll") for (int i = 0; i < 3; ++i) { t = Q[i * 3 + ca]; Q[i * 3 + ca] = Q[i * 3 + cb]; Q[i * 3 + cb] = t; } \
+  }
+  B2R_EIG_CSWAP(d0, d1, 0, 1)
+  B2R_EIG_CSWAP(d1, d2, 1, 2)
+  B2R_EIG_CSWAP(d0, d1, 0, 1)
+#undef B2R_EIG_CSWAP
   evals[0] = d0; evals[1] = d1; evals[2] = d2;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    V[i * 3 + 0] = Q[i * 3 + i0];
-    V[i * 3 + 1] = Q[i * 3 + i1];
-    V[i * 3 + 2] = Q[i * 3 + i2];
-  }
+  for (int i = 0; i < 9; ++i) V[i] = Q[i];
 }
 
 }  // namespace b2r

@@ -214,21 +214,21 @@ void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, dou
 }
 
 // ------------------------------------------------------------------------------------------------ statistical outlier removal
-// one warp per (cell-sorted) point: (mean_k+1)-NN; distances[i] = (float)(sum_{j=1..k} sqrt(d2_j) / k), double sum in
+// one thread per (cell-sorted) point: (mean_k+1)-NN; distances[i] = (float)(sum_{j=1..k} sqrt(d2_j) / k), double sum in
 // ascending-distance order with float sqrt, as PCL does
-__global__ void __launch_bounds__(256) sor_distance_kernel(const CloudView* __restrict__ views, int mean_k, float* __restrict__ distances) {
-  __shared__ KnnScratch scratch[8];
+template <int K>
+__global__ void __launch_bounds__(128) sor_distance_kernel(const CloudView* __restrict__ views, int mean_k, float* __restrict__ distances) {
   const CloudView& c = views[0];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
-  for (int q = blockIdx.x * (blockDim.x >> 5) + warp; q < c.n; q += nwarps) {
-    const float4 p = __ldg(&c.spts[q]);
-    const unsigned long long key = warp_knn(c, p.x, p.y, p.z, mean_k + 1, lane, scratch[warp]);
-    const float d = __fsqrt_rn(__uint_as_float((unsigned)(key >> 32)));
-    double sum = 0.0;
-    for (int j = 1; j <= mean_k; ++j) sum += (double)__shfl_sync(0xffffffffu, d, j);
-    if (lane == 0) distances[__float_as_int(p.w)] = (float)(sum / (double)mean_k);
-  }
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= c.n) return;
+  const float4 p = __ldg(&c.spts[qi]);
+  TopkVisitor<K> v(c, p.x, p.y, p.z);
+  knn_topk<K>(c, query_cell(c, p.x, p.y, p.z), mean_k + 1, v);
+  double sum = 0.0;
+#pragma unroll
+  for (int j = 1; j < K; ++j)
+    if (j <= mean_k) sum += (double)__fsqrt_rn(v.d[j]);
+  distances[__float_as_int(p.w)] = (float)(sum / (double)mean_k);
 }
 // two-stage deterministic reduction of sum and sum of (float) squares
 __global__ void __launch_bounds__(256) sor_stats_kernel(const float* __restrict__ distances, int n, double* __restrict__ partials) {
@@ -271,7 +271,13 @@ void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n
   DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
   DBuf<float> dist; dist.alloc(n, ctx.stream);
-  B2R_LAUNCH(ctx, sor_distance_kernel, std::max(1, std::min((n + 63) / 64, 8 * ctx.num_sms)), 256, 0, dv.p, mean_k, dist.p);
+  {
+    const int kk = mean_k + 1, nb128 = (n + 127) / 128;
+    if (kk <= 8) B2R_LAUNCH(ctx, sor_distance_kernel<8>, nb128, 128, 0, dv.p, mean_k, dist.p);
+    else if (kk <= 16) B2R_LAUNCH(ctx, sor_distance_kernel<16>, nb128, 128, 0, dv.p, mean_k, dist.p);
+    else if (kk <= 24) B2R_LAUNCH(ctx, sor_distance_kernel<24>, nb128, 128, 0, dv.p, mean_k, dist.p);
+    else B2R_LAUNCH(ctx, sor_distance_kernel<32>, nb128, 128, 0, dv.p, mean_k, dist.p);
+  }
   const int nb = std::max(1, std::min(2 * ctx.num_sms, (n + 1023) / 1024));
   DBuf<double> part; part.alloc((size_t)nb * 2 + 1, ctx.stream);
   B2R_LAUNCH(ctx, sor_stats_kernel, nb, 256, 0, dist.p, n, part.p);

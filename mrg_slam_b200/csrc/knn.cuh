@@ -5,162 +5,34 @@
 // radius counts for RadiusOutlierRemoval (A17).  Distances use FLANN's L2_Simple float association so that
 // neighbour sets and squared distances are bit-identical to the kd-tree oracle (ties aside).
 //
-// warp_knn: one warp per query.  Lane i ends up holding the i-th nearest neighbour as a 64-bit key
-// (float bits of d^2 << 32 | position in the cell-sorted array); ~0 = none.  The search scans the cube of
-// cells around the query, then grows shell by shell until the k-th distance is proven (<= r*h).
-// A ring is enumerated as runs (contiguous spans of the cell-sorted array): every lane fetches the bounds of
-// one run (one memory latency for up to 32 rows), then the warp streams the concatenated candidates in full
-// 32-wide chunks.  Candidates that beat the current k-th distance are appended to a per-warp shared-memory
-// buffer; a full buffer is bitonic-sorted and merged into the sorted top-32 list held across the lanes.
+// All searches are ONE THREAD PER QUERY.  Queries are issued in cell-sorted order, so the 32 lanes of a warp sit in
+// the same few cells: their candidate runs coincide (broadcast loads, L1-resident) and their control flow is nearly
+// uniform.  A search scans the 3x3x3 cube of cells around the query (centre row first), then grows shell by shell
+// until the k-th distance is proven (<= the distance to the border of the scanned cube).  A row of cells along x is a
+// contiguous run of the cell-sorted array, so a ring costs two table loads per (y,z) row; rows whose distance
+// lower bound already exceeds the current k-th distance are skipped.
+//
+// topk<K>: the K smallest squared distances, ascending, in registers; insertion is a 2-instruction-per-slot
+// min/max chain and is skipped when the candidate does not beat the current K-th value.  Callers that need the
+// neighbours themselves (covariances) make a second pass over the same cells with the proven k-th distance as the
+// acceptance radius: no index list is kept, which keeps the register footprint at K floats.
 #pragma once
+#include <climits>
+
 #include "common.cuh"
 
 namespace b2r {
 
 #define B2R_FULL 0xffffffffu
+#ifndef B2R_NN1_XPRUNE
+#define B2R_NN1_XPRUNE true
+#endif
 
-__device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
-__device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
-
-// ascending bitonic sort of one key per lane
-__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long v, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(B2R_FULL, v, j);
-      const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
-      v = ((v > o) == keep_min) ? o : v;  // one 64-bit compare per exchange
-    }
-  }
-  return v;
-}
-// both ascending; returns the 32 smallest of the union, ascending
-__device__ __forceinline__ unsigned long long warp_merge32(unsigned long long list, unsigned long long cand, int lane) {
-  const unsigned long long rev = __shfl_sync(B2R_FULL, cand, 31 - lane);
-  unsigned long long m = u64min(list, rev);
-#pragma unroll
-  for (int j = 16; j > 0; j >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(B2R_FULL, m, j);
-    m = ((m > o) == ((lane & j) == 0)) ? o : m;
-  }
-  return m;
-}
-
-struct KnnScratch {  // per-warp shared memory
-  unsigned long long pend[32];
-};
-
-struct KnnState {
-  unsigned long long list;  // lane i: i-th best so far
-  unsigned long long kth;   // key of the current k-th best (warp-uniform)
-  int npend;                // candidates waiting in the scratch buffer
-};
-
-__device__ __forceinline__ void knn_flush(KnnState& s, KnnScratch& sm, int k, int lane) {
-  if (s.npend == 0) return;
-  __syncwarp();
-  const unsigned long long v = lane < s.npend ? sm.pend[lane] : ~0ull;
-  __syncwarp();
-  s.list = warp_merge32(s.list, warp_sort32(v, lane), lane);
-  s.kth = __shfl_sync(B2R_FULL, s.list, k - 1);
-  s.npend = 0;
-}
-
-__device__ __forceinline__ void knn_push(KnnState& s, KnnScratch& sm, unsigned long long key, int k, int lane) {
-  const bool want = key < s.kth;
-  const unsigned m = __ballot_sync(B2R_FULL, want);
-  if (!m) return;
-  const int cnum = __popc(m);
-  if (s.npend + cnum > 32) knn_flush(s, sm, k, lane);
-  if (want) sm.pend[s.npend + __popc(m & ((1u << lane) - 1u))] = key;
-  s.npend += cnum;
-}
-
-// Every lane owns one run [s,e) of the cell-sorted array; the warp scans the concatenation of the 32 runs.
-__device__ __forceinline__ void knn_scan_runs(const CloudView& c, float qx, float qy, float qz, int s, int e, KnnState& st, KnnScratch& sm,
-                                              int k, int lane) {
-  const int len = e - s;
-  int incl = len;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(B2R_FULL, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int total = __shfl_sync(B2R_FULL, incl, 31);
-  const int excl = incl - len;
-  for (int base = 0; base < total; base += 32) {
-    const int j = base + lane;
-    int lo = 0;  // number of runs that end at or before j  (= index of the run containing j)
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int v = __shfl_sync(B2R_FULL, incl, lo + step - 1);
-      if (v <= j) lo += step;
-    }
-    const int rs = __shfl_sync(B2R_FULL, s, lo), rx = __shfl_sync(B2R_FULL, excl, lo);
-    unsigned long long key = ~0ull;
-    if (j < total) {
-      const int pos = rs + (j - rx);
-      const float4 p = __ldg(&c.spts[pos]);
-      const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
-      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)pos;
-    }
-    knn_push(st, sm, key, k, lane);
-  }
-}
-
-// Bounds of run `id` of the cube (shell == false) or shell (shell == true) of Chebyshev radius r around (cx,cy,cz).
-// Rows are enumerated over the part of the (y,z) window that lies inside the grid; a shell contributes one full
-// x-span for face rows and two single cells (x = cx-r, cx+r) for inner rows.
-struct RingEnum {
-  int ylo, zlo, wy, nrows, nruns;
-};
-__device__ __forceinline__ RingEnum ring_enum(const CloudView& c, int cy, int cz, int r, bool shell) {
-  RingEnum e;
-  e.ylo = max(cy - r, 0);
-  e.zlo = max(cz - r, 0);
-  const int yhi = min(cy + r, c.gd[1] - 1), zhi = min(cz + r, c.gd[2] - 1);
-  e.wy = max(yhi - e.ylo + 1, 0);
-  const int wz = max(zhi - e.zlo + 1, 0);
-  e.nrows = e.wy * wz;
-  e.nruns = shell ? 2 * e.nrows : e.nrows;
-  return e;
-}
-__device__ __forceinline__ void ring_run_bounds(const CloudView& c, const RingEnum& en, int cx, int cy, int cz, int r, bool shell, int id,
-                                                int& s, int& e) {
-  s = e = 0;
-  if (id >= en.nruns) return;
-  int row = shell ? (id >> 1) : id;
-  const int seg = shell ? (id & 1) : 0;
-  if (!shell && r == 1 && en.nrows == 9) {
-    // centre row first: a good k-th distance early prunes the rest
-    row = (int)((0x862075314ull >> (4 * row)) & 0xfull);  // order 4,1,3,5,7,0,2,6,8
-  }
-  const int y = en.ylo + row % en.wy, z = en.zlo + row / en.wy;
-  const int rowbase = (z * c.gd[1] + y) * c.gd[0];
-  const bool face = !shell || (y - cy == r) || (cy - y == r) || (z - cz == r) || (cz - z == r);
-  if (face) {
-    if (seg) return;
-    const int x0 = max(cx - r, 0), x1 = min(cx + r, c.gd[0] - 1);
-    if (x0 > x1) return;
-    s = __ldg(&c.cell_start[rowbase + x0]);
-    e = __ldg(&c.cell_start[rowbase + x1 + 1]);
-  } else {
-    const int x = seg ? cx + r : cx - r;
-    if (x < 0 || x >= c.gd[0]) return;
-    s = __ldg(&c.cell_start[rowbase + x]);
-    e = __ldg(&c.cell_start[rowbase + x + 1]);
-  }
-}
-
-__device__ __forceinline__ void knn_scan_ring(const CloudView& c, float qx, float qy, float qz, int cx, int cy, int cz, int r, bool shell,
-                                              KnnState& st, KnnScratch& sm, int k, int lane) {
-  const RingEnum en = ring_enum(c, cy, cz, r, shell);
-  for (int base = 0; base < en.nruns; base += 32) {
-    int s, e;
-    ring_run_bounds(c, en, cx, cy, cz, r, shell, base + lane, s, e);
-    if (__ballot_sync(B2R_FULL, e > s)) knn_scan_runs(c, qx, qy, qz, s, e, st, sm, k, lane);
-  }
+// Everything closer than this (squared) to a query is inside the cube of Chebyshev radius r around the query's cell.
+// The 2e-3-cell margin covers the float rounding of (p - bmin) * inv_h for grids up to a few thousand cells per axis.
+__device__ __forceinline__ float ring_safe_d2(int r, float h) {
+  const float b = ((float)r - 2e-3f) * h;
+  return b * b;
 }
 
 __device__ __forceinline__ int cells_outside(const CloudView& c, int cx, int cy, int cz) {
@@ -174,80 +46,197 @@ __device__ __forceinline__ bool ring_covers_grid(const CloudView& c, int cx, int
   return cx - r <= 0 && cx + r >= c.gd[0] - 1 && cy - r <= 0 && cy + r >= c.gd[1] - 1 && cz - r <= 0 && cz + r >= c.gd[2] - 1;
 }
 
-__device__ __forceinline__ unsigned long long warp_knn(const CloudView& c, float qx, float qy, float qz, int k, int lane, KnnScratch& sm) {
-  KnnState st;
-  st.list = ~0ull; st.kth = ~0ull; st.npend = 0;
+// Query position in cell units: integer cell (unclamped, may lie outside the grid) + fraction inside the cell.
+struct QueryCell {
   int cx, cy, cz;
-  nn_cell_of_unclamped(c, qx, qy, qz, cx, cy, cz);
-  int r = cells_outside(c, cx, cy, cz) + 1;
-  knn_scan_ring(c, qx, qy, qz, cx, cy, cz, r, false, st, sm, k, lane);
-  knn_flush(st, sm, k, lane);
-  for (;;) {
-    if (st.kth != ~0ull) {
-      const float kd2 = __uint_as_float((unsigned)(st.kth >> 32));
-      const float bound = (float)r * c.h;
-      if (kd2 <= bound * bound * (1.0f - 1e-5f)) break;
-    }
-    if (ring_covers_grid(c, cx, cy, cz, r)) break;
-    ++r;
-    knn_scan_ring(c, qx, qy, qz, cx, cy, cz, r, true, st, sm, k, lane);
-    knn_flush(st, sm, k, lane);
-  }
-  return st.list;
+  float fx, fy, fz;  // fractional position inside the cell, in [0,1]
+};
+__device__ __forceinline__ QueryCell query_cell(const CloudView& c, float x, float y, float z) {
+  const float big = 1.0e9f;
+  QueryCell q;
+  const float vx = (x - c.bmin[0]) * c.inv_h, vy = (y - c.bmin[1]) * c.inv_h, vz = (z - c.bmin[2]) * c.inv_h;
+  const float ux = floorf(vx), uy = floorf(vy), uz = floorf(vz);
+  q.cx = (int)fminf(fmaxf(ux, -big), big);
+  q.cy = (int)fminf(fmaxf(uy, -big), big);
+  q.cz = (int)fminf(fmaxf(uz, -big), big);
+  q.fx = fminf(fmaxf(vx - ux, 0.f), 1.f);
+  q.fy = fminf(fmaxf(vy - uy, 0.f), 1.f);
+  q.fz = fminf(fmaxf(vz - uz, 0.f), 1.f);
+  return q;
+}
+// lower bound (in cell units, with a 2e-3-cell safety margin for the float rounding of the cell assignment) of the
+// distance along one axis from a query at fraction f of its cell to the cell d cells away
+__device__ __forceinline__ float axis_gap(float f, int d) {
+  const float g = d > 0 ? (float)d - f : (d < 0 ? f - (float)(d + 1) : 0.f);
+  return fmaxf(g - 2e-3f, 0.f);
 }
 
-// ---- one thread per query: exact 1-NN within max_d2 (pass INFINITY for unbounded).  Returns position in spts or -1.
-__device__ __forceinline__ void nn1_scan_run(const CloudView& c, float qx, float qy, float qz, int s, int e, float& best, int& best_pos) {
-  for (int j = s; j < e; ++j) {
-    const float4 p = __ldg(&c.spts[j]);
-    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
-    if (d2 < best || (d2 == best && j < best_pos)) { best = d2; best_pos = j; }
+// Visits the runs of the cube (shell == false) or of the shell (shell == true) of Chebyshev radius r around the query's
+// cell.  V::thr() is the squared distance beyond which points cannot matter any more (it may shrink while scanning);
+// V::run(s, e) scans positions [s, e) of spts.  Rows whose distance lower bound exceeds thr() are skipped.  For the
+// cube the query's own row is visited first: a good k-th distance early prunes most of the rest.
+// XPRUNE additionally trims each row to the cells that can still matter.  That pays for scattered queries (1-NN of
+// transformed points); for a cloud's own points in cell order it does not: lanes of one cell then stop sharing
+// identical runs (broadcast loads, uniform trip counts), which costs more than the skipped candidates save.
+template <bool XPRUNE, typename V>
+__device__ __forceinline__ void visit_ring(const CloudView& c, const QueryCell& q, int r, bool shell, V& v) {
+  const int z0 = max(q.cz - r, 0), z1 = min(q.cz + r, c.gd[2] - 1);
+  const int y0 = max(q.cy - r, 0), y1 = min(q.cy + r, c.gd[1] - 1);
+  const int fx0 = max(q.cx - r, 0), fx1 = min(q.cx + r, c.gd[0] - 1);
+  const float inv_h2 = c.inv_h * c.inv_h;
+  const bool centre_first = !shell && q.cy >= y0 && q.cy <= y1 && q.cz >= z0 && q.cz <= z1;
+  if (centre_first && fx0 <= fx1) {
+    const int rowbase = (q.cz * c.gd[1] + q.cy) * c.gd[0];
+    v.run(__ldg(&c.cell_start[rowbase + fx0]), __ldg(&c.cell_start[rowbase + fx1 + 1]));
   }
-}
-__device__ __forceinline__ void nn1_scan_ring(const CloudView& c, float qx, float qy, float qz, int cx, int cy, int cz, int r, bool shell,
-                                              float& best, int& best_pos) {
-  const int z0 = max(cz - r, 0), z1 = min(cz + r, c.gd[2] - 1);
-  const int y0 = max(cy - r, 0), y1 = min(cy + r, c.gd[1] - 1);
   for (int z = z0; z <= z1; ++z) {
-    const bool zface = (z - cz == r) || (cz - z == r);
+    const int dz = z - q.cz;
+    const bool zface = dz == r || dz == -r;
+    const float gz = axis_gap(q.fz, dz);
     for (int y = y0; y <= y1; ++y) {
+      const int dy = y - q.cy;
+      if (centre_first && dy == 0 && dz == 0) continue;
+      const float gy = axis_gap(q.fy, dy);
+      // budget left for the x axis, in cells^2 (thr() == INFINITY: everything)
+      const float bx2 = v.thr() * inv_h2 - (gy * gy + gz * gz);
+      if (!(bx2 > 0.f)) continue;
       const int rowbase = (z * c.gd[1] + y) * c.gd[0];
-      const bool full = !shell || zface || (y - cy == r) || (cy - y == r);
-      if (full) {
-        const int x0 = max(cx - r, 0), x1 = min(cx + r, c.gd[0] - 1);
-        if (x0 <= x1) nn1_scan_run(c, qx, qy, qz, __ldg(&c.cell_start[rowbase + x0]), __ldg(&c.cell_start[rowbase + x1 + 1]), best, best_pos);
+      if (!shell || zface || dy == r || dy == -r) {
+        int x0 = fx0, x1 = fx1;
+        if (XPRUNE) {
+          const float bx = fminf(sqrtf(bx2), (float)r + 1.f) + 2e-3f;
+          x0 = max(q.cx - min(r, (int)floorf(bx + 1.f - q.fx)), 0);
+          x1 = min(q.cx + min(r, (int)floorf(bx + q.fx)), c.gd[0] - 1);
+        }
+        if (x0 <= x1) v.run(__ldg(&c.cell_start[rowbase + x0]), __ldg(&c.cell_start[rowbase + x1 + 1]));
       } else {
-        const int xa = cx - r, xb = cx + r;
-        if (xa >= 0 && xa < c.gd[0]) nn1_scan_run(c, qx, qy, qz, __ldg(&c.cell_start[rowbase + xa]), __ldg(&c.cell_start[rowbase + xa + 1]), best, best_pos);
-        if (xb >= 0 && xb < c.gd[0]) nn1_scan_run(c, qx, qy, qz, __ldg(&c.cell_start[rowbase + xb]), __ldg(&c.cell_start[rowbase + xb + 1]), best, best_pos);
+        const int xa = q.cx - r, xb = q.cx + r;
+        const float ga = axis_gap(q.fx, -r), gb = axis_gap(q.fx, r);
+        if (xa >= 0 && xa < c.gd[0] && ga * ga < bx2) v.run(__ldg(&c.cell_start[rowbase + xa]), __ldg(&c.cell_start[rowbase + xa + 1]));
+        if (xb >= 0 && xb < c.gd[0] && gb * gb < bx2) v.run(__ldg(&c.cell_start[rowbase + xb]), __ldg(&c.cell_start[rowbase + xb + 1]));
       }
     }
   }
 }
+
+// ---- K smallest squared distances, ascending, in registers
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&d)[K], float v) {
+#pragma unroll
+  for (int i = K - 1; i > 0; --i) d[i] = fmaxf(d[i - 1], fminf(d[i], v));
+  d[0] = fminf(d[0], v);
+}
+// d[k-1] for a runtime k in [1, K]
+template <int K>
+__device__ __forceinline__ float topk_kth(const float (&d)[K], int k) {
+  float r = d[K - 1];
+#pragma unroll
+  for (int i = K - 2; i >= 0; --i)
+    r = (i >= k - 1) ? d[i] : r;  // (an equality test here lets the compiler fold it into a dynamic index = local memory)
+  return r;
+}
+
+template <int K>
+struct TopkVisitor {
+  const CloudView& c;
+  float qx, qy, qz;
+  float d[K];
+  __device__ __forceinline__ TopkVisitor(const CloudView& cv, float x, float y, float z) : c(cv), qx(x), qy(y), qz(z) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) d[i] = INFINITY;
+  }
+  __device__ __forceinline__ float thr() const { return d[K - 1]; }
+  __device__ __forceinline__ void run(int s, int e) {
+    for (int j = s; j < e; ++j) {
+      const float4 p = __ldg(&c.spts[j]);
+      const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+      if (d2 < d[K - 1]) topk_insert<K>(d, d2);
+    }
+  }
+};
+
+// Exact k smallest squared distances (k <= K, ascending in v.d[0..k)) of the query in cloud c.
+// Returns the Chebyshev radius of the scanned cube; v.d[k-1] == INFINITY if the cloud has fewer than k points.
+template <int K>
+__device__ __forceinline__ int knn_topk(const CloudView& c, const QueryCell& q, int k, TopkVisitor<K>& v) {
+  int r = cells_outside(c, q.cx, q.cy, q.cz) + 1;
+  visit_ring<false>(c, q, r, false, v);
+  for (;;) {
+    if (topk_kth<K>(v.d, k) <= ring_safe_d2(r, c.h)) break;
+    if (ring_covers_grid(c, q.cx, q.cy, q.cz, r)) break;
+    ++r;
+    visit_ring<false>(c, q, r, true, v);
+  }
+  return r;
+}
+
+// ---- same search keeping (distance, position) pairs as 64-bit keys: float bits of d^2 << 32 | position in spts.
+// Used where the neighbour identities are wanted in ascending order (debug / test entry point).
+__device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+template <int K>
+struct TopkKeyVisitor {
+  const CloudView& c;
+  float qx, qy, qz;
+  unsigned long long d[K];
+  __device__ __forceinline__ TopkKeyVisitor(const CloudView& cv, float x, float y, float z) : c(cv), qx(x), qy(y), qz(z) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) d[i] = ~0ull;
+  }
+  __device__ __forceinline__ float worst() const { return __uint_as_float((unsigned)(d[K - 1] >> 32)); }
+  __device__ __forceinline__ float thr() const { return d[K - 1] == ~0ull ? INFINITY : worst() * (1.f + 1e-6f); }
+  __device__ __forceinline__ void run(int s, int e) {
+    for (int j = s; j < e; ++j) {
+      const float4 p = __ldg(&c.spts[j]);
+      const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+      if (key < d[K - 1]) {
+#pragma unroll
+        for (int i = K - 1; i > 0; --i) d[i] = u64max(d[i - 1], u64min(d[i], key));
+        d[0] = u64min(d[0], key);
+      }
+    }
+  }
+};
+
+// ---- one thread per query: exact 1-NN within max_d2 (pass INFINITY for unbounded).  Returns position in spts or -1.
+// Ties go to the lower position.
+struct Nn1Visitor {
+  const CloudView& c;
+  float qx, qy, qz, cut;  // rows farther than `cut` (squared) cannot matter
+  float best;
+  int best_pos;
+  __device__ __forceinline__ float thr() const { return fminf(best, cut) * (1.f + 1e-6f); }
+  __device__ __forceinline__ void run(int s, int e) {
+    for (int j = s; j < e; ++j) {
+      const float4 p = __ldg(&c.spts[j]);
+      const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+      if (d2 < best || (d2 == best && j < best_pos)) { best = d2; best_pos = j; }
+    }
+  }
+};
 __device__ __forceinline__ int nn1_search(const CloudView& c, float qx, float qy, float qz, float max_d2, float& best_out) {
-  float best = INFINITY;
-  int best_pos = -1;
-  if (c.n == 0) { best_out = best; return -1; }
-  int cx, cy, cz;
-  nn_cell_of_unclamped(c, qx, qy, qz, cx, cy, cz);
-  int r = cells_outside(c, cx, cy, cz) + 1;
+  Nn1Visitor v{c, qx, qy, qz, max_d2, INFINITY, -1};
+  if (c.n == 0) { best_out = v.best; return -1; }
+  const QueryCell q = query_cell(c, qx, qy, qz);
+  int r = cells_outside(c, q.cx, q.cy, q.cz) + 1;
   // nothing closer than (r-2)*h can exist when the query is outside the grid
   {
     const float lb = (float)(r - 2) * c.h;
-    if (r >= 3 && lb * lb > max_d2) { best_out = best; return -1; }
+    if (r >= 3 && lb * lb > max_d2) { best_out = v.best; return -1; }
   }
-  nn1_scan_ring(c, qx, qy, qz, cx, cy, cz, r, false, best, best_pos);
+  visit_ring<B2R_NN1_XPRUNE>(c, q, r, false, v);
   for (;;) {
-    const float bound = (float)r * c.h;
-    const float b2 = bound * bound * (1.0f - 1e-5f);
-    if (best <= b2) break;       // proven nearest
+    const float b2 = ring_safe_d2(r, c.h);
+    if (v.best <= b2) break;     // proven nearest
     if (b2 > max_d2) break;      // anything farther is out of range anyway
-    if (ring_covers_grid(c, cx, cy, cz, r)) break;
+    if (ring_covers_grid(c, q.cx, q.cy, q.cz, r)) break;
     ++r;
-    nn1_scan_ring(c, qx, qy, qz, cx, cy, cz, r, true, best, best_pos);
+    visit_ring<B2R_NN1_XPRUNE>(c, q, r, true, v);
   }
-  best_out = best;
-  return best_pos;
+  best_out = v.best;
+  return v.best_pos;
 }
 
 // ---- one thread per query: number of points with d2 < r2 (strict), early exit once count > stop_above.
