@@ -96,12 +96,8 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<
     pairs[i].tgt = add(targets[i], true);
     src_sizes[i] = sources[i]->n;
   }
-  clouds_prepare(ctx, h.cfg, uniq, needs);
-  std::vector<CloudView> hv(uniq.size());
-  for (size_t i = 0; i < uniq.size(); ++i) hv[i] = uniq[i]->view();
   DBuf<CloudView> dv;
-  dv.alloc(hv.size(), ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+  clouds_prepare(ctx, h.cfg, uniq, needs, dv);
   B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
   if (h.cfg.method == B2R_NDT_OMP) ndt_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
   else lsq_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
@@ -126,12 +122,7 @@ void prepare_current(Handle& h, DBuf<CloudView>& dv, bool want_fitness) {
   if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set first");
   std::vector<Cloud*> cl{h.source, h.target};
   std::vector<Needs> nd{needs_for(h.cfg, false, false), needs_for(h.cfg, true, want_fitness)};
-  clouds_prepare(h.ctx, h.cfg, cl, nd);
-  // source == target (same object) still yields two identical views
-  CloudView hv[2] = {h.source->view(), h.target->view()};
-  dv.alloc(2, h.ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dv.p, hv, sizeof(hv), cudaMemcpyHostToDevice, h.ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+  clouds_prepare(h.ctx, h.cfg, cl, nd, dv);  // source == target (same object) still yields two identical views
 }
 
 }  // namespace
@@ -222,8 +213,8 @@ b2r_status b2r_cloud_create(b2r_handle* hh, const void* points, size_t n, size_t
     if (!points && n) throw Error(B2R_ERR_INVALID_ARG, "null points");
     b2r_cloud* c = new b2r_cloud();
     try {
-      cloud_upload(h.ctx, c->c, points, n, stride_bytes, memspace);
-      B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+      Cloud* cp = &c->c;
+      clouds_upload(h.ctx, &cp, &points, &n, 1, stride_bytes, memspace);
     } catch (...) {
       delete c;
       throw;
@@ -238,12 +229,13 @@ b2r_status b2r_cloud_create_batch(b2r_handle* hh, const void* const* points, con
   for (size_t i = 0; i < count; ++i) out[i] = nullptr;
   return guarded(hh, [&](Handle& h) {
     try {
+      std::vector<Cloud*> cl(count);
       for (size_t i = 0; i < count; ++i) {
         if (!points[i] && n[i]) throw Error(B2R_ERR_INVALID_ARG, "null points");
         out[i] = new b2r_cloud();
-        cloud_upload(h.ctx, out[i]->c, points[i], n[i], stride_bytes, memspace);
+        cl[i] = &out[i]->c;
       }
-      B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+      clouds_upload(h.ctx, cl.data(), points, n, count, stride_bytes, memspace);
     } catch (...) {
       for (size_t i = 0; i < count; ++i) { delete out[i]; out[i] = nullptr; }
       throw;
@@ -262,8 +254,8 @@ b2r_status b2r_set_target(b2r_handle* hh, const void* points, size_t n, size_t s
   return guarded(hh, [&](Handle& h) {
     if (!points || n == 0) throw Error(B2R_ERR_INVALID_ARG, "empty target");
     std::unique_ptr<Cloud> c(new Cloud());
-    cloud_upload(h.ctx, *c, points, n, stride_bytes, memspace);
-    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    Cloud* cp = c.get();
+    clouds_upload(h.ctx, &cp, &points, &n, 1, stride_bytes, memspace);
     h.owned_target = std::move(c);
     h.target = h.owned_target.get();
   });
@@ -272,8 +264,8 @@ b2r_status b2r_set_source(b2r_handle* hh, const void* points, size_t n, size_t s
   return guarded(hh, [&](Handle& h) {
     if (!points || n == 0) throw Error(B2R_ERR_INVALID_ARG, "empty source");
     std::unique_ptr<Cloud> c(new Cloud());
-    cloud_upload(h.ctx, *c, points, n, stride_bytes, memspace);
-    B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
+    Cloud* cp = c.get();
+    clouds_upload(h.ctx, &cp, &points, &n, 1, stride_bytes, memspace);
     h.owned_source = std::move(c);
     h.source = h.owned_source.get();
   });
@@ -333,11 +325,8 @@ b2r_status b2r_fitness(b2r_handle* hh, double max_range, double* out) {
     std::vector<Cloud*> cl{h.source, h.target};
     std::vector<Needs> nd(2);
     nd[1].grid = true;
-    clouds_prepare(h.ctx, h.cfg, cl, nd);
-    CloudView hv[2] = {h.source->view(), h.target->view()};
     DBuf<CloudView> dv;
-    dv.alloc(2, h.ctx.stream);
-    B2R_CUDA(cudaMemcpyAsync(dv.p, hv, sizeof(hv), cudaMemcpyHostToDevice, h.ctx.stream));
+    clouds_prepare(h.ctx, h.cfg, cl, nd, dv);
     std::vector<PairDesc> pairs{PairDesc{0, 1}};
     int ns = h.source->n;
     fitness_batch(h.ctx, dv.p, pairs, &ns, h.final_T, max_range, out);
@@ -350,11 +339,8 @@ b2r_status b2r_fitness_pair(b2r_handle* hh, b2r_cloud* target, b2r_cloud* source
     std::vector<Cloud*> cl{&source->c, &target->c};
     std::vector<Needs> nd(2);
     nd[1].grid = true;
-    clouds_prepare(h.ctx, h.cfg, cl, nd);
-    CloudView hv[2] = {source->c.view(), target->c.view()};
     DBuf<CloudView> dv;
-    dv.alloc(2, h.ctx.stream);
-    B2R_CUDA(cudaMemcpyAsync(dv.p, hv, sizeof(hv), cudaMemcpyHostToDevice, h.ctx.stream));
+    clouds_prepare(h.ctx, h.cfg, cl, nd, dv);
     std::vector<PairDesc> pairs{PairDesc{0, 1}};
     int ns = source->c.n;
     fitness_batch(h.ctx, dv.p, pairs, &ns, T, max_range, out);
@@ -531,7 +517,8 @@ b2r_status b2r_debug_covariances(b2r_handle* hh, int which, double* cov6_out, in
       std::vector<Cloud*> cl{c};
       std::vector<Needs> nd(1);
       nd[0].cov_k = k;
-      clouds_prepare(h.ctx, h.cfg, cl, nd);
+      DBuf<CloudView> dvtmp;
+      clouds_prepare(h.ctx, h.cfg, cl, nd, dvtmp);
     }
     if (cov6_out) {
       B2R_CUDA(cudaMemcpyAsync(cov6_out, c->cov.p, sizeof(double) * 6 * c->n, cudaMemcpyDeviceToHost, h.ctx.stream));
@@ -548,7 +535,8 @@ b2r_status b2r_debug_voxelmap(b2r_handle* hh, int32_t* coords_out, int32_t* npts
     std::vector<Needs> nd(1);
     nd[0].cov_k = h.cfg.correspondence_randomness;
     nd[0].vres = h.cfg.resolution;
-    clouds_prepare(h.ctx, h.cfg, cl, nd);
+    DBuf<CloudView> dvtmp;
+    clouds_prepare(h.ctx, h.cfg, cl, nd, dvtmp);
     int nrec = 0;
     B2R_CUDA(cudaMemcpyAsync(&nrec, c->v_nrec.p, sizeof(int), cudaMemcpyDeviceToHost, h.ctx.stream));
     B2R_CUDA(cudaStreamSynchronize(h.ctx.stream));
@@ -598,7 +586,8 @@ b2r_status b2r_debug_ndt_grid(b2r_handle* hh, int32_t* idx_out, int32_t* npts_ou
     std::vector<Cloud*> cl{c};
     std::vector<Needs> nd(1);
     nd[0].leaf = (float)h.cfg.resolution;
-    clouds_prepare(h.ctx, h.cfg, cl, nd);
+    DBuf<CloudView> dvtmp;
+    clouds_prepare(h.ctx, h.cfg, cl, nd, dvtmp);
     for (int d = 0; d < 3; ++d) { min_b[d] = c->min_b[d]; div_b[d] = c->div_b[d]; }
     *V = 0;
     if (c->ncell_ndt == 0) return;

@@ -24,7 +24,7 @@ CloudView Cloud::view() const {
   for (int d = 0; d < 3; ++d) { v.bmin[d] = bmin[d]; v.bmax[d] = bmax[d]; }
   v.h = h; v.inv_h = h > 0 ? 1.0f / h : 0.f;
   for (int d = 0; d < 3; ++d) v.gd[d] = gd[d];
-  v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.spts = spts.p;
+  v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.cell_tmp = cell_tmp.p; v.spts = spts.p;
   v.cov = cov.p;
   v.vres = vres;
   for (int d = 0; d < 3; ++d) { v.vmin[d] = vmin[d]; v.vd[d] = vd[d]; }
@@ -86,15 +86,6 @@ void store_points(Ctx& ctx, const float4* src, size_t n, void* out, size_t strid
     if (memspace != B2R_DEVICE) B2R_CUDA(cudaMemcpyAsync(out, raw.p, n * 32, kind, ctx.stream));
   }
   if (memspace != B2R_DEVICE) B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-}
-
-void cloud_upload(Ctx& ctx, Cloud& c, const void* points, size_t n, size_t stride_bytes, int memspace) {
-  if (n > (size_t)INT_MAX / 8) throw Error(B2R_ERR_INVALID_ARG, "cloud too large");
-  c.device = ctx.device;
-  c.n = (int)n;
-  load_points(ctx, points, n, stride_bytes, memspace, c.pts);
-  c.has_bbox = c.has_grid = false;
-  c.cov_k = 0; c.vres = 0.0; c.leaf = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ bbox
@@ -309,69 +300,38 @@ __global__ void __launch_bounds__(1024) grid_scan_apply_kernel(const CloudView* 
   }
 }
 
+// scatter of the point indices into their cells (atomic cursor: arbitrary order inside a cell) ...
 template <int MODE>
 __global__ void grid_scatter_kernel(const CloudView* __restrict__ views) {
   const CloudView& c = views[blockIdx.y];
   int* cnt = grid_cnt<MODE>(c);
   const int* start = grid_start<MODE>(c);
+  int* tmp = MODE == GRID_NN ? c.cell_tmp : (MODE == GRID_VGICP ? c.v_order + c.n : c.n_order + c.n);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
-    float4 p = __ldg(&c.pts[i]);
-    int key = cell_key<MODE>(c, p);
-    int pos = start[key] + atomicAdd(&cnt[key], 1);
-    if (MODE == GRID_NN) c.spts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-    else if (MODE == GRID_VGICP) c.v_order[pos] = i;
-    else c.n_order[pos] = i;
+    const float4 p = __ldg(&c.pts[i]);
+    const int key = cell_key<MODE>(c, p);
+    tmp[start[key] + atomicAdd(&cnt[key], 1)] = i;
   }
 }
-
-// NN grid: the atomic scatter leaves the points of a cell in arbitrary order; sort each cell by original index so that the
-// cell-sorted copy (and with it every tie-break by position in the searches) is identical from run to run.
-__global__ void grid_cellsort_kernel(const CloudView* __restrict__ views) {
+// ... then every entry finds its rank among the indices of its cell and moves there: cells end up sorted by original
+// index, so the cell-sorted copy (tie-breaks by position, summation orders) is identical from run to run.  One thread
+// per entry; the cell's index list is read by all of its entries (L1-resident).
+template <int MODE>
+__global__ void grid_rank_kernel(const CloudView* __restrict__ views) {
   const CloudView& c = views[blockIdx.y];
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < c.ncell; cell += gridDim.x * blockDim.x) {
-    const int s = c.cell_start[cell], e = c.cell_start[cell + 1];
-    for (int i = s + 1; i < e; ++i) {
-      const float4 v = c.spts[i];
-      const int key = __float_as_int(v.w);
-      int j = i - 1;
-      while (j >= s && __float_as_int(c.spts[j].w) > key) { c.spts[j + 1] = c.spts[j]; --j; }
-      c.spts[j + 1] = v;
-    }
-  }
-}
-
-__device__ __forceinline__ int warp_sort32_int(int v, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const int o = __shfl_xor_sync(0xffffffffu, v, j);
-      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-      v = (lower == up) ? min(v, o) : max(v, o);
-    }
-  }
-  return v;
-}
-// One warp sorts the point list [s, s+n) of a voxel ascending (the atomic scatter left it in arbitrary order), so that the
-// per-voxel sums below are evaluated in a fixed order: deterministic run to run.  Lists longer than a warp are rank-sorted
-// into the scratch half of `order` (order + n_total).  Returns the sorted list.
-__device__ __forceinline__ const int* warp_sort_segment(int* order, int n_total, int s, int n, int lane) {
-  if (n <= 32) {
-    int v = lane < n ? order[s + lane] : INT_MAX;
-    v = warp_sort32_int(v, lane);
-    if (lane < n) order[s + lane] = v;
-    __syncwarp();
-    return order + s;
-  }
-  int* dst = order + n_total + s;
-  for (int i = lane; i < n; i += 32) {
-    const int vi = order[s + i];
+  const int* start = grid_start<MODE>(c);
+  const int* tmp = MODE == GRID_NN ? c.cell_tmp : (MODE == GRID_VGICP ? c.v_order + c.n : c.n_order + c.n);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.n; j += gridDim.x * blockDim.x) {
+    const int i = tmp[j];
+    const float4 p = __ldg(&c.pts[i]);
+    const int key = cell_key<MODE>(c, p);
+    const int s = start[key], e = start[key + 1];
     int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (order[s + j] < vi) ? 1 : 0;
-    dst[rank] = vi;
+    for (int t = s; t < e; ++t) rank += (tmp[t] < i) ? 1 : 0;
+    if (MODE == GRID_NN) c.spts[s + rank] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    else if (MODE == GRID_VGICP) c.v_order[s + rank] = i;
+    else c.n_order[s + rank] = i;
   }
-  __syncwarp();
-  return dst;
 }
 
 // VGICP: one warp per occupied voxel: sum of the points' positions and covariances (fast_gicp create_voxelmap,
@@ -384,7 +344,7 @@ __global__ void __launch_bounds__(256) vgicp_reduce_kernel(const CloudView* __re
   for (int rec = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rec < nrec; rec += nwarps) {
     const int cell = c.v_reccell[rec];
     const int s = c.v_start[cell], n = c.v_start[cell + 1] - s;
-    const int* idx = warp_sort_segment(c.v_order, c.n, s, n, lane);
+    const int* idx = c.v_order + s;  // ascending point index: fixed summation order
     double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int j = lane; j < n; j += 32) {
       const int i = idx[j];
@@ -418,7 +378,7 @@ __global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __rest
   for (int rec = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rec < nrec; rec += nwarps) {
     const int cell = c.n_reccell[rec];
     const int s = c.n_start[cell], e = c.n_start[cell + 1];
-    const int* idx = warp_sort_segment(c.n_order, c.n, s, e - s, lane);
+    const int* idx = c.n_order + s;  // ascending point index: fixed summation order
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // sum x,y,z ; sum xx,xy,xz,yy,yz,zz
     for (int j = lane; j < e - s; j += 32) {
       const float4 p = __ldg(&c.pts[idx[j]]);
@@ -506,6 +466,9 @@ __global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __rest
 //           d2 <= dk (the k nearest; ties beyond k are resolved towards the lower position on a rare slow path);
 //   then    covariance = E[d d^T] - E[d] E[d]^T (shift-invariant, so identical to the centred sum of the reference up
 //           to rounding ~1e-15), symmetric 3x3 Jacobi eigen-decomposition, PLANE regularisation (1, 1, 1e-3).
+#ifndef B2R_COV_PASS2_XPRUNE
+#define B2R_COV_PASS2_XPRUNE true
+#endif
 struct CovAccum {
   double s[9];
   int cnt;
@@ -582,7 +545,7 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const CloudView* __restric
     dk = topk_kth<K>(tv.d, k);
   }
   CovVisitor v{c, sp.x, sp.y, sp.z, dk, true, k, knn_out ? knn_out + (size_t)orig * k : nullptr, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
-  visit_ring<false>(c, q, r, false, v);
+  visit_ring<B2R_COV_PASS2_XPRUNE>(c, q, r, false, v);  // dk is final and tight here: trimming rows pays
   if (v.a.cnt > k) v.a = cov_accumulate_ties(&c, sp.x, sp.y, sp.z, r, dk, k, v.knn_row);
   const double kk = (double)k;
   const double mx = v.a.s[0] / kk, my = v.a.s[1] / kk, mz = v.a.s[2] / kk;
@@ -678,6 +641,7 @@ static void launch_knn_cov(Ctx& ctx, const CloudView* dviews, const std::vector<
   else B2R_LAUNCH(ctx, knn_cov_kernel<32>, grid, 128, 0, dviews, k, knn_out);
 }
 
+// bounding boxes of the clouds that lack one: one kernel over all of them, one D2H, one synchronisation
 void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
   std::vector<Cloud*> todo;
   for (Cloud* c : clouds)
@@ -691,7 +655,7 @@ void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
   DBuf<int> db; db.alloc((size_t)nc * 6, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * nc, cudaMemcpyHostToDevice, ctx.stream));
   B2R_LAUNCH(ctx, bbox_init_kernel, (nc * 6 + 255) / 256, 256, 0, db.p, nc);
-  dim3 g(blocks_for(maxn, 256 * 8, 64), nc);
+  dim3 g(blocks_for(maxn, 256 * 8, std::max(1, 4 * ctx.num_sms / nc)), nc);
   B2R_LAUNCH(ctx, bbox_kernel, g, 256, 0, dv.p, db.p);
   std::vector<int> hb((size_t)nc * 6);
   B2R_CUDA(cudaMemcpyAsync(hb.data(), db.p, sizeof(int) * nc * 6, cudaMemcpyDeviceToHost, ctx.stream));
@@ -706,25 +670,67 @@ void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
   }
 }
 
-template <int MODE>
-static void run_grid_build(Ctx& ctx, const CloudView* dviews, int nc, int maxn, int maxcell) {
-  dim3 g(blocks_for(maxn, 256 * 4, 4 * ctx.num_sms), nc);
-  const int max_tiles = (maxcell + kScanTile - 1) / kScanTile;
-  DBuf<unsigned long long> tile_tot;
-  tile_tot.alloc((size_t)nc * max_tiles, ctx.stream);
-  ProfScope ps(ctx, PROF_GRID_BUILD, 0.0);
-  B2R_LAUNCH(ctx, grid_count_kernel<MODE>, g, 256, 0, dviews);
-  B2R_LAUNCH(ctx, grid_scan_tile_kernel<MODE>, dim3(max_tiles, nc), 1024, 0, dviews, tile_tot.p, max_tiles);
-  B2R_LAUNCH(ctx, grid_scan_tops_kernel<MODE>, nc, 1024, 0, dviews, tile_tot.p, max_tiles);
-  B2R_LAUNCH(ctx, grid_scan_apply_kernel<MODE>, dim3(max_tiles, nc), 1024, 0, dviews, tile_tot.p, max_tiles);
-  B2R_LAUNCH(ctx, grid_scatter_kernel<MODE>, g, 256, 0, dviews);
-  if (MODE == GRID_NN) B2R_LAUNCH(ctx, grid_cellsort_kernel, dim3(blocks_for(maxcell, 256, 8 * ctx.num_sms), nc), 256, 0, dviews);
+void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, const size_t* n, size_t count, size_t stride_bytes, int memspace) {
+  if (stride_bytes != 16 && stride_bytes != 32) throw Error(B2R_ERR_INVALID_ARG, "stride_bytes must be 16 or 32");
+  ArenaPlan plan;
+  std::vector<uint8_t*> raw(count, nullptr);
+  const bool stage = stride_bytes == 32 && memspace != B2R_DEVICE;
+  for (size_t i = 0; i < count; ++i) {
+    if (n[i] > (size_t)INT_MAX / 8) throw Error(B2R_ERR_INVALID_ARG, "cloud too large");
+    Cloud& c = *clouds[i];
+    c = Cloud();
+    c.device = ctx.device;
+    c.n = (int)n[i];
+    plan.want(c.pts.p, n[i]);
+  }
+  std::shared_ptr<Arena> arena = plan.commit(ctx.stream);
+  DBuf<uint8_t> staging;
+  if (stage) {
+    size_t tot = 0;
+    for (size_t i = 0; i < count; ++i) tot += ArenaPlan::up(n[i] * 32);
+    staging.alloc(tot, ctx.stream);
+    size_t off = 0;
+    for (size_t i = 0; i < count; ++i) { raw[i] = staging.p + off; off += ArenaPlan::up(n[i] * 32); }
+  }
+  const cudaMemcpyKind kind = memspace == B2R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  std::vector<Cloud*> all;
+  for (size_t i = 0; i < count; ++i) {
+    Cloud& c = *clouds[i];
+    c.mem.push_back(arena);
+    all.push_back(&c);
+    if (n[i] == 0) continue;
+    if (stride_bytes == 16) {
+      B2R_CUDA(cudaMemcpyAsync(c.pts.p, points[i], n[i] * 16, kind, ctx.stream));
+    } else {
+      const uint8_t* src = (const uint8_t*)points[i];
+      if (stage) {
+        B2R_CUDA(cudaMemcpyAsync(raw[i], points[i], n[i] * 32, kind, ctx.stream));
+        src = raw[i];
+      }
+      B2R_LAUNCH(ctx, repack32_kernel, (unsigned)((n[i] + 255) / 256), 256, 0, src, (int)n[i], c.pts.p);
+    }
+  }
+  clouds_compute_bbox(ctx, all);  // synchronises
 }
 
-void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds_in, const std::vector<Needs>& needs_in) {
-  // merge duplicate clouds
+template <int MODE>
+static void run_grid_build(Ctx& ctx, const CloudView* dviews, int nc, int maxn, int maxcell, unsigned long long* tile_tot, int max_tiles) {
+  dim3 g(blocks_for(maxn, 256 * 4, std::max(1, 8 * ctx.num_sms / nc)), nc);
+  ProfScope ps(ctx, PROF_GRID_BUILD, 0.0);
+  B2R_LAUNCH(ctx, grid_count_kernel<MODE>, g, 256, 0, dviews);
+  B2R_LAUNCH(ctx, grid_scan_tile_kernel<MODE>, dim3((maxcell + kScanTile - 1) / kScanTile, nc), 1024, 0, dviews, tile_tot, max_tiles);
+  B2R_LAUNCH(ctx, grid_scan_tops_kernel<MODE>, nc, 1024, 0, dviews, tile_tot, max_tiles);
+  B2R_LAUNCH(ctx, grid_scan_apply_kernel<MODE>, dim3((maxcell + kScanTile - 1) / kScanTile, nc), 1024, 0, dviews, tile_tot, max_tiles);
+  B2R_LAUNCH(ctx, grid_scatter_kernel<MODE>, g, 256, 0, dviews);
+  B2R_LAUNCH(ctx, grid_rank_kernel<MODE>, dim3(blocks_for(maxn, 128, std::max(1, 16 * ctx.num_sms / nc)), nc), 128, 0, dviews);
+}
+
+void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds_in, const std::vector<Needs>& needs_in,
+                    DBuf<CloudView>& dviews) {
+  // ---- merge duplicate clouds
   std::vector<Cloud*> clouds;
   std::vector<Needs> needs;
+  std::vector<int> slot_of(clouds_in.size());
   for (size_t i = 0; i < clouds_in.size(); ++i) {
     Cloud* c = clouds_in[i];
     if (c->device != ctx.device) throw Error(B2R_ERR_INVALID_ARG, "cloud lives on another device");
@@ -732,6 +738,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     for (; j < clouds.size(); ++j)
       if (clouds[j] == c) break;
     if (j == clouds.size()) { clouds.push_back(c); needs.push_back(Needs()); }
+    slot_of[i] = (int)j;
     Needs& nd = needs[j];
     const Needs& in = needs_in[i];
     nd.grid = nd.grid || in.grid || in.cov_k > 0;
@@ -740,144 +747,148 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     if (in.leaf > 0) nd.leaf = in.leaf;
     if (nd.vres > 0 && nd.cov_k == 0) throw Error(B2R_ERR_STATE, "voxel map needs covariances");
   }
-  clouds_compute_bbox(ctx, clouds);
+  clouds_compute_bbox(ctx, clouds);  // the only synchronisation (skipped when the clouds came through clouds_upload)
 
-  // ---- NN grids
-  {
-    std::vector<Cloud*> todo;
-    for (size_t i = 0; i < clouds.size(); ++i)
-      if (needs[i].grid && !clouds[i]->has_grid && clouds[i]->n > 0) todo.push_back(clouds[i]);
-    if (!todo.empty()) {
-      int maxn = 1, maxcell = 1;
-      for (Cloud* c : todo) {
-        grid_dims(*c, auto_cell_size(*c, cfg));
-        maxcell = std::max(maxcell, c->ncell);
-        c->cell_start.alloc((size_t)c->ncell + 1, ctx.stream);
-        c->cell_cnt.alloc((size_t)c->ncell, ctx.stream);
-        c->cell_cnt.zero(ctx.stream);
-        c->spts.alloc((size_t)c->n, ctx.stream);
-        maxn = std::max(maxn, c->n);
+  // ---- plan: dimensions of everything that is missing, and ONE allocation for all of it
+  std::vector<int> todo_grid, todo_cov, todo_vox, todo_ndt;
+  ArenaPlan plan;
+  int cov_k = 0;
+  for (size_t i = 0; i < clouds.size(); ++i) {
+    Cloud* c = clouds[i];
+    const Needs& nd = needs[i];
+    if (c->n == 0) continue;
+    if (nd.grid && !c->has_grid) {
+      grid_dims(*c, auto_cell_size(*c, cfg));
+      plan.want(c->cell_start.p, (size_t)c->ncell + 1);
+      plan.want_zeroed(c->cell_cnt.p, (size_t)c->ncell);
+      plan.want(c->cell_tmp.p, (size_t)c->n);
+      plan.want(c->spts.p, (size_t)c->n);
+      todo_grid.push_back((int)i);
+    }
+    const bool new_cov = nd.cov_k > 0 && c->cov_k != nd.cov_k;
+    if (new_cov) {
+      if (nd.cov_k > 32) throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be <= 32");
+      if (c->n < nd.cov_k) throw Error(B2R_ERR_INVALID_ARG, "cloud has fewer points than correspondence_randomness");
+      if (cov_k && cov_k != nd.cov_k) throw Error(B2R_ERR_INVALID_ARG, "one correspondence_randomness per call");
+      cov_k = nd.cov_k;
+      plan.want(c->cov.p, (size_t)c->n * 6);
+      c->vres = 0.0;  // a voxel map built from older covariances is stale
+      todo_cov.push_back((int)i);
+    }
+    if (nd.vres > 0 && c->vres != nd.vres) {
+      const double res = nd.vres;
+      long tot = 1;
+      for (int d = 0; d < 3; ++d) {
+        c->vmin[d] = (int)std::floor((double)c->bmin[d] / res - 0.5);
+        int vmax = (int)std::floor((double)c->bmax[d] / res - 0.5);
+        c->vd[d] = vmax - c->vmin[d] + 1;
+        tot *= c->vd[d];
       }
-      std::vector<CloudView> hv;
-      for (Cloud* c : todo) hv.push_back(c->view());
-      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
-      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      run_grid_build<GRID_NN>(ctx, dv.p, (int)hv.size(), maxn, maxcell);
-      B2R_CUDA(cudaStreamSynchronize(ctx.stream));  // hv must outlive the async copy
-      for (Cloud* c : todo) c->has_grid = true;
+      if (tot > (1l << 26)) throw Error(B2R_ERR_CAPACITY, "VGICP voxel table too large for this extent/resolution");
+      c->vcell = (int)tot;
+      const size_t maxrec = (size_t)std::min<long>(tot, c->n);
+      plan.want(c->v_start.p, (size_t)tot + 1);
+      plan.want_zeroed(c->v_cnt.p, (size_t)tot);
+      plan.want(c->v_table.p, (size_t)tot);
+      plan.want(c->v_order.p, (size_t)c->n * 2);
+      plan.want(c->v_reccell.p, maxrec);
+      plan.want(c->vrec.p, maxrec);
+      plan.want(c->v_nrec.p, 1);
+      todo_vox.push_back((int)i);
+    }
+    if (nd.leaf > 0 && c->leaf != nd.leaf) {
+      const float leaf = nd.leaf, inv_leaf = 1.0f / leaf;
+      int64_t dx = (int64_t)((c->bmax[0] - c->bmin[0]) * inv_leaf) + 1, dy = (int64_t)((c->bmax[1] - c->bmin[1]) * inv_leaf) + 1,
+              dz = (int64_t)((c->bmax[2] - c->bmin[2]) * inv_leaf) + 1;
+      const bool overflow = dx * dy * dz > (int64_t)INT32_MAX;  // PCL: warn, grid stays empty
+      long tot = 1;
+      for (int d = 0; d < 3; ++d) {
+        c->min_b[d] = (int)std::floor(c->bmin[d] * inv_leaf);
+        c->max_b[d] = (int)std::floor(c->bmax[d] * inv_leaf);
+        c->div_b[d] = c->max_b[d] - c->min_b[d] + 1;
+        tot *= c->div_b[d];
+      }
+      c->ndt_overflow = overflow;
+      if (overflow) { c->ncell_ndt = 0; c->leaf = leaf; continue; }
+      if (tot > (1l << 26)) throw Error(B2R_ERR_CAPACITY, "NDT voxel table too large for this extent/resolution");
+      c->ncell_ndt = (int)tot;
+      const size_t maxrec = (size_t)std::min<long>(tot, c->n);
+      plan.want(c->n_start.p, (size_t)tot + 1);
+      plan.want_zeroed(c->n_cnt.p, (size_t)tot);
+      plan.want(c->n_table.p, (size_t)tot);
+      plan.want(c->n_order.p, (size_t)c->n * 2);
+      plan.want(c->n_reccell.p, maxrec);
+      plan.want(c->nrec.p, maxrec);
+      plan.want(c->n_nrec.p, 1);
+      todo_ndt.push_back((int)i);
     }
   }
-  // ---- covariances
-  {
-    std::vector<Cloud*> todo;
-    int k = 0;
-    for (size_t i = 0; i < clouds.size(); ++i)
-      if (needs[i].cov_k > 0 && clouds[i]->cov_k != needs[i].cov_k && clouds[i]->n > 0) { todo.push_back(clouds[i]); k = needs[i].cov_k; }
-    if (!todo.empty()) {
-      if (k > 32) throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be <= 32");
-      int maxn = 1;
-      for (Cloud* c : todo) {
-        if (c->n < k) throw Error(B2R_ERR_INVALID_ARG, "cloud has fewer points than correspondence_randomness");
-        c->cov.alloc((size_t)c->n * 6, ctx.stream);
-        maxn = std::max(maxn, c->n);
-        c->vres = 0.0;  // a voxel map built from older covariances is stale
-      }
-      std::vector<CloudView> hv;
-      for (Cloud* c : todo) hv.push_back(c->view());
-      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
-      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      launch_knn_cov(ctx, dv.p, todo, k, maxn, nullptr);
-      B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-      for (Cloud* c : todo) c->cov_k = k;
-    }
+  if (!plan.empty()) {
+    std::shared_ptr<Arena> arena = plan.commit(ctx.stream);
+    for (const std::vector<int>* t : {&todo_grid, &todo_cov, &todo_vox, &todo_ndt})
+      for (int i : *t)
+        if (clouds[i]->mem.empty() || clouds[i]->mem.back() != arena) clouds[i]->mem.push_back(arena);
   }
-  // ---- VGICP voxel maps
-  {
-    std::vector<Cloud*> todo;
-    for (size_t i = 0; i < clouds.size(); ++i)
-      if (needs[i].vres > 0 && clouds[i]->vres != needs[i].vres && clouds[i]->n > 0) {
-        Cloud* c = clouds[i];
-        const double res = needs[i].vres;
-        long tot = 1;
-        for (int d = 0; d < 3; ++d) {
-          c->vmin[d] = (int)std::floor((double)c->bmin[d] / res - 0.5);
-          int vmax = (int)std::floor((double)c->bmax[d] / res - 0.5);
-          c->vd[d] = vmax - c->vmin[d] + 1;
-          tot *= c->vd[d];
-        }
-        if (tot > (1l << 26)) throw Error(B2R_ERR_CAPACITY, "VGICP voxel table too large for this extent/resolution");
-        c->vcell = (int)tot;
-        c->v_start.alloc((size_t)tot + 1, ctx.stream);
-        c->v_cnt.alloc((size_t)tot, ctx.stream);
-        c->v_cnt.zero(ctx.stream);
-        c->v_table.alloc((size_t)tot, ctx.stream);
-        c->v_order.alloc((size_t)c->n * 2, ctx.stream);  // second half: sort scratch
-        c->v_reccell.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
-        c->vrec.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
-        c->v_nrec.alloc(1, ctx.stream);
-        c->vres = res;
-        todo.push_back(c);
-      }
-    if (!todo.empty()) {
-      int maxn = 1, maxcell = 1;
-      std::vector<CloudView> hv;
-      for (Cloud* c : todo) { hv.push_back(c->view()); maxn = std::max(maxn, c->n); maxcell = std::max(maxcell, c->vcell); }
-      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
-      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      run_grid_build<GRID_VGICP>(ctx, dv.p, (int)hv.size(), maxn, maxcell);
-      dim3 g(blocks_for(std::min(maxcell, maxn), 8, std::max(1, 8 * ctx.num_sms / (int)hv.size())), (unsigned)hv.size());
-      {
-        ProfScope ps(ctx, PROF_VOXEL_REDUCE, 0.0);
-        B2R_LAUNCH(ctx, vgicp_reduce_kernel, g, 256, 0, dv.p);
-      }
-      B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  // the flags go up now: the views below must describe the finished structures
+  for (int i : todo_grid) clouds[i]->has_grid = true;
+  for (int i : todo_cov) clouds[i]->cov_k = cov_k;
+  for (int i : todo_vox) clouds[i]->vres = needs[i].vres;
+  for (int i : todo_ndt) clouds[i]->leaf = needs[i].leaf;
+
+  // ---- one upload: [views in caller order | grid todo | cov todo | voxel todo | ndt todo]
+  std::vector<CloudView> hv;
+  hv.reserve(clouds_in.size() + todo_grid.size() + todo_cov.size() + todo_vox.size() + todo_ndt.size());
+  for (size_t i = 0; i < clouds_in.size(); ++i) hv.push_back(clouds[slot_of[i]]->view());
+  size_t off_grid = hv.size();
+  for (int i : todo_grid) hv.push_back(clouds[i]->view());
+  size_t off_cov = hv.size();
+  for (int i : todo_cov) hv.push_back(clouds[i]->view());
+  size_t off_vox = hv.size();
+  for (int i : todo_vox) hv.push_back(clouds[i]->view());
+  size_t off_ndt = hv.size();
+  for (int i : todo_ndt) hv.push_back(clouds[i]->view());
+  dviews.alloc(std::max<size_t>(1, hv.size()), ctx.stream);
+  if (!hv.empty()) B2R_CUDA(cudaMemcpyAsync(dviews.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
+
+  // scratch for the scans: the largest (clouds x tiles) of the three grid kinds
+  auto stage_dims = [&](const std::vector<int>& todo, int kind, int& maxn, int& maxcell) {
+    maxn = 1; maxcell = 1;
+    for (int i : todo) {
+      maxn = std::max(maxn, clouds[i]->n);
+      maxcell = std::max(maxcell, kind == 0 ? clouds[i]->ncell : (kind == 1 ? clouds[i]->vcell : clouds[i]->ncell_ndt));
     }
+  };
+  size_t tile_need = 0;
+  int mn[3], mc[3];
+  const std::vector<int>* todos[3] = {&todo_grid, &todo_vox, &todo_ndt};
+  for (int kd = 0; kd < 3; ++kd) {
+    stage_dims(*todos[kd], kd, mn[kd], mc[kd]);
+    tile_need = std::max(tile_need, todos[kd]->size() * (size_t)((mc[kd] + kScanTile - 1) / kScanTile));
   }
-  // ---- NDT grids
-  {
-    std::vector<Cloud*> todo;
-    for (size_t i = 0; i < clouds.size(); ++i)
-      if (needs[i].leaf > 0 && clouds[i]->leaf != needs[i].leaf && clouds[i]->n > 0) {
-        Cloud* c = clouds[i];
-        const float leaf = needs[i].leaf, inv_leaf = 1.0f / leaf;
-        int64_t dx = (int64_t)((c->bmax[0] - c->bmin[0]) * inv_leaf) + 1, dy = (int64_t)((c->bmax[1] - c->bmin[1]) * inv_leaf) + 1,
-                dz = (int64_t)((c->bmax[2] - c->bmin[2]) * inv_leaf) + 1;
-        c->leaf = leaf;
-        c->ndt_overflow = dx * dy * dz > (int64_t)INT32_MAX;  // PCL: warn, grid stays empty
-        long tot = 1;
-        for (int d = 0; d < 3; ++d) {
-          c->min_b[d] = (int)std::floor(c->bmin[d] * inv_leaf);
-          c->max_b[d] = (int)std::floor(c->bmax[d] * inv_leaf);
-          c->div_b[d] = c->max_b[d] - c->min_b[d] + 1;
-          tot *= c->div_b[d];
-        }
-        if (c->ndt_overflow) { c->ncell_ndt = 0; continue; }
-        if (tot > (1l << 26)) throw Error(B2R_ERR_CAPACITY, "NDT voxel table too large for this extent/resolution");
-        c->ncell_ndt = (int)tot;
-        c->n_start.alloc((size_t)tot + 1, ctx.stream);
-        c->n_cnt.alloc((size_t)tot, ctx.stream);
-        c->n_cnt.zero(ctx.stream);
-        c->n_table.alloc((size_t)tot, ctx.stream);
-        c->n_order.alloc((size_t)c->n * 2, ctx.stream);
-        c->n_reccell.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
-        c->nrec.alloc((size_t)std::min<long>(tot, c->n), ctx.stream);
-        c->n_nrec.alloc(1, ctx.stream);
-        todo.push_back(c);
-      }
-    if (!todo.empty()) {
-      int maxn = 1, maxcell = 1;
-      std::vector<CloudView> hv;
-      for (Cloud* c : todo) { hv.push_back(c->view()); maxn = std::max(maxn, c->n); maxcell = std::max(maxcell, c->ncell_ndt); }
-      DBuf<CloudView> dv; dv.alloc(hv.size(), ctx.stream);
-      B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * hv.size(), cudaMemcpyHostToDevice, ctx.stream));
-      run_grid_build<GRID_NDT>(ctx, dv.p, (int)hv.size(), maxn, maxcell);
-      dim3 g(blocks_for(std::min(maxcell, maxn), 8, std::max(1, 8 * ctx.num_sms / (int)hv.size())), (unsigned)hv.size());
-      {
-        ProfScope ps(ctx, PROF_VOXEL_REDUCE, 0.0);
-        B2R_LAUNCH(ctx, ndt_reduce_kernel, g, 256, 0, dv.p);
-      }
-      B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-    }
+  DBuf<unsigned long long> tile_tot;
+  if (tile_need) tile_tot.alloc(tile_need, ctx.stream);
+
+  if (!todo_grid.empty())
+    run_grid_build<GRID_NN>(ctx, dviews.p + off_grid, (int)todo_grid.size(), mn[0], mc[0], tile_tot.p, (mc[0] + kScanTile - 1) / kScanTile);
+  if (!todo_cov.empty()) {
+    std::vector<Cloud*> cl;
+    int maxn = 1;
+    for (int i : todo_cov) { cl.push_back(clouds[i]); maxn = std::max(maxn, clouds[i]->n); }
+    launch_knn_cov(ctx, dviews.p + off_cov, cl, cov_k, maxn, nullptr);
+  }
+  if (!todo_vox.empty()) {
+    const int nc = (int)todo_vox.size();
+    run_grid_build<GRID_VGICP>(ctx, dviews.p + off_vox, nc, mn[1], mc[1], tile_tot.p, (mc[1] + kScanTile - 1) / kScanTile);
+    dim3 g(blocks_for(std::min(mc[1], mn[1]), 8, std::max(1, 8 * ctx.num_sms / nc)), (unsigned)nc);
+    ProfScope ps(ctx, PROF_VOXEL_REDUCE, 0.0);
+    B2R_LAUNCH(ctx, vgicp_reduce_kernel, g, 256, 0, dviews.p + off_vox);
+  }
+  if (!todo_ndt.empty()) {
+    const int nc = (int)todo_ndt.size();
+    run_grid_build<GRID_NDT>(ctx, dviews.p + off_ndt, nc, mn[2], mc[2], tile_tot.p, (mc[2] + kScanTile - 1) / kScanTile);
+    dim3 g(blocks_for(std::min(mc[2], mn[2]), 8, std::max(1, 8 * ctx.num_sms / nc)), (unsigned)nc);
+    ProfScope ps(ctx, PROF_VOXEL_REDUCE, 0.0);
+    B2R_LAUNCH(ctx, ndt_reduce_kernel, g, 256, 0, dviews.p + off_ndt);
   }
 }
 
@@ -886,10 +897,8 @@ void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, 
   std::vector<Cloud*> cl{&c};
   std::vector<Needs> nd(1);
   nd[0].grid = true;
-  clouds_prepare(ctx, cfg, cl, nd);
-  CloudView hv = c.view();
-  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<CloudView> dv;
+  clouds_prepare(ctx, cfg, cl, nd, dv);
   DBuf<float4> dq; dq.alloc(nq, ctx.stream);
   DBuf<int32_t> di; di.alloc(nq * k, ctx.stream);
   DBuf<float> dd; dd.alloc(nq * k, ctx.stream);
@@ -904,8 +913,13 @@ void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* kn
   std::vector<Cloud*> cl{&c};
   std::vector<Needs> nd(1);
   nd[0].grid = true;
-  clouds_prepare(ctx, cfg, cl, nd);
-  c.cov.alloc((size_t)c.n * 6, ctx.stream);
+  DBuf<CloudView> dv0;
+  clouds_prepare(ctx, cfg, cl, nd, dv0);
+  if (!c.cov.p || c.cov_k == 0) {
+    ArenaPlan plan;
+    plan.want(c.cov.p, (size_t)c.n * 6);
+    c.mem.push_back(plan.commit(ctx.stream));
+  }
   CloudView hv = c.view();
   DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));

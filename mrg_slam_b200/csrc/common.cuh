@@ -150,6 +150,7 @@ struct CloudView {
   int ncell;
   int* cell_start;  // ncell + 1
   int* cell_cnt;    // ncell (count, then scatter cursor)
+  int* cell_tmp;    // n: point indices grouped by cell in scatter (arbitrary) order, before the in-cell ranking
   float4* spts;
   // per-point covariances (original order)
   double* cov;
@@ -159,7 +160,7 @@ struct CloudView {
   int vcell;
   int* v_start;   // vcell + 1
   int* v_cnt;     // vcell
-  int* v_order;   // n, point indices grouped by voxel
+  int* v_order;   // 2n: [0,n) point indices grouped by voxel, ascending inside a voxel; [n,2n) the same in scatter order
   int* v_table;   // vcell: record id or -1
   VoxRec* vrec;
   int* v_nrec;    // [1] number of records

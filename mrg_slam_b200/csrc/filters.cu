@@ -186,11 +186,11 @@ __global__ void radius_keep_kernel(const CloudView* __restrict__ views, float r2
   keep[__float_as_int(p.w)] = k > min_nb ? 1 : 0;
 }
 
+// a cloud object over the caller's device points (borrowed: the filters only need it for the duration of the call)
 static void with_temp_cloud(Ctx& ctx, const float4* in, int n, Cloud& tmp) {
   tmp.device = ctx.device;
   tmp.n = n;
-  tmp.pts.alloc(n, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(tmp.pts.p, in, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx.stream));
+  tmp.pts.p = const_cast<float4*>(in);
 }
 
 void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out) {
@@ -203,10 +203,8 @@ void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, dou
   std::vector<Cloud*> cl{&tmp};
   std::vector<Needs> nd(1);
   nd[0].grid = true;
-  clouds_prepare(ctx, c2, cl, nd);
-  CloudView hv = tmp.view();
-  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<CloudView> dv;
+  clouds_prepare(ctx, c2, cl, nd, dv);
   DBuf<uint8_t> keep; keep.alloc(n, ctx.stream);
   const float r2 = (float)(radius * radius);
   B2R_LAUNCH(ctx, radius_keep_kernel, (n + 127) / 128, 128, 0, dv.p, r2, min_nb, keep.p);
@@ -266,10 +264,8 @@ void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n
   std::vector<Cloud*> cl{&tmp};
   std::vector<Needs> nd(1);
   nd[0].grid = true;
-  clouds_prepare(ctx, cfg, cl, nd);
-  CloudView hv = tmp.view();
-  DBuf<CloudView> dv; dv.alloc(1, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<CloudView> dv;
+  clouds_prepare(ctx, cfg, cl, nd, dv);
   DBuf<float> dist; dist.alloc(n, ctx.stream);
   {
     const int kk = mean_k + 1, nb128 = (n + 127) / 128;

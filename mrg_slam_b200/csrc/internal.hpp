@@ -8,11 +8,50 @@
 
 namespace b2r {
 
+// One stream-ordered device allocation shared by the structures carved out of it (cudaFreeAsync when the last user dies).
+struct Arena {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t s = nullptr;
+  Arena() = default;
+  Arena(const Arena&) = delete;
+  Arena& operator=(const Arena&) = delete;
+  ~Arena() { if (p) cudaFreeAsync(p, s); }
+};
+// Collects the buffers of a build step, then carves all of them out of ONE allocation: a batch of clouds costs one
+// cudaMallocAsync and one memset (the zero-initialised buffers come first) instead of a dozen per cloud.
+struct ArenaPlan {
+  struct Slot { void** dst; size_t off; bool zeroed; };
+  std::vector<Slot> slots;
+  size_t zbytes = 0, bytes = 0;
+  static size_t up(size_t v) { return (v + 255) & ~(size_t)255; }
+  template <typename T> void want(T*& dst, size_t count) { slots.push_back({(void**)&dst, bytes, false}); bytes = up(bytes + count * sizeof(T)); }
+  template <typename T> void want_zeroed(T*& dst, size_t count) { slots.push_back({(void**)&dst, zbytes, true}); zbytes = up(zbytes + count * sizeof(T)); }
+  bool empty() const { return slots.empty(); }
+  std::shared_ptr<Arena> commit(cudaStream_t stream) {
+    auto a = std::make_shared<Arena>();
+    a->s = stream;
+    a->bytes = zbytes + bytes;
+    if (a->bytes) {
+      B2R_CUDA(cudaMallocAsync(&a->p, a->bytes, stream));
+      if (zbytes) B2R_CUDA(cudaMemsetAsync(a->p, 0, zbytes, stream));
+    }
+    for (const Slot& sl : slots) *sl.dst = (char*)a->p + (sl.zeroed ? sl.off : zbytes + sl.off);
+    return a;
+  }
+};
+
+template <typename T>
+struct Ref {  // non-owning device pointer into one of the cloud's arenas
+  T* p = nullptr;
+};
+
 // Device-resident cloud with lazily built, cached search structures.
 struct Cloud {
   int device = 0;
   int n = 0;
-  DBuf<float4> pts;
+  std::vector<std::shared_ptr<Arena>> mem;  // keeps every buffer below alive
+  Ref<float4> pts;
   bool has_bbox = false;
   float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
   // NN grid
@@ -20,24 +59,24 @@ struct Cloud {
   float h = 0.f;
   int gd[3] = {0, 0, 0};
   int ncell = 0;
-  DBuf<int> cell_start, cell_cnt;
-  DBuf<float4> spts;
+  Ref<int> cell_start, cell_cnt, cell_tmp;
+  Ref<float4> spts;
   // covariances
   int cov_k = 0;  // k the covariances were built with (0 = none)
-  DBuf<double> cov;
+  Ref<double> cov;
   // VGICP voxel map
   double vres = 0.0;  // resolution the map was built with (0 = none)
   int vmin[3] = {0, 0, 0}, vd[3] = {0, 0, 0};
   int vcell = 0;
-  DBuf<int> v_start, v_cnt, v_order, v_table, v_nrec, v_reccell;
-  DBuf<VoxRec> vrec;
+  Ref<int> v_start, v_cnt, v_order, v_table, v_nrec, v_reccell;
+  Ref<VoxRec> vrec;
   // NDT grid
   float leaf = 0.f;  // leaf the grid was built with (0 = none)
   int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0};
   int ncell_ndt = 0;
   bool ndt_overflow = false;
-  DBuf<int> n_start, n_cnt, n_order, n_table, n_nrec, n_reccell;
-  DBuf<NdtRec> nrec;
+  Ref<int> n_start, n_cnt, n_order, n_table, n_nrec, n_reccell;
+  Ref<NdtRec> nrec;
 
   CloudView view() const;
 };
@@ -67,9 +106,12 @@ struct Handle {
 };
 
 // ---- cloud.cu ----
-void cloud_upload(Ctx& ctx, Cloud& c, const void* points, size_t n, size_t stride_bytes, int memspace);
-// builds whatever of `needs[i]` is missing in clouds[i]; batched launches over all clouds
-void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds, const std::vector<Needs>& needs);
+// uploads `count` clouds into one shared allocation and computes their bounding boxes; one synchronisation at the end
+void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, const size_t* n, size_t count, size_t stride_bytes, int memspace);
+// Builds whatever of `needs[i]` is missing in clouds[i] (batched launches over all clouds, no synchronisation after the
+// bounding boxes are known) and returns the device array of the clouds' views, in the order given: dviews.p[i].
+void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds, const std::vector<Needs>& needs,
+                    DBuf<CloudView>& dviews);
 void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, size_t nq, int k, int32_t* idx_out, float* d2_out);
 void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* knn_out);
 
