@@ -23,6 +23,7 @@ CloudView Cloud::view() const {
   v.pts = pts.p; v.n = n;
   for (int d = 0; d < 3; ++d) { v.bmin[d] = bmin[d]; v.bmax[d] = bmax[d]; }
   v.h = h; v.inv_h = h > 0 ? 1.0f / h : 0.f;
+  v.hx = hx; v.inv_hx = hx > 0 ? 1.0f / hx : 0.f;
   for (int d = 0; d < 3; ++d) v.gd[d] = gd[d];
   v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.cell_tmp = cell_tmp.p; v.spts = spts.p;
   v.cov = cov.p;
@@ -306,31 +307,45 @@ __global__ void grid_scatter_kernel(const CloudView* __restrict__ views) {
   const CloudView& c = views[blockIdx.y];
   int* cnt = grid_cnt<MODE>(c);
   const int* start = grid_start<MODE>(c);
-  int* tmp = MODE == GRID_NN ? c.cell_tmp : (MODE == GRID_VGICP ? c.v_order + c.n : c.n_order + c.n);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(&c.pts[i]);
     const int key = cell_key<MODE>(c, p);
-    tmp[start[key] + atomicAdd(&cnt[key], 1)] = i;
+    const int pos = start[key] + atomicAdd(&cnt[key], 1);
+    if (MODE == GRID_NN) c.cell_tmp[pos] = make_int2(float_order_key(p.x), i);
+    else if (MODE == GRID_VGICP) c.v_order[c.n + pos] = i;
+    else c.n_order[c.n + pos] = i;
   }
 }
-// ... then every entry finds its rank among the indices of its cell and moves there: cells end up sorted by original
-// index, so the cell-sorted copy (tie-breaks by position, summation orders) is identical from run to run.  One thread
-// per entry; the cell's index list is read by all of its entries (L1-resident).
+// ... then every entry finds its rank inside its cell and moves there, so that the result is identical from run to run
+// (tie-breaks by position, summation orders).  Voxel lists: ascending point index.  NN grid: ascending (x, point index),
+// which makes every row of cells along x one run sorted by x (knn.cuh sweeps it outwards from the query).  One thread
+// per entry; the cell's list is read by all of its entries (L1-resident).
 template <int MODE>
 __global__ void grid_rank_kernel(const CloudView* __restrict__ views) {
   const CloudView& c = views[blockIdx.y];
   const int* start = grid_start<MODE>(c);
-  const int* tmp = MODE == GRID_NN ? c.cell_tmp : (MODE == GRID_VGICP ? c.v_order + c.n : c.n_order + c.n);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c.n; j += gridDim.x * blockDim.x) {
-    const int i = tmp[j];
-    const float4 p = __ldg(&c.pts[i]);
-    const int key = cell_key<MODE>(c, p);
-    const int s = start[key], e = start[key + 1];
-    int rank = 0;
-    for (int t = s; t < e; ++t) rank += (tmp[t] < i) ? 1 : 0;
-    if (MODE == GRID_NN) c.spts[s + rank] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-    else if (MODE == GRID_VGICP) c.v_order[s + rank] = i;
-    else c.n_order[s + rank] = i;
+    if (MODE == GRID_NN) {
+      const int2 me = c.cell_tmp[j];
+      const float4 p = __ldg(&c.pts[me.y]);
+      const int key = cell_key<MODE>(c, p);
+      const int s = start[key], e = start[key + 1];
+      int rank = 0;
+      for (int t = s; t < e; ++t) {
+        const int2 o = c.cell_tmp[t];
+        rank += (o.x < me.x || (o.x == me.x && o.y < me.y)) ? 1 : 0;
+      }
+      c.spts[s + rank] = make_float4(p.x, p.y, p.z, __int_as_float(me.y));
+    } else {
+      int* order = MODE == GRID_VGICP ? c.v_order : c.n_order;
+      const int* tmp = order + c.n;
+      const int i = tmp[j];
+      const int key = cell_key<MODE>(c, __ldg(&c.pts[i]));
+      const int s = start[key], e = start[key + 1];
+      int rank = 0;
+      for (int t = s; t < e; ++t) rank += (tmp[t] < i) ? 1 : 0;
+      order[s + rank] = i;
+    }
   }
 }
 
@@ -466,21 +481,18 @@ __global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __rest
 //           d2 <= dk (the k nearest; ties beyond k are resolved towards the lower position on a rare slow path);
 //   then    covariance = E[d d^T] - E[d] E[d]^T (shift-invariant, so identical to the centred sum of the reference up
 //           to rounding ~1e-15), symmetric 3x3 Jacobi eigen-decomposition, PLANE regularisation (1, 1, 1e-3).
-#ifndef B2R_COV_PASS2_XPRUNE
-#define B2R_COV_PASS2_XPRUNE true
-#endif
 struct CovAccum {
   double s[9];
   int cnt;
 };
 struct CovVisitor {
-  const CloudView& c;
   float qx, qy, qz, dk;
   bool ties;  // accept d2 == dk as well as d2 < dk
   int k;
   int32_t* knn_row;
   CovAccum a;
   __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
+  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > dk; }
   __device__ __forceinline__ void add(const float4& p) {
     const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;
     a.s[0] += dx; a.s[1] += dy; a.s[2] += dz;
@@ -488,26 +500,19 @@ struct CovVisitor {
     if (knn_row && a.cnt < k) knn_row[a.cnt] = __float_as_int(p.w);
     ++a.cnt;
   }
-  __device__ __forceinline__ void run(int s, int e) {
-    for (int j = s; j < e; ++j) {
-      const float4 p = __ldg(&c.spts[j]);
-      const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
-      if (d2 < dk || (ties && d2 == dk)) add(p);
-    }
+  __device__ __forceinline__ void test(const float4& p, int) {
+    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+    if (d2 < dk || (ties && d2 == dk)) add(p);
   }
 };
 // lowest position > after whose distance equals dk exactly
 struct TieVisitor {
-  const CloudView& c;
   float qx, qy, qz, dk;
   int after, found;
   __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
-  __device__ __forceinline__ void run(int s, int e) {
-    for (int j = max(s, after + 1); j < e; ++j) {
-      if (j >= found) break;
-      const float4 p = __ldg(&c.spts[j]);
-      if (dist2_flann(qx, qy, qz, p.x, p.y, p.z) == dk) found = j;
-    }
+  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > dk; }
+  __device__ __forceinline__ void test(const float4& p, int j) {
+    if (j > after && j < found && dist2_flann(qx, qy, qz, p.x, p.y, p.z) == dk) found = j;
   }
 };
 // more than k points within dk (exact ties at the k-th distance): strictly closer ones, then ties by ascending position.
@@ -516,12 +521,12 @@ __device__ __noinline__ CovAccum cov_accumulate_ties(const CloudView* cp, float 
                                                      int32_t* knn_row) {
   const CloudView& c = *cp;
   const QueryCell q = query_cell(c, qx, qy, qz);
-  CovVisitor v{c, qx, qy, qz, dk, false, k, knn_row, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
-  visit_ring<false>(c, q, r, false, v);
+  CovVisitor v{qx, qy, qz, dk, false, k, knn_row, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
+  visit_rows(c, q, qx, r, false, v);
   int last = -1;
   while (v.a.cnt < k) {
-    TieVisitor tv{c, qx, qy, qz, dk, last, INT_MAX};
-    visit_ring<false>(c, q, r, false, tv);
+    TieVisitor tv{qx, qy, qz, dk, last, INT_MAX};
+    visit_rows(c, q, qx, r, false, tv);
     if (tv.found == INT_MAX) break;
     v.add(__ldg(&c.spts[tv.found]));
     last = tv.found;
@@ -540,12 +545,12 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const CloudView* __restric
   float dk;
   int r;
   {
-    TopkVisitor<K> tv(c, sp.x, sp.y, sp.z);
+    TopkVisitor<K> tv(sp.x, sp.y, sp.z);
     r = knn_topk<K>(c, q, k, tv);
     dk = topk_kth<K>(tv.d, k);
   }
-  CovVisitor v{c, sp.x, sp.y, sp.z, dk, true, k, knn_out ? knn_out + (size_t)orig * k : nullptr, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
-  visit_ring<B2R_COV_PASS2_XPRUNE>(c, q, r, false, v);  // dk is final and tight here: trimming rows pays
+  CovVisitor v{sp.x, sp.y, sp.z, dk, true, k, knn_out ? knn_out + (size_t)orig * k : nullptr, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
+  visit_rows(c, q, sp.x, r, false, v);  // same rows again, now with the final k-th distance as the radius
   if (v.a.cnt > k) v.a = cov_accumulate_ties(&c, sp.x, sp.y, sp.z, r, dk, k, v.knn_row);
   const double kk = (double)k;
   const double mx = v.a.s[0] / kk, my = v.a.s[1] / kk, mz = v.a.s[2] / kk;
@@ -576,17 +581,17 @@ __global__ void __launch_bounds__(64) knn_query_kernel(const CloudView* __restri
   if (qi >= nq) return;
   const float4 p = __ldg(&queries[qi]);
   const QueryCell q = query_cell(c, p.x, p.y, p.z);
-  TopkKeyVisitor<32> v(c, p.x, p.y, p.z);
-  int r = cells_outside(c, q.cx, q.cy, q.cz) + 1;
-  visit_ring<false>(c, q, r, false, v);
+  TopkKeyVisitor<32> v(p.x, p.y, p.z);
+  int r = rows_outside(c, q) + 1;
+  visit_rows(c, q, p.x, r, false, v);
   for (;;) {
     unsigned long long kth = v.d[31];
 #pragma unroll
     for (int i = 30; i >= 0; --i) kth = (i >= k - 1) ? v.d[i] : kth;
-    if (kth != ~0ull && __uint_as_float((unsigned)(kth >> 32)) <= ring_safe_d2(r, c.h)) break;
-    if (ring_covers_grid(c, q.cx, q.cy, q.cz, r)) break;
+    if (kth != ~0ull && __uint_as_float((unsigned)(kth >> 32)) <= ring_safe_d2(r, c.h) + q.xout2) break;
+    if (ring_covers_grid(c, q, r)) break;
     ++r;
-    visit_ring<false>(c, q, r, true, v);
+    visit_rows(c, q, p.x, r, true, v);
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -604,23 +609,28 @@ __global__ void __launch_bounds__(64) knn_query_kernel(const CloudView* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ host orchestration
+// Cell size along y and z.  Rows of cells are swept along x from the query outwards (knn.cuh), so the y/z size trades
+// the number of rows a query touches against the width of the strip it sweeps; ~2 mean point spacings works best.
 static float auto_cell_size(const Cloud& c, const b2r_config& cfg) {
   if (cfg.nn_cell_size > 0) return (float)cfg.nn_cell_size;
   double dx = std::max(1e-3f, c.bmax[0] - c.bmin[0]), dy = std::max(1e-3f, c.bmax[1] - c.bmin[1]);
-  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 2.0; }();
+  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 3.0; }();
   double h = factor * std::sqrt(dx * dy / std::max(1, c.n));
   return (float)std::min(4.0, std::max(0.05, h));
 }
 
 static void grid_dims(Cloud& c, float h) {
+  // cells along x only index into the sorted rows: smaller ones shorten the part of a row scanned unconditionally
+  static const float xfactor = [] { const char* e = getenv("B2R_NN_XCELL_FACTOR"); return e ? (float)atof(e) : 0.34f; }();
   const long cap = 1l << 24;
   for (;;) {
+    const float hx = h * xfactor;
     long tot = 1;
     for (int d = 0; d < 3; ++d) {
-      c.gd[d] = (int)std::floor((c.bmax[d] - c.bmin[d]) / h) + 1;
+      c.gd[d] = (int)std::floor((c.bmax[d] - c.bmin[d]) / (d == 0 ? hx : h)) + 1;
       tot *= c.gd[d];
     }
-    if (tot <= cap) { c.ncell = (int)tot; c.h = h; return; }
+    if (tot <= cap) { c.ncell = (int)tot; c.h = h; c.hx = hx; return; }
     h *= 1.26f;
   }
 }

@@ -144,13 +144,15 @@ struct CloudView {
   const float4* pts;  // original order: x,y,z,intensity
   int n;
   float bmin[3], bmax[3];
-  // exact-NN grid (uniform, dense cell table; points copied in cell order, w = original index bits)
+  // exact-NN grid (dense cell table; cells of size hx along x and h along y, z; points copied in cell order and, inside a
+  // cell, in ascending x: every row of cells along x is one run of the array sorted by x; w = original index bits)
   float h, inv_h;
+  float hx, inv_hx;
   int gd[3];
   int ncell;
   int* cell_start;  // ncell + 1
   int* cell_cnt;    // ncell (count, then scatter cursor)
-  int* cell_tmp;    // n: point indices grouped by cell in scatter (arbitrary) order, before the in-cell ranking
+  int2* cell_tmp;   // n: (ordered x bits, point index) grouped by cell in scatter (arbitrary) order, before the in-cell ranking
   float4* spts;
   // per-point covariances (original order)
   double* cov;
@@ -227,16 +229,14 @@ __device__ __forceinline__ float dist2_flann(float ax, float ay, float az, float
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ void nn_cell_of(const CloudView& c, float x, float y, float z, int& cx, int& cy, int& cz) {
-  cx = clampi((int)floorf((x - c.bmin[0]) * c.inv_h), 0, c.gd[0] - 1);
+  cx = clampi((int)floorf((x - c.bmin[0]) * c.inv_hx), 0, c.gd[0] - 1);
   cy = clampi((int)floorf((y - c.bmin[1]) * c.inv_h), 0, c.gd[1] - 1);
   cz = clampi((int)floorf((z - c.bmin[2]) * c.inv_h), 0, c.gd[2] - 1);
 }
-// unclamped variant for queries that may lie outside the grid
-__device__ __forceinline__ void nn_cell_of_unclamped(const CloudView& c, float x, float y, float z, int& cx, int& cy, int& cz) {
-  const float big = 1.0e9f;
-  cx = (int)fminf(fmaxf(floorf((x - c.bmin[0]) * c.inv_h), -big), big);
-  cy = (int)fminf(fmaxf(floorf((y - c.bmin[1]) * c.inv_h), -big), big);
-  cz = (int)fminf(fmaxf(floorf((z - c.bmin[2]) * c.inv_h), -big), big);
+// total order on floats as ints (negative values reversed; NaNs sort to the ends): keeps "ascending x" well defined
+__device__ __forceinline__ int float_order_key(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
 }
 
 // fast_gicp voxel_coord: floor(x / resolution - 0.5) in double

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(128) sor_distance_kernel(const CloudView* __re
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= c.n) return;
   const float4 p = __ldg(&c.spts[qi]);
-  TopkVisitor<K> v(c, p.x, p.y, p.z);
+  TopkVisitor<K> v(p.x, p.y, p.z);
   knn_topk<K>(c, query_cell(c, p.x, p.y, p.z), mean_k + 1, v);
   double sum = 0.0;
 #pragma unroll

@@ -56,10 +56,11 @@ struct Cloud {
   float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
   // NN grid
   bool has_grid = false;
-  float h = 0.f;
+  float h = 0.f, hx = 0.f;
   int gd[3] = {0, 0, 0};
   int ncell = 0;
-  Ref<int> cell_start, cell_cnt, cell_tmp;
+  Ref<int> cell_start, cell_cnt;
+  Ref<int2> cell_tmp;
   Ref<float4> spts;
   // covariances
   int cov_k = 0;  // k the covariances were built with (0 = none)

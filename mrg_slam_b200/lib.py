@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIB_PATH") or os.path.join(_DIR, "libb2r.so")  # override: kernel experiments only
 
 NDT_OMP, FAST_GICP, FAST_VGICP = 0, 1, 2
 DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
