@@ -41,7 +41,7 @@ SEED_SCAN0 = 100
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2r", choices=["b2r", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
@@ -77,7 +77,7 @@ class ClockSampler:
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
                                           str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -139,22 +139,25 @@ def oracle_chain(O, method, clouds):
     return n_ok
 
 
-def cpu_sample(method, budget_s=12.0, max_pairs=16):
+def cpu_sample(method, budget_s=12.0, n_pairs=16):
+    """Bounded CPU sample: the first `n_pairs` pairs of the same chain, repeated until ~budget_s of CPU work is done."""
     from tests import oraclelib as O
-    raws = make_scans(max_pairs + 1, SEED_SCAN0)
+    raws = make_scans(n_pairs + 1, SEED_SCAN0)
     clouds = [oracle_prefilter(O, r) for r in raws]
     O.set_num_threads(0)
     cores = O.max_threads()
     oracle_chain(O, method, clouds[:2])  # warm-up
     t0 = time.perf_counter()
     done = 0
-    while done < max_pairs and time.perf_counter() - t0 < budget_s:
-        oracle_chain(O, method, clouds[done:done + 2])
+    while time.perf_counter() - t0 < budget_s:
+        i = done % n_pairs
+        oracle_chain(O, method, clouds[i:i + 2])
         done += 1
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{done} consecutive-scan pairs of the same workload (~{int(np.mean([len(c) for c in clouds]))} pts/cloud), "
-                      f"oracle restatement of fast_gicp/pclomp with OpenMP on {cores} threads, {dt:.1f} s"}, clouds
+            "sample": f"{done} aligns over the first {n_pairs} consecutive-scan pairs of the same workload "
+                      f"(~{int(np.mean([len(c) for c in clouds]))} pts/cloud), oracle restatement of fast_gicp/pclomp with OpenMP on "
+                      f"{cores} threads, {dt:.1f} s"}, clouds
 
 
 def run_reference(args):
@@ -251,6 +254,7 @@ def run_b2r(args):
     total_ms = 0.0
     conv = 0
     barrier()
+    torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed steps (no effect otherwise)
     for _ in range(args.steps):
         flush.fill_(1)
         barrier()
@@ -266,7 +270,7 @@ def run_b2r(args):
         total_ms += ms + (t0.elapsed_time(t1) if world > 1 else 0.0)
         conv += sum(r.converged for r in res)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    torch.cuda.profiler.stop()
     launches = reg.kernel_launches() - launches0
     prof = {k: reg.profile_read(k) for k in B.PROFILE_KERNELS}
     reg.profile_enable(False)
@@ -283,6 +287,7 @@ def run_b2r(args):
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
 
     tt = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -300,6 +305,21 @@ def run_b2r(args):
         dom = max(prof, key=lambda k: prof[k]["ms"])
         d = prof[dom]
         achieved = (d["bytes"] / max(d["launches"], 1)) / (d["ms"] / max(d["launches"], 1) * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same workload
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(f"{args.method}:{P}", {}).get(dom)
+            if ent:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+        except Exception:
+            pass
+        per_kernel = {}
+        for k, v in prof.items():
+            if v["ms"] > 0:
+                gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+                per_kernel[k] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                                 "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -310,11 +330,13 @@ def run_b2r(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+                         "kernel_us_per_launch": 1e3 * d["ms"] / max(d["launches"], 1),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "algorithmic bytes (SURVEY 8d: 40 B/point for kNN covariances) / CUDA-event duration of the dominant "
                                  "kernel; exact 20-NN search is compute/latency-bound, not HBM-bound (DESIGN.md)",
-                         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+                         "kernels": per_kernel},
             "converged_fraction": conv / float(P * args.steps),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -146,6 +146,9 @@ b2r_status b2r_prefilter(b2r_handle* h, const b2r_prefilter_config* cfg, const v
 /* ---- introspection for parity tests and benchmarks ---- */
 uint64_t b2r_kernel_launches(const b2r_handle* h); /* kernels launched by this handle so far */
 b2r_status b2r_synchronize(b2r_handle* h);
+/* kNN-covariance queries (on this device, since library load) whose in-kernel candidate log overflowed and took the
+ * second-traversal path: a tuning counter for the exact-kNN grid, results are identical either way */
+b2r_status b2r_debug_knn_list_overflows(b2r_handle* h, uint64_t* out);
 /* which: 0 = source, 1 = target.  cov6 = xx,xy,xz,yy,yz,zz per point; knn (n*k int32, ascending distance) optional */
 b2r_status b2r_debug_covariances(b2r_handle* h, int which, double* cov6_out, int32_t* knn_out);
 /* VGICP voxel map of the target, sorted by (x,y,z) voxel coordinate; arrays sized for *V <= n_target voxels */

@@ -465,6 +465,11 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
 // ------------------------------------------------------------------------------------------------ introspection
 uint64_t b2r_kernel_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.launches : 0; }
 
+b2r_status b2r_debug_knn_list_overflows(b2r_handle* hh, uint64_t* out) {
+  if (!out) return B2R_ERR_INVALID_ARG;
+  return guarded(hh, [&](Handle& h) { *out = debug_knn_list_overflows(h.ctx); });
+}
+
 b2r_status b2r_synchronize(b2r_handle* hh) {
   return guarded(hh, [&](Handle& h) { B2R_CUDA(cudaStreamSynchronize(h.ctx.stream)); });
 }

@@ -534,23 +534,52 @@ __device__ __noinline__ CovAccum cov_accumulate_ties(const CloudView* cp, float 
   return v.a;
 }
 
+__device__ unsigned long long g_knn_list_overflows = 0;  // queries whose candidate log overflowed (second traversal taken)
+#ifdef B2R_KNN_STATS
+__device__ unsigned long long g_knn_hist[66];
+#endif
+constexpr int kKnnThreads = 128;
+constexpr int kKnnListCap = 56;     // logged candidates per query kept in shared memory (28 KB per block)
+constexpr int kKnnListSpill = 72;   // further ones in per-thread local memory (~5 % of the queries of a prefiltered HDL-64 scan)
+
 template <int K>
-__global__ void __launch_bounds__(128) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+__global__ void __launch_bounds__(kKnnThreads, 7) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+  __shared__ int s_list[kKnnListCap * kKnnThreads];
   const CloudView& c = views[blockIdx.y];
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= c.n) return;
   const float4 sp = __ldg(&c.spts[qi]);
   const int orig = __float_as_int(sp.w);
   const QueryCell q = query_cell(c, sp.x, sp.y, sp.z);
-  float dk;
-  int r;
-  {
-    TopkVisitor<K> tv(sp.x, sp.y, sp.z);
-    r = knn_topk<K>(c, q, k, tv);
-    dk = topk_kth<K>(tv.d, k);
-  }
+  int spill[kKnnListSpill];
+  TopkListVisitor<K, kKnnListCap, kKnnListSpill> tv(sp.x, sp.y, sp.z, s_list + threadIdx.x, kKnnThreads, spill);
+  const int r = knn_topk<K>(c, q, k, tv);
+  const float dk = topk_kth<K>(tv.d, k);
+  const int logged = tv.cnt;
+#ifdef B2R_KNN_STATS
+  atomicAdd(&g_knn_hist[min(logged / 4, 63)], 1ull);
+  atomicAdd(&g_knn_hist[64], (unsigned long long)tv.tested);
+  atomicAdd(&g_knn_hist[65], (unsigned long long)r);
+#endif
   CovVisitor v{sp.x, sp.y, sp.z, dk, true, k, knn_out ? knn_out + (size_t)orig * k : nullptr, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
-  visit_rows(c, q, sp.x, r, false, v);  // same rows again, now with the final k-th distance as the radius
+  if (logged <= kKnnListCap + kKnnListSpill) {
+    // pass 2 over the logged candidates only, in traversal order.  Branch-free: a rejected candidate is replaced by the
+    // query itself, whose differences are exactly +0.0 and leave every sum unchanged.
+    const double qxd = (double)sp.x, qyd = (double)sp.y, qzd = (double)sp.z;
+    for (int t = 0; t < logged; ++t) {
+      const float4 p = __ldg(&c.spts[tv.logged(t)]);
+      const float d2 = dist2_flann(sp.x, sp.y, sp.z, p.x, p.y, p.z);
+      const bool ok = d2 <= dk;
+      const double dx = (double)(ok ? p.x : sp.x) - qxd, dy = (double)(ok ? p.y : sp.y) - qyd, dz = (double)(ok ? p.z : sp.z) - qzd;
+      v.a.s[0] += dx; v.a.s[1] += dy; v.a.s[2] += dz;
+      v.a.s[3] += dx * dx; v.a.s[4] += dx * dy; v.a.s[5] += dx * dz; v.a.s[6] += dy * dy; v.a.s[7] += dy * dz; v.a.s[8] += dz * dz;
+      if (v.knn_row && ok && v.a.cnt < k) v.knn_row[v.a.cnt] = __float_as_int(p.w);
+      v.a.cnt += ok ? 1 : 0;
+    }
+  } else {
+    atomicAdd(&g_knn_list_overflows, 1ull);
+    visit_rows(c, q, sp.x, r, false, v);  // log overflowed: same rows again, radius = k-th distance
+  }
   if (v.a.cnt > k) v.a = cov_accumulate_ties(&c, sp.x, sp.y, sp.z, r, dk, k, v.knn_row);
   const double kk = (double)k;
   const double mx = v.a.s[0] / kk, my = v.a.s[1] / kk, mz = v.a.s[2] / kk;
@@ -917,6 +946,22 @@ void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, 
   B2R_CUDA(cudaMemcpyAsync(idx_out, di.p, nq * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(d2_out, dd.p, nq * k * 4, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+unsigned long long debug_knn_list_overflows(Ctx& ctx) {
+  unsigned long long v = 0;
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  B2R_CUDA(cudaMemcpyFromSymbol(&v, g_knn_list_overflows, sizeof(v)));
+#ifdef B2R_KNN_STATS
+  unsigned long long hst[66];
+  B2R_CUDA(cudaMemcpyFromSymbol(hst, g_knn_hist, sizeof(hst)));
+  unsigned long long tot = 0;
+  for (int i = 0; i < 64; ++i) tot += hst[i];
+  fprintf(stderr, "knn stats: queries %llu, tested/query %.1f, mean ring %.2f\nlogged histogram (bucket of 4):", tot, (double)hst[64] / tot, (double)hst[65] / tot);
+  for (int i = 0; i < 64; ++i) fprintf(stderr, " %d:%.4f", i * 4, (double)hst[i] / tot);
+  fprintf(stderr, "\n");
+#endif
+  return v;
 }
 
 void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* knn_out) {

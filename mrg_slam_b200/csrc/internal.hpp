@@ -114,6 +114,7 @@ void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, co
 void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& clouds, const std::vector<Needs>& needs,
                     DBuf<CloudView>& dviews);
 void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, size_t nq, int k, int32_t* idx_out, float* d2_out);
+unsigned long long debug_knn_list_overflows(Ctx& ctx);  // per device, since library load
 void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* knn_out);
 
 // ---- lsq.cu (FAST_GICP / FAST_VGICP) ----

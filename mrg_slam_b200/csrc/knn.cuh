@@ -155,10 +155,50 @@ struct TopkVisitor {
   }
 };
 
+// Same top-K, and every candidate that entered it (or tied with its K-th value) is also logged by position: the first
+// CAP in a caller-provided shared-memory column (element t at list[t * stride]), the next SPILL in a per-thread
+// local-memory array (rare; L1-resident).  Every point whose distance is <= the final k-th distance was necessarily
+// logged when it was seen, in traversal order, so a caller that needs the neighbours themselves re-reads just the
+// logged ones instead of traversing the rows a second time.  cnt counts all logged candidates; cnt > CAP + SPILL
+// means entries were dropped and the caller must fall back to a second traversal.
+template <int K, int CAP, int SPILL>
+struct TopkListVisitor {
+  float qx, qy, qz;
+  float d[K];
+  int* list;
+  int stride;
+  int cnt;
+  int* spill;  // SPILL ints of per-thread local memory, kept outside this struct so that d[] stays in registers
+#ifdef B2R_KNN_STATS
+  int tested = 0;
+#endif
+  __device__ __forceinline__ TopkListVisitor(float x, float y, float z, int* l, int s, int* sp)
+      : qx(x), qy(y), qz(z), list(l), stride(s), cnt(0), spill(sp) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) d[i] = INFINITY;
+  }
+  // tie-inclusive pruning: a candidate at exactly the K-th distance must still be seen (and logged)
+  __device__ __forceinline__ float thr() const { return d[K - 1] * (1.f + 1e-6f); }
+  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > d[K - 1]; }
+  __device__ __forceinline__ void test(const float4& p, int j) {
+    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+#ifdef B2R_KNN_STATS
+    ++tested;
+#endif
+    if (d2 <= d[K - 1]) {
+      topk_insert<K>(d, d2);
+      if (cnt < CAP) list[cnt * stride] = j;
+      else if (cnt < CAP + SPILL) spill[cnt - CAP] = j;
+      ++cnt;
+    }
+  }
+  __device__ __forceinline__ int logged(int t) const { return t < CAP ? list[t * stride] : spill[t - CAP]; }
+};
+
 // Exact k smallest squared distances (k <= K, ascending in v.d[0..k)) of the query in cloud c.
 // Returns the (y, z) radius of the scanned rows; v.d[k-1] == INFINITY if the cloud has fewer than k points.
-template <int K>
-__device__ __forceinline__ int knn_topk(const CloudView& c, const QueryCell& q, int k, TopkVisitor<K>& v) {
+template <int K, typename V>
+__device__ __forceinline__ int knn_topk(const CloudView& c, const QueryCell& q, int k, V& v) {
   int r = rows_outside(c, q) + 1;
   visit_rows(c, q, v.qx, r, false, v);
   for (;;) {

@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "b2r_align", "b2r_fitness", "b2r_transform_source", "b2r_fitness_pair", "b2r_align_batch",
     "b2r_distance_filter", "b2r_voxelgrid", "b2r_radius_outlier", "b2r_statistical_outlier",
     "b2r_default_prefilter_config", "b2r_prefilter",
-    "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_covariances", "b2r_debug_voxelmap",
+    "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_knn_list_overflows", "b2r_debug_covariances", "b2r_debug_voxelmap",
     "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
     "b2r_debug_knn", "b2r_last_timings", "b2r_event_record", "b2r_event_elapsed_ms", "b2r_profile_enable", "b2r_profile_read",
 ]
@@ -131,6 +131,7 @@ def load():
     L.b2r_kernel_launches.argtypes = [vp]
     L.b2r_kernel_launches.restype = ctypes.c_uint64
     L.b2r_synchronize.argtypes = [vp]
+    L.b2r_debug_knn_list_overflows.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     L.b2r_debug_covariances.argtypes = [vp, ci, vp, vp]
     L.b2r_debug_voxelmap.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(sz)]
     L.b2r_debug_linearize.argtypes = [vp, vp, vp, vp, ctypes.POINTER(cd), vp, vp]
@@ -371,6 +372,11 @@ class Registration:
         ms, n, by = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
         self._check(self._lib.b2r_profile_read(self._h, PROFILE_KERNELS[kernel], ctypes.byref(ms), ctypes.byref(n), ctypes.byref(by)))
         return dict(ms=ms.value, launches=int(n.value), bytes=by.value)
+
+    def knn_list_overflows(self):
+        v = ctypes.c_uint64(0)
+        self._check(self._lib.b2r_debug_knn_list_overflows(self._h, ctypes.byref(v)))
+        return int(v.value)
 
     def synchronize(self):
         self._check(self._lib.b2r_synchronize(self._h))

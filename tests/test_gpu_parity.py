@@ -119,6 +119,25 @@ def test_knn_bit_exact(reg, vlp16_pair):
     cl.close()
 
 
+def test_knn_cov_candidate_log_overflow_path(vlp16_pair):
+    """knn_cov keeps the candidates that entered the top-k in a bounded shared-memory log; a coarse NN grid makes the log
+    overflow, which must take the second-traversal path and give the same neighbours and covariances."""
+    a, b, _ = vlp16_pair
+    ocov, oknn = O.knn_covariances(b, 20, want_idx=True)
+    for cell in (0.0, 3.0):
+        g = B.Registration(B.default_config(B.FAST_GICP, nn_cell_size=cell))
+        before = g.knn_list_overflows()
+        g.setInputTarget(a); g.setInputSource(b)
+        g.align(np.eye(4))  # builds covariances through the production path (no neighbour export)
+        gcov = g.debug_covariances(0)
+        np.testing.assert_allclose(gcov, ocov, atol=1e-11)
+        took_fallback = g.knn_list_overflows() - before
+        if cell > 0:
+            assert took_fallback > 0
+        _, gknn = g.debug_covariances(0, want_knn=True)
+        assert np.array_equal(np.sort(oknn, 1), np.sort(gknn, 1))
+
+
 # ------------------------------------------------------------------------------------------------ GICP / VGICP
 @pytest.mark.parametrize("method", [B.FAST_VGICP, B.FAST_GICP])
 def test_lsq_intermediates(vlp16_pair, method):

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs into small tracked files under profiles/.
+
+  launches:  tools/ncu_summarize.py launches gpurun_out/launches_X.csv  > profiles/rN/launches_X.md
+  kernel:    tools/ncu_summarize.py kernel gpurun_out/ncu_X.ncu-rep     > profiles/rN/ncu_X.md   (needs ncu here: import only)
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
+    "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.avg.per_cycle_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except Exception:
+            continue
+        if row.get("Metric Unit", "ns") in ("us", "usecond"):
+            v *= 1e3
+        k = row["Kernel Name"].split("(")[0]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"| kernel | launches | total us | share |\n|---|---|---|---|")
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print(f"| `{k[:100]}` | {a[0]} | {a[1] / 1e3:.1f} | {100 * a[1] / tot:.1f}% |")
+    print(f"| **total** | {sum(a[0] for a in agg.values())} | {tot / 1e3:.1f} | |")
+
+
+def kernel(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    print(f"kernel: `{d.get('Kernel Name', ('?',))[0][:120]}`  grid {d.get('Grid Size', ('?',))[0]} block {d.get('Block Size', ('?',))[0]}\n")
+    print("| metric | value | unit |\n|---|---|---|")
+    for k in KEYS:
+        if k in d:
+            print(f"| {k} | {d[k][0]} | {d[k][1]} |")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
