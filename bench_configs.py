@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""The other BASELINE.json configurations (bench.py measures the headline one).  One JSON line per run.
+
+  python bench_configs.py --config ndt_vlp16      configs[0]  single VLP-16 pair, NDT_OMP 0.5 m DIRECT7 (also the CPU-runnable case)
+  python bench_configs.py --config odometry       configs[1]  literal: SERIAL scan_matching_odometry over an HDL-64 sequence
+                                                              (prefilter + FAST_VGICP per scan, keyframe state machine), ms/scan
+  python bench_configs.py --config prefilter      configs[2]  VoxelGrid 0.1 + RADIUS / STATISTICAL on 121,600-ray and 1M-ray clouds
+  python bench_configs.py --config loop_closure   configs[3]  4096 candidate pairs (256 new keyframes x 16 candidates), --method
+                                                              FAST_GICP | NDT_OMP | FAST_VGICP; under torchrun the pairs are sharded
+                                                              by target over the ranks (STRONG scaling) and results all-gathered
+  python bench_configs.py --config submap         configs[4]  3 robots x 50 keyframes against ~200k-point submaps, FAST_VGICP
+
+Timing: CUDA events on the library's stream (`device_ms`) and wall clock around the public call with host buffers
+(`e2e_ms`, H2D/D2H inside).  `--cpu` adds the oracle (CPU restatement, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mrg_slam_b200 import lib as B  # noqa: E402
+from mrg_slam_b200 import loop_closure as LC  # noqa: E402
+from mrg_slam_b200 import synth  # noqa: E402
+from mrg_slam_b200.odometry import OdometryParams, ScanMatchingOdometry  # noqa: E402
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def kernel_table(reg, steps=1):
+    peak = float(peaks().get("hbm_gbs", 6650.0))
+    out = {}
+    for k in B.PROFILE_KERNELS:
+        v = reg.profile_read(k)
+        if v["ms"] > 0:
+            gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            out[k] = {"ms": v["ms"] / steps, "launches": v["launches"] / steps, "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    return out
+
+
+def perturbation(rng, max_t=1.0, max_r=0.1):
+    """U(+-max_t m, +-max_r rad) on each axis."""
+    t = rng.uniform(-max_t, max_t, 3)
+    w = rng.uniform(-max_r, max_r, 3)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + (np.sin(th) / th) * K + ((1 - np.cos(th)) / th ** 2) * K @ K if th > 1e-12 else np.eye(3)
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, t
+    return T
+
+
+def oracle_prefilter(O, c):
+    c = O.distance_filter(c, 0.1, 35.0)
+    c, _ = O.voxelgrid(c, 0.1, 1)
+    return c[O.radius_outlier(c, 0.5, 2)]
+
+
+# ------------------------------------------------------------------------------------------------ configs[0]
+def run_ndt_vlp16(args):
+    reg = B.Registration(B.default_config(B.NDT_OMP, resolution=0.5, neighbor_search=B.DIRECT7))
+    a, b = synth.scan(synth.VLP16, 0), synth.scan(synth.VLP16, 1)
+    variants = {"raw": (a, b), "voxelgrid_0.5": (reg.voxelgrid(a, 0.5)[0], reg.voxelgrid(b, 0.5)[0])}
+    out = {}
+    for name, (ta, sb) in variants.items():
+        ms_dev, ms_e2e, res = [], [], None
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            reg.event_record(0)
+            reg.setInputTarget(ta)
+            reg.setInputSource(sb)
+            res = reg.align(np.eye(4))
+            reg.event_record(1)
+            reg.synchronize()
+            if it >= args.warmup:
+                ms_e2e.append(1e3 * (time.perf_counter() - t0))
+                ms_dev.append(reg.event_elapsed_ms(0, 1))
+        out[name] = {"n_target": len(ta), "n_source": len(sb), "device_ms_median": float(np.median(ms_dev)),
+                     "e2e_ms_median": float(np.median(ms_e2e)), "converged": bool(res.converged), "iterations": res.iterations,
+                     "evals": res.evals}
+        if args.cpu:
+            from tests import oraclelib as O
+            O.set_num_threads(0)
+            o = O.Registration(O.default_params(O.NDT_OMP, resolution=0.5, neighbor_search=O.DIRECT7))
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                o.setInputTarget(ta); o.setInputSource(sb)
+                ro = o.align(np.eye(4))
+                ts.append(1e3 * (time.perf_counter() - t0))
+            d = np.linalg.inv(o.getFinalTransformation()) @ reg.getFinalTransformation()
+            out[name]["cpu_oracle_ms_median"] = float(np.median(ts))
+            out[name]["cpu_cores"] = O.max_threads()
+            out[name]["oracle_iterations"] = ro.iterations
+            out[name]["dT_vs_oracle_m"] = float(np.linalg.norm(d[:3, 3]))
+    return {"config": "configs[0] single VLP-16 pair, NDT_OMP res 0.5 DIRECT7 eps 0.1 max_iter 64, identity guess; every repeat uploads both "
+                      "clouds and rebuilds the NDT grid", "results": out}
+
+
+# ------------------------------------------------------------------------------------------------ configs[1]
+def run_odometry(args):
+    reg = B.Registration(B.default_config(B.FAST_VGICP))
+    n = args.scans
+    raws = [synth.scan(synth.HDL64, args.first_scan + i) for i in range(n)]
+    odo = ScanMatchingOdometry(reg, OdometryParams(), make_cloud=lambda pts: B.Cloud(reg, pts))
+    # warm-up on a throw-away instance (allocator pools, module load)
+    w = ScanMatchingOdometry(reg, OdometryParams(), make_cloud=lambda pts: B.Cloud(reg, pts))
+    for i in range(min(5, n)):
+        w.matching(0.1 * i, reg.prefilter(raws[i]))
+    ms, ms_pre, ms_match, poses, npts = [], [], [], [], []
+    reg.profile_enable(True)
+    l0 = reg.kernel_launches()
+    for i, raw in enumerate(raws):
+        t0 = time.perf_counter()
+        f = reg.prefilter(raw)                      # prefiltering_component (host in, host out — a separate ROS node upstream)
+        t1 = time.perf_counter()
+        poses.append(odo.matching(0.1 * i, f))      # scan_matching_odometry_component::matching
+        reg.synchronize()
+        t2 = time.perf_counter()
+        ms.append(1e3 * (t2 - t0)); ms_pre.append(1e3 * (t1 - t0)); ms_match.append(1e3 * (t2 - t1)); npts.append(len(f))
+    launches = reg.kernel_launches() - l0
+    kt = kernel_table(reg, n)
+    reg.profile_enable(False)
+    gt = [np.linalg.inv(synth.pose(args.first_scan)) @ synth.pose(args.first_scan + i) for i in range(n)]
+    err = [float(np.linalg.norm(p[:3, 3] - g[:3, 3])) for p, g in zip(poses, gt)]
+    path = float(sum(np.linalg.norm(gt[i][:3, 3] - gt[i - 1][:3, 3]) for i in range(1, n)))
+    m = np.array(ms[1:])
+    out = {"config": f"configs[1] literal: serial scan_matching_odometry over {n} synthetic HDL-64 scans (121,600 rays): prefilter "
+                     "(dist 0.1-35, VoxelGrid 0.1, RADIUS 0.5/2) -> FAST_VGICP (res 1.0, k 20) with the keyframe state machine of "
+                     "scan_matching_odometry_component.cpp:195-350; host buffers in and out every scan",
+           "metric": "odom ms/scan", "unit": "ms", "higher_is_better": False,
+           "scans": n, "points_after_prefilter_mean": float(np.mean(npts)),
+           "ms_per_scan": {"p50": float(np.percentile(m, 50)), "p95": float(np.percentile(m, 95)), "max": float(m.max()), "mean": float(m.mean())},
+           "prefilter_ms_p50": float(np.percentile(ms_pre[1:], 50)), "matching_ms_p50": float(np.percentile(ms_match[1:], 50)),
+           "scans_per_s": float(1e3 / m.mean()), "keyframe_switches": odo.keyframe_switches, "not_converged": odo.not_converged,
+           "gpu_launches_per_scan": launches / n, "final_position_error_m": err[-1], "path_length_m": path, "kernels_per_scan": kt}
+    if args.cpu:
+        from tests import oraclelib as O
+        O.set_num_threads(0)
+        nc = min(n, args.cpu_scans)
+        oo = ScanMatchingOdometry(O.Registration(O.default_params(O.FAST_VGICP)), OdometryParams())
+        t, dmax = [], 0.0
+        for i in range(nc):
+            t0 = time.perf_counter()
+            po = oo.matching(0.1 * i, oracle_prefilter(O, raws[i]))
+            t.append(1e3 * (time.perf_counter() - t0))
+            dmax = max(dmax, float(np.linalg.norm(po[:3, 3] - poses[i][:3, 3])))
+        out["cpu_oracle"] = {"scans": nc, "ms_per_scan_p50": float(np.percentile(t[1:], 50)), "cores": O.max_threads(), "kind": "port",
+                             "max_position_difference_vs_gpu_m": dmax, "keyframe_switches": oo.keyframe_switches}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ configs[2]
+def run_prefilter(args):
+    reg = B.Registration(B.default_config(B.FAST_VGICP))
+    out = {}
+    for name, sensor in (("hdl64_121600", synth.HDL64), ("os1_128_1M", synth.OS1_128_1M)):
+        raw = synth.scan(sensor, 7)
+        cases = {}
+        for oname, method in (("radius_0.5_2", 2), ("statistical_30_1.2", 1), ("voxelgrid_only", 0)):
+            cfg = B.PrefilterConfig()
+            reg._lib.b2r_default_prefilter_config(__import__("ctypes").byref(cfg))
+            cfg.outlier_removal_method = method
+            e2e, dev, f = [], [], None
+            for it in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                reg.event_record(0)
+                f = reg.prefilter(raw, cfg)
+                reg.event_record(1)
+                reg.synchronize()
+                if it >= args.warmup:
+                    e2e.append(1e3 * (time.perf_counter() - t0)); dev.append(reg.event_elapsed_ms(0, 1))
+            cases[oname] = {"points_in": len(raw), "points_out": len(f), "device_ms_median": float(np.median(dev)),
+                            "e2e_ms_median": float(np.median(e2e)), "Mpts_per_s_e2e": len(raw) / np.median(e2e) / 1e3,
+                            "Mpts_per_s_device": len(raw) / np.median(dev) / 1e3}
+            if args.cpu:
+                from tests import oraclelib as O
+                O.set_num_threads(0)
+                t0 = time.perf_counter()
+                c = O.distance_filter(raw, 0.1, 35.0)
+                c, _ = O.voxelgrid(c, 0.1, 1)
+                if method == 2:
+                    c = c[O.radius_outlier(c, 0.5, 2)]
+                elif method == 1:
+                    c = c[O.statistical_outlier(c, 30, 1.2)[0]]
+                cases[oname]["cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+                cases[oname]["cpu_cores"] = O.max_threads()
+                cases[oname]["bit_exact_vs_oracle"] = bool(len(c) == len(f) and np.array_equal(c.view(np.uint32), f.view(np.uint32)))
+        out[name] = cases
+    return {"config": "configs[2] prefilter chain (distance 0.1-35 m -> VoxelGrid 0.1 -> outlier removal) through b2r_prefilter with host "
+                      "buffers; the distance filter runs first as the component does (prefiltering_component.cpp:149-151)", "results": out}
+
+
+# ------------------------------------------------------------------------------------------------ configs[3]
+def keyframe_pool(reg, count, first, leaf):
+    """`count` keyframe clouds: prefiltered HDL-64 scans decimated to ~20k points (north-star size) + their ground-truth poses."""
+    clouds, poses = [], []
+    for i in range(count):
+        c = reg.prefilter(synth.scan(synth.HDL64, first + i))
+        c, _ = reg.voxelgrid(c, leaf)
+        clouds.append(c)
+        poses.append(synth.pose(first + i))
+    return clouds, poses
+
+
+def run_loop_closure(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    method = getattr(B, args.method)
+    reg = B.Registration(B.default_config(method, device=local_rank, **({"resolution": 0.5} if args.method == "NDT_OMP" and args.ndt_res05 else {})))
+    n_targets, n_cand = args.pairs // args.candidates, args.candidates
+    half = n_cand // 2
+    pool_np, poses = keyframe_pool(reg, n_targets + n_cand, args.first_scan, args.leaf)
+    rng = np.random.default_rng(0x5EED0004)
+    pairs, guesses = [], []
+    for t in range(n_targets):
+        ti = t + half
+        cands = [ti + o for o in range(-half, half + 1) if o != 0][:n_cand]
+        for ci in cands:
+            pairs.append((ti, ci))
+            gt = np.linalg.inv(poses[ti]) @ poses[ci]          # new keyframe <- candidate
+            guesses.append(gt @ perturbation(rng, args.perturb_t, args.perturb_r))
+    shards = LC.partition_by_target([p[0] for p in pairs], world)
+    mine = shards[rank]
+    needed = sorted({c for i in mine for c in pairs[i]})
+    pin = {c: torch.from_numpy(pool_np[c]).pin_memory() for c in needed}
+    n_mean = float(np.mean([len(pool_np[c]) for c in needed]))
+
+    def step():
+        cl = B.create_clouds(reg, [pin[c].data_ptr() for c in needed], [pin[c].shape[0] for c in needed], B.HOST)
+        byid = dict(zip(needed, cl))
+        full = [byid.get(i) for i in range(len(pool_np))]
+        loops, table = LC.detect_loops(reg, full, pairs, guesses, rank=rank, world_size=world, device=dev)
+        for c in cl:
+            c.close()
+        return loops, table
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    reg.profile_enable(True)
+    l0 = reg.kernel_launches()
+    tt = 0.0
+    barrier()
+    torch.cuda.profiler.start()
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        loops, table = step()
+        torch.cuda.synchronize()
+        tt += time.perf_counter() - t0
+    torch.cuda.profiler.stop()
+    barrier()
+    launches = reg.kernel_launches() - l0
+    kt = kernel_table(reg, args.steps)
+    stage = reg.last_timings()
+    t = torch.tensor([tt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        sec = float(t[0]) / args.steps
+        conv = table[:, 16] != 0
+        accepted = sum(1 for lp in loops if lp.best_candidate is not None)
+        # error of the converged results against ground truth
+        terr = []
+        for i, (ti, ci) in enumerate(pairs):
+            if conv[i]:
+                T = B.from_colmajor(table[i, :16])
+                gt = np.linalg.inv(poses[ti]) @ poses[ci]
+                terr.append(np.linalg.norm((np.linalg.inv(gt) @ T)[:3, 3]))
+        out = {"config": f"configs[3] loop-closure batch: {len(pairs)} candidate pairs = {n_targets} new keyframes x {n_cand} candidates "
+                         f"(target = new keyframe, loop_detector.cpp:104), {args.method}, clouds ~{int(n_mean)} pts (prefiltered HDL-64 + "
+                         f"VoxelGrid {args.leaf}), guesses = ground truth perturbed U(+-{args.perturb_t} m, +-{args.perturb_r} rad), align + "
+                         "getFitnessScore per pair, best-candidate rule on the gathered table; every step uploads the clouds from pinned "
+                         "host memory and rebuilds all search structures",
+               "metric": f"{args.method} loop-closure aligns/s (4096-pair batch)", "unit": "aligns/s", "higher_is_better": True,
+               "scaling": "strong", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "value": len(pairs) / sec, "ms_per_batch": 1e3 * sec, "timing": "e2e wall clock, max over ranks, host clouds -> gathered table",
+               "pairs": len(pairs), "distinct_clouds": len(pool_np), "converged_fraction": float(conv.mean()),
+               "iterations_mean": float(table[:, 17].mean()), "evals_mean": float(table[:, 19].mean()),
+               "loops_accepted": accepted, "median_translation_error_m": float(np.median(terr)) if terr else None,
+               "gpu_launches_per_batch_rank0": launches / args.steps, "rank0_stage_ms_last": stage,
+               "kernels_rank0": kt}
+        if args.cpu and world == 1:
+            from tests import oraclelib as O
+            O.set_num_threads(0)
+            o = O.Registration(O.default_params(getattr(O, args.method)))
+            t0 = time.perf_counter()
+            done, same = 0, 0
+            ns = min(args.cpu_pairs, len(pairs))
+            for i in range(ns):
+                ti, ci = pairs[i]
+                if i == 0 or pairs[i - 1][0] != ti:
+                    o.setInputTarget(pool_np[ti])
+                o.setInputSource(pool_np[ci])
+                r = o.align(guesses[i])
+                fo = o.getFitnessScore()
+                done += 1
+                d = np.linalg.inv(o.getFinalTransformation()) @ B.from_colmajor(table[i, :16])
+                if bool(r.converged) == bool(conv[i]) and np.linalg.norm(d[:3, 3]) < 1e-4 and (not conv[i] or abs(fo - table[i, 20]) <= 1e-3 * abs(fo)):
+                    same += 1
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": done / dt, "unit": "aligns/s", "cores": O.max_threads(), "kind": "port",
+                                   "sample": f"first {ns} pairs of the same batch (align + fitness), oracle with OpenMP, {dt:.1f} s",
+                                   "pairs_matching_gpu_within_tolerance": same}
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ configs[4]
+def run_submap(args):
+    reg = B.Registration(B.default_config(B.FAST_VGICP))
+    robots, per_robot, nb = 3, args.keyframes_per_robot, 10
+    pairs, guesses, clouds_np = [], [], []
+    rng = np.random.default_rng(0x5EED0005)
+    submap_sizes = []
+    for r in range(robots):
+        first = args.first_scan + 400 * r
+        kf, poses = keyframe_pool(reg, per_robot + nb, first, args.leaf)
+        # accumulated submap = union of 10 neighbouring keyframes in the frame of the first of them, voxelised 0.1 m
+        for k in range(per_robot):
+            base = poses[k]
+            parts = []
+            for j in range(k, k + nb):
+                rel = (np.linalg.inv(base) @ poses[j]).astype(np.float32)
+                raw = reg.prefilter(synth.scan(synth.HDL64, first + j))
+                parts.append(np.concatenate([raw[:, :3] @ rel[:3, :3].T + rel[:3, 3], raw[:, 3:]], axis=1).astype(np.float32))
+            sub, _ = reg.voxelgrid(np.concatenate(parts), 0.1)
+            submap_sizes.append(len(sub))
+            si = len(clouds_np); clouds_np.append(sub)
+            qi = len(clouds_np); clouds_np.append(kf[k + nb // 2])
+            gt = np.linalg.inv(base) @ poses[k + nb // 2]          # submap <- keyframe
+            pairs.append((si, qi)); guesses.append(gt @ perturbation(rng, 0.5, 0.05))
+    import torch
+    pin = [torch.from_numpy(c).pin_memory() for c in clouds_np]
+
+    def step():
+        cl = B.create_clouds(reg, [p.data_ptr() for p in pin], [p.shape[0] for p in pin], B.HOST)
+        res = reg.align_batch([cl[q] for _, q in pairs], [cl[s] for s, _ in pairs], guesses, with_fitness=True)
+        for c in cl:
+            c.close()
+        return res
+    for _ in range(args.warmup):
+        step()
+    reg.profile_enable(True)
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = step()
+        reg.synchronize()
+        ts.append(time.perf_counter() - t0)
+    kt = kernel_table(reg, args.steps)
+    sec = float(np.median(ts))
+    return {"config": f"configs[4] multi-robot keyframe-to-submap: {robots} robots x {per_robot} keyframes (~{int(np.mean([len(clouds_np[q]) for _, q in pairs]))} pts) "
+                      f"against accumulated submaps (union of {nb} neighbouring prefiltered scans, VoxelGrid 0.1: ~{int(np.mean(submap_sizes))} pts), "
+                      "FAST_VGICP, target = submap; uploads + structure builds inside the timed region",
+            "metric": "keyframe-to-submap VGICP aligns/s", "unit": "aligns/s", "value": len(pairs) / sec, "ms_per_batch": 1e3 * sec,
+            "pairs": len(pairs), "converged_fraction": float(np.mean([r.converged for r in res])),
+            "iterations_mean": float(np.mean([r.iterations for r in res])), "kernels": kt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=["ndt_vlp16", "odometry", "prefilter", "loop_closure", "submap"])
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a bounded sample")
+    ap.add_argument("--method", default="FAST_GICP", choices=["FAST_VGICP", "FAST_GICP", "NDT_OMP"])
+    ap.add_argument("--pairs", type=int, default=4096)
+    ap.add_argument("--candidates", type=int, default=16)
+    ap.add_argument("--leaf", type=float, default=0.175)
+    ap.add_argument("--perturb-t", type=float, default=1.0)
+    ap.add_argument("--perturb-r", type=float, default=0.1)
+    ap.add_argument("--ndt-res05", action="store_true")
+    ap.add_argument("--cpu-pairs", type=int, default=32)
+    ap.add_argument("--scans", type=int, default=200)
+    ap.add_argument("--cpu-scans", type=int, default=24)
+    ap.add_argument("--first-scan", type=int, default=100)
+    ap.add_argument("--keyframes-per-robot", type=int, default=50)
+    args = ap.parse_args()
+    fn = {"ndt_vlp16": run_ndt_vlp16, "odometry": run_odometry, "prefilter": run_prefilter, "loop_closure": run_loop_closure,
+          "submap": run_submap}[args.config]
+    out = fn(args)
+    if out is not None:
+        out = {"bench": "bench_configs.py", "name": args.config, "data": "synthetic", **out}
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

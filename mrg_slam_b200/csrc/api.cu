@@ -168,6 +168,9 @@ b2r_status b2r_create(const b2r_config* cfg, b2r_handle** out) {
     h.ctx.device = cfg->device;
     B2R_CUDA(cudaSetDevice(cfg->device));
     B2R_CUDA(cudaStreamCreateWithFlags(&h.ctx.stream, cudaStreamNonBlocking));
+    h.ctx.stream_owner = std::make_shared<StreamOwner>();
+    h.ctx.stream_owner->s = h.ctx.stream;
+    h.ctx.stream_owner->device = cfg->device;
     int sms = 0;
     B2R_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     h.ctx.num_sms = sms > 0 ? sms : 148;
@@ -200,7 +203,8 @@ void b2r_destroy(b2r_handle* hh) {
   h.ctx.prof_resolve();
   for (cudaEvent_t e : h.ctx.ev_pool) cudaEventDestroy(e);
   h.ctx.ev_pool.clear();
-  if (h.ctx.stream) { cudaStreamSynchronize(h.ctx.stream); cudaStreamDestroy(h.ctx.stream); }
+  if (h.ctx.stream) cudaStreamSynchronize(h.ctx.stream);
+  h.ctx.stream_owner.reset();  // the stream itself goes away with the last allocation made on it (clouds may outlive the handle)
   delete hh;
 }
 

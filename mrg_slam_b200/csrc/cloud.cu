@@ -722,7 +722,7 @@ void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, co
     c.n = (int)n[i];
     plan.want(c.pts.p, n[i]);
   }
-  std::shared_ptr<Arena> arena = plan.commit(ctx.stream);
+  std::shared_ptr<Arena> arena = plan.commit(ctx);
   DBuf<uint8_t> staging;
   if (stage) {
     size_t tot = 0;
@@ -863,7 +863,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     }
   }
   if (!plan.empty()) {
-    std::shared_ptr<Arena> arena = plan.commit(ctx.stream);
+    std::shared_ptr<Arena> arena = plan.commit(ctx);
     for (const std::vector<int>* t : {&todo_grid, &todo_cov, &todo_vox, &todo_ndt})
       for (int i : *t)
         if (clouds[i]->mem.empty() || clouds[i]->mem.back() != arena) clouds[i]->mem.push_back(arena);
@@ -973,7 +973,7 @@ void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* kn
   if (!c.cov.p || c.cov_k == 0) {
     ArenaPlan plan;
     plan.want(c.cov.p, (size_t)c.n * 6);
-    c.mem.push_back(plan.commit(ctx.stream));
+    c.mem.push_back(plan.commit(ctx));
   }
   CloudView hv = c.view();
   DBuf<CloudView> dv; dv.alloc(1, ctx.stream);

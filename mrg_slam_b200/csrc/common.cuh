@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -35,10 +36,21 @@ struct ProfRec {
   double bytes;
 };
 
+// The handle's stream, shared with every allocation made on it: a cloud may outlive the handle that created it
+// (b2r_cloud_destroy after b2r_destroy), and its stream-ordered frees still need a live stream.
+struct StreamOwner {
+  cudaStream_t s = nullptr;
+  int device = 0;
+  ~StreamOwner() {
+    if (s) { cudaSetDevice(device); cudaStreamDestroy(s); }
+  }
+};
+
 // Execution context of one handle: device, stream, launch counter, optional per-kernel event timing.
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  std::shared_ptr<StreamOwner> stream_owner;
   uint64_t launches = 0;
   int num_sms = 148;
   bool profile = false;
@@ -215,6 +227,18 @@ __device__ __forceinline__ void block_reduce_to(double* v, double* smem, double*
     out[k] = s;
   }
   __syncthreads();
+}
+
+// Block-wide integer sum (every thread gets the result).  smem: blockDim/32 ints; ends with a barrier.
+__device__ __forceinline__ int block_sum_int(int v, int* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  int s = 0;
+  for (int w = 0; w < nwarp; ++w) s += smem[w];
+  __syncthreads();
+  return s;
 }
 
 // FLANN L2_Simple squared distance: float accumulation in dimension order, no FMA contraction.

@@ -13,6 +13,7 @@ struct Arena {
   void* p = nullptr;
   size_t bytes = 0;
   cudaStream_t s = nullptr;
+  std::shared_ptr<StreamOwner> keep;  // keeps s alive until the free below has been enqueued
   Arena() = default;
   Arena(const Arena&) = delete;
   Arena& operator=(const Arena&) = delete;
@@ -28,9 +29,11 @@ struct ArenaPlan {
   template <typename T> void want(T*& dst, size_t count) { slots.push_back({(void**)&dst, bytes, false}); bytes = up(bytes + count * sizeof(T)); }
   template <typename T> void want_zeroed(T*& dst, size_t count) { slots.push_back({(void**)&dst, zbytes, true}); zbytes = up(zbytes + count * sizeof(T)); }
   bool empty() const { return slots.empty(); }
-  std::shared_ptr<Arena> commit(cudaStream_t stream) {
+  std::shared_ptr<Arena> commit(const Ctx& ctx) {
+    cudaStream_t stream = ctx.stream;
     auto a = std::make_shared<Arena>();
     a->s = stream;
+    a->keep = ctx.stream_owner;
     a->bytes = zbytes + bytes;
     if (a->bytes) {
       B2R_CUDA(cudaMallocAsync(&a->p, a->bytes, stream));

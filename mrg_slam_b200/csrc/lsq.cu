@@ -15,7 +15,8 @@
 namespace b2r {
 
 enum { PH_LINEARIZE = 0, PH_TRIAL = 1, PH_DONE = 2 };
-constexpr int kAcc = 28;  // Hrr(6) Hrt(9) Htt(6) b(6) err(1)
+constexpr int kAcc = 28;   // Hrr(6) Hrt(9) Htt(6) b(6) err(1)
+constexpr int kPart = 29;  // per-block partials: the kAcc sums + the number of correspondences (measurement only)
 
 struct LsqState {
   double x0[12];  // R row-major (9), t (3)
@@ -24,6 +25,8 @@ struct LsqState {
   double H[36], b[6], d[6];
   double y0, yi, lambda, nu;
   int phase, outer, inner, converged, nr_iterations, evals, failed, pad;
+  double corr_last;  // correspondences of the last linearisation
+  double work_pts, work_corr;  // source points / correspondences processed over all evaluations (algorithmic-bytes accounting)
 };
 
 struct LsqParams {
@@ -89,6 +92,7 @@ __device__ __forceinline__ void accumulate(double* acc, const double* M, double 
 // Phase TRIAL: err at xi with the correspondences and M of x0 (fast_gicp compute_error semantics).
 __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                         const LsqState* __restrict__ states, LsqParams prm, double* __restrict__ partials,
+                                                        int32_t* __restrict__ corr_cache, const long long* __restrict__ corr_off,
                                                         int32_t* __restrict__ corr_out, uint8_t* __restrict__ corr_valid) {
   const int pair = blockIdx.y;
   const LsqState& st = states[pair];
@@ -104,6 +108,10 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
   double acc[kAcc];
 #pragma unroll
   for (int t = 0; t < kAcc; ++t) acc[t] = 0.0;
+  int ncorr = 0;
+  // FastGICP keeps correspondences_ from update_correspondences (linearize) for compute_error: position in the
+  // target's cell-sorted copy or -1, one int per source point of the pair
+  int32_t* cc = corr_cache ? corr_cache + corr_off[pair] : nullptr;
   float Tf[12];
   if (prm.method == B2R_FAST_GICP) {
 #pragma unroll
@@ -140,6 +148,7 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
         sym3_inverse(S, M);
         const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
         const double w = sqrt((double)__ldg(&v.n));
+        ++ncorr;
         if (lin) {
           accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
         } else {
@@ -163,11 +172,20 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
         s = __fadd_rn(s, __fmul_rn(Tf[r * 3 + 2], p.z));
         q[r] = __fadd_rn(s, Tf[9 + r]);
       }
-      float d2;
-      const int pos = nn1_search(tgt, q[0], q[1], q[2], prm.corr_max_d2, d2);
-      const bool ok = pos >= 0 && (double)d2 < prm.corr_thr2;
+      int pos;
+      bool ok;
+      if (!lin && cc) {
+        pos = cc[i];
+        ok = pos >= 0;
+      } else {
+        float d2;
+        pos = nn1_search(tgt, q[0], q[1], q[2], prm.corr_max_d2, d2);
+        ok = pos >= 0 && (double)d2 < prm.corr_thr2;
+        if (cc) cc[i] = ok ? pos : -1;
+      }
       if (corr_out) corr_out[i] = ok ? __float_as_int(tgt.spts[pos].w) : -1;
       if (ok) {
+        ++ncorr;
         const float4 tq = __ldg(&tgt.spts[pos]);
         const double* pcb = tgt.cov + (size_t)__float_as_int(tq.w) * 6;
         double S[6], M[6];
@@ -185,9 +203,11 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
       }
     }
   }
-  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kAcc;
+  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kPart;
   if (lin) {
     block_reduce_to<kAcc>(acc, red, out);
+    const int bc = block_sum_int(ncorr, (int*)red);
+    if (threadIdx.x == 0) out[28] = (double)bc;
   } else {
     double e[1] = {acc[27]};
     block_reduce_to<1>(e, red, out + 27);
@@ -278,7 +298,7 @@ __device__ void lsq_finish(LsqState& s, int* done_count) {
 // One warp per pair: fixed-order sum of the chunk partials, then the LM state machine of
 // LsqRegistration::computeTransformation / step_lm advanced by one evaluation.
 __global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqParams prm, const double* __restrict__ partials, int chunks,
-                                int* __restrict__ done_count) {
+                                const int* __restrict__ src_n, int* __restrict__ done_count) {
   const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= npairs) return;
@@ -286,15 +306,19 @@ __global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqPa
   const int phase = s.phase;
   if (phase == PH_DONE) return;
   double v = 0.0;
-  if (lane < kAcc && (phase == PH_LINEARIZE || lane == 27)) {
-    const double* p = partials + (size_t)pair * chunks * kAcc + lane;
-    for (int c = 0; c < chunks; ++c) v += p[(size_t)c * kAcc];
+  if (lane < kPart && (phase == PH_LINEARIZE || lane == 27)) {
+    const double* p = partials + (size_t)pair * chunks * kPart + lane;
+    for (int c = 0; c < chunks; ++c) v += p[(size_t)c * kPart];
   }
+  const double ncorr = __shfl_sync(0xffffffffu, v, 28);
   double a[kAcc];
 #pragma unroll
   for (int t = 0; t < kAcc; ++t) a[t] = __shfl_sync(0xffffffffu, v, t);
   if (lane != 0) return;
   s.evals++;
+  if (phase == PH_LINEARIZE) s.corr_last = ncorr;
+  s.work_pts += (double)src_n[pair];
+  s.work_corr += s.corr_last;
   if (phase == PH_LINEARIZE) {
     // unpack the symmetric system
     const int rr[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
@@ -385,6 +409,7 @@ __global__ void lsq_init_kernel(LsqState* __restrict__ states, int npairs, const
   s.nu = 2.0;
   s.phase = PH_LINEARIZE;
   s.outer = 0; s.inner = 0; s.converged = 0; s.nr_iterations = 0; s.evals = 0; s.failed = 0;
+  s.corr_last = 0.0; s.work_pts = 0.0; s.work_corr = 0.0;
   if (max_iterations <= 0) { s.phase = PH_DONE; atomicAdd(done_count, 1); }
 }
 
@@ -413,16 +438,29 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   const int np = (int)pairs.size();
   if (np == 0) return;
   int maxn = 1;
-  double total_pts = 0.0;
-  for (int i = 0; i < np; ++i) { maxn = std::max(maxn, src_sizes[i]); total_pts += src_sizes[i]; }
+  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
   const int chunks = pick_chunks(ctx, np, maxn);
   const LsqParams prm = make_params(cfg);
   DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
   DBuf<LsqState> ds; ds.alloc(np, ctx.stream);
   DBuf<float> dg; dg.alloc((size_t)np * 16, ctx.stream);
-  DBuf<double> part; part.alloc((size_t)np * chunks * kAcc, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)np * chunks * kPart, ctx.stream);
   DBuf<int> done; done.alloc(1, ctx.stream);
   done.zero(ctx.stream);
+  DBuf<int> dn; dn.alloc(np, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dn.p, src_sizes, sizeof(int) * np, cudaMemcpyHostToDevice, ctx.stream));
+  // FAST_GICP: correspondence cache, one int per source point of every pair
+  DBuf<int32_t> corr;
+  DBuf<long long> coff;
+  std::vector<long long> hoff;
+  if (cfg.method == B2R_FAST_GICP) {
+    hoff.resize(np);
+    long long tot = 0;
+    for (int i = 0; i < np; ++i) { hoff[i] = tot; tot += src_sizes[i]; }
+    corr.alloc((size_t)std::max(1ll, tot), ctx.stream);
+    coff.alloc(np, ctx.stream);
+    B2R_CUDA(cudaMemcpyAsync(coff.p, hoff.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, ctx.stream));
+  }
   B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(dg.p, guesses_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, dg.p, cfg.maximum_iterations, done.p);
@@ -435,12 +473,11 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   while (hdone < np && rounds < max_rounds) {
     for (int r = 0; r < rounds_per_check; ++r) {
       {
-        // 40 B per source point + one 64 B voxel record (VGICP) or 40 B target point+cov (GICP)
-        // per correspondence; upper bound with every point matched and every pair still active
-        ProfScope ps(ctx, PROF_LSQ_EVAL, total_pts * (cfg.method == B2R_FAST_VGICP ? 104.0 : 80.0));
-        B2R_LAUNCH(ctx, lsq_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr, (uint8_t*)nullptr);
+        ProfScope ps(ctx, PROF_LSQ_EVAL, 0.0);  // bytes are added below from the work the device actually did
+        B2R_LAUNCH(ctx, lsq_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, prm, part.p, corr.p, coff.p, (int32_t*)nullptr,
+                   (uint8_t*)nullptr);
       }
-      B2R_LAUNCH(ctx, lsq_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, done.p);
+      B2R_LAUNCH(ctx, lsq_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, dn.p, done.p);
     }
     rounds += rounds_per_check;
     B2R_CUDA(cudaMemcpyAsync(&hdone, done.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
@@ -450,6 +487,13 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   std::vector<LsqState> hs(np);
   B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(LsqState) * np, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  if (ctx.profile) {
+    // per evaluation pass 40 B per source point + one 64 B voxel record (VGICP) or 40 B target
+    // point + covariance (GICP) per correspondence, summed over the passes each pair actually ran
+    double wp = 0.0, wc = 0.0;
+    for (int i = 0; i < np; ++i) { wp += hs[i].work_pts; wc += hs[i].work_corr; }
+    ctx.prof_bytes[PROF_LSQ_EVAL] += 40.0 * wp + (cfg.method == B2R_FAST_VGICP ? 64.0 : 40.0) * wc;
+  }
   for (int i = 0; i < np; ++i) {
     const LsqState& s = hs[i];
     b2r_result& r = out[i];
@@ -482,7 +526,7 @@ void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_vie
   PairDesc pd{0, 1};
   DBuf<PairDesc> dp; dp.alloc(1, ctx.stream);
   DBuf<LsqState> ds; ds.alloc(1, ctx.stream);
-  DBuf<double> part; part.alloc((size_t)chunks * kAcc, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)chunks * kPart, ctx.stream);
   part.zero(ctx.stream);
   DBuf<int32_t> dc;
   DBuf<uint8_t> dvld;
@@ -495,9 +539,9 @@ void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_vie
   }
   B2R_CUDA(cudaMemcpyAsync(dp.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, &s, sizeof(s), cudaMemcpyHostToDevice, ctx.stream));
-  B2R_LAUNCH(ctx, lsq_eval_kernel, dim3(chunks, 1), 256, 0, d_views, dp.p, ds.p, prm, part.p, corr_out ? dc.p : nullptr,
-             corr_out ? dvld.p : nullptr);
-  std::vector<double> hp((size_t)chunks * kAcc);
+  B2R_LAUNCH(ctx, lsq_eval_kernel, dim3(chunks, 1), 256, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr, (const long long*)nullptr,
+             corr_out ? dc.p : nullptr, corr_out ? dvld.p : nullptr);
+  std::vector<double> hp((size_t)chunks * kPart);
   B2R_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, ctx.stream));
   if (corr_out) {
     B2R_CUDA(cudaMemcpyAsync(corr_out, dc.p, sizeof(int32_t) * n_src * (vg ? 3 : 1), cudaMemcpyDeviceToHost, ctx.stream));
@@ -506,7 +550,7 @@ void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_vie
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
   double a[kAcc] = {0};
   for (int c = 0; c < chunks; ++c)
-    for (int t = 0; t < kAcc; ++t) a[t] += hp[(size_t)c * kAcc + t];
+    for (int t = 0; t < kAcc; ++t) a[t] += hp[(size_t)c * kPart + t];
   *err = a[27];
   if (H && !trial) {
     const int rr[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};

@@ -14,7 +14,8 @@ namespace b2r {
 
 enum { NP_INIT = 0, NP_MT_FIRST = 1, NP_MT_LOOP = 2, NP_MT_HESS = 3, NP_DONE = 4 };
 enum { EV_GRAD_HESS = 0, EV_GRAD = 1, EV_HESS = 2 };
-constexpr int kNdtAcc = 43;  // score, g(6), H(36)
+constexpr int kNdtAcc = 43;   // score, g(6), H(36)
+constexpr int kNdtPart = 44;  // per-block partials: the kNdtAcc sums + the number of voxel hits (measurement only)
 
 struct NdtState {
   double p[6], x_t[6], dir[6], p_eval[6];
@@ -23,6 +24,7 @@ struct NdtState {
   float M[16];  // column-major transform used by the pending evaluation (= final_transformation_)
   int interval_converged, open_interval, step_iterations;
   int phase, eval_mode, nr_iterations, converged, evals;
+  double work_pts, work_hits;  // source points / voxel hits processed over all evaluations (algorithmic-bytes accounting)
 };
 
 struct NdtParams {
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restri
   for (int t = 0; t < kNdtAcc; ++t) acc[t] = 0.0;
   const int noff = prm.neighbor_search == B2R_DIRECT1 ? 1 : (prm.neighbor_search == B2R_DIRECT7 ? 7 : 27);
   const bool have_grid = tgt.ncell_ndt > 0;
+  int nhits = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
     const float4 xo = __ldg(&src.pts[i]);
     // transformPointCloud, PCL association (x*c0 + y*c1) + (z*c2 + c3)
@@ -196,8 +199,12 @@ __global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restri
       }
     }
     if (hits_out) hits_out[i] = hits;
+    nhits += hits;
   }
-  block_reduce_to<kNdtAcc>(acc, red, partials + ((size_t)pair * gridDim.x + blockIdx.x) * kNdtAcc);
+  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kNdtPart;
+  block_reduce_to<kNdtAcc>(acc, red, out);
+  const int bh = block_sum_int(nhits, (int*)red);
+  if (threadIdx.x == 0) out[43] = (double)bh;
 }
 
 // ---- step-kernel helpers (one thread per pair) ----
@@ -416,7 +423,7 @@ __device__ bool ndt_mt_continue(NdtState& s, const NdtParams& prm) {
 }
 
 __global__ void ndt_step_kernel(NdtState* __restrict__ states, int npairs, NdtParams prm, const double* __restrict__ partials, int chunks,
-                                int* __restrict__ done_count) {
+                                const int* __restrict__ src_n, int* __restrict__ done_count) {
   const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= npairs) return;
@@ -426,17 +433,20 @@ __global__ void ndt_step_kernel(NdtState* __restrict__ states, int npairs, NdtPa
   // fixed-order sum of the chunk partials: lane l sums elements l and l+32
   double v0 = 0.0, v1 = 0.0;
   {
-    const double* p = partials + (size_t)pair * chunks * kNdtAcc;
+    const double* p = partials + (size_t)pair * chunks * kNdtPart;
     for (int c = 0; c < chunks; ++c) {
-      v0 += p[(size_t)c * kNdtAcc + lane];
-      if (lane + 32 < kNdtAcc) v1 += p[(size_t)c * kNdtAcc + lane + 32];
+      v0 += p[(size_t)c * kNdtPart + lane];
+      if (lane + 32 < kNdtPart) v1 += p[(size_t)c * kNdtPart + lane + 32];
     }
   }
+  const double nhits = __shfl_sync(0xffffffffu, v1, 43 - 32);
   double a[kNdtAcc];
 #pragma unroll
   for (int t = 0; t < kNdtAcc; ++t) a[t] = t < 32 ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
   if (lane != 0) return;
   s.evals++;
+  s.work_pts += (double)src_n[pair];
+  s.work_hits += nhits;
   const int mode = s.eval_mode;
   if (mode != EV_HESS) {
     s.score = a[0];
@@ -535,17 +545,18 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   const int np = (int)pairs.size();
   if (np == 0) return;
   int maxn = 1;
-  double total_pts = 0.0;
-  for (int i = 0; i < np; ++i) { maxn = std::max(maxn, src_sizes[i]); total_pts += src_sizes[i]; }
+  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
   const int chunks = ndt_chunks(ctx, np, maxn);
   const NdtParams prm = make_ndt_params(cfg);
   std::vector<NdtState> hs(np);
   for (int i = 0; i < np; ++i) ndt_init_state(hs[i], guesses_colmajor + (size_t)i * 16);
   DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
   DBuf<NdtState> ds; ds.alloc(np, ctx.stream);
-  DBuf<double> part; part.alloc((size_t)np * chunks * kNdtAcc, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)np * chunks * kNdtPart, ctx.stream);
   DBuf<int> done; done.alloc(1, ctx.stream);
   done.zero(ctx.stream);
+  DBuf<int> dn; dn.alloc(np, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dn.p, src_sizes, sizeof(int) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, hs.data(), sizeof(NdtState) * np, cudaMemcpyHostToDevice, ctx.stream));
   const dim3 ge(chunks, np);
@@ -558,11 +569,10 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   while (hdone < np && rounds < max_rounds) {
     for (int r = 0; r < rounds_per_check; ++r) {
       {
-        // 16 B per source point + 64 B per voxel hit; upper bound with 7 hits (DIRECT7) per point
-        ProfScope ps(ctx, PROF_NDT_EVAL, total_pts * (16.0 + 64.0 * (cfg.neighbor_search == B2R_DIRECT1 ? 1 : 7)));
+        ProfScope ps(ctx, PROF_NDT_EVAL, 0.0);  // bytes are added below from the work the device actually did
         B2R_LAUNCH(ctx, ndt_eval_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
       }
-      B2R_LAUNCH(ctx, ndt_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, done.p);
+      B2R_LAUNCH(ctx, ndt_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, dn.p, done.p);
     }
     rounds += rounds_per_check;
     B2R_CUDA(cudaMemcpyAsync(&hdone, done.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
@@ -571,6 +581,12 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   }
   B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(NdtState) * np, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  if (ctx.profile) {
+    // per derivative pass 16 B per source point + 64 B per voxel hit, over the passes each pair ran
+    double wp = 0.0, wh = 0.0;
+    for (int i = 0; i < np; ++i) { wp += hs[i].work_pts; wh += hs[i].work_hits; }
+    ctx.prof_bytes[PROF_NDT_EVAL] += 16.0 * wp + 64.0 * wh;
+  }
   for (int i = 0; i < np; ++i) {
     const NdtState& s = hs[i];
     b2r_result& r = out[i];
@@ -596,19 +612,19 @@ void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_v
   PairDesc pd{0, 1};
   DBuf<PairDesc> dp; dp.alloc(1, ctx.stream);
   DBuf<NdtState> ds; ds.alloc(1, ctx.stream);
-  DBuf<double> part; part.alloc((size_t)chunks * kNdtAcc, ctx.stream);
+  DBuf<double> part; part.alloc((size_t)chunks * kNdtPart, ctx.stream);
   DBuf<int32_t> dh;
   if (hits_out) dh.alloc(n_src, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dp.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, &s, sizeof(s), cudaMemcpyHostToDevice, ctx.stream));
   B2R_LAUNCH(ctx, ndt_eval_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
-  std::vector<double> hp((size_t)chunks * kNdtAcc);
+  std::vector<double> hp((size_t)chunks * kNdtPart);
   B2R_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, ctx.stream));
   if (hits_out) B2R_CUDA(cudaMemcpyAsync(hits_out, dh.p, sizeof(int32_t) * n_src, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
   double a[kNdtAcc] = {0};
   for (int c = 0; c < chunks; ++c)
-    for (int t = 0; t < kNdtAcc; ++t) a[t] += hp[(size_t)c * kNdtAcc + t];
+    for (int t = 0; t < kNdtAcc; ++t) a[t] += hp[(size_t)c * kNdtPart + t];
   *score = a[0];
   for (int i = 0; i < 6; ++i) grad6[i] = a[1 + i];
   for (int i = 0; i < 36; ++i) hess36[i] = a[7 + i];

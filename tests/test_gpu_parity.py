@@ -375,3 +375,21 @@ def test_error_behaviour():
     launches = g.kernel_launches()
     assert launches > 0
     g.close(); g3.close()
+
+
+def test_cloud_may_outlive_its_handle(vlp16_pair):
+    """b2r_cloud_destroy after b2r_destroy of the creating handle (Python GC order is arbitrary) must be safe, and a
+    cloud created through one handle is usable from another handle on the same device."""
+    a, b, _ = vlp16_pair
+    r1 = B.Registration(B.default_config(B.FAST_VGICP))
+    ca, cb = B.Cloud(r1, a), B.Cloud(r1, b)
+    r1.setInputTarget(ca); r1.setInputSource(cb)
+    ref = r1.align(np.eye(4))
+    T1 = r1.getFinalTransformation()
+    r1.close()
+    r2 = B.Registration(B.default_config(B.FAST_VGICP))
+    r2.setInputTarget(ca); r2.setInputSource(cb)
+    res = r2.align(np.eye(4))
+    assert res.iterations == ref.iterations and np.array_equal(T1, r2.getFinalTransformation())
+    r2.close()
+    ca.close(); cb.close()
