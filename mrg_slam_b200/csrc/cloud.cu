@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(64) knn_query_kernel(const CloudView* __restri
 static float auto_cell_size(const Cloud& c, const b2r_config& cfg) {
   if (cfg.nn_cell_size > 0) return (float)cfg.nn_cell_size;
   double dx = std::max(1e-3f, c.bmax[0] - c.bmin[0]), dy = std::max(1e-3f, c.bmax[1] - c.bmin[1]);
-  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 3.0; }();
+  static const double factor = [] { const char* e = getenv("B2R_NN_CELL_FACTOR"); return e ? atof(e) : 2.5; }();
   double h = factor * std::sqrt(dx * dy / std::max(1, c.n));
   return (float)std::min(4.0, std::max(0.05, h));
 }

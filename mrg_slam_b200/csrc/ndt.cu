@@ -84,8 +84,13 @@ __device__ __forceinline__ float mad3(float a0, float b0, float a1, float b1, fl
   return s;
 }
 
+__device__ __forceinline__ float mad2(float a1, float b1, float a2, float b2) {
+  return __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2));
+}
+
 // grid = (chunks, pairs).  Evaluates score / gradient / Hessian of the pending transform of each active pair.
-__global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+constexpr int kNdtThreads = 128;
+__global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                         const NdtState* __restrict__ states, NdtParams prm, double* __restrict__ partials,
                                                         int32_t* __restrict__ hits_out) {
   const int pair = blockIdx.y;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restri
   __shared__ AngTables tab;
   __shared__ float T[16];
   __shared__ double red[kNdtAcc * 4];
+  __shared__ int s_rec[27 * kNdtThreads];  // usable leaves of each thread's current point (<= 27 with DIRECT27)
   if (threadIdx.x == 0) ndt_angle_tables(st.p_eval, tab);
   if (threadIdx.x < 16) T[threadIdx.x] = st.M[threadIdx.x];
   __syncthreads();
@@ -117,10 +123,10 @@ __global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restri
     const float xt2 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[2]), __fmul_rn(xo.y, T[6])), __fadd_rn(__fmul_rn(xo.z, T[10]), T[14]));
     // lookup key: float DIVISION by the leaf size (getNeighborhoodAtPoint)
     const int i0 = (int)floorf(__fdiv_rn(xt0, tgt.leaf)), i1 = (int)floorf(__fdiv_rn(xt1, tgt.leaf)), i2 = (int)floorf(__fdiv_rn(xt2, tgt.leaf));
+    // getNeighborhoodAtPoint: collect the usable leaves first (same order as the reference visits them), then process
+    // them hit by hit — the lanes of a warp then work on their k-th hit together instead of idling through the
+    // neighbour offsets where only some of them have a leaf
     int hits = 0;
-    bool have_pd = false;
-    float pg[8];   // point_gradient entries (1,3) (2,3) (0,4) (1,4) (2,4) (0,5) (1,5) (2,5)
-    float ph[15];  // a(1,2) b(1,2) c(1,2) d(0..2) e(0..2) f(0..2)
     for (int o = 0; o < noff && have_grid; ++o) {
       int ox, oy, oz;
       neighbor_offset(prm.neighbor_search, o, ox, oy, oz);
@@ -129,18 +135,22 @@ __global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restri
       const int idx = (c0 - tgt.min_b[0]) + (c1 - tgt.min_b[1]) * tgt.div_b[0] + (c2 - tgt.min_b[2]) * tgt.div_b[0] * tgt.div_b[1];
       const int rec = __ldg(&tgt.n_table[idx]);
       if (rec < 0) continue;
-      const NdtRec& L = tgt.nrec[rec];
-      if (__ldg(&L.n) < 6) continue;
+      if (__ldg(&tgt.nrec[rec].n) < 6) continue;
+      s_rec[hits * kNdtThreads + threadIdx.x] = rec;
       ++hits;
-      if (!have_pd) {  // computePointDerivatives (float), once per point
-        have_pd = true;
+    }
+    float pg[8];   // point_gradient entries (1,3) (2,3) (0,4) (1,4) (2,4) (0,5) (1,5) (2,5)
+    float ph[15];  // a(1,2) b(1,2) c(1,2) d(0..2) e(0..2) f(0..2)
+    if (hits > 0) {  // computePointDerivatives (float), once per point
 #pragma unroll
-        for (int r = 0; r < 8; ++r) pg[r] = dot3f(tab.j[r], xo.x, xo.y, xo.z);
-        if (do_hess) {
+      for (int r = 0; r < 8; ++r) pg[r] = dot3f(tab.j[r], xo.x, xo.y, xo.z);
+      if (do_hess) {
 #pragma unroll
-          for (int r = 0; r < 15; ++r) ph[r] = dot3f(tab.h[r], xo.x, xo.y, xo.z);
-        }
+        for (int r = 0; r < 15; ++r) ph[r] = dot3f(tab.h[r], xo.x, xo.y, xo.z);
       }
+    }
+    for (int hh = 0; hh < hits; ++hh) {
+      const NdtRec& L = tgt.nrec[s_rec[hh * kNdtThreads + threadIdx.x]];
       // updateDerivatives (float inner math)
       const float x0 = (float)((double)xt0 - __ldg(&L.mean[0]));
       const float x1 = (float)((double)xt1 - __ldg(&L.mean[1]));
@@ -158,40 +168,48 @@ __global__ void __launch_bounds__(128) ndt_eval_kernel(const CloudView* __restri
       if (e > 1.0f || e < 0.0f || e != e) continue;
       e = (float)((double)e * gd1);
       acc[0] += (double)score_inc;
-      // point_gradient (3x6): columns 0..2 identity; col 3 = (0, pg0, pg1); col 4 = (pg2, pg3, pg4); col 5 = (pg5, pg6, pg7)
-      const float PG[3][6] = {{1.f, 0.f, 0.f, 0.f, pg[2], pg[5]}, {0.f, 1.f, 0.f, pg[0], pg[3], pg[6]}, {0.f, 0.f, 1.f, pg[1], pg[4], pg[7]}};
+      // point_gradient (3x6): columns 0..2 identity; col 3 = (0, pg0, pg1); col 4 = (pg2, pg3, pg4); col 5 = (pg5, pg6, pg7).
+      // The reference multiplies through the full matrices in float; the products with the structural 1 and 0 entries
+      // are exact (x*1 = x, x*0 = +-0, y + +-0 = y), so they are skipped here and every remaining operation is the
+      // reference's own, in its order: cg(:,c) = c_inv * point_gradient.col(c) is column c of c_inv for c < 3, etc.
       float cg[3][6];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+      for (int a = 0; a < 3; ++a) {
+        cg[a][0] = C[a * 3 + 0]; cg[a][1] = C[a * 3 + 1]; cg[a][2] = C[a * 3 + 2];
+        cg[a][3] = mad2(C[a * 3 + 1], pg[0], C[a * 3 + 2], pg[1]);
+        cg[a][4] = mad3(C[a * 3 + 0], pg[2], C[a * 3 + 1], pg[3], C[a * 3 + 2], pg[4]);
+        cg[a][5] = mad3(C[a * 3 + 0], pg[5], C[a * 3 + 1], pg[6], C[a * 3 + 2], pg[7]);
+      }
+      float xcg[6] = {xC0, xC1, xC2, 0.f, 0.f, 0.f};  // x . cg(:,c); for c < 3 this is x . c_inv(:,c), computed above
 #pragma unroll
-        for (int c = 0; c < 6; ++c) cg[a][c] = mad3(C[a * 3 + 0], PG[0][c], C[a * 3 + 1], PG[1][c], C[a * 3 + 2], PG[2][c]);
-      float xcg[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) xcg[c] = mad3(x0, cg[0][c], x1, cg[1][c], x2, cg[2][c]);
+      for (int c = 3; c < 6; ++c) xcg[c] = mad3(x0, cg[0][c], x1, cg[1][c], x2, cg[2][c]);
       if (do_grad) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) acc[1 + c] += (double)__fmul_rn(e, xcg[c]);
       }
       if (do_hess) {
-        // point_hessian blocks (3 live rows each): (3,3)=a (4,3)=b (5,3)=c (3,4)=b (4,4)=d (5,4)=e (3,5)=c (4,5)=e (5,5)=f
-        const float va[3] = {0.f, ph[0], ph[1]}, vb[3] = {0.f, ph[2], ph[3]}, vc[3] = {0.f, ph[4], ph[5]};
-        const float vd[3] = {ph[6], ph[7], ph[8]}, ve[3] = {ph[9], ph[10], ph[11]}, vf[3] = {ph[12], ph[13], ph[14]};
-        const float xa = mad3(xC0, va[0], xC1, va[1], xC2, va[2]);
-        const float xb = mad3(xC0, vb[0], xC1, vb[1], xC2, vb[2]);
-        const float xc = mad3(xC0, vc[0], xC1, vc[1], xC2, vc[2]);
-        const float xd = mad3(xC0, vd[0], xC1, vd[1], xC2, vd[2]);
-        const float xe = mad3(xC0, ve[0], xC1, ve[1], xC2, ve[2]);
-        const float xf = mad3(xC0, vf[0], xC1, vf[1], xC2, vf[2]);
-        // xh[i][j] = xC . block(i, j)
+        // point_hessian blocks (first component of a, b, c is structurally 0):
+        // (3,3)=a (4,3)=b (5,3)=c (3,4)=b (4,4)=d (5,4)=e (3,5)=c (4,5)=e (5,5)=f
+        const float xa = mad2(xC1, ph[0], xC2, ph[1]);
+        const float xb = mad2(xC1, ph[2], xC2, ph[3]);
+        const float xc = mad2(xC1, ph[4], xC2, ph[5]);
+        const float xd = mad3(xC0, ph[6], xC1, ph[7], xC2, ph[8]);
+        const float xe = mad3(xC0, ph[9], xC1, ph[10], xC2, ph[11]);
+        const float xf = mad3(xC0, ph[12], xC1, ph[13], xC2, ph[14]);
         const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
 #pragma unroll
         for (int i2_ = 0; i2_ < 6; ++i2_) {
+          const float ti = __fmul_rn(-gd2, xcg[i2_]);
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
-            const float G = mad3(PG[0][j], cg[0][i2_], PG[1][j], cg[1][i2_], PG[2][j], cg[2][i2_]);  // (pg^T cg)(j,i)
-            const float xh = (i2_ >= 3 && j >= 3) ? XH[i2_ - 3][j - 3] : 0.f;
-            float v = __fmul_rn(__fmul_rn(-gd2, xcg[i2_]), xcg[j]);
-            v = __fadd_rn(v, xh);
+            // G = point_gradient.col(j) . cg(:,i)
+            float G;
+            if (j < 3) G = cg[j][i2_];
+            else if (j == 3) G = mad2(pg[0], cg[1][i2_], pg[1], cg[2][i2_]);
+            else if (j == 4) G = mad3(pg[2], cg[0][i2_], pg[3], cg[1][i2_], pg[4], cg[2][i2_]);
+            else G = mad3(pg[5], cg[0][i2_], pg[6], cg[1][i2_], pg[7], cg[2][i2_]);
+            float v = __fmul_rn(ti, xcg[j]);
+            if (i2_ >= 3 && j >= 3) v = __fadd_rn(v, XH[i2_ - 3][j - 3]);  // elsewhere the block of point_hessian is 0
             v = __fadd_rn(v, G);
             acc[7 + i2_ * 6 + j] += (double)__fmul_rn(e, v);
           }

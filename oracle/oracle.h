@@ -89,6 +89,12 @@ double orc_fitness_score(const float* target, int nt, const float* source, int n
                          int* nr_out);
 void orc_knn(const float* xyzi, int n, const float* queries, int nq, int k, int* idx_out, float* d2_out);
 
+/* MapCloudGenerator::generate + pcl::ApproximateMeanVoxelGrid (both in-tree: src/mrg_slam/map_cloud_generator.cpp:14-86,
+ * include/pcl/filters/ApproximateMeanVoxelGrid.hpp:63-126); see mapcloud.cpp */
+int orc_map_cloud(const float* const* clouds, const int* n, const double* poses_colmajor, const uint8_t* first_keyframe, int count,
+                  float resolution, int min_points_per_voxel, float distance_far_thresh, int skip_first_cloud, float* out,
+                  int* voxel_keys_out);
+
 void orc_set_num_threads(int n);
 int orc_get_max_threads(void);
 
