@@ -143,6 +143,18 @@ b2r_status b2r_default_prefilter_config(b2r_prefilter_config* cfg); /* values of
 b2r_status b2r_prefilter(b2r_handle* h, const b2r_prefilter_config* cfg, const void* in, size_t n, size_t stride_bytes, int memspace,
                          void* out, size_t* m);
 
+/* ---- map cloud.  MapCloudGenerator::generate (src/mrg_slam/map_cloud_generator.cpp:14-86): every keyframe cloud is
+ * transformed by keyframe->pose (Isometry3d matrix, 16 doubles column-major each, cast to float as :36 does), points farther than
+ * distance_far_thresh from their sensor are skipped when distance_far_thresh > 0 (:38-42), keyframes with first_keyframe[k] != 0 are
+ * skipped when skip_first_cloud != 0 (:33-35), the rest is concatenated in keyframe order and, when resolution > 0, reduced by
+ * pcl::ApproximateMeanVoxelGrid (include/pcl/filters/ApproximateMeanVoxelGrid.hpp:63-126: voxel = floor(p / leaf), float sums in
+ * input order, mean = sum / count, kept iff count >= min_points_per_voxel).  The hash-map iteration order of the output is
+ * implementation-defined upstream; here voxels come out in ascending (z, y, x) voxel order.  `out` has room for sum(n) packed
+ * 16 B points in `memspace`; *is_null = 1 where generate() returns nullptr (no keyframes, or nothing left of several). ---- */
+b2r_status b2r_map_cloud(b2r_handle* h, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe,
+                         size_t count, size_t stride_bytes, int memspace, float resolution, int min_points_per_voxel,
+                         float distance_far_thresh, int skip_first_cloud, void* out, size_t* m, int* is_null);
+
 /* ---- introspection for parity tests and benchmarks ---- */
 uint64_t b2r_kernel_launches(const b2r_handle* h); /* kernels launched by this handle so far */
 b2r_status b2r_synchronize(b2r_handle* h);

@@ -466,6 +466,20 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
   });
 }
 
+b2r_status b2r_map_cloud(b2r_handle* hh, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe,
+                         size_t count, size_t stride_bytes, int memspace, float resolution, int min_points_per_voxel, float distance_far_thresh,
+                         int skip_first_cloud, void* out, size_t* m, int* is_null) {
+  return guarded(hh, [&](Handle& h) {
+    if (count && (!clouds || !n || !poses_colmajor)) throw Error(B2R_ERR_INVALID_ARG, "null keyframe arrays");
+    DevCloud res;
+    bool null_result = false;
+    map_cloud(h.ctx, clouds, n, poses_colmajor, first_keyframe, count, stride_bytes, memspace, resolution, min_points_per_voxel,
+              distance_far_thresh, skip_first_cloud, res, null_result);
+    if (is_null) *is_null = null_result ? 1 : 0;
+    finish_filter(h, res, out, m, memspace);
+  });
+}
+
 // ------------------------------------------------------------------------------------------------ introspection
 uint64_t b2r_kernel_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.launches : 0; }
 

@@ -284,3 +284,162 @@ void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n
 }
 
 }  // namespace b2r
+
+// ------------------------------------------------------------------------------------------------ map cloud
+// MapCloudGenerator::generate (src/mrg_slam/map_cloud_generator.cpp:14-86) + pcl::ApproximateMeanVoxelGrid<PointXYZI>
+// (include/pcl/filters/ApproximateMeanVoxelGrid.hpp:63-126), both in the reference tree.
+namespace b2r {
+
+struct MapSegment {  // one keyframe inside the concatenated input
+  int begin;         // first point of the keyframe in the concatenation
+  int n;
+  float pose[16];    // keyframe->pose.matrix().cast<float>(), column-major
+};
+
+// One thread per input point: far-distance test in the sensor frame (float Vector3f::squaredNorm, x^2 + (y^2 + z^2) as
+// Eigen's unrolled 3-element reduction associates it — the same order as the distance filter above; :40-42),
+// then dst = pose * (x, y, z, 1) as Eigen's fixed-size product evaluates it: ((c0 x + c1 y) + c2 z) + c3 (:44).
+__global__ void map_transform_kernel(const float4* __restrict__ in, int n, const MapSegment* __restrict__ segs, int nseg, int use_far,
+                                     float far_sq, int drop_nonfinite, float4* __restrict__ out, uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = nseg - 1;  // segment of point i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].begin <= i) lo = mid; else hi = mid - 1;
+  }
+  const float* T = segs[lo].pose;
+  const float4 p = in[i];
+  bool k = true;
+  if (use_far) {
+    const float sq = __fadd_rn(__fmul_rn(p.x, p.x), __fadd_rn(__fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z)));
+    if (sq > far_sq) k = false;
+  }
+  float4 o;
+  o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], p.x), __fmul_rn(T[4], p.y)), __fmul_rn(T[8], p.z)), T[12]);
+  o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[1], p.x), __fmul_rn(T[5], p.y)), __fmul_rn(T[9], p.z)), T[13]);
+  o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[2], p.x), __fmul_rn(T[6], p.y)), __fmul_rn(T[10], p.z)), T[14]);
+  o.w = p.w;
+  // the voxel filter casts floor(p * inv_leaf) to int, undefined for non-finite points upstream: they are dropped here
+  if (drop_nonfinite && !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z))) k = false;
+  out[i] = o;
+  keep[i] = k ? 1 : 0;
+}
+
+struct AmvgParams {
+  float inv_leaf;
+  int min_b[3];
+  long long mul[3];
+};
+// key = (ix - min) + nx * ((iy - min) + ny * (iz - min)), ixyz = (int)floor(p * inv_leaf) (hpp:88-90): one key per
+// ApproximateMeanVoxelGrid hash-map entry; sorting by it only fixes the (implementation-defined) output order
+__global__ void amvg_key_kernel(const float4* __restrict__ in, int n, AmvgParams prm, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  const long long i0 = (long long)(int)floorf(__fmul_rn(p.x, prm.inv_leaf)) - prm.min_b[0];
+  const long long i1 = (long long)(int)floorf(__fmul_rn(p.y, prm.inv_leaf)) - prm.min_b[1];
+  const long long i2 = (long long)(int)floorf(__fmul_rn(p.z, prm.inv_leaf)) - prm.min_b[2];
+  keys[i] = (unsigned long long)(i0 * prm.mul[0] + i1 * prm.mul[1] + i2 * prm.mul[2]);
+  vals[i] = i;
+}
+__global__ void amvg_head_kernel(const unsigned long long* __restrict__ keys, int n, uint8_t* __restrict__ head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  head[i] = (i == 0 || keys[i - 1] != keys[i]) ? 1 : 0;
+}
+
+void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe, size_t count,
+               size_t stride_bytes, int memspace, float resolution, int min_points_per_voxel, float distance_far_thresh, int skip_first_cloud,
+               DevCloud& out, bool& null_result) {
+  null_result = false;
+  out.n = 0;
+  if (count == 0) { null_result = true; return; }  // :20-23
+  // ---- concatenate the keyframes that take part (:31-35) and describe them for the transform kernel
+  std::vector<MapSegment> segs;
+  size_t total = 0;
+  for (size_t k = 0; k < count; ++k) {
+    if (first_keyframe && first_keyframe[k] && skip_first_cloud) continue;
+    if (n[k] == 0) continue;
+    MapSegment s;
+    s.begin = (int)total;
+    s.n = (int)n[k];
+    for (int i = 0; i < 16; ++i) s.pose[i] = (float)poses_colmajor[k * 16 + i];
+    segs.push_back(s);
+    total += n[k];
+    if (total > (size_t)INT32_MAX) throw Error(B2R_ERR_CAPACITY, "map cloud: more than 2^31 input points");
+  }
+  if (total == 0) { null_result = count > 1; return; }  // :58-61
+  DBuf<float4> cat; cat.alloc(total, ctx.stream);
+  {
+    size_t si = 0;
+    for (size_t k = 0; k < count; ++k) {
+      if (first_keyframe && first_keyframe[k] && skip_first_cloud) continue;
+      if (n[k] == 0) continue;
+      float4* dst = cat.p + segs[si].begin;
+      if (stride_bytes == 16) {
+        B2R_CUDA(cudaMemcpyAsync(dst, clouds[k], n[k] * 16, memspace == B2R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx.stream));
+      } else {
+        DBuf<float4> tmp;
+        load_points(ctx, clouds[k], n[k], stride_bytes, memspace, tmp);
+        B2R_CUDA(cudaMemcpyAsync(dst, tmp.p, n[k] * 16, cudaMemcpyDeviceToDevice, ctx.stream));
+      }
+      ++si;
+    }
+  }
+  DBuf<MapSegment> dsegs; dsegs.alloc(segs.size(), ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dsegs.p, segs.data(), sizeof(MapSegment) * segs.size(), cudaMemcpyHostToDevice, ctx.stream));
+  const int N = (int)total;
+  DBuf<float4> tr; tr.alloc(total, ctx.stream);
+  DBuf<uint8_t> keep; keep.alloc(total, ctx.stream);
+  const bool filter = resolution > 0.0f;
+  B2R_LAUNCH(ctx, map_transform_kernel, (N + 255) / 256, 256, 0, cat.p, N, dsegs.p, (int)segs.size(), distance_far_thresh > 0 ? 1 : 0,
+             distance_far_thresh * distance_far_thresh, filter ? 1 : 0, tr.p, keep.p);
+  DevCloud world;
+  compact_points(ctx, tr.p, keep.p, N, world);  // order-preserving: keyframe order, then point order, like push_back
+  if (world.n == 0) { null_result = count > 1; return; }
+  if (!filter) { out = std::move(world); return; }  // :67-71 full-resolution cloud
+
+  // ---- ApproximateMeanVoxelGrid: per voxel float sums of x, y, z, intensity in input order, / float(count)
+  const int M = world.n;
+  float mn[3], mx[3];
+  compute_bbox(ctx, world.pts.p, M, mn, mx);
+  AmvgParams prm;
+  prm.inv_leaf = 1.0f / resolution;  // Array3f::Ones() / leaf_size_.array()
+  long long ext[3];
+  for (int d = 0; d < 3; ++d) {
+    prm.min_b[d] = (int)std::floor(mn[d] * prm.inv_leaf);
+    ext[d] = (long long)(int)std::floor(mx[d] * prm.inv_leaf) - prm.min_b[d] + 1;
+  }
+  if ((double)ext[0] * (double)ext[1] * (double)ext[2] > 9.0e18) throw Error(B2R_ERR_CAPACITY, "map cloud: voxel index range exceeds 63 bits");
+  prm.mul[0] = 1; prm.mul[1] = ext[0]; prm.mul[2] = ext[0] * ext[1];
+  const unsigned long long max_key = (unsigned long long)(ext[0] * ext[1] * ext[2]);
+  int end_bit = 1;
+  while (end_bit < 64 && (1ull << end_bit) <= max_key) ++end_bit;
+  DBuf<unsigned long long> k0, k1;
+  DBuf<int> v0, v1;
+  k0.alloc(M, ctx.stream); k1.alloc(M, ctx.stream); v0.alloc(M, ctx.stream); v1.alloc(M, ctx.stream);
+  const int nb = (M + 255) / 256;
+  B2R_LAUNCH(ctx, amvg_key_kernel, nb, 256, 0, world.pts.p, M, prm, k0.p, v0.p);
+  size_t tmp_bytes = 0;  // stable LSD radix sort (CUB): equal keys keep ascending input order = the hash map's accumulation order
+  B2R_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0.p, k1.p, v0.p, v1.p, M, 0, end_bit, ctx.stream));
+  DBuf<uint8_t> tmp; tmp.alloc(tmp_bytes, ctx.stream);
+  B2R_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k0.p, k1.p, v0.p, v1.p, M, 0, end_bit, ctx.stream));
+  ctx.launches += 1 + (end_bit + 7) / 8;
+  DBuf<uint8_t> head; head.alloc(M, ctx.stream);
+  DBuf<int> cnt; cnt.alloc((size_t)nb + 1, ctx.stream);
+  B2R_LAUNCH(ctx, amvg_head_kernel, nb, 256, 0, k1.p, M, head.p);
+  flags_block_offsets(ctx, head.p, M, cnt.p);
+  int nseg = 0;
+  B2R_CUDA(cudaMemcpyAsync(&nseg, cnt.p + nb, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  DBuf<int> seg; seg.alloc(nseg, ctx.stream);
+  B2R_LAUNCH(ctx, vg_seg_kernel, nb, 256, 0, head.p, M, cnt.p, seg.p);
+  DBuf<float4> cen; cen.alloc(nseg, ctx.stream);
+  DBuf<uint8_t> vkeep; vkeep.alloc(nseg, ctx.stream);
+  // count_threshold_: keep iff count >= min_points_per_voxel (hpp:114)
+  B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 127) / 128, 128, 0, world.pts.p, v1.p, seg.p, nseg, M, min_points_per_voxel, cen.p, vkeep.p);
+  compact_points(ctx, cen.p, vkeep.p, nseg, out);
+}
+
+}  // namespace b2r

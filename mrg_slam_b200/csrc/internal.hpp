@@ -151,6 +151,11 @@ void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts
 void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out);
 void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out);
 
+// MapCloudGenerator::generate + ApproximateMeanVoxelGrid; null_result mirrors the reference's nullptr returns
+void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe, size_t count,
+               size_t stride_bytes, int memspace, float resolution, int min_points_per_voxel, float distance_far_thresh, int skip_first_cloud,
+               DevCloud& out, bool& null_result);
+
 // shared utilities (cloud.cu)
 void compact_points(Ctx& ctx, const float4* in, const uint8_t* keep, int n, DevCloud& out);
 void load_points(Ctx& ctx, const void* points, size_t n, size_t stride_bytes, int memspace, DBuf<float4>& dst);

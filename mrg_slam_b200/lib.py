@@ -75,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "b2r_set_target", "b2r_set_source", "b2r_set_target_cloud", "b2r_set_source_cloud",
     "b2r_align", "b2r_fitness", "b2r_transform_source", "b2r_fitness_pair", "b2r_align_batch",
     "b2r_distance_filter", "b2r_voxelgrid", "b2r_radius_outlier", "b2r_statistical_outlier",
-    "b2r_default_prefilter_config", "b2r_prefilter",
+    "b2r_default_prefilter_config", "b2r_prefilter", "b2r_map_cloud",
     "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_knn_list_overflows", "b2r_debug_covariances", "b2r_debug_voxelmap",
     "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
     "b2r_debug_knn", "b2r_last_timings", "b2r_event_record", "b2r_event_elapsed_ms", "b2r_profile_enable", "b2r_profile_read",
@@ -128,6 +128,8 @@ def load():
     L.b2r_statistical_outlier.argtypes = [vp, vp, sz, sz, ci, ci, cd, vp, ctypes.POINTER(sz)]
     L.b2r_default_prefilter_config.argtypes = [ctypes.POINTER(PrefilterConfig)]
     L.b2r_prefilter.argtypes = [vp, ctypes.POINTER(PrefilterConfig), vp, sz, sz, ci, vp, ctypes.POINTER(sz)]
+    L.b2r_map_cloud.argtypes = [vp, vp, vp, vp, vp, sz, sz, ci, ctypes.c_float, ci, ctypes.c_float, ci, vp, ctypes.POINTER(sz),
+                                ctypes.POINTER(ci)]
     L.b2r_kernel_launches.argtypes = [vp]
     L.b2r_kernel_launches.restype = ctypes.c_uint64
     L.b2r_synchronize.argtypes = [vp]
@@ -347,6 +349,23 @@ class Registration:
         self._check(self._lib.b2r_prefilter(self._h, ctypes.byref(cfg), a.ctypes.data, len(a), a.shape[1] * 4, HOST, out.ctypes.data,
                                             ctypes.byref(m)))
         return out[: m.value].copy()
+
+    def map_cloud(self, clouds, poses, first_keyframe=None, resolution=0.05, min_points_per_voxel=1, distance_far_thresh=-1.0,
+                  skip_first_cloud=False):
+        """MapCloudGenerator::generate (map_cloud_generator.cpp:14-86).  clouds: list of (n,4) float32 arrays; poses: 4x4 float64
+        (world <- keyframe).  Returns the map cloud (voxels in ascending (z, y, x) order) or None where the reference returns nullptr."""
+        cs = [_points(c) for c in clouds]
+        n = len(cs)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[c.ctypes.data for c in cs])
+        ns = (ctypes.c_size_t * max(n, 1))(*[len(c) for c in cs])
+        P = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64).T.reshape(16) for p in poses])) if n else np.zeros((0, 16))
+        fk = np.zeros(max(n, 1), dtype=np.uint8) if first_keyframe is None else np.ascontiguousarray(first_keyframe, dtype=np.uint8)
+        out = np.empty((max(sum(len(c) for c in cs), 1), 4), dtype=np.float32)
+        m, null = ctypes.c_size_t(), ctypes.c_int()
+        stride = cs[0].shape[1] * 4 if n else 16
+        self._check(self._lib.b2r_map_cloud(self._h, ptrs, ns, P.ctypes.data, fk.ctypes.data, n, stride, HOST, resolution, min_points_per_voxel,
+                                            distance_far_thresh, int(skip_first_cloud), out.ctypes.data, ctypes.byref(m), ctypes.byref(null)))
+        return None if null.value else out[: m.value].copy()
 
     # ---- introspection ----
     def kernel_launches(self):

@@ -9,6 +9,7 @@
 //   Matrix4f * Vector4f (fixed-size lazy product)  -> per row ((m0*x + m1*y) + m2*z) + m3*w, w = 1
 //   VectorXf += VectorXf, VectorXf /= float        -> element-wise float add / true division
 //   Array3f::Ones() / leaf.array()                 -> 1.0f / leaf
+//   Vector3f::squaredNorm                          -> x*x + (y*y + z*z) (non-vectorised unrolled reduction splits 3 as 1 + 2)
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -56,7 +57,7 @@ int orc_map_cloud(const float* const* clouds, const int* n, const double* poses_
     for (int i = 0; i < n[k]; ++i) {
       const float* p = src + 4 * (size_t)i;
       if (use_distance_filter) {
-        const float sq = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];  // Vector3f::squaredNorm: ((x^2 + y^2) + z^2)
+        const float sq = p[0] * p[0] + (p[1] * p[1] + p[2] * p[2]);  // Vector3f::squaredNorm, Eigen's unrolled 3-element redux
         if (sq > distance_far_thresh_sq) continue;  // :40-42
       }
       float d[3];

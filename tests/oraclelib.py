@@ -91,6 +91,8 @@ def lib():
         L.orc_fitness_score.restype = cd
         L.orc_fitness_score.argtypes = [vp, ci, vp, ci, vp, cd, ctypes.POINTER(ci)]
         L.orc_knn.argtypes = [vp, ci, vp, ci, ci, vp, vp]
+        L.orc_map_cloud.restype = ci
+        L.orc_map_cloud.argtypes = [vp, vp, vp, vp, ci, ctypes.c_float, ci, ctypes.c_float, ci, vp, vp]
         L.orc_set_num_threads.argtypes = [ci]
         L.orc_get_max_threads.restype = ci
         _lib = L
@@ -264,6 +266,24 @@ def fitness_score(target, source, T, max_range=np.finfo(np.float64).max):
     nr = ctypes.c_int()
     f = lib().orc_fitness_score(_p(t), len(t), _p(s), len(s), _p(g), max_range, ctypes.byref(nr))
     return f, nr.value
+
+
+def map_cloud(clouds, poses, first_keyframe=None, resolution=0.05, min_points_per_voxel=1, distance_far_thresh=-1.0, skip_first_cloud=False):
+    """MapCloudGenerator::generate.  poses: 4x4 float64 (world <- keyframe).  Returns (points, voxel keys) or None for nullptr.
+    Points come in the oracle's unordered_map iteration order; sort by the keys to compare."""
+    cs = [_pts(c) for c in clouds]
+    n = len(cs)
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[c.ctypes.data for c in cs])
+    ns = np.array([len(c) for c in cs], dtype=np.int32)
+    P = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64).T.reshape(16) for p in poses])) if n else np.zeros((0, 16))
+    fk = np.zeros(max(n, 1), dtype=np.uint8) if first_keyframe is None else np.asarray(first_keyframe, dtype=np.uint8)
+    out = np.empty((max(int(ns.sum()), 1), 4), dtype=np.float32)
+    keys = np.zeros((len(out), 3), dtype=np.int32)
+    m = lib().orc_map_cloud(ptrs, _p(ns), _p(P), _p(fk), n, resolution, min_points_per_voxel, distance_far_thresh, int(skip_first_cloud), _p(out),
+                            _p(keys))
+    if m < 0:
+        return None
+    return out[:m].copy(), keys[:m].copy()
 
 
 def knn(cloud, queries, k):
