@@ -37,7 +37,8 @@ typedef enum b2r_status {
 typedef enum b2r_method {
   B2R_NDT_OMP = 0,   /* "NDT_OMP"    registrations.cpp:130-147 -> pclomp::NormalDistributionsTransform */
   B2R_FAST_GICP = 1, /* "FAST_GICP"  registrations.cpp:55-63   -> fast_gicp::FastGICP ("GICP" row) */
-  B2R_FAST_VGICP = 2 /* "FAST_VGICP" registrations.cpp:76-84   -> fast_gicp::FastVGICP */
+  B2R_FAST_VGICP = 2, /* "FAST_VGICP" registrations.cpp:76-84   -> fast_gicp::FastVGICP */
+  B2R_SMALL_GICP = 3  /* "SMALL_GICP" registrations.cpp:46-54   -> small_gicp::RegistrationPCL (GICP), the YAML default */
 } b2r_method;
 
 typedef enum b2r_neighbor_search { B2R_DIRECT1 = 0, B2R_DIRECT7 = 1, B2R_DIRECT27 = 2 } b2r_neighbor_search;

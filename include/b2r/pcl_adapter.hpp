@@ -36,7 +36,10 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
   using Ptr = std::shared_ptr<PclRegistration>;
 
   explicit PclRegistration(int method, int device = 0) : impl_(method, device) {
-    this->reg_name_ = method == B2R_NDT_OMP ? "b2r::NDT_OMP" : (method == B2R_FAST_GICP ? "b2r::FAST_GICP" : "b2r::FAST_VGICP");
+    this->reg_name_ = method == B2R_NDT_OMP      ? "b2r::NDT_OMP"
+                      : method == B2R_FAST_GICP  ? "b2r::FAST_GICP"
+                      : method == B2R_SMALL_GICP ? "b2r::SMALL_GICP"
+                                                 : "b2r::FAST_VGICP";
     static_assert(sizeof(PointT) == sizeof(::b2r::PointXYZI), "pcl::PointXYZI layout changed");
   }
 

@@ -185,6 +185,15 @@ struct RegistrationParams {
 // unknown strings warn and fall back to NDT exactly like :117-120 (NDT_OMP, the engine's NDT).
 inline Registration::Ptr select_registration_method(const RegistrationParams& p) {
   const std::string& m = p.registration_method;
+  if (m == "SMALL_GICP") {  // registrations.cpp:46-54, the shipped YAML default (config/mrg_slam.yaml:100)
+    auto r = std::make_shared<Registration>(B2R_SMALL_GICP, p.device);
+    r->setNumThreads(p.reg_num_threads);
+    r->setTransformationEpsilon(p.reg_transformation_epsilon);
+    r->setMaximumIterations(p.reg_maximum_iterations);
+    r->setMaxCorrespondenceDistance(p.reg_max_correspondence_distance);
+    r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
+    return r;
+  }
   if (m == "FAST_GICP") {
     auto r = std::make_shared<Registration>(B2R_FAST_GICP, p.device);
     r->setNumThreads(p.reg_num_threads);
@@ -203,7 +212,7 @@ inline Registration::Ptr select_registration_method(const RegistrationParams& p)
     r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
     return r;
   }
-  if (m == "SMALL_GICP" || m == "FAST_VGICP_CUDA" || m == "ICP" || m.find("GICP") != std::string::npos || m == "NDT") {
+  if (m == "FAST_VGICP_CUDA" || m == "ICP" || m.find("GICP") != std::string::npos || m == "NDT") {
     std::fprintf(stderr, "b2r: registration_method %s is outside this engine's scope\n", m.c_str());
     return nullptr;
   }

@@ -22,6 +22,7 @@ Needs needs_for(const b2r_config& cfg, bool is_target, bool want_fitness) {
       nd.cov_k = cfg.correspondence_randomness;
       if (is_target) nd.vres = cfg.resolution;
       break;
+    case B2R_SMALL_GICP:
     case B2R_FAST_GICP:
       nd.cov_k = cfg.correspondence_randomness;
       if (is_target) nd.grid = true;
@@ -53,7 +54,7 @@ b2r_status guarded(b2r_handle* hh, F&& f) {
 }
 
 void check_cfg(const b2r_config& cfg) {
-  if (cfg.method < B2R_NDT_OMP || cfg.method > B2R_FAST_VGICP) throw Error(B2R_ERR_INVALID_ARG, "unknown method");
+  if (cfg.method < B2R_NDT_OMP || cfg.method > B2R_SMALL_GICP) throw Error(B2R_ERR_INVALID_ARG, "unknown method");
   if (cfg.resolution <= 0) throw Error(B2R_ERR_INVALID_ARG, "resolution must be > 0");
   if (cfg.method != B2R_NDT_OMP && (cfg.correspondence_randomness < 4 || cfg.correspondence_randomness > 32))
     throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be in [4,32]");

@@ -273,6 +273,55 @@ __device__ __forceinline__ int nn1_search(const CloudView& c, float qx, float qy
   return v.best_pos;
 }
 
+// ---- one thread per query: exact 1-NN of a DOUBLE query under double squared distance, Eigen Vector4d/Packet2d order
+// (dx^2 + dz^2) + dy^2 — small_gicp's kd-tree metric.  The rows are pruned with float arithmetic on the rounded query and a
+// margin that covers the rounding of the query (<= 4e-6 m at 64 m) and of the float differences; candidates are compared
+// in double.  Ties go to the lower position.  Returns the position in spts or -1 (nothing within max_d2).
+struct Nn1VisitorD {
+  double qx, qy, qz, best;
+  float fx, fy, fz, cutf;  // cutf: float bound on the squared distance of anything that can still win
+  int best_pos;
+  __device__ __forceinline__ static float bound_of(double d2) {
+    const double r = sqrt(d2) + 1e-4;
+    return (float)(r * r * (1.0 + 1e-6));
+  }
+  __device__ __forceinline__ float thr() const { return cutf; }
+  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > cutf; }
+  __device__ __forceinline__ void test(const float4& p, int j) {
+    const double d0 = (double)p.x - qx, d1 = (double)p.y - qy, d2 = (double)p.z - qz;
+    const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d2, d2)), __dmul_rn(d1, d1));
+    if (d < best || (d == best && j < best_pos)) {
+      best = d;
+      best_pos = j;
+      cutf = fminf(cutf, bound_of(d));
+    }
+  }
+};
+__device__ __forceinline__ int nn1_search_d(const CloudView& c, double qx, double qy, double qz, double max_d2, double& best_out) {
+  Nn1VisitorD v;
+  v.qx = qx; v.qy = qy; v.qz = qz; v.best = INFINITY; v.best_pos = -1;
+  v.fx = (float)qx; v.fy = (float)qy; v.fz = (float)qz;
+  v.cutf = max_d2 < 1e30 ? Nn1VisitorD::bound_of(max_d2) : INFINITY;
+  best_out = v.best;
+  if (c.n == 0) return -1;
+  const QueryCell q = query_cell(c, v.fx, v.fy, v.fz);
+  int r = rows_outside(c, q) + 1;
+  {
+    const float lb = (float)(r - 2) * c.h;
+    if ((r >= 3 && lb * lb > v.cutf) || q.xout2 > v.cutf) return -1;
+  }
+  visit_rows(c, q, v.fx, r, false, v);
+  for (;;) {
+    const float b2 = ring_safe_d2(r, c.h) + q.xout2;
+    if (v.cutf <= b2) break;  // everything that could still win lies inside the visited rows
+    if (ring_covers_grid(c, q, r)) break;
+    ++r;
+    visit_rows(c, q, v.fx, r, true, v);
+  }
+  best_out = v.best;
+  return (v.best_pos >= 0 && v.best <= max_d2) ? v.best_pos : -1;
+}
+
 // ---- one thread per query: number of points with d2 < r2 (strict), early exit once count > stop_above.
 // Requires c.h >= radius so that the 3x3 rows around the query's row suffice.
 struct RadiusVisitor {

@@ -30,7 +30,7 @@ struct LsqState {
 };
 
 struct LsqParams {
-  int method;  // B2R_FAST_GICP / B2R_FAST_VGICP
+  int method;  // B2R_FAST_GICP / B2R_FAST_VGICP / B2R_SMALL_GICP
   int neighbor_search;
   double corr_thr2;  // max_correspondence_distance^2 (double compare as upstream)
   float corr_max_d2; // search cut-off
@@ -90,7 +90,8 @@ __device__ __forceinline__ void accumulate(double* acc, const double* M, double 
 
 // grid = (chunks, pairs).  Phase LINEARIZE: correspondences + M at x0, accumulate H, b, err.
 // Phase TRIAL: err at xi with the correspondences and M of x0 (fast_gicp compute_error semantics).
-__global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+template <int METHOD>
+__global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                         const LsqState* __restrict__ states, LsqParams prm, double* __restrict__ partials,
                                                         int32_t* __restrict__ corr_cache, const long long* __restrict__ corr_off,
                                                         int32_t* __restrict__ corr_out, uint8_t* __restrict__ corr_valid) {
@@ -100,9 +101,10 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
   if (phase == PH_DONE) return;
   const CloudView& src = views[pairs[pair].src];
   const CloudView& tgt = views[pairs[pair].tgt];
-  __shared__ double sx0[12], sxi[12];
+  __shared__ double sx0[12], sxi[12], sx0t[9];
   __shared__ double red[kAcc * 8];
   if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
+  if (threadIdx.x < 9) sx0t[threadIdx.x] = st.x0[(threadIdx.x % 3) * 3 + threadIdx.x / 3];  // R^T of the linearisation pose
   __syncthreads();
   const bool lin = phase == PH_LINEARIZE;
   double acc[kAcc];
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
   // target's cell-sorted copy or -1, one int per source point of the pair
   int32_t* cc = corr_cache ? corr_cache + corr_off[pair] : nullptr;
   float Tf[12];
-  if (prm.method == B2R_FAST_GICP) {
+  if constexpr (METHOD == B2R_FAST_GICP) {
 #pragma unroll
     for (int t = 0; t < 12; ++t) Tf[t] = (float)sx0[t];
   }
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
     }
     double RCR[6];
     rsrt(sx0, CA, RCR);
-    if (prm.method == B2R_FAST_VGICP) {
+    if constexpr (METHOD == B2R_FAST_VGICP) {
       const int vx = vgicp_coord_d(ax, tgt.vres), vy = vgicp_coord_d(ay, tgt.vres), vz = vgicp_coord_d(az, tgt.vres);
       bool first = true;
       const int noff = prm.neighbor_search == B2R_DIRECT1 ? 1 : (prm.neighbor_search == B2R_DIRECT7 ? 7 : 27);
@@ -160,6 +162,43 @@ __global__ void __launch_bounds__(256) lsq_eval_kernel(const CloudView* __restri
           corr_out[(size_t)i * 3 + 0] = vx + ox; corr_out[(size_t)i * 3 + 1] = vy + oy; corr_out[(size_t)i * 3 + 2] = vz + oz;
           corr_valid[i] = 1;
           first = false;
+        }
+      }
+    } else if constexpr (METHOD == B2R_SMALL_GICP) {
+      // small_gicp GICPFactor (registrations.cpp:46-54): nearest neighbour of T*p in DOUBLE, rejected when its squared
+      // distance exceeds max_dist_sq; M = (C_B + R C_A R^T)^-1; residual r = q - T*p; J = [R skew(p) | -R];
+      // H = J^T M J, b = J^T M r, e = r^T M r / 2 (the 1/2 is applied by the step kernel).  With M' = R^T M R and
+      // r' = R^T r this is the same accumulation as above on [skew(p) | -I].
+      int pos;
+      if (!lin && cc) {
+        pos = cc[i];
+      } else {
+        double d2;
+        pos = nn1_search_d(tgt, ax, ay, az, prm.corr_thr2, d2);
+        if (cc) cc[i] = pos;
+      }
+      if (corr_out) corr_out[i] = pos >= 0 ? __float_as_int(tgt.spts[pos].w) : -1;
+      if (pos >= 0) {
+        ++ncorr;
+        const float4 tq = __ldg(&tgt.spts[pos]);
+        const double* pcb = tgt.cov + (size_t)__float_as_int(tq.w) * 6;
+        double S[6], M[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) S[t] = __ldg(&pcb[t]) + RCR[t];
+        sym3_inverse(S, M);
+        const double m0 = (double)tq.x, m1 = (double)tq.y, m2 = (double)tq.z;
+        if (lin) {
+          double Mr[6];
+          rsrt(sx0t, M, Mr);
+          const double r0 = m0 - ax, r1 = m1 - ay, r2 = m2 - az;
+          const double e0 = sx0t[0] * r0 + sx0t[1] * r1 + sx0t[2] * r2;
+          const double e1 = sx0t[3] * r0 + sx0t[4] * r1 + sx0t[5] * r2;
+          const double e2 = sx0t[6] * r0 + sx0t[7] * r1 + sx0t[8] * r2;
+          accumulate(acc, Mr, px, py, pz, e0, e1, e2, 1.0, true);
+        } else {
+          double bx, by, bz;
+          apply_pose(sxi, px, py, pz, bx, by, bz);
+          accumulate(acc, M, bx, by, bz, m0 - bx, m1 - by, m2 - bz, 1.0, false);
         }
       }
     } else {
@@ -290,6 +329,40 @@ __device__ void lsq_propose(LsqState& s) {
   }
 }
 
+// small_gicp se3_exp (Sophus form): rotation so3_exp(omega), translation V(omega) * v
+__device__ void se3_exp_dev(const double* a, double* R, double* t) {
+  const double th2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+  const double th = sqrt(th2);
+  so3_exp_dev(a, R);
+  if (th < 1e-10) {
+    for (int r = 0; r < 3; ++r) t[r] = R[r * 3 + 0] * a[3] + R[r * 3 + 1] * a[4] + R[r * 3 + 2] * a[5];
+    return;
+  }
+  const double Om[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+  double Om2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Om2[r * 3 + c] = Om[r * 3 + 0] * Om[0 * 3 + c] + Om[r * 3 + 1] * Om[1 * 3 + c] + Om[r * 3 + 2] * Om[2 * 3 + c];
+  const double c1 = (1.0 - cos(th)) / th2, c2 = (th - sin(th)) / (th2 * th);
+  for (int r = 0; r < 3; ++r) {
+    double acc = 0.0;
+    for (int c = 0; c < 3; ++c) acc += (((r == c) ? 1.0 : 0.0) + c1 * Om[r * 3 + c] + c2 * Om2[r * 3 + c]) * a[3 + c];
+    t[r] = acc;
+  }
+}
+
+// small_gicp LevenbergMarquardtOptimizer: d = solve(H + lambda I, -b); xi = x0 * se3_exp(d)  (right-multiplied update)
+__device__ void sg_propose(LsqState& s) {
+  double A[36], nb[6];
+  for (int i = 0; i < 36; ++i) A[i] = s.H[i];
+  for (int j = 0; j < 6; ++j) { A[j * 6 + j] += s.lambda; nb[j] = -s.b[j]; }
+  ldlt6_solve_dev(A, nb, s.d);
+  se3_exp_dev(s.d, s.dR, s.dt);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) s.xi[r * 3 + c] = s.x0[r * 3 + 0] * s.dR[0 * 3 + c] + s.x0[r * 3 + 1] * s.dR[1 * 3 + c] + s.x0[r * 3 + 2] * s.dR[2 * 3 + c];
+    s.xi[9 + r] = s.x0[r * 3 + 0] * s.dt[0] + s.x0[r * 3 + 1] * s.dt[1] + s.x0[r * 3 + 2] * s.dt[2] + s.x0[9 + r];
+  }
+}
+
 __device__ void lsq_finish(LsqState& s, int* done_count) {
   s.phase = PH_DONE;
   atomicAdd(done_count, 1);
@@ -319,6 +392,52 @@ __global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqPa
   if (phase == PH_LINEARIZE) s.corr_last = ncorr;
   s.work_pts += (double)src_n[pair];
   s.work_corr += s.corr_last;
+  if (prm.method == B2R_SMALL_GICP) {
+    // LevenbergMarquardtOptimizer::optimize (small_gicp; init_lambda 1e-3, lambda_factor 10, max_inner_iterations =
+    // lm_max_iterations) advanced by one evaluation.  s.outer = i, s.inner = j, s.y0 = e.
+    constexpr double kLambdaFactor = 10.0;
+    if (phase == PH_LINEARIZE) {
+      const int rr[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+      for (int t = 0; t < 6; ++t) {
+        s.H[rr[t][0] * 6 + rr[t][1]] = a[t];
+        s.H[rr[t][1] * 6 + rr[t][0]] = a[t];
+        s.H[(3 + rr[t][0]) * 6 + 3 + rr[t][1]] = a[15 + t];
+        s.H[(3 + rr[t][1]) * 6 + 3 + rr[t][0]] = a[15 + t];
+      }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          s.H[r * 6 + 3 + c] = a[6 + r * 3 + c];
+          s.H[(3 + c) * 6 + r] = a[6 + r * 3 + c];
+        }
+      for (int t = 0; t < 6; ++t) s.b[t] = a[21 + t];
+      s.y0 = 0.5 * a[27];
+      s.nr_iterations = s.outer;
+      s.inner = 0;
+      if (prm.lm_max_iterations <= 0) { lsq_finish(s, done_count); return; }  // no inner iteration: success stays false
+      sg_propose(s);
+      s.phase = PH_TRIAL;
+      return;
+    }
+    s.yi = 0.5 * a[27];
+    if (s.yi <= s.y0) {
+      const double rn = sqrt(s.d[0] * s.d[0] + s.d[1] * s.d[1] + s.d[2] * s.d[2]);
+      const double tn = sqrt(s.d[3] * s.d[3] + s.d[4] * s.d[4] + s.d[5] * s.d[5]);
+      s.converged = (rn <= prm.rot_eps && tn <= prm.trans_eps) ? 1 : 0;
+      for (int t = 0; t < 12; ++t) s.x0[t] = s.xi[t];
+      s.lambda /= kLambdaFactor;
+      s.y0 = s.yi;
+      s.nr_iterations = s.outer;
+      s.outer++;
+      if (s.converged || s.outer >= prm.max_iterations) { lsq_finish(s, done_count); return; }
+      s.phase = PH_LINEARIZE;
+      return;
+    }
+    s.lambda *= kLambdaFactor;
+    s.inner++;
+    if (s.inner >= prm.lm_max_iterations) { lsq_finish(s, done_count); return; }  // !success: break, converged stays false
+    sg_propose(s);
+    return;
+  }
   if (phase == PH_LINEARIZE) {
     // unpack the symmetric system
     const int rr[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
@@ -392,7 +511,7 @@ __global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqPa
 }
 
 __global__ void lsq_init_kernel(LsqState* __restrict__ states, int npairs, const float* __restrict__ guesses, int max_iterations,
-                                int* __restrict__ done_count) {
+                                double init_lambda, int* __restrict__ done_count) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= npairs) return;
   LsqState& s = states[pair];
@@ -405,12 +524,23 @@ __global__ void lsq_init_kernel(LsqState* __restrict__ states, int npairs, const
   for (int t = 0; t < 9; ++t) s.dR[t] = (t % 4 == 0) ? 1.0 : 0.0;
   s.dt[0] = s.dt[1] = s.dt[2] = 0.0;
   s.y0 = s.yi = 0.0;
-  s.lambda = -1.0;
+  s.lambda = init_lambda;  // < 0: fast_gicp derives it from the first Hessian; small_gicp starts at 1e-3
   s.nu = 2.0;
   s.phase = PH_LINEARIZE;
   s.outer = 0; s.inner = 0; s.converged = 0; s.nr_iterations = 0; s.evals = 0; s.failed = 0;
   s.corr_last = 0.0; s.work_pts = 0.0; s.work_corr = 0.0;
   if (max_iterations <= 0) { s.phase = PH_DONE; atomicAdd(done_count, 1); }
+}
+
+static void launch_lsq_eval(Ctx& ctx, int method, dim3 grid, const CloudView* views, const PairDesc* pairs, const LsqState* states,
+                            const LsqParams& prm, double* partials, int32_t* corr_cache, const long long* corr_off, int32_t* corr_out,
+                            uint8_t* corr_valid) {
+  if (method == B2R_FAST_VGICP)
+    B2R_LAUNCH(ctx, lsq_eval_kernel<B2R_FAST_VGICP>, grid, 256, 0, views, pairs, states, prm, partials, corr_cache, corr_off, corr_out, corr_valid);
+  else if (method == B2R_FAST_GICP)
+    B2R_LAUNCH(ctx, lsq_eval_kernel<B2R_FAST_GICP>, grid, 256, 0, views, pairs, states, prm, partials, corr_cache, corr_off, corr_out, corr_valid);
+  else
+    B2R_LAUNCH(ctx, lsq_eval_kernel<B2R_SMALL_GICP>, grid, 256, 0, views, pairs, states, prm, partials, corr_cache, corr_off, corr_out, corr_valid);
 }
 
 static LsqParams make_params(const b2r_config& cfg) {
@@ -419,6 +549,7 @@ static LsqParams make_params(const b2r_config& cfg) {
   p.neighbor_search = cfg.method == B2R_FAST_VGICP ? cfg.neighbor_search : B2R_DIRECT1;
   p.corr_thr2 = cfg.max_correspondence_distance * cfg.max_correspondence_distance;
   p.corr_max_d2 = p.corr_thr2 >= (double)FLT_MAX ? INFINITY : (float)(p.corr_thr2 * 1.0001);
+  if (cfg.method == B2R_SMALL_GICP && !(p.corr_thr2 < 1e30)) p.corr_thr2 = INFINITY;
   p.rot_eps = cfg.rotation_epsilon;
   p.trans_eps = cfg.transformation_epsilon;
   p.max_iterations = cfg.maximum_iterations;
@@ -453,7 +584,7 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   DBuf<int32_t> corr;
   DBuf<long long> coff;
   std::vector<long long> hoff;
-  if (cfg.method == B2R_FAST_GICP) {
+  if (cfg.method == B2R_FAST_GICP || cfg.method == B2R_SMALL_GICP) {
     hoff.resize(np);
     long long tot = 0;
     for (int i = 0; i < np; ++i) { hoff[i] = tot; tot += src_sizes[i]; }
@@ -463,7 +594,8 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   }
   B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(dg.p, guesses_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
-  B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, dg.p, cfg.maximum_iterations, done.p);
+  B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, dg.p, cfg.maximum_iterations,
+             cfg.method == B2R_SMALL_GICP ? 1e-3 : -1.0, done.p);
   const dim3 ge(chunks, np);
   const int step_blocks = (np + 3) / 4;
   int rounds_per_check = 6;
@@ -474,8 +606,7 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
     for (int r = 0; r < rounds_per_check; ++r) {
       {
         ProfScope ps(ctx, PROF_LSQ_EVAL, 0.0);  // bytes are added below from the work the device actually did
-        B2R_LAUNCH(ctx, lsq_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, prm, part.p, corr.p, coff.p, (int32_t*)nullptr,
-                   (uint8_t*)nullptr);
+        launch_lsq_eval(ctx, cfg.method, ge, d_views, dp.p, ds.p, prm, part.p, corr.p, coff.p, nullptr, nullptr);
       }
       B2R_LAUNCH(ctx, lsq_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, dn.p, done.p);
     }
@@ -539,8 +670,8 @@ void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_vie
   }
   B2R_CUDA(cudaMemcpyAsync(dp.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, &s, sizeof(s), cudaMemcpyHostToDevice, ctx.stream));
-  B2R_LAUNCH(ctx, lsq_eval_kernel, dim3(chunks, 1), 256, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr, (const long long*)nullptr,
-             corr_out ? dc.p : nullptr, corr_out ? dvld.p : nullptr);
+  launch_lsq_eval(ctx, cfg.method, dim3(chunks, 1), d_views, dp.p, ds.p, prm, part.p, nullptr, nullptr, corr_out ? dc.p : nullptr,
+                  corr_out ? dvld.p : nullptr);
   std::vector<double> hp((size_t)chunks * kPart);
   B2R_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, ctx.stream));
   if (corr_out) {

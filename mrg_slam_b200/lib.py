@@ -15,7 +15,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2R_LIB_PATH") or os.path.join(_DIR, "libb2r.so")  # override: kernel experiments only
 
-NDT_OMP, FAST_GICP, FAST_VGICP = 0, 1, 2
+NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP = 0, 1, 2, 3
 DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
 HOST, DEVICE = 0, 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_STATE = range(6)
@@ -483,7 +483,10 @@ def select_registration_method(params):
     elif name == "FAST_VGICP":
         cfg = default_config(FAST_VGICP, resolution=params.get("reg_resolution", 1.0),
                              correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
-    elif name in ("SMALL_GICP", "FAST_VGICP_CUDA", "ICP", "GICP", "GICP_OMP", "NDT"):
+    elif name == "SMALL_GICP":  # registrations.cpp:46-54: epsilon, iterations, correspondence distance and randomness are set
+        cfg = default_config(SMALL_GICP, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
+                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
+    elif name in ("FAST_VGICP_CUDA", "ICP", "GICP", "GICP_OMP", "NDT"):
         raise NotImplementedError(f"registration_method {name} is outside this engine's scope (see DESIGN.md)")
     else:
         if "NDT" not in name:

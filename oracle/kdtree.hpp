@@ -62,6 +62,17 @@ struct KdTree {
     return m;
   }
 
+  // Exact nearest neighbour of a DOUBLE query under double squared distance (small_gicp's own kd-tree searches in
+  // double: `(traits::point(points, index) - query).squaredNorm()` on Vector4d, Packet2d order (dx^2 + dz^2) + dy^2).
+  // Ties go to the lower index.  Returns the index or -1 if the tree is empty.
+  int nn_double(const double* q, double* d2_out) const {
+    int best = -1;
+    double bd = INFINITY;
+    if (n_) search_nn_d(0, q, best, bd);
+    *d2_out = bd;
+    return best;
+  }
+
   // Count of points with d2 < r2 (strict, FLANN RadiusResultSet); stops early
   // once the count exceeds `stop_above` (pass INT32_MAX for a full count).
   int radius_count(const float* q, float r2, int stop_above) const {
@@ -148,6 +159,27 @@ struct KdTree {
     search_knn(first, q, h);
     double bound = dsec > 0 ? dsec * dsec : 0.0;
     if (bound * (1.0 - 1e-6) <= (double)h.worst()) search_knn(second, q, h);
+  }
+
+  void search_nn_d(int id, const double* q, int& best, double& bd) const {
+    const Node& nd = nodes_[id];
+    if (nd.dim < 0) {
+      for (int i = nd.begin; i < nd.end; ++i) {
+        const int pi = idx_[i];
+        const float* p = pts_ + 4 * (size_t)pi;
+        const double d0 = (double)p[0] - q[0], d1 = (double)p[1] - q[1], d2 = (double)p[2] - q[2];
+        const double d = (d0 * d0 + d2 * d2) + d1 * d1;
+        if (d < bd || (d == bd && pi < best)) { bd = d; best = pi; }
+      }
+      return;
+    }
+    const double dl = q[nd.dim] - (double)nd.lo, dr = (double)nd.hi - q[nd.dim];
+    int first = nd.left, second = nd.right;
+    double dsec = dr;
+    if (q[nd.dim] >= (double)nd.split) { first = nd.right; second = nd.left; dsec = dl; }
+    search_nn_d(first, q, best, bd);
+    const double bound = dsec > 0 ? dsec * dsec : 0.0;
+    if (bound * (1.0 - 1e-12) <= bd) search_nn_d(second, q, best, bd);
   }
 
   void search_radius(int id, const float* q, float r2, int stop_above, int& cnt) const {

@@ -613,6 +613,154 @@ struct orc_reg {
     return 0;
   }
 
+  // ------------------------------------------------------------------ SMALL_GICP
+  // small_gicp::RegistrationPCL with reg_type GICP, as src/mrg_slam/registrations.cpp:46-54 configures it (the shipped YAML
+  // default, config/mrg_slam.yaml:100).  small_gicp is not vendored in /root/reference; restated from its public sources:
+  //   GICPFactor::linearize / error, NearestNeighbor rejector (max_dist_sq), LevenbergMarquardtOptimizer::optimize
+  //   (init_lambda 1e-3, lambda_factor 10, max_inner_iterations 10), TerminationCriteria (|rot| <= rotation_eps 2e-3,
+  //   |trans| <= translation_eps), se3_exp, covariance estimation with k neighbours and (1e-3, 1, 1) regularisation.
+  // Stated simplifications (oracle and GPU alike): the k-neighbour sets are selected with float32 squared distances like
+  // FAST_GICP's (small_gicp ranks them in float64: sets differ only on near-ties), and the plane normal comes from the
+  // Jacobi eigen-solver used everywhere here instead of Eigen's closed-form computeDirect.
+  std::vector<int> sg_corr;
+  std::vector<double> sg_M;  // 9 per source point, Mahalanobis matrix of the linearisation pose
+
+  static void se3_exp(const double* a, Pose& out) {
+    const double th2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    const double th = std::sqrt(th2);
+    so3_exp_matrix(a, out.R);
+    if (th < 1e-10) {
+      m3_vec(out.R, a + 3, out.t);
+      return;
+    }
+    const double Om[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    double Om2[9];
+    m3_mul(Om, Om, Om2);
+    const double c1 = (1.0 - std::cos(th)) / th2, c2 = (th - std::sin(th)) / (th2 * th);
+    double V[9];
+    for (int i = 0; i < 9; ++i) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + c1 * Om[i] + c2 * Om2[i];
+    m3_vec(V, a + 3, out.t);
+  }
+
+  double sg_linearize(const Pose& T, double* H, double* b) {
+    ++evals;
+    if (!tgt_tree_valid) { tgt_tree.build(target.data(), nt); tgt_tree_valid = true; }
+    sg_corr.assign(ns, -1);
+    sg_M.assign((size_t)ns * 9, 0.0);
+    const double max_d2 = prm.max_correspondence_distance * prm.max_correspondence_distance;
+    const int nth = threads();
+    std::vector<double> Hs((size_t)nth * 36, 0.0), bs((size_t)nth * 6, 0.0), es(nth, 0.0);
+#pragma omp parallel for schedule(static) num_threads(nth)
+    for (int i = 0; i < ns; ++i) {
+      const int tid = omp_get_thread_num();
+      const double p[3] = {(double)source[4 * (size_t)i], (double)source[4 * (size_t)i + 1], (double)source[4 * (size_t)i + 2]};
+      double a[3];
+      pose_apply(T, p, a);
+      double d2;
+      const int j = tgt_tree.nn_double(a, &d2);
+      if (j < 0 || d2 > max_d2) continue;  // rejector: sq_dist > max_dist_sq
+      sg_corr[i] = j;
+      double CA[9], CB[9], RC[9], RCR[9], S[9], M[9];
+      cov6_to_m3(&source_covs[(size_t)i * 6], CA);
+      cov6_to_m3(&target_covs[(size_t)j * 6], CB);
+      m3_mul(T.R, CA, RC);
+      m3_mul_bt(RC, T.R, RCR);
+      for (int t = 0; t < 9; ++t) S[t] = CB[t] + RCR[t];
+      m3_inverse(S, M);
+      std::memcpy(&sg_M[(size_t)i * 9], M, sizeof(M));
+      const float* q = &target[4 * (size_t)j];
+      const double r[3] = {(double)q[0] - a[0], (double)q[1] - a[1], (double)q[2] - a[2]};
+      // J = [R skew(p) | -R]
+      const double Sk[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
+      double RS[9];
+      m3_mul(T.R, Sk, RS);
+      double J[18];
+      for (int rr = 0; rr < 3; ++rr)
+        for (int c = 0; c < 3; ++c) { J[rr * 6 + c] = RS[rr * 3 + c]; J[rr * 6 + 3 + c] = -T.R[rr * 3 + c]; }
+      double MJ[18], Mr[3];
+      for (int rr = 0; rr < 3; ++rr)
+        for (int c = 0; c < 6; ++c) MJ[rr * 6 + c] = M[rr * 3 + 0] * J[0 * 6 + c] + M[rr * 3 + 1] * J[1 * 6 + c] + M[rr * 3 + 2] * J[2 * 6 + c];
+      m3_vec(M, r, Mr);
+      double* Ht = &Hs[(size_t)tid * 36];
+      double* bt = &bs[(size_t)tid * 6];
+      for (int rr = 0; rr < 6; ++rr) {
+        for (int c = 0; c < 6; ++c) Ht[rr * 6 + c] += J[0 * 6 + rr] * MJ[0 * 6 + c] + J[1 * 6 + rr] * MJ[1 * 6 + c] + J[2 * 6 + rr] * MJ[2 * 6 + c];
+        bt[rr] += J[0 * 6 + rr] * Mr[0] + J[1 * 6 + rr] * Mr[1] + J[2 * 6 + rr] * Mr[2];
+      }
+      es[tid] += 0.5 * (r[0] * Mr[0] + r[1] * Mr[1] + r[2] * Mr[2]);
+    }
+    double err = 0;
+    std::fill(H, H + 36, 0.0);
+    std::fill(b, b + 6, 0.0);
+    for (int t = 0; t < nth; ++t) {
+      err += es[t];
+      for (int a = 0; a < 36; ++a) H[a] += Hs[(size_t)t * 36 + a];
+      for (int a = 0; a < 6; ++a) b[a] += bs[(size_t)t * 6 + a];
+    }
+    return err;
+  }
+
+  double sg_error(const Pose& T) {  // GICPFactor::error with the correspondences and Mahalanobis matrices of the last linearize
+    ++evals;
+    const int nth = threads();
+    std::vector<double> es(nth, 0.0);
+#pragma omp parallel for schedule(static) num_threads(nth)
+    for (int i = 0; i < ns; ++i) {
+      if (sg_corr[i] < 0) continue;
+      const double p[3] = {(double)source[4 * (size_t)i], (double)source[4 * (size_t)i + 1], (double)source[4 * (size_t)i + 2]};
+      double a[3], Mr[3];
+      pose_apply(T, p, a);
+      const float* q = &target[4 * (size_t)sg_corr[i]];
+      const double r[3] = {(double)q[0] - a[0], (double)q[1] - a[1], (double)q[2] - a[2]};
+      m3_vec(&sg_M[(size_t)i * 9], r, Mr);
+      es[omp_get_thread_num()] += 0.5 * (r[0] * Mr[0] + r[1] * Mr[1] + r[2] * Mr[2]);
+    }
+    double err = 0;
+    for (int t = 0; t < nth; ++t) err += es[t];
+    return err;
+  }
+
+  int align_small_gicp(const float* guess, orc_result* out) {
+    ensure_covariances();
+    Pose T = pose_from_colmajor_f(guess);
+    const double lambda_factor = 10.0;
+    double lambda = 1e-3;  // init_lambda
+    converged = false;
+    evals = 0;
+    nr_iterations = 0;
+    double e = 0;
+    for (int i = 0; i < prm.maximum_iterations && !converged; ++i) {
+      double H[36], b[6];
+      e = sg_linearize(T, H, b);
+      bool success = false;
+      for (int j = 0; j < prm.lm_max_iterations; ++j) {  // max_inner_iterations = 10
+        double A[36], nb[6], d[6];
+        std::memcpy(A, H, sizeof(A));
+        for (int k = 0; k < 6; ++k) { A[k * 6 + k] += lambda; nb[k] = -b[k]; }
+        ldlt6_solve(A, nb, d);
+        Pose dT;
+        se3_exp(d, dT);
+        const Pose new_T = pose_mul(T, dT);  // right-multiplied update
+        const double new_e = sg_error(new_T);
+        if (new_e <= e) {
+          const double rn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), tn = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+          converged = rn <= prm.rotation_epsilon && tn <= prm.transformation_epsilon;
+          T = new_T;
+          lambda /= lambda_factor;
+          success = true;
+          e = new_e;
+          break;
+        }
+        lambda *= lambda_factor;
+      }
+      nr_iterations = i;
+      if (!success) break;
+    }
+    pose_to_colmajor_f(T, final_T);
+    if (out) out->error = e;
+    return 0;
+  }
+
   // ------------------------------------------------------------------------ NDT
   void ndt_angle_derivatives(const double* p) {
     double cx, cy, cz, sx, sy, sz;
@@ -982,7 +1130,9 @@ int orc_reg_align(orc_reg* r, const float* guess, orc_result* out) {
   r->converged = false;
   for (int i = 0; i < 16; ++i) r->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   if (out) out->error = 0;
-  int rc = (r->prm.method == ORC_NDT_OMP) ? r->align_ndt(guess, out) : r->align_lsq(guess, out);
+  int rc = (r->prm.method == ORC_NDT_OMP)      ? r->align_ndt(guess, out)
+           : (r->prm.method == ORC_SMALL_GICP) ? r->align_small_gicp(guess, out)
+                                               : r->align_lsq(guess, out);
   if (out) {
     std::memcpy(out->T, r->final_T, sizeof(r->final_T));
     out->converged = r->converged ? 1 : 0;
@@ -1025,6 +1175,12 @@ int orc_vgicp_voxelmap(const float* xyzi, int n, const double* cov6, double reso
 double orc_reg_linearize(orc_reg* r, const double* T_rowmajor, double* H, double* b, int* corr_out, uint8_t* corr_valid) {
   r->ensure_covariances();
   Pose T = pose_from_rowmajor_d(T_rowmajor);
+  if (r->prm.method == ORC_SMALL_GICP) {
+    const double err = r->sg_linearize(T, H, b);
+    if (corr_out)
+      for (int i = 0; i < r->ns; ++i) corr_out[i] = r->sg_corr[i];
+    return err;
+  }
   double err = r->lsq_linearize(T, H, b);
   if (corr_out) {
     if (r->prm.method == ORC_FAST_VGICP) {
@@ -1043,6 +1199,7 @@ double orc_reg_linearize(orc_reg* r, const double* T_rowmajor, double* H, double
 }
 double orc_reg_compute_error(orc_reg* r, const double* T_rowmajor) {
   Pose T = pose_from_rowmajor_d(T_rowmajor);
+  if (r->prm.method == ORC_SMALL_GICP) return r->sg_error(T);
   return r->lsq_compute_error(T);
 }
 

@@ -50,7 +50,11 @@ int main(int argc, char** argv) {
   prm.registration_method = "BOGUS";
   auto fb = b2r::select_registration_method(prm);
   CHECK(fb && fb->config().method == B2R_NDT_OMP);  // unknown -> warning + NDT
-  prm.registration_method = "SMALL_GICP";
+  prm.registration_method = "SMALL_GICP";  // the YAML default (registrations.cpp:46-54)
+  prm.reg_max_correspondence_distance = 1.5;
+  auto sg = b2r::select_registration_method(prm);
+  CHECK(sg && sg->config().method == B2R_SMALL_GICP && sg->config().max_correspondence_distance == 1.5);
+  prm.registration_method = "GICP_OMP";  // PCL's BFGS GICP: outside the engine
   CHECK(b2r::select_registration_method(prm) == nullptr);
 
   auto a = make_cloud(3), b = make_cloud(4), c = make_cloud(5);

@@ -100,8 +100,10 @@ def test_factory_string_dispatch(monkeypatch, capsys):
     assert made[-1].neighbor_search == B.DIRECT7  # registrations.cpp:144-146: anything else -> DIRECT7
     B.select_registration_method({"registration_method": "BOGUS"})
     assert made[-1].method == B.NDT_OMP and "unknown registration type(BOGUS)" in capsys.readouterr().err
+    B.select_registration_method({"registration_method": "SMALL_GICP", "reg_max_correspondence_distance": 1.5})  # the YAML default
+    assert made[-1].method == B.SMALL_GICP and made[-1].max_correspondence_distance == 1.5
     with pytest.raises(NotImplementedError):
-        B.select_registration_method({"registration_method": "SMALL_GICP"})
+        B.select_registration_method({"registration_method": "GICP_OMP"})
 
 
 def test_synth_is_deterministic_and_shaped():

@@ -212,7 +212,30 @@ def test_linearize_matches_finite_differences(small_pair):
     np.testing.assert_allclose(grad, 2 * bb, rtol=2e-4, atol=1e-3 * np.abs(bb).max())
 
 
-@pytest.mark.parametrize("method", [O.FAST_GICP, O.FAST_VGICP, O.NDT_OMP])
+def test_small_gicp_linearisation_is_the_gauss_newton_model(small_pair):
+    """small_gicp's factor: e(T exp(d)) with the linearisation's correspondences and Mahalanobis matrices must follow
+    e0 + b.d + d.H.d/2 (right-multiplied se3 update; pins the Jacobian [R skew(p) | -R] and its signs)."""
+    a, b, gt = small_pair
+    r = O.Registration(O.default_params(O.SMALL_GICP))
+    r.setInputTarget(a); r.setInputSource(b)
+    T0 = gt.copy(); T0[0, 3] += 0.05
+    e0, H, bb, corr, _ = r.linearize(T0)
+    assert (corr >= 0).sum() > 0.5 * len(b) and np.allclose(H, H.T)
+    assert abs(r.compute_error(T0) - e0) < 1e-12 * e0
+    rng = np.random.default_rng(3)
+    for _ in range(4):
+        d = rng.normal(size=6) * 1e-3
+        D = np.eye(4); D[:3, :3] = Rotation.from_rotvec(d[:3]).as_matrix(); D[:3, 3] = d[3:]  # se3_exp to first order in |d|
+        pred = e0 + bb @ d + 0.5 * d @ H @ d
+        got = r.compute_error(T0 @ D)
+        assert abs(got - pred) <= 2e-3 * abs(bb @ d) + 1e-9 * e0, (got, pred)
+    # and the solver's descent direction reduces the error
+    step = np.linalg.solve(H + 1e-3 * np.eye(6), -bb)
+    D = np.eye(4); D[:3, :3] = Rotation.from_rotvec(step[:3]).as_matrix(); D[:3, 3] = step[3:]
+    assert r.compute_error(T0 @ D) < e0
+
+
+@pytest.mark.parametrize("method", [O.FAST_GICP, O.FAST_VGICP, O.NDT_OMP, O.SMALL_GICP])
 def test_identity_on_identical_clouds(small_pair, method):
     a, _, _ = small_pair
     r = O.Registration(O.default_params(method))
@@ -222,13 +245,13 @@ def test_identity_on_identical_clouds(small_pair, method):
     te, re = pose_error(np.eye(4), r.getFinalTransformation())
     # NDT at eps=0.1 takes a clamped >= 0.05 step even from the optimum; GICP (point-to-point
     # correspondences) stays put exactly; VGICP's voxel means pull it a fraction of a millimetre
-    t_tol = {O.NDT_OMP: 0.11, O.FAST_VGICP: 5e-3, O.FAST_GICP: 1e-6}[method]
-    r_tol = {O.NDT_OMP: 0.05, O.FAST_VGICP: 1e-3, O.FAST_GICP: 1e-6}[method]
+    t_tol = {O.NDT_OMP: 0.11, O.FAST_VGICP: 5e-3, O.FAST_GICP: 1e-6, O.SMALL_GICP: 1e-6}[method]
+    r_tol = {O.NDT_OMP: 0.05, O.FAST_VGICP: 1e-3, O.FAST_GICP: 1e-6, O.SMALL_GICP: 1e-6}[method]
     assert te < t_tol and re < r_tol
-    assert r.getFitnessScore() < {O.NDT_OMP: 0.02, O.FAST_VGICP: 1e-4, O.FAST_GICP: 1e-10}[method]
+    assert r.getFitnessScore() < {O.NDT_OMP: 0.02, O.FAST_VGICP: 1e-4, O.FAST_GICP: 1e-10, O.SMALL_GICP: 1e-10}[method]
 
 
-@pytest.mark.parametrize("method,tol", [(O.FAST_GICP, 0.02), (O.FAST_VGICP, 0.02), (O.NDT_OMP, 0.03)])
+@pytest.mark.parametrize("method,tol", [(O.FAST_GICP, 0.02), (O.FAST_VGICP, 0.02), (O.NDT_OMP, 0.03), (O.SMALL_GICP, 0.02)])
 def test_recovers_known_transform(small_pair, method, tol):
     """Source = target moved by a known SE(3): the alignment must find its inverse (tight epsilon)."""
     a, _, _ = small_pair
