@@ -144,6 +144,13 @@ b2r_status b2r_default_prefilter_config(b2r_prefilter_config* cfg); /* values of
 b2r_status b2r_prefilter(b2r_handle* h, const b2r_prefilter_config* cfg, const void* in, size_t n, size_t stride_bytes, int memspace,
                          void* out, size_t* m);
 
+/* ---- other robots' points (apps/mrg_slam_component.cpp:395-427): before a keyframe is created, every point within
+ * robot_remove_points_radius of another robot is dropped.  others_xyz: n_others * 3 floats on the HOST, the other robots' positions
+ * already in the sensor frame ((odom^-1 * map2odom * p).cast<float>(), :397-403); radius_sqr = radius^2 as a float (:405-406).
+ * kept_out / removed_out (optional) have room for n packed points in `memspace`; both keep the input order. ---- */
+b2r_status b2r_remove_robot_points(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int memspace, const float* others_xyz,
+                                   size_t n_others, float radius_sqr, void* kept_out, size_t* n_kept, void* removed_out, size_t* n_removed);
+
 /* ---- map cloud.  MapCloudGenerator::generate (src/mrg_slam/map_cloud_generator.cpp:14-86): every keyframe cloud is
  * transformed by keyframe->pose (Isometry3d matrix, 16 doubles column-major each, cast to float as :36 does), points farther than
  * distance_far_thresh from their sensor are skipped when distance_far_thresh > 0 (:38-42), keyframes with first_keyframe[k] != 0 are

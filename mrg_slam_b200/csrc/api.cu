@@ -467,6 +467,20 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
   });
 }
 
+b2r_status b2r_remove_robot_points(b2r_handle* hh, const void* in, size_t n, size_t stride_bytes, int memspace, const float* others_xyz,
+                                   size_t n_others, float radius_sqr, void* kept_out, size_t* n_kept, void* removed_out, size_t* n_removed) {
+  return guarded(hh, [&](Handle& h) {
+    if (n_others && !others_xyz) throw Error(B2R_ERR_INVALID_ARG, "null robot positions");
+    DBuf<float4> src;
+    load_points(h.ctx, in, n, stride_bytes, memspace, src);
+    DevCloud kept, removed;
+    filter_robot_points(h.ctx, src.p, (int)n, others_xyz, (int)n_others, radius_sqr, kept, removed_out ? &removed : nullptr);
+    if (removed_out && removed.n) store_points(h.ctx, removed.pts.p, removed.n, removed_out, 16, memspace);
+    if (n_removed) *n_removed = removed_out ? (size_t)removed.n : (size_t)((int)n - kept.n);
+    finish_filter(h, kept, kept_out, n_kept, memspace);
+  });
+}
+
 b2r_status b2r_map_cloud(b2r_handle* hh, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe,
                          size_t count, size_t stride_bytes, int memspace, float resolution, int min_points_per_voxel, float distance_far_thresh,
                          int skip_first_cloud, void* out, size_t* m, int* is_null) {

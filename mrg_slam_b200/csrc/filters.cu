@@ -443,3 +443,39 @@ void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const doubl
 }
 
 }  // namespace b2r
+
+// ------------------------------------------------------------------------------------------------ other-robot points
+// mrg_slam_component.cpp:395-427: a point is removed when it lies within robot_remove_points_radius of any
+// other robot's position (sensor frame, float): distSqr = (point - other).squaredNorm() < radius^2, first hit wins.
+namespace b2r {
+
+__global__ void robot_flag_kernel(const float4* __restrict__ in, int n, const float* __restrict__ others, int n_others, float r2,
+                                  uint8_t* __restrict__ keep, uint8_t* __restrict__ removed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  bool hit = false;
+  for (int k = 0; k < n_others && !hit; ++k) {
+    const float dx = __fsub_rn(p.x, others[3 * k]), dy = __fsub_rn(p.y, others[3 * k + 1]), dz = __fsub_rn(p.z, others[3 * k + 2]);
+    const float d = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));  // Vector3f::squaredNorm
+    hit = d < r2;
+  }
+  keep[i] = hit ? 0 : 1;
+  removed[i] = hit ? 1 : 0;
+}
+
+void filter_robot_points(Ctx& ctx, const float4* in, int n, const float* others_xyz_host, int n_others, float radius_sqr, DevCloud& kept,
+                         DevCloud* removed) {
+  kept.n = 0;
+  if (removed) removed->n = 0;
+  if (n == 0) return;
+  DBuf<float> dothers; dothers.alloc((size_t)std::max(1, 3 * n_others), ctx.stream);
+  if (n_others) B2R_CUDA(cudaMemcpyAsync(dothers.p, others_xyz_host, sizeof(float) * 3 * n_others, cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<uint8_t> keep, rem;
+  keep.alloc(n, ctx.stream); rem.alloc(n, ctx.stream);
+  B2R_LAUNCH(ctx, robot_flag_kernel, (n + 255) / 256, 256, 0, in, n, dothers.p, n_others, radius_sqr, keep.p, rem.p);
+  compact_points(ctx, in, keep.p, n, kept);
+  if (removed) compact_points(ctx, in, rem.p, n, *removed);
+}
+
+}  // namespace b2r

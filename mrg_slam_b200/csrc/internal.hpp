@@ -156,6 +156,10 @@ void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const doubl
                size_t stride_bytes, int memspace, float resolution, int min_points_per_voxel, float distance_far_thresh, int skip_first_cloud,
                DevCloud& out, bool& null_result);
 
+// other robots' points (mrg_slam_component.cpp:395-427); others_xyz_host: n_others * 3 floats, sensor frame
+void filter_robot_points(Ctx& ctx, const float4* in, int n, const float* others_xyz_host, int n_others, float radius_sqr, DevCloud& kept,
+                         DevCloud* removed);
+
 // shared utilities (cloud.cu)
 void compact_points(Ctx& ctx, const float4* in, const uint8_t* keep, int n, DevCloud& out);
 void load_points(Ctx& ctx, const void* points, size_t n, size_t stride_bytes, int memspace, DBuf<float4>& dst);

@@ -75,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "b2r_set_target", "b2r_set_source", "b2r_set_target_cloud", "b2r_set_source_cloud",
     "b2r_align", "b2r_fitness", "b2r_transform_source", "b2r_fitness_pair", "b2r_align_batch",
     "b2r_distance_filter", "b2r_voxelgrid", "b2r_radius_outlier", "b2r_statistical_outlier",
-    "b2r_default_prefilter_config", "b2r_prefilter", "b2r_map_cloud",
+    "b2r_default_prefilter_config", "b2r_prefilter", "b2r_map_cloud", "b2r_remove_robot_points",
     "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_knn_list_overflows", "b2r_debug_covariances", "b2r_debug_voxelmap",
     "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
     "b2r_debug_knn", "b2r_last_timings", "b2r_event_record", "b2r_event_elapsed_ms", "b2r_profile_enable", "b2r_profile_read",
@@ -130,6 +130,7 @@ def load():
     L.b2r_prefilter.argtypes = [vp, ctypes.POINTER(PrefilterConfig), vp, sz, sz, ci, vp, ctypes.POINTER(sz)]
     L.b2r_map_cloud.argtypes = [vp, vp, vp, vp, vp, sz, sz, ci, ctypes.c_float, ci, ctypes.c_float, ci, vp, ctypes.POINTER(sz),
                                 ctypes.POINTER(ci)]
+    L.b2r_remove_robot_points.argtypes = [vp, vp, sz, sz, ci, vp, sz, ctypes.c_float, vp, ctypes.POINTER(sz), vp, ctypes.POINTER(sz)]
     L.b2r_kernel_launches.argtypes = [vp]
     L.b2r_kernel_launches.restype = ctypes.c_uint64
     L.b2r_synchronize.argtypes = [vp]
@@ -349,6 +350,21 @@ class Registration:
         self._check(self._lib.b2r_prefilter(self._h, ctypes.byref(cfg), a.ctypes.data, len(a), a.shape[1] * 4, HOST, out.ctypes.data,
                                             ctypes.byref(m)))
         return out[: m.value].copy()
+
+    def remove_robot_points(self, cloud, others_positions_map, map2sensor, radius):
+        """mrg_slam_component.cpp:395-427.  others_positions_map: (m,3) float64 positions of the other robots in the map frame;
+        map2sensor: 4x4 float64 (odom^-1 * map2odom).  Returns (kept, removed), both in input order."""
+        a = _points(cloud)
+        others = np.asarray(others_positions_map, dtype=np.float64).reshape(-1, 3)
+        M = np.asarray(map2sensor, dtype=np.float64)
+        sensor = (others @ M[:3, :3].T + M[:3, 3]).astype(np.float32)  # (map2sensor * p).cast<float>()  (:399-403)
+        sensor = np.ascontiguousarray(sensor)
+        r2 = np.float32(np.float64(radius) * np.float64(radius))       # float robot_radius_sqr = double * double (:405-406)
+        kept = np.empty((len(a), 4), dtype=np.float32); removed = np.empty((len(a), 4), dtype=np.float32)
+        nk, nr = ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self._lib.b2r_remove_robot_points(self._h, a.ctypes.data, len(a), a.shape[1] * 4, HOST, sensor.ctypes.data, len(sensor),
+                                                      r2, kept.ctypes.data, ctypes.byref(nk), removed.ctypes.data, ctypes.byref(nr)))
+        return kept[: nk.value].copy(), removed[: nr.value].copy()
 
     def map_cloud(self, clouds, poses, first_keyframe=None, resolution=0.05, min_points_per_voxel=1, distance_far_thresh=-1.0,
                   skip_first_cloud=False):
