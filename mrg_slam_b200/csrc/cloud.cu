@@ -102,11 +102,17 @@ static inline float ordered_to_float(int i) {
 }
 
 // bbox_out[cloud][6] ordered-int encoded (min x,y,z, max x,y,z); must be pre-initialised.
-__global__ void bbox_kernel(const CloudView* __restrict__ views, int* __restrict__ bbox_out) {
+// COPY: the points are still in the caller's device buffers srcs[cloud]; the same pass copies them into the cloud's own
+// storage (one kernel for a whole batch of clouds instead of one memcpy per cloud plus a second read for the boxes).
+template <bool COPY>
+__global__ void bbox_kernel(const CloudView* __restrict__ views, int* __restrict__ bbox_out, const float4* const* __restrict__ srcs) {
   const CloudView& c = views[blockIdx.y];
+  const float4* __restrict__ src = COPY ? srcs[blockIdx.y] : c.pts;
+  float4* __restrict__ dst = const_cast<float4*>(c.pts);
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
-    float4 p = __ldg(&c.pts[i]);
+    float4 p = __ldg(&src[i]);
+    if (COPY) dst[i] = p;
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
       mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
       mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
@@ -680,13 +686,25 @@ static void launch_knn_cov(Ctx& ctx, const CloudView* dviews, const std::vector<
   else B2R_LAUNCH(ctx, knn_cov_kernel<32>, grid, 128, 0, dviews, k, knn_out);
 }
 
-// bounding boxes of the clouds that lack one: one kernel over all of them, one D2H, one synchronisation
-void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
+// bounding boxes of the clouds that lack one: one kernel over all of them, one D2H, one synchronisation.
+// device_srcs (optional, one per cloud, same order): packed device buffers the points are copied from in the same pass.
+void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds, const void* const* device_srcs = nullptr) {
   std::vector<Cloud*> todo;
-  for (Cloud* c : clouds)
-    if (!c->has_bbox && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
+  std::vector<const float4*> srcs;
+  for (size_t i = 0; i < clouds.size(); ++i) {
+    Cloud* c = clouds[i];
+    if (!c->has_bbox && std::find(todo.begin(), todo.end(), c) == todo.end()) {
+      todo.push_back(c);
+      if (device_srcs) srcs.push_back((const float4*)device_srcs[i]);
+    }
+  }
   if (todo.empty()) return;
   const int nc = (int)todo.size();
+  DBuf<const float4*> dsrc;
+  if (device_srcs) {
+    dsrc.alloc(nc, ctx.stream);
+    B2R_CUDA(cudaMemcpyAsync(dsrc.p, srcs.data(), sizeof(const float4*) * nc, cudaMemcpyHostToDevice, ctx.stream));
+  }
   std::vector<CloudView> hv(nc);
   int maxn = 1;
   for (int i = 0; i < nc; ++i) { hv[i] = todo[i]->view(); maxn = std::max(maxn, todo[i]->n); }
@@ -695,7 +713,8 @@ void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds) {
   B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * nc, cudaMemcpyHostToDevice, ctx.stream));
   B2R_LAUNCH(ctx, bbox_init_kernel, (nc * 6 + 255) / 256, 256, 0, db.p, nc);
   dim3 g(blocks_for(maxn, 256 * 8, std::max(1, 4 * ctx.num_sms / nc)), nc);
-  B2R_LAUNCH(ctx, bbox_kernel, g, 256, 0, dv.p, db.p);
+  if (device_srcs) B2R_LAUNCH(ctx, bbox_kernel<true>, g, 256, 0, dv.p, db.p, dsrc.p);
+  else B2R_LAUNCH(ctx, bbox_kernel<false>, g, 256, 0, dv.p, db.p, (const float4* const*)nullptr);
   std::vector<int> hb((size_t)nc * 6);
   B2R_CUDA(cudaMemcpyAsync(hb.data(), db.p, sizeof(int) * nc * 6, cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -732,12 +751,26 @@ void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, co
     for (size_t i = 0; i < count; ++i) { raw[i] = staging.p + off; off += ArenaPlan::up(n[i] * 32); }
   }
   const cudaMemcpyKind kind = memspace == B2R_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  // Copy inside the bounding-box kernel: device buffers, or PINNED host buffers (device-readable under unified addressing —
+  // the kernel then pulls them over PCIe itself: one launch instead of one DMA call per cloud).  Pageable host memory
+  // keeps the cudaMemcpyAsync path.
+  bool fused_copy = stride_bytes == 16 && count > 1;
+  if (fused_copy && memspace != B2R_DEVICE) {
+    static const bool zero_copy = [] { const char* e = getenv("B2R_ZERO_COPY_UPLOAD"); return !e || atoi(e) != 0; }();
+    fused_copy = zero_copy;
+    for (size_t i = 0; i < count && fused_copy; ++i) {
+      if (n[i] == 0) continue;
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, points[i]) != cudaSuccess) { cudaGetLastError(); fused_copy = false; break; }
+      if (at.type != cudaMemoryTypeHost || at.devicePointer != points[i]) fused_copy = false;
+    }
+  }
   std::vector<Cloud*> all;
   for (size_t i = 0; i < count; ++i) {
     Cloud& c = *clouds[i];
     c.mem.push_back(arena);
     all.push_back(&c);
-    if (n[i] == 0) continue;
+    if (n[i] == 0 || fused_copy) continue;
     if (stride_bytes == 16) {
       B2R_CUDA(cudaMemcpyAsync(c.pts.p, points[i], n[i] * 16, kind, ctx.stream));
     } else {
@@ -749,7 +782,7 @@ void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, co
       B2R_LAUNCH(ctx, repack32_kernel, (unsigned)((n[i] + 255) / 256), 256, 0, src, (int)n[i], c.pts.p);
     }
   }
-  clouds_compute_bbox(ctx, all);  // synchronises
+  clouds_compute_bbox(ctx, all, fused_copy ? points : nullptr);  // synchronises
 }
 
 template <int MODE>
@@ -1086,7 +1119,7 @@ void compute_bbox(Ctx& ctx, const float4* pts, int n, float mn[3], float mx[3]) 
   DBuf<int> db; db.alloc(6, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dv.p, &hv, sizeof(hv), cudaMemcpyHostToDevice, ctx.stream));
   B2R_LAUNCH(ctx, bbox_init_kernel, 1, 32, 0, db.p, 1);
-  B2R_LAUNCH(ctx, bbox_kernel, dim3(blocks_for(n, 256 * 8, 2 * ctx.num_sms), 1), 256, 0, dv.p, db.p);
+  B2R_LAUNCH(ctx, bbox_kernel<false>, dim3(blocks_for(n, 256 * 8, 2 * ctx.num_sms), 1), 256, 0, dv.p, db.p, (const float4* const*)nullptr);
   int hb[6];
   B2R_CUDA(cudaMemcpyAsync(hb, db.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
   B2R_CUDA(cudaStreamSynchronize(ctx.stream));

@@ -84,3 +84,62 @@ def test_gpu_matches_golden(golden):
             assert np.abs(H - golden[f"{name}_lin_H"]).max() <= 1e-9 * np.abs(H).max()
         g.close()
     reg.close()
+
+
+# ------------------------------------------------------------------------------------------------ golden_v2
+from tests.golden import make_golden_v2 as G2  # noqa: E402
+
+PATH2 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz")
+
+
+@pytest.fixture(scope="module")
+def golden2():
+    return dict(np.load(PATH2, allow_pickle=False))
+
+
+def test_oracle_reproduces_golden_v2(golden2):
+    now = G2.build()
+    assert set(now) == set(golden2)
+    for k, v in golden2.items():
+        if v.dtype.kind in "US" or v.dtype.kind in "iub":
+            assert np.array_equal(now[k], v), k
+        elif v.dtype == np.float32:
+            np.testing.assert_allclose(now[k], v, rtol=1e-5, atol=1e-6, err_msg=k)
+        else:
+            np.testing.assert_allclose(now[k], v, rtol=1e-8, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_v2(golden2):
+    from mrg_slam_b200 import lib as B
+    from mrg_slam_b200 import synth
+    from mrg_slam_b200.odometry import ScanMatchingOdometry
+
+    reg = B.Registration(B.default_config(B.SMALL_GICP))
+    pre = B.Registration(B.default_config(B.FAST_VGICP))
+    A, Bc = pre.prefilter(synth.scan(synth.VLP16, 3)), pre.prefilter(synth.scan(synth.VLP16, 4))
+    gt = np.linalg.inv(synth.pose(3)) @ synth.pose(4)
+    reg.setInputTarget(A); reg.setInputSource(Bc)
+    for i, guess in enumerate(G.guesses(gt)):
+        res = reg.align(guess)
+        assert (res.converged, res.iterations) == (int(golden2["sgicp_conv"][i]), int(golden2["sgicp_iters"][i]))
+        te, re = pose_error(B.from_colmajor(golden2["sgicp_T"][i]), reg.getFinalTransformation())
+        assert te <= 1e-4 and re <= 1e-4
+        f = reg.getFitnessScore()
+        assert abs(f - golden2["sgicp_fitness"][i]) <= 1e-3 * golden2["sgicp_fitness"][i]
+    far = gt.copy(); far[:3, 3] += [0.8, -0.6, 0.1]
+    err, H, b, corr, _ = reg.debug_linearize(far)
+    assert G.sha(corr) == str(golden2["sgicp_corr_sha"])  # double-precision nearest neighbours + rejections
+    assert abs(0.5 * err - golden2["sgicp_lin_err"]) <= 1e-9 * abs(golden2["sgicp_lin_err"])
+    assert np.abs(H - golden2["sgicp_lin_H"]).max() <= 1e-9 * np.abs(H).max()
+    clouds = [pre.prefilter(synth.scan(synth.VLP16, G2.MAP_FIRST + G2.MAP_STEP * i)) for i in range(G2.MAP_COUNT)]
+    _, poses = G2.map_inputs()
+    for tag, (res_, mp, far_) in {"fine": (0.05, 1, -1.0), "coarse": (0.5, 2, 25.0)}.items():
+        m = pre.map_cloud(clouds, poses, [1, 0, 0, 0], res_, mp, far_, True)
+        assert (len(m), G.sha(m)) == (int(golden2[f"map_{tag}_n"]), str(golden2[f"map_{tag}_sha"]))
+    odo = ScanMatchingOdometry(pre, make_cloud=lambda pts: B.Cloud(pre, pts))
+    for i in range(G2.ODO_COUNT):
+        p = odo.matching(0.1 * i, pre.prefilter(synth.scan(synth.VLP16, G2.ODO_FIRST + i)))
+        te, re = pose_error(golden2["odo_traj"][i].astype(np.float64), p.astype(np.float64))
+        assert te <= 1e-4 and re <= 1e-4
+    assert odo.keyframe_switches == int(golden2["odo_switches"])
