@@ -11,8 +11,9 @@ odometry component pays on a scan that becomes the next keyframe.
   value : aligns/s, raw scans already resident in HBM when the timed region starts (device events on the library's stream)
   e2e   : same metric through the reference-facing C ABI with pinned HOST buffers: H2D of every scan and D2H of every
           result inside the timed region (wall clock between device synchronisations)
-  N > 1 : weak scaling — every rank runs its own chain of P pairs (independent units, no data-path collective); the
-          per-step result records are all-gathered over NCCL like the loop-closure batch path does.
+  N > 1 : weak scaling — every rank runs its own chain of P pairs (independent units, no data-path collective, SURVEY 8e);
+          steps are bracketed by a barrier, the time is the max over ranks.  The sharded batch path WITH its result
+          all-gather is `bench_configs.py --config loop_closure` (strong scaling).
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, kind "port": the real pclomp/fast_gicp
 sources are not vendored in /root/reference) with all host threads on a bounded sample of the same workload.
@@ -230,8 +231,11 @@ def run_b2r(args):
         return res
 
     def gather(res):
+        # Outside the timed region: the chain workload has no exchange step (independent scans per rank);
+        # it only checks after the run that every rank's results can be collected like the loop-closure path does.
         if world > 1:
-            LC.gather_results(LC.pack_results(res, list(range(rank * P, rank * P + P))), world * P, device=dev)
+            return LC.gather_results(LC.pack_results(res, list(range(rank * P, rank * P + P))), world * P, device=dev)
+        return None
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,13 +265,7 @@ def run_b2r(args):
         reg.event_record(0)
         res = step(dev_bufs, True)
         reg.event_record(1)
-        ms = reg.event_elapsed_ms(0, 1)
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        gather(res)
-        t1.record()
-        torch.cuda.synchronize()
-        total_ms += ms + (t0.elapsed_time(t1) if world > 1 else 0.0)
+        total_ms += reg.event_elapsed_ms(0, 1)
         conv += sum(r.converged for r in res)
     barrier()
     torch.cuda.profiler.stop()
@@ -283,7 +281,6 @@ def run_b2r(args):
         barrier()
         t0 = time.perf_counter()
         res = step(pin_bufs, False)
-        gather(res)
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
     barrier()

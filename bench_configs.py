@@ -236,19 +236,26 @@ def run_loop_closure(args):
             pairs.append((ti, ci))
             gt = np.linalg.inv(poses[ti]) @ poses[ci]          # new keyframe <- candidate
             guesses.append(gt @ perturbation(rng, args.perturb_t, args.perturb_r))
-    shards = LC.partition_by_target([p[0] for p in pairs], world)
+    weights = [len(pool_np[c]) for _, c in pairs]  # cost of a pair ~ source points it evaluates
+    shards = LC.partition_by_target([p[0] for p in pairs], world, weights)
     mine = shards[rank]
     needed = sorted({c for i in mine for c in pairs[i]})
     pin = {c: torch.from_numpy(pool_np[c]).pin_memory() for c in needed}
     n_mean = float(np.mean([len(pool_np[c]) for c in needed]))
 
+    host_ms = {}
+
     def step():
+        t0 = time.perf_counter()
         cl = B.create_clouds(reg, [pin[c].data_ptr() for c in needed], [pin[c].shape[0] for c in needed], B.HOST)
         byid = dict(zip(needed, cl))
         full = [byid.get(i) for i in range(len(pool_np))]
-        loops, table = LC.detect_loops(reg, full, pairs, guesses, rank=rank, world_size=world, device=dev)
+        t1 = time.perf_counter()
+        loops, table = LC.detect_loops(reg, full, pairs, guesses, rank=rank, world_size=world, device=dev, pair_weights=weights)
+        t2 = time.perf_counter()
         for c in cl:
             c.close()
+        host_ms.update(upload_ms=1e3 * (t1 - t0), detect_loops_ms=1e3 * (t2 - t1), **LC.LAST_TIMINGS)
         return loops, table
 
     def barrier():
@@ -301,7 +308,8 @@ def run_loop_closure(args):
                "pairs": len(pairs), "distinct_clouds": len(pool_np), "converged_fraction": float(conv.mean()),
                "iterations_mean": float(table[:, 17].mean()), "evals_mean": float(table[:, 19].mean()),
                "loops_accepted": accepted, "median_translation_error_m": float(np.median(terr)) if terr else None,
-               "gpu_launches_per_batch_rank0": launches / args.steps, "rank0_stage_ms_last": stage,
+               "gpu_launches_per_batch_rank0": launches / args.steps, "rank0_stage_ms_last": stage, "rank0_host_ms_last": host_ms,
+               "rank0_clouds": len(needed), "rank0_pairs": len(mine),
                "kernels_rank0": kt}
         if args.cpu and world == 1:
             from tests import oraclelib as O

@@ -561,6 +561,10 @@ static LsqParams make_params(const b2r_config& cfg) {
 static int pick_chunks(const Ctx& ctx, int npairs, int maxn) {
   int by_size = std::max(1, (maxn + 1023) / 1024);
   int by_fill = std::max(1, (8 * ctx.num_sms + npairs - 1) / npairs);
+  // large batches: still split every pair into blocks of <= ~8k points, so that a pair whose correspondence search is slow
+  // (far guess) cannot leave the last wave of the launch to a few long-running blocks
+  static const int tail_pts = [] { const char* e = getenv("B2R_CHUNK_POINTS"); return e ? atoi(e) : 8192; }();
+  by_fill = std::max(by_fill, (maxn + tail_pts - 1) / tail_pts);
   return std::max(1, std::min(by_size, by_fill));
 }
 

@@ -52,6 +52,14 @@ class Result(ctypes.Structure):
     ]
 
 
+# numpy view of b2r_result (natural C alignment, matches ctypes' layout of Result)
+RESULT_DTYPE = np.dtype({"names": ["T", "converged", "iterations", "error", "evals", "fitness"],
+                         "formats": [("<f4", 16), "<i4", "<i4", "<f8", "<i4", "<f8"],
+                         "offsets": [Result.T.offset, Result.converged.offset, Result.iterations.offset, Result.error.offset,
+                                     Result.evals.offset, Result.fitness.offset],
+                         "itemsize": ctypes.sizeof(Result)})
+
+
 class PrefilterConfig(ctypes.Structure):
     _fields_ = [
         ("enable_distance_filter", ctypes.c_int),
@@ -310,6 +318,17 @@ class Registration:
         R = (Result * n)()
         self._check(self._lib.b2r_align_batch(self._h, S, T, G.ctypes.data, n, int(with_fitness), fitness_max_range, R))
         return list(R)
+
+    def align_batch_table(self, sources, targets, guesses, with_fitness=False, fitness_max_range=np.finfo(np.float64).max):
+        """align_batch returning the results as one numpy structured array (a view of the b2r_result array): no per-pair
+        Python objects, for large batches."""
+        n = len(sources)
+        S = (ctypes.c_void_p * n)(*[c._h for c in sources])
+        T = (ctypes.c_void_p * n)(*[c._h for c in targets])
+        G = np.ascontiguousarray(np.asarray(guesses, dtype=np.float64).reshape(n, 4, 4).transpose(0, 2, 1).reshape(n, 16).astype(np.float32))
+        R = (Result * max(n, 1))()
+        self._check(self._lib.b2r_align_batch(self._h, S, T, G.ctypes.data, n, int(with_fitness), fitness_max_range, R))
+        return np.frombuffer(R, dtype=RESULT_DTYPE, count=n).copy()
 
     def fitness_pair(self, target, source, T, max_range=np.finfo(np.float64).max):
         out = ctypes.c_double()

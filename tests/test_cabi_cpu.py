@@ -142,3 +142,29 @@ def test_partition_by_target():
     big = LC.partition_by_target([i // 16 for i in range(4096)], 8)
     assert [len(s) for s in big] == [512] * 8
     assert LC.partition_by_target([], 4) == [[], [], [], []]
+
+
+def test_grouped_best_candidate_rule_matches_the_sequential_one():
+    """select_best_grouped (vectorised) == select_best (loop_detector.cpp:106-145 restated), ties and all-unconverged groups included."""
+    from mrg_slam_b200 import loop_closure as LC
+    rng = np.random.default_rng(11)
+    scores = rng.integers(0, 4, size=(200, 7)).astype(np.float64) * 0.25
+    conv = rng.random((200, 7)) > 0.3
+    conv[5] = False
+    best, sc = LC.select_best_grouped(scores, conv)
+    for g in range(200):
+        b, s_ = LC.select_best(scores[g], conv[g])
+        assert (b if b is not None else -1) == best[g] and s_ == sc[g]
+
+
+def test_partition_by_target_balances_weights():
+    from mrg_slam_b200 import loop_closure as LC
+    targets = [i // 16 for i in range(4096)]
+    w = [30000 - 5 * (i // 16) for i in range(4096)]  # clouds shrink along the trajectory
+    for ws in (2, 4, 8):
+        shards = LC.partition_by_target(targets, ws, w)
+        assert sorted(i for s in shards for i in s) == list(range(4096))
+        loads = [sum(w[i] for i in s) for s in shards]
+        assert max(loads) <= 1.02 * sum(w) / ws  # within one target group of the ideal share
+        for s in shards:  # targets never split
+            assert len({targets[i] for i in s}) * 16 == len(s)
