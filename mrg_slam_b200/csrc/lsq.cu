@@ -253,6 +253,108 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
   }
 }
 
+// ---- FAST_VGICP with DIRECT1 lookup (the only mode mrg_slam reaches: registrations.cpp:76-84 calls no search-method setter):
+// same arithmetic as lsq_eval_kernel<B2R_FAST_VGICP>, software-pipelined.  A point costs three DEPENDENT memory round
+// trips (point -> table cell -> voxel record) and the 28 f64 accumulators leave room for only 16 warps per SM, so the plain
+// loop is bound by that latency chain.  Here every thread keeps three points in flight:
+//   i + 3s : point load issued                       (s = stride of the thread's points)
+//   i + 2s : point has arrived -> transform, voxel coordinate, table probe issued
+//   i + 1s : probe has arrived -> voxel record and the point's covariance prefetched into L1 (CCTL.PF1, no registers)
+//   i      : Mahalanobis + accumulation, every operand an L1 hit
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ int vgicp_probe(const CloudView& tgt, const double* x, const float4& p) {
+  double ax, ay, az;
+  apply_pose(x, (double)p.x, (double)p.y, (double)p.z, ax, ay, az);
+  const double res = tgt.vres;
+  int cx, cy, cz;
+  if (res == 1.0) {  // the reference's reg_resolution (config/mrg_slam.yaml:108): x / 1.0 == x exactly, no division needed
+    cx = (int)floor(ax - 0.5); cy = (int)floor(ay - 0.5); cz = (int)floor(az - 0.5);
+  } else {
+    cx = vgicp_coord_d(ax, res); cy = vgicp_coord_d(ay, res); cz = vgicp_coord_d(az, res);
+  }
+  cx -= tgt.vmin[0]; cy -= tgt.vmin[1]; cz -= tgt.vmin[2];
+  if (cx < 0 || cy < 0 || cz < 0 || cx >= tgt.vd[0] || cy >= tgt.vd[1] || cz >= tgt.vd[2]) return -1;
+  return __ldg(&tgt.v_table[(cz * tgt.vd[1] + cy) * tgt.vd[0] + cx]);
+}
+
+__global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+                                                          const LsqState* __restrict__ states, double* __restrict__ partials) {
+  const int pair = blockIdx.y;
+  const LsqState& st = states[pair];
+  const int phase = st.phase;
+  if (phase == PH_DONE) return;
+  const CloudView& src = views[pairs[pair].src];
+  const CloudView& tgt = views[pairs[pair].tgt];
+  __shared__ double sx0[12], sxi[12];
+  __shared__ double red[kAcc * 8];
+  if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
+  __syncthreads();
+  const bool lin = phase == PH_LINEARIZE;
+  double acc[kAcc];
+#pragma unroll
+  for (int t = 0; t < kAcc; ++t) acc[t] = 0.0;
+  int ncorr = 0;
+  const int n = src.n, s = gridDim.x * blockDim.x;
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // prologue: fill the pipeline
+  float4 p0 = i0 < n ? __ldg(&src.pts[i0]) : zero4;
+  float4 p1 = i0 + s < n ? __ldg(&src.pts[i0 + s]) : zero4;
+  float4 p2 = i0 + 2 * s < n ? __ldg(&src.pts[i0 + 2 * s]) : zero4;
+  int rec0 = i0 < n ? vgicp_probe(tgt, sx0, p0) : -1;
+  int rec1 = i0 + s < n ? vgicp_probe(tgt, sx0, p1) : -1;
+  for (int i = i0; i < n; i += s) {
+    const float4 p3 = i + 3 * s < n ? __ldg(&src.pts[i + 3 * s]) : zero4;
+    const int rec2 = i + 2 * s < n ? vgicp_probe(tgt, sx0, p2) : -1;
+    if (rec1 >= 0) {
+      const char* vr = (const char*)&tgt.vrec[rec1];
+      prefetch_l1(vr); prefetch_l1(vr + 32); prefetch_l1(vr + 64); prefetch_l1(vr + sizeof(VoxRec) - 1);
+      const char* pc = (const char*)(src.cov + (size_t)(i + s) * 6);
+      prefetch_l1(pc); prefetch_l1(pc + 32); prefetch_l1(pc + 47);
+    }
+    if (rec0 >= 0) {
+      const double px = (double)p0.x, py = (double)p0.y, pz = (double)p0.z;
+      double ax, ay, az;
+      apply_pose(sx0, px, py, pz, ax, ay, az);
+      double CA[6];
+      {
+        const double* pc = src.cov + (size_t)i * 6;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) CA[t] = __ldg(&pc[t]);
+      }
+      double RCR[6];
+      rsrt(sx0, CA, RCR);
+      const VoxRec& v = tgt.vrec[rec0];
+      double S[6], M[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) S[t] = __ldg(&v.cov[t]) + RCR[t];
+      sym3_inverse(S, M);
+      const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
+      const double w = sqrt((double)__ldg(&v.n));
+      ++ncorr;
+      if (lin) {
+        accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
+      } else {
+        double bx, by, bz;
+        apply_pose(sxi, px, py, pz, bx, by, bz);
+        accumulate(acc, M, bx, by, bz, m0 - bx, m1 - by, m2 - bz, w, false);
+      }
+    }
+    p0 = p1; p1 = p2; p2 = p3;
+    rec0 = rec1; rec1 = rec2;
+  }
+  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kPart;
+  if (lin) {
+    block_reduce_to<kAcc>(acc, red, out);
+    const int bc = block_sum_int(ncorr, (int*)red);
+    if (threadIdx.x == 0) out[28] = (double)bc;
+  } else {
+    double e[1] = {acc[27]};
+    block_reduce_to<1>(e, red, out + 27);
+  }
+}
+
 // ---- small dense math for the step kernel (one thread per pair) ----
 __device__ void ldlt6_solve_dev(const double* Ain, const double* rhs, double* x) {
   double A[36];
@@ -535,7 +637,10 @@ __global__ void lsq_init_kernel(LsqState* __restrict__ states, int npairs, const
 static void launch_lsq_eval(Ctx& ctx, int method, dim3 grid, const CloudView* views, const PairDesc* pairs, const LsqState* states,
                             const LsqParams& prm, double* partials, int32_t* corr_cache, const long long* corr_off, int32_t* corr_out,
                             uint8_t* corr_valid) {
-  if (method == B2R_FAST_VGICP)
+  static const bool pipelined = [] { const char* e = getenv("B2R_VGICP_PIPE"); return !e || atoi(e) != 0; }();
+  if (method == B2R_FAST_VGICP && prm.neighbor_search == B2R_DIRECT1 && !corr_out && pipelined)
+    B2R_LAUNCH(ctx, vgicp_eval_kernel, grid, 256, 0, views, pairs, states, partials);
+  else if (method == B2R_FAST_VGICP)
     B2R_LAUNCH(ctx, lsq_eval_kernel<B2R_FAST_VGICP>, grid, 256, 0, views, pairs, states, prm, partials, corr_cache, corr_off, corr_out, corr_valid);
   else if (method == B2R_FAST_GICP)
     B2R_LAUNCH(ctx, lsq_eval_kernel<B2R_FAST_GICP>, grid, 256, 0, views, pairs, states, prm, partials, corr_cache, corr_off, corr_out, corr_valid);
