@@ -88,6 +88,75 @@ __device__ __forceinline__ float mad2(float a1, float b1, float a2, float b2) {
   return __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2));
 }
 
+// updateDerivatives for one (point, leaf) hit.  xt: transformed point; pg / ph: the point's computePointDerivatives rows.
+__device__ __forceinline__ void ndt_hit(double* acc, const NdtRec& L, float xt0, float xt1, float xt2, const float* pg, const float* ph,
+                                        float gd2, double gd1, bool do_grad, bool do_hess) {
+  // updateDerivatives (float inner math)
+  const float x0 = (float)((double)xt0 - __ldg(&L.mean[0]));
+  const float x1 = (float)((double)xt1 - __ldg(&L.mean[1]));
+  const float x2 = (float)((double)xt2 - __ldg(&L.mean[2]));
+  float C[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) C[t] = __ldg(&L.icov[t]);
+  const float xC0 = mad3(x0, C[0], x1, C[3], x2, C[6]);
+  const float xC1 = mad3(x0, C[1], x1, C[4], x2, C[7]);
+  const float xC2 = mad3(x0, C[2], x1, C[5], x2, C[8]);
+  const float xCx = mad3(x0, xC0, x1, xC1, x2, xC2);
+  float e = (float)exp((double)__fmul_rn(__fmul_rn(-gd2, xCx), 0.5f));
+  const float score_inc = (float)(-gd1 * (double)e);
+  e = __fmul_rn(gd2, e);
+  if (e > 1.0f || e < 0.0f || e != e) return;
+  e = (float)((double)e * gd1);
+  acc[0] += (double)score_inc;
+  // point_gradient (3x6): columns 0..2 identity; col 3 = (0, pg0, pg1); col 4 = (pg2, pg3, pg4); col 5 = (pg5, pg6, pg7).
+  // The reference multiplies through the full matrices in float; the products with the structural 1 and 0 entries
+  // are exact (x*1 = x, x*0 = +-0, y + +-0 = y), so they are skipped here and every remaining operation is the
+  // reference's own, in its order: cg(:,c) = c_inv * point_gradient.col(c) is column c of c_inv for c < 3, etc.
+  float cg[3][6];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    cg[a][0] = C[a * 3 + 0]; cg[a][1] = C[a * 3 + 1]; cg[a][2] = C[a * 3 + 2];
+    cg[a][3] = mad2(C[a * 3 + 1], pg[0], C[a * 3 + 2], pg[1]);
+    cg[a][4] = mad3(C[a * 3 + 0], pg[2], C[a * 3 + 1], pg[3], C[a * 3 + 2], pg[4]);
+    cg[a][5] = mad3(C[a * 3 + 0], pg[5], C[a * 3 + 1], pg[6], C[a * 3 + 2], pg[7]);
+  }
+  float xcg[6] = {xC0, xC1, xC2, 0.f, 0.f, 0.f};  // x . cg(:,c); for c < 3 this is x . c_inv(:,c), computed above
+#pragma unroll
+  for (int c = 3; c < 6; ++c) xcg[c] = mad3(x0, cg[0][c], x1, cg[1][c], x2, cg[2][c]);
+  if (do_grad) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[1 + c] += (double)__fmul_rn(e, xcg[c]);
+  }
+  if (do_hess) {
+    // point_hessian blocks (first component of a, b, c is structurally 0):
+    // (3,3)=a (4,3)=b (5,3)=c (3,4)=b (4,4)=d (5,4)=e (3,5)=c (4,5)=e (5,5)=f
+    const float xa = mad2(xC1, ph[0], xC2, ph[1]);
+    const float xb = mad2(xC1, ph[2], xC2, ph[3]);
+    const float xc = mad2(xC1, ph[4], xC2, ph[5]);
+    const float xd = mad3(xC0, ph[6], xC1, ph[7], xC2, ph[8]);
+    const float xe = mad3(xC0, ph[9], xC1, ph[10], xC2, ph[11]);
+    const float xf = mad3(xC0, ph[12], xC1, ph[13], xC2, ph[14]);
+    const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
+#pragma unroll
+    for (int i2_ = 0; i2_ < 6; ++i2_) {
+      const float ti = __fmul_rn(-gd2, xcg[i2_]);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        // G = point_gradient.col(j) . cg(:,i)
+        float G;
+        if (j < 3) G = cg[j][i2_];
+        else if (j == 3) G = mad2(pg[0], cg[1][i2_], pg[1], cg[2][i2_]);
+        else if (j == 4) G = mad3(pg[2], cg[0][i2_], pg[3], cg[1][i2_], pg[4], cg[2][i2_]);
+        else G = mad3(pg[5], cg[0][i2_], pg[6], cg[1][i2_], pg[7], cg[2][i2_]);
+        float v = __fmul_rn(ti, xcg[j]);
+        if (i2_ >= 3 && j >= 3) v = __fadd_rn(v, XH[i2_ - 3][j - 3]);  // elsewhere the block of point_hessian is 0
+        v = __fadd_rn(v, G);
+        acc[7 + i2_ * 6 + j] += (double)__fmul_rn(e, v);
+      }
+    }
+  }
+}
+
 // grid = (chunks, pairs).  Evaluates score / gradient / Hessian of the pending transform of each active pair.
 constexpr int kNdtThreads = 128;
 __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
@@ -150,71 +219,7 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* 
       }
     }
     for (int hh = 0; hh < hits; ++hh) {
-      const NdtRec& L = tgt.nrec[s_rec[hh * kNdtThreads + threadIdx.x]];
-      // updateDerivatives (float inner math)
-      const float x0 = (float)((double)xt0 - __ldg(&L.mean[0]));
-      const float x1 = (float)((double)xt1 - __ldg(&L.mean[1]));
-      const float x2 = (float)((double)xt2 - __ldg(&L.mean[2]));
-      float C[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) C[t] = __ldg(&L.icov[t]);
-      const float xC0 = mad3(x0, C[0], x1, C[3], x2, C[6]);
-      const float xC1 = mad3(x0, C[1], x1, C[4], x2, C[7]);
-      const float xC2 = mad3(x0, C[2], x1, C[5], x2, C[8]);
-      const float xCx = mad3(x0, xC0, x1, xC1, x2, xC2);
-      float e = (float)exp((double)__fmul_rn(__fmul_rn(-gd2, xCx), 0.5f));
-      const float score_inc = (float)(-gd1 * (double)e);
-      e = __fmul_rn(gd2, e);
-      if (e > 1.0f || e < 0.0f || e != e) continue;
-      e = (float)((double)e * gd1);
-      acc[0] += (double)score_inc;
-      // point_gradient (3x6): columns 0..2 identity; col 3 = (0, pg0, pg1); col 4 = (pg2, pg3, pg4); col 5 = (pg5, pg6, pg7).
-      // The reference multiplies through the full matrices in float; the products with the structural 1 and 0 entries
-      // are exact (x*1 = x, x*0 = +-0, y + +-0 = y), so they are skipped here and every remaining operation is the
-      // reference's own, in its order: cg(:,c) = c_inv * point_gradient.col(c) is column c of c_inv for c < 3, etc.
-      float cg[3][6];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        cg[a][0] = C[a * 3 + 0]; cg[a][1] = C[a * 3 + 1]; cg[a][2] = C[a * 3 + 2];
-        cg[a][3] = mad2(C[a * 3 + 1], pg[0], C[a * 3 + 2], pg[1]);
-        cg[a][4] = mad3(C[a * 3 + 0], pg[2], C[a * 3 + 1], pg[3], C[a * 3 + 2], pg[4]);
-        cg[a][5] = mad3(C[a * 3 + 0], pg[5], C[a * 3 + 1], pg[6], C[a * 3 + 2], pg[7]);
-      }
-      float xcg[6] = {xC0, xC1, xC2, 0.f, 0.f, 0.f};  // x . cg(:,c); for c < 3 this is x . c_inv(:,c), computed above
-#pragma unroll
-      for (int c = 3; c < 6; ++c) xcg[c] = mad3(x0, cg[0][c], x1, cg[1][c], x2, cg[2][c]);
-      if (do_grad) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc[1 + c] += (double)__fmul_rn(e, xcg[c]);
-      }
-      if (do_hess) {
-        // point_hessian blocks (first component of a, b, c is structurally 0):
-        // (3,3)=a (4,3)=b (5,3)=c (3,4)=b (4,4)=d (5,4)=e (3,5)=c (4,5)=e (5,5)=f
-        const float xa = mad2(xC1, ph[0], xC2, ph[1]);
-        const float xb = mad2(xC1, ph[2], xC2, ph[3]);
-        const float xc = mad2(xC1, ph[4], xC2, ph[5]);
-        const float xd = mad3(xC0, ph[6], xC1, ph[7], xC2, ph[8]);
-        const float xe = mad3(xC0, ph[9], xC1, ph[10], xC2, ph[11]);
-        const float xf = mad3(xC0, ph[12], xC1, ph[13], xC2, ph[14]);
-        const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
-#pragma unroll
-        for (int i2_ = 0; i2_ < 6; ++i2_) {
-          const float ti = __fmul_rn(-gd2, xcg[i2_]);
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            // G = point_gradient.col(j) . cg(:,i)
-            float G;
-            if (j < 3) G = cg[j][i2_];
-            else if (j == 3) G = mad2(pg[0], cg[1][i2_], pg[1], cg[2][i2_]);
-            else if (j == 4) G = mad3(pg[2], cg[0][i2_], pg[3], cg[1][i2_], pg[4], cg[2][i2_]);
-            else G = mad3(pg[5], cg[0][i2_], pg[6], cg[1][i2_], pg[7], cg[2][i2_]);
-            float v = __fmul_rn(ti, xcg[j]);
-            if (i2_ >= 3 && j >= 3) v = __fadd_rn(v, XH[i2_ - 3][j - 3]);  // elsewhere the block of point_hessian is 0
-            v = __fadd_rn(v, G);
-            acc[7 + i2_ * 6 + j] += (double)__fmul_rn(e, v);
-          }
-        }
-      }
+      ndt_hit(acc, tgt.nrec[s_rec[hh * kNdtThreads + threadIdx.x]], xt0, xt1, xt2, pg, ph, gd2, gd1, do_grad, do_hess);
     }
     if (hits_out) hits_out[i] = hits;
     nhits += hits;
@@ -223,6 +228,134 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* 
   block_reduce_to<kNdtAcc>(acc, red, out);
   const int bh = block_sum_int(nhits, (int*)red);
   if (threadIdx.x == 0) out[43] = (double)bh;
+}
+
+// Same evaluation with the (point, leaf) hits compacted across the block.  A point has 0..7 usable leaves (DIRECT7), so in
+// ndt_eval_kernel the lanes of a warp idle while the one with the most hits finishes.  Here every round of kNdtThreads
+// points only LISTS its hits: a block-wide exclusive scan of the hit counts gives each thread the slots of a ring buffer in
+// shared memory (order = point order, then the reference's neighbour order: deterministic), and the hits are then processed
+// kNdtThreads at a time, one per thread, whichever point they belong to; what does not fill a round waits for the next
+// points.  The point's own derivative rows are recomputed per hit (23 dot products against ~800 instructions per hit).
+constexpr int kNdtQueueOff = 7;  // DIRECT1 / DIRECT7 (registrations.cpp:140-146); DIRECT27 keeps ndt_eval_kernel
+constexpr int kNdtQueue = 1024;   // >= (kNdtThreads - 1) left over + kNdtQueueOff * kNdtThreads new hits
+__global__ void __launch_bounds__(kNdtThreads, 3) ndt_eval_queue_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+                                                              const NdtState* __restrict__ states, NdtParams prm,
+                                                              double* __restrict__ partials, int32_t* __restrict__ hits_out) {
+  const int pair = blockIdx.y;
+  const NdtState& st = states[pair];
+  if (st.phase == NP_DONE) return;
+  const int mode = st.eval_mode;
+  const bool do_grad = mode != EV_HESS, do_hess = mode != EV_GRAD;
+  const CloudView& src = views[pairs[pair].src];
+  const CloudView& tgt = views[pairs[pair].tgt];
+  __shared__ AngTables tab;
+  __shared__ float T[16];
+  __shared__ double red[kNdtAcc * 4];
+  __shared__ int2 s_q[kNdtQueue];  // (source point, leaf record)
+  __shared__ int s_wsum[kNdtThreads / 32];
+  if (threadIdx.x == 0) ndt_angle_tables(st.p_eval, tab);
+  if (threadIdx.x < 16) T[threadIdx.x] = st.M[threadIdx.x];
+  __syncthreads();
+  const float gd2 = (float)prm.gauss_d2;
+  const double gd1 = prm.gauss_d1;
+  double acc[kNdtAcc];
+#pragma unroll
+  for (int t = 0; t < kNdtAcc; ++t) acc[t] = 0.0;
+  const int noff = prm.neighbor_search == B2R_DIRECT1 ? 1 : 7;
+  const bool have_grid = tgt.ncell_ndt > 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nhits = 0;
+  int head = 0, tail = 0;  // ring positions (block-uniform)
+  const int n = src.n;
+  for (int base = blockIdx.x * blockDim.x; base < n || tail - head > 0; base += gridDim.x * blockDim.x) {
+    const bool more = base < n;
+    if (more) {
+      // ---- list the usable leaves of this round's points
+      const int i = base + threadIdx.x;
+      int recs[kNdtQueueOff];
+      int hits = 0;
+      if (i < n && have_grid) {
+        const float4 xo = __ldg(&src.pts[i]);
+        const float xt0 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[0]), __fmul_rn(xo.y, T[4])), __fadd_rn(__fmul_rn(xo.z, T[8]), T[12]));
+        const float xt1 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[1]), __fmul_rn(xo.y, T[5])), __fadd_rn(__fmul_rn(xo.z, T[9]), T[13]));
+        const float xt2 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[2]), __fmul_rn(xo.y, T[6])), __fadd_rn(__fmul_rn(xo.z, T[10]), T[14]));
+        const int i0 = (int)floorf(__fdiv_rn(xt0, tgt.leaf)), i1 = (int)floorf(__fdiv_rn(xt1, tgt.leaf)), i2 = (int)floorf(__fdiv_rn(xt2, tgt.leaf));
+        // probe all neighbour cells first (independent loads), then the leaves' point counts
+#pragma unroll
+        for (int o = 0; o < kNdtQueueOff; ++o) {
+          recs[o] = -1;
+          if (o < noff) {
+            int ox, oy, oz;
+            neighbor_offset(prm.neighbor_search, o, ox, oy, oz);
+            const int c0 = i0 + ox, c1 = i1 + oy, c2 = i2 + oz;
+            if (!(c0 < tgt.min_b[0] || c0 > tgt.max_b[0] || c1 < tgt.min_b[1] || c1 > tgt.max_b[1] || c2 < tgt.min_b[2] || c2 > tgt.max_b[2]))
+              recs[o] = __ldg(&tgt.n_table[(c0 - tgt.min_b[0]) + (c1 - tgt.min_b[1]) * tgt.div_b[0] + (c2 - tgt.min_b[2]) * tgt.div_b[0] * tgt.div_b[1]]);
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < kNdtQueueOff; ++o)
+          if (o < noff && recs[o] >= 0 && __ldg(&tgt.nrec[recs[o]].n) < 6) recs[o] = -1;
+#pragma unroll
+        for (int o = 0; o < kNdtQueueOff; ++o) hits += (o < noff && recs[o] >= 0) ? 1 : 0;
+        if (hits_out) hits_out[i] = hits;
+      }
+      nhits += hits;
+      // ---- block-wide exclusive scan of the hit counts
+      int incl = hits;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int off = incl - hits, total = 0;
+#pragma unroll
+      for (int w = 0; w < kNdtThreads / 32; ++w) {
+        const int ws = s_wsum[w];
+        if (w < warp) off += ws;
+        total += ws;
+      }
+      int slot = tail + off;
+#pragma unroll
+      for (int o = 0; o < kNdtQueueOff; ++o)
+        if (o < noff && recs[o] >= 0) { s_q[slot & (kNdtQueue - 1)] = make_int2(i, recs[o]); ++slot; }
+      tail += total;
+      __syncthreads();
+    }
+    // ---- process full rounds (and the remainder once the points are exhausted)
+    const bool last = base + (int)(gridDim.x * blockDim.x) >= n;
+    while (tail - head >= kNdtThreads || (last && tail - head > 0)) {
+      const int pos = head + threadIdx.x;
+      if (pos < tail) {
+        const int2 it = s_q[pos & (kNdtQueue - 1)];
+        const float4 xo = __ldg(&src.pts[it.x]);
+        const float xt0 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[0]), __fmul_rn(xo.y, T[4])), __fadd_rn(__fmul_rn(xo.z, T[8]), T[12]));
+        const float xt1 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[1]), __fmul_rn(xo.y, T[5])), __fadd_rn(__fmul_rn(xo.z, T[9]), T[13]));
+        const float xt2 = __fadd_rn(__fadd_rn(__fmul_rn(xo.x, T[2]), __fmul_rn(xo.y, T[6])), __fadd_rn(__fmul_rn(xo.z, T[10]), T[14]));
+        float pg[8], ph[15];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) pg[r] = dot3f(tab.j[r], xo.x, xo.y, xo.z);
+        if (do_hess) {
+#pragma unroll
+          for (int r = 0; r < 15; ++r) ph[r] = dot3f(tab.h[r], xo.x, xo.y, xo.z);
+        }
+        ndt_hit(acc, tgt.nrec[it.y], xt0, xt1, xt2, pg, ph, gd2, gd1, do_grad, do_hess);
+      }
+      head = min(head + kNdtThreads, tail);
+    }
+    if (last) { __syncthreads(); }
+    if (!more) break;
+  }
+  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kNdtPart;
+  block_reduce_to<kNdtAcc>(acc, red, out);
+  const int bh = block_sum_int(nhits, (int*)red);
+  if (threadIdx.x == 0) out[43] = (double)bh;
+}
+
+static bool ndt_use_queue() {
+  static const bool q = [] { const char* e = getenv("B2R_NDT_QUEUE"); return !e || atoi(e) != 0; }();
+  return q;
 }
 
 // ---- step-kernel helpers (one thread per pair) ----
@@ -590,7 +723,8 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
     for (int r = 0; r < rounds_per_check; ++r) {
       {
         ProfScope ps(ctx, PROF_NDT_EVAL, 0.0);  // bytes are added below from the work the device actually did
-        B2R_LAUNCH(ctx, ndt_eval_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
+        if (ndt_use_queue() && prm.neighbor_search != B2R_DIRECT27) B2R_LAUNCH(ctx, ndt_eval_queue_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
+        else B2R_LAUNCH(ctx, ndt_eval_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
       }
       B2R_LAUNCH(ctx, ndt_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, dn.p, done.p);
     }
@@ -637,7 +771,8 @@ void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_v
   if (hits_out) dh.alloc(n_src, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dp.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, &s, sizeof(s), cudaMemcpyHostToDevice, ctx.stream));
-  B2R_LAUNCH(ctx, ndt_eval_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
+  if (ndt_use_queue() && prm.neighbor_search != B2R_DIRECT27) B2R_LAUNCH(ctx, ndt_eval_queue_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
+  else B2R_LAUNCH(ctx, ndt_eval_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
   std::vector<double> hp((size_t)chunks * kNdtPart);
   B2R_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, ctx.stream));
   if (hits_out) B2R_CUDA(cudaMemcpyAsync(hits_out, dh.p, sizeof(int32_t) * n_src, cudaMemcpyDeviceToHost, ctx.stream));
