@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--method", default="FAST_VGICP", choices=["FAST_VGICP", "FAST_GICP", "NDT_OMP"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-handles", type=int, default=2, help="registration handles (streams + host threads) of the overlapped e2e leg")
     return ap.parse_args()
 
 
@@ -273,26 +274,76 @@ def run_b2r(args):
     prof = {k: reg.profile_read(k) for k in B.PROFILE_KERNELS}
     reg.profile_enable(False)
 
-    # ---- timed: e2e (pinned host buffers through the C ABI; H2D + D2H inside)
+    # ---- timed: e2e (pinned host buffers through the C ABI; H2D of every scan + D2H of every result inside)
+    # serial: one handle, one step at a time, L2 flushed between steps
     barrier()
-    e2e_s = 0.0
+    e2e_serial_s = 0.0
     for _ in range(args.steps):
         flush.fill_(1)
         barrier()
         t0 = time.perf_counter()
         res = step(pin_bufs, False)
         torch.cuda.synchronize()
-        e2e_s += time.perf_counter() - t0
+        e2e_serial_s += time.perf_counter() - t0
     barrier()
+    # overlapped (the headline e2e): `--e2e-handles` registration objects, each with its own CUDA stream and host thread,
+    # work through the same K steps concurrently (the reference runs odometry and loop detection on separate objects
+    # and threads the same way, SURVEY 8b "Threading"), so one step's PCIe upload and host-side synchronisations overlap
+    # another step's kernels.  Every step still uploads all its scans and reads back all its results; no L2 flush here:
+    # the inputs come from host memory and the ~0.3 GB per-step working set exceeds L2.
+    import threading
+    nh = max(1, args.e2e_handles)
+    regs = [reg] + [B.Registration(B.default_config(method, device=local_rank)) for _ in range(nh - 1)]
+
+    def step_on(r):
+        cl = B.create_clouds(r, [b.data_ptr() for b in pin_bufs], [b.shape[0] for b in pin_bufs], B.HOST)
+        out = r.align_batch(cl[1:], cl[:-1], guesses)
+        for c in cl:
+            c.close()
+        return out
+
+    for r in regs[1:]:
+        step_on(r)  # warm-up of the additional handles
+    counter = {"next": 0, "conv": 0}
+    lock = threading.Lock()
+
+    def worker(r):
+        torch.cuda.set_device(local_rank)
+        while True:
+            with lock:
+                k = counter["next"]
+                if k >= args.steps:
+                    return
+                counter["next"] = k + 1
+            out = step_on(r)
+            with lock:
+                counter["conv"] += sum(x.converged for x in out)
+
+    barrier()
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=worker, args=(r,)) for r in regs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_conv = counter["conv"]
     clocks = sampler.stop() if rank == 0 else None
 
-    tt = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms, e2e_s * 1000.0, e2e_serial_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    max_ms, max_e2e_ms = float(tt[0]), float(tt[1])
+    max_ms, max_e2e_ms, max_e2e_serial_ms = float(tt[0]), float(tt[1]), float(tt[2])
     if rank == 0:
         value = P * world * args.steps / (max_ms / 1000.0)
-        e2e = P * world * args.steps / (max_e2e_ms / 1000.0)
+        e2e_overlapped = P * world * args.steps / (max_e2e_ms / 1000.0)
+        e2e_serial = P * world * args.steps / (max_e2e_serial_ms / 1000.0)
+        # both schedules are measured in every run, through the same public calls on the same host buffers; the line
+        # reports the better one as e2e.value and keeps both (on an 8-GPU box the concurrent PCIe pulls of 16 handles were
+        # slower than 8, profiles/r1/configs/bench_n8.jsonl)
+        e2e = max(e2e_overlapped, e2e_serial)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -323,7 +374,13 @@ def run_b2r(args):
             "data": "synthetic", "config": workload_config(args, n_mean),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(sum(b.numel() * 4 for b in pin_bufs)),
                     "d2h_bytes_per_step": int(P * __import__("ctypes").sizeof(B.Result)),
-                    "timing": "wall clock between device synchronisations"},
+                    "schedule": "overlapped" if e2e_overlapped >= e2e_serial else "serial",
+                    "overlapped_value": e2e_overlapped, "serial_value": e2e_serial,
+                    "overlapped_timing": f"wall clock over all K steps, {nh} registration handles (one stream + one host thread each) "
+                                         "working concurrently; every step uploads its scans from pinned host memory and reads its "
+                                         "results back",
+                    "handles": nh, "converged_fraction": e2e_conv / float(P * args.steps),
+                    "serial_timing": "one handle, one step at a time, L2 flushed between steps, wall clock between device synchronisations"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,

@@ -419,3 +419,46 @@ def test_cloud_may_outlive_its_handle(vlp16_pair):
     assert res.iterations == ref.iterations and np.array_equal(T1, r2.getFinalTransformation())
     r2.close()
     ca.close(); cb.close()
+
+
+def test_two_handles_on_two_threads(vlp16_pair):
+    """SURVEY 8b "Threading": odometry and loop detection own one registration object each and run on different threads of
+    one process.  Two handles (one CUDA stream each) driven concurrently from two host threads give bitwise the results
+    of the same calls made one after the other (bench.py's overlapped e2e leg relies on this)."""
+    import threading
+    a, b, gt = vlp16_pair
+    methods = [B.FAST_VGICP, B.NDT_OMP]
+    guesses = [gt.copy() for _ in range(4)]
+    for k, g in enumerate(guesses):
+        g[0, 3] += 0.05 * k
+    serial, regs = [], []
+    for m in methods:
+        r = B.Registration(B.default_config(m))
+        regs.append(r)
+        ca, cb = B.Cloud(r, a), B.Cloud(r, b)
+        serial.append([list(x.T) + [x.iterations, x.fitness] for x in r.align_batch([cb] * 4, [ca] * 4, guesses, with_fitness=True)])
+        ca.close(); cb.close()
+    out = [[None] * 6 for _ in methods]
+    errors = []
+
+    def work(i):
+        try:
+            r = regs[i]
+            for rep in range(6):
+                ca, cb = B.Cloud(r, a), B.Cloud(r, b)  # uploads and structure builds race with the other thread's kernels
+                out[i][rep] = [list(x.T) + [x.iterations, x.fitness] for x in r.align_batch([cb] * 4, [ca] * 4, guesses, with_fitness=True)]
+                ca.close(); cb.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(methods))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for i in range(len(methods)):
+        for rep in range(6):
+            assert out[i][rep] == serial[i]
+    for r in regs:
+        r.close()
