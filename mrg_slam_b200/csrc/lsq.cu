@@ -665,7 +665,8 @@ static LsqParams make_params(const b2r_config& cfg) {
 
 static int pick_chunks(const Ctx& ctx, int npairs, int maxn) {
   int by_size = std::max(1, (maxn + 1023) / 1024);
-  int by_fill = std::max(1, (8 * ctx.num_sms + npairs - 1) / npairs);
+  static const int fill = [] { const char* e = getenv("B2R_FILL_PER_SM"); return e ? atoi(e) : 32; }();  // blocks per SM a launch should offer: short tails when few pairs are active
+  int by_fill = std::max(1, (fill * ctx.num_sms + npairs - 1) / npairs);
   // large batches: still split every pair into blocks of <= ~8k points, so that a pair whose correspondence search is slow
   // (far guess) cannot leave the last wave of the launch to a few long-running blocks
   static const int tail_pts = [] { const char* e = getenv("B2R_CHUNK_POINTS"); return e ? atoi(e) : 8192; }();

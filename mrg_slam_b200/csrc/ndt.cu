@@ -668,7 +668,8 @@ static NdtParams make_ndt_params(const b2r_config& cfg) {
 
 static int ndt_chunks(const Ctx& ctx, int npairs, int maxn) {
   int by_size = std::max(1, (maxn + 511) / 512);
-  int by_fill = std::max(1, (8 * ctx.num_sms + npairs - 1) / npairs);
+  static const int fill = [] { const char* e = getenv("B2R_FILL_PER_SM"); return e ? atoi(e) : 48; }();  // blocks per SM a launch should offer: short tails when few pairs are active
+  int by_fill = std::max(1, (fill * ctx.num_sms + npairs - 1) / npairs);
   static const int tail_pts = [] { const char* e = getenv("B2R_CHUNK_POINTS"); return e ? atoi(e) : 8192; }();
   by_fill = std::max(by_fill, (maxn + tail_pts - 1) / tail_pts);  // see pick_chunks (lsq.cu): bounds the tail of large batches
   return std::max(1, std::min(by_size, by_fill));

@@ -7,6 +7,12 @@ best_score <= fitness_score_thresh (:156).  The K aligns are independent, so bat
 pairs are sharded across GPUs by target id — all candidates of one keyframe on one rank, so its voxel map /
 covariances are built once — and the fixed-size results are all-gathered (NCCL on GPUs, gloo in CPU tests).
 There is no collective inside the optimiser.
+
+perform_loop_closure_consistency_check (:190-303, enabled in config/mrg_slam.yaml:177) follows the candidate loop: the
+new keyframe is aligned once more against the best candidate's previous (and, if that fails, next) keyframe and the
+composition new -> best -> prev -> new must be the identity within 0.3 m / 3 degrees.  check_consistency() runs those
+aligns as up to two further (much smaller) batches through the same sharded path; match_keyframes() is the whole of
+LoopDetector::matching for many new keyframes at once.
 """
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
@@ -93,8 +99,11 @@ def pack_results(results, pair_indices) -> np.ndarray:
     return out
 
 
-def gather_results(local: np.ndarray, n_pairs: int, device=None, group=None) -> np.ndarray:
-    """All-gathers the per-rank result rows into an (n_pairs, RESULT_WIDTH) array ordered by pair index."""
+def gather_results(local: np.ndarray, n_pairs: int, device=None, group=None, counts: Optional[Sequence[int]] = None) -> np.ndarray:
+    """All-gathers the per-rank result rows into an (n_pairs, RESULT_WIDTH) array ordered by pair index.
+
+    counts: rows per rank when every rank already knows them (detect_loops: all ranks compute the same partition), which
+    saves the size exchange; one collective and one device-to-host copy then carry the whole table."""
     import torch
     import torch.distributed as dist
 
@@ -104,20 +113,23 @@ def gather_results(local: np.ndarray, n_pairs: int, device=None, group=None) -> 
         return full
     ws = dist.get_world_size(group)
     dev = device if device is not None else torch.device("cpu")
-    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros_like(cnt) for _ in range(ws)]
-    dist.all_gather(cnts, cnt, group=group)
-    mx = int(max(int(c.item()) for c in cnts))
+    if counts is None:
+        cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(ws)]
+        dist.all_gather(cnts, cnt, group=group)
+        counts = [int(c.item()) for c in cnts]
+    assert len(counts) == ws and counts[dist.get_rank(group)] == local.shape[0]
+    mx = max(1, int(max(counts)))
     buf = torch.zeros((mx, RESULT_WIDTH), dtype=torch.float64, device=dev)
     if local.shape[0]:
         buf[: local.shape[0]] = torch.from_numpy(local).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(ws)]
-    dist.all_gather(bufs, buf, group=group)
+    allbuf = torch.empty((ws, mx, RESULT_WIDTH), dtype=torch.float64, device=dev)
+    dist.all_gather(list(allbuf.unbind(0)), buf, group=group)
+    rows_all = allbuf.cpu().numpy()
     full = np.zeros((n_pairs, RESULT_WIDTH))
-    for c, b in zip(cnts, bufs):
-        k = int(c.item())
+    for r, k in enumerate(counts):
         if k:
-            rows = b[:k].cpu().numpy()
+            rows = rows_all[r, :k]
             full[rows[:, 21].astype(np.int64)] = rows
     return full
 
@@ -131,6 +143,38 @@ class Loop:
     best_candidate: Optional[int]  # index into that target's candidate list
     best_score: float
     relative_pose: Optional[np.ndarray]  # new keyframe <- best candidate, 4x4
+    source: Optional[int] = None  # cloud index of the best candidate
+
+
+def _cloud(clouds, i):
+    return clouds(i) if callable(clouds) else clouds[i]
+
+
+def sharded_align(reg, clouds, pairs, guesses, with_fitness=True, fitness_score_max_range=DBL_MAX, rank=0, world_size=1, device=None,
+                  group=None, pair_weights=None) -> np.ndarray:
+    """One batch of (target, source) pairs: partition by target, this rank's slice through reg.align_batch, all-gather.
+    Returns the full (len(pairs), RESULT_WIDTH) table on every rank.  `clouds` is a list or a callable index -> cloud."""
+    import time
+
+    t_start = time.perf_counter()
+    target_ids = [p[0] for p in pairs]
+    shards = partition_by_target(target_ids, world_size, pair_weights)  # every rank computes the same partition
+    mine = shards[rank]
+    if mine and not hasattr(reg, "align_batch_table"):  # any object with the plain align_batch surface
+        local = pack_results(reg.align_batch([_cloud(clouds, pairs[i][1]) for i in mine], [_cloud(clouds, pairs[i][0]) for i in mine],
+                                             [guesses[i] for i in mine], with_fitness=with_fitness,
+                                             fitness_max_range=fitness_score_max_range), mine)
+    elif mine:
+        res = reg.align_batch_table([_cloud(clouds, pairs[i][1]) for i in mine], [_cloud(clouds, pairs[i][0]) for i in mine],
+                                    [guesses[i] for i in mine], with_fitness=with_fitness, fitness_max_range=fitness_score_max_range)
+        local = pack_table(res, mine)
+    else:
+        local = np.zeros((0, RESULT_WIDTH))
+    t_aligned = time.perf_counter()
+    table = gather_results(local, len(pairs), device=device, group=group, counts=[len(x) for x in shards])
+    t_gathered = time.perf_counter()
+    LAST_TIMINGS.update(align_ms=1e3 * (t_aligned - t_start), gather_ms=1e3 * (t_gathered - t_aligned))
+    return table
 
 
 def detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range=DBL_MAX, fitness_score_thresh=1.25, rank=0, world_size=1,
@@ -142,27 +186,10 @@ def detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range=DBL_MAX, f
             candidate order (the tie rule depends on it)
     Returns (loops per target in order of first appearance, full result table).
     """
-    import time
-
     from .lib import from_colmajor
 
-    t_start = time.perf_counter()
     target_ids = [p[0] for p in pairs]
-    shards = partition_by_target(target_ids, world_size, pair_weights)  # every rank computes the same partition
-    mine = shards[rank]
-    if mine and not hasattr(reg, "align_batch_table"):  # any object with the plain align_batch surface
-        local = pack_results(reg.align_batch([clouds[pairs[i][1]] for i in mine], [clouds[pairs[i][0]] for i in mine],
-                                             [guesses[i] for i in mine], with_fitness=True, fitness_max_range=fitness_score_max_range), mine)
-    elif mine:
-        res = reg.align_batch_table([clouds[pairs[i][1]] for i in mine], [clouds[pairs[i][0]] for i in mine], [guesses[i] for i in mine],
-                                    with_fitness=True, fitness_max_range=fitness_score_max_range)
-        local = pack_table(res, mine)
-    else:
-        local = np.zeros((0, RESULT_WIDTH))
-    t_aligned = time.perf_counter()
-    table = gather_results(local, len(pairs), device=device, group=group)
-    t_gathered = time.perf_counter()
-    LAST_TIMINGS.update(align_ms=1e3 * (t_aligned - t_start), gather_ms=1e3 * (t_gathered - t_aligned))
+    table = sharded_align(reg, clouds, pairs, guesses, True, fitness_score_max_range, rank, world_size, device, group, pair_weights)
     loops, seen = [], {}
     for i, t in enumerate(target_ids):
         seen.setdefault(t, []).append(i)
@@ -178,12 +205,176 @@ def detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range=DBL_MAX, f
             if b < 0 or sc > fitness_score_thresh:
                 loops.append(Loop(t, None, float(sc), None))
             else:
-                loops.append(Loop(t, int(b), float(sc), from_colmajor(table[idxs[int(b)], :16])))
+                loops.append(Loop(t, int(b), float(sc), from_colmajor(table[idxs[int(b)], :16]), pairs[idxs[int(b)]][1]))
         return loops, table
     for t, idxs in seen.items():
         best, score = select_best(table[idxs, 20], table[idxs, 16] != 0)
         if best is None or score > fitness_score_thresh:
             loops.append(Loop(t, None, score, None))
         else:
-            loops.append(Loop(t, best, score, from_colmajor(table[idxs[best], :16])))
+            loops.append(Loop(t, best, score, from_colmajor(table[idxs[best], :16]), pairs[idxs[best]][1]))
     return loops, table
+
+
+# ------------------------------------------------------------------------------------------------ consistency check
+@dataclass
+class KeyframeLinks:
+    """What perform_loop_closure_consistency_check reads from the best-matched KeyFrame (loop_detector.cpp:190-303)."""
+    first_keyframe: bool = False
+    static_keyframe: bool = False
+    prev: Optional[int] = None                     # cloud index of prev_edge->to_keyframe
+    rel_pose_to_prev: Optional[np.ndarray] = None  # prev_edge->relative_pose(), 4x4
+    next: Optional[int] = None                     # cloud index of next_edge->from_keyframe
+    rel_pose_from_next: Optional[np.ndarray] = None  # next_edge->relative_pose(), 4x4
+
+
+def _quat_from_matrix(R, dtype=np.float64):
+    """Eigen::Quaternion(rotation matrix) (w, x, y, z), in the scalar type of the matrix; not normalised."""
+    R = np.asarray(R, dtype=dtype)
+    one, half = dtype(1.0), dtype(0.5)
+    t = R[0, 0] + R[1, 1] + R[2, 2]
+    if t > 0:
+        r = np.sqrt(t + one)
+        w = half * r
+        r = half / r
+        return w, (R[2, 1] - R[1, 2]) * r, (R[0, 2] - R[2, 0]) * r, (R[1, 0] - R[0, 1]) * r
+    i = 0
+    if R[1, 1] > R[0, 0]:
+        i = 1
+    if R[2, 2] > R[i, i]:
+        i = 2
+    j, k = (i + 1) % 3, (i + 2) % 3
+    r = np.sqrt(R[i, i] - R[j, j] - R[k, k] + one)
+    q = [dtype(0)] * 3
+    q[i] = half * r
+    r = half / r
+    w = (R[k, j] - R[j, k]) * r
+    q[j] = (R[j, i] + R[i, j]) * r
+    q[k] = (R[k, i] + R[i, k]) * r
+    return w, q[0], q[1], q[2]
+
+
+def normalize_estimate(T: np.ndarray) -> np.ndarray:
+    """LoopDetector::normalize_estimate (:182-188): rotation -> Eigen::Quaterniond -> normalized -> rotation matrix."""
+    T = np.asarray(T, dtype=np.float64)
+    w, x, y, z = _quat_from_matrix(T[:3, :3])
+    n = np.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    out = np.eye(4)
+    out[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                   [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                   [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]]
+    out[:3, 3] = T[:3, 3]
+    return out
+
+
+def registration_guess(new_estimate: np.ndarray, other_estimate: np.ndarray, planar: bool = False) -> np.ndarray:
+    """( new_keyframe_estimate.inverse() * other_estimate ).matrix().cast<float>() with both estimates normalised
+    (loop_detector.cpp:124-131, :235-240, :278-283); z translation zeroed for use_planar_registration_guess."""
+    a, b = normalize_estimate(new_estimate), normalize_estimate(other_estimate)
+    inv = np.eye(4)
+    inv[:3, :3] = a[:3, :3].T
+    inv[:3, 3] = -a[:3, :3].T @ a[:3, 3]
+    g = (inv @ b).astype(np.float32)
+    if planar:
+        g[2, 3] = 0.0
+    return g
+
+
+def _delta(M: np.ndarray):
+    """Translation norm and Quaternionf(rotation block).angularDistance(Identity) = 2 atan2(|vec|, |w|) of a Matrix4f that
+    should be the identity (:248-250, :294-296)."""
+    M = np.asarray(M, dtype=np.float32)
+    delta_trans = float(np.sqrt(np.float32(M[0, 3] * M[0, 3] + M[1, 3] * M[1, 3] + M[2, 3] * M[2, 3])))
+    w, x, y, z = _quat_from_matrix(M[:3, :3], np.float32)
+    delta_angle = float(np.float32(2.0) * np.arctan2(np.sqrt(x * x + y * y + z * z), np.abs(w)))
+    return delta_trans, delta_angle
+
+
+def identity_check_prev(T_new_prev, T_new_best, T_cand_prev):
+    """rel_pose_new_to_prev.inverse() * rel_pose_new_to_best_matched * rel_pose_candidate_to_prev (:247), Matrix4f."""
+    f = lambda M: np.asarray(M, dtype=np.float32)
+    return _delta(np.linalg.inv(f(T_new_prev)) @ f(T_new_best) @ f(T_cand_prev))
+
+
+def identity_check_next(T_new_next, T_new_best, T_next_cand):
+    """rel_pose_new_to_best_matched.inverse() * rel_pose_new_to_next * rel_pose_next_to_candidate (:290), Matrix4f."""
+    f = lambda M: np.asarray(M, dtype=np.float32)
+    return _delta(np.linalg.inv(f(T_new_best)) @ f(T_new_next) @ f(T_next_cand))
+
+
+def check_consistency(reg, clouds, loops: Sequence[Loop], estimates, links, max_delta_trans=0.3, max_delta_angle=0.0523599,
+                      use_planar_registration_guess=False, enable=True, rank=0, world_size=1, device=None, group=None):
+    """perform_loop_closure_consistency_check (:190-218) for every loop of detect_loops at once.
+
+    estimates: cloud index -> 4x4 graph estimate of that keyframe (node->estimate()); links: cloud index -> KeyframeLinks.
+    The prev-keyframe aligns of all loops form one batch; the next-keyframe aligns of those that failed (or have no
+    prev edge) a second one, as the reference only tries `next` after `prev` failed.  As in the reference the aligns'
+    converged flags are not consulted.  Returns (passed per loop, details per loop)."""
+    from .lib import from_colmajor
+
+    n = len(loops)
+    passed = [False] * n
+    details = [dict() for _ in range(n)]
+    todo = []
+    for i, lp in enumerate(loops):
+        if lp.best_candidate is None:
+            continue  # best_matched == nullptr or best_score > fitness_score_thresh: false (:201-204)
+        lk = links[lp.source]
+        if lk.first_keyframe or lk.static_keyframe:
+            passed[i] = True  # :197-199, before the enable flag is looked at
+            details[i]["skipped"] = "first_or_static_keyframe"
+            continue
+        if enable:
+            todo.append(i)
+
+    def run(stage, idxs):
+        key = "prev" if stage == 0 else "next"
+        sel = [i for i in idxs if getattr(links[loops[i].source], key) is not None]
+        if not sel:
+            return {}
+        pairs, guesses = [], []
+        for i in sel:
+            other = getattr(links[loops[i].source], key)
+            pairs.append((loops[i].target, other))  # the target is still the new keyframe (:104)
+            guesses.append(registration_guess(estimates[loops[i].target], estimates[other], use_planar_registration_guess).astype(np.float64))
+        table = sharded_align(reg, clouds, pairs, guesses, False, DBL_MAX, rank, world_size, device, group)
+        out = {}
+        for row, i in zip(table, sel):
+            lk = links[loops[i].source]
+            T_other = from_colmajor(row[:16])
+            if stage == 0:
+                dt, da = identity_check_prev(T_other, loops[i].relative_pose, lk.rel_pose_to_prev)
+            else:
+                dt, da = identity_check_next(T_other, loops[i].relative_pose, lk.rel_pose_from_next)
+            ok = not (dt > max_delta_trans or da > max_delta_angle)
+            details[i][key] = {"delta_trans": dt, "delta_angle": da, "consistent": ok, "keyframe": getattr(lk, key)}
+            out[i] = ok
+        return out
+
+    ok_prev = run(0, todo)
+    for i, ok in ok_prev.items():
+        passed[i] = ok
+    ok_next = run(1, [i for i in todo if not passed[i]])
+    for i, ok in ok_next.items():
+        passed[i] = ok
+    return passed, details
+
+
+def match_keyframes(reg, clouds, pairs, guesses, estimates, links, fitness_score_max_range=DBL_MAX, fitness_score_thresh=1.25,
+                    enable_loop_closure_consistency_check=True, max_delta_trans=0.3, max_delta_angle=0.0523599,
+                    use_planar_registration_guess=False, rank=0, world_size=1, device=None, group=None, pair_weights=None):
+    """LoopDetector::matching (:97-180) for many new keyframes at once: candidate batch, best-candidate rule, consistency
+    check, acceptance.  Returns (accepted loops, all loops, consistency details, result table)."""
+    loops, table = detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range, fitness_score_thresh, rank, world_size, device,
+                                group, pair_weights)
+    passed, details = check_consistency(reg, clouds, loops, estimates, links, max_delta_trans, max_delta_angle,
+                                        use_planar_registration_guess, enable_loop_closure_consistency_check, rank, world_size, device, group)
+    accepted = []
+    for lp, ok in zip(loops, passed):
+        if lp.best_candidate is None:
+            continue  # :156-160 loop not found
+        if enable_loop_closure_consistency_check and not links[lp.source].first_keyframe and not ok:
+            continue  # :162-166
+        accepted.append(lp)
+    return accepted, loops, details, table
