@@ -58,8 +58,9 @@ def main(outdir):
             if mm:
                 n += 1
                 ops[mm.group(1).split(".")[0]] += 1
-        with gzip.open(os.path.join(outdir, short + ".sass.gz"), "wt") as f:
-            f.write(b)
+        with open(os.path.join(outdir, short + ".sass.gz"), "wb") as raw:  # mtime=0: unchanged kernels give unchanged files
+            with gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as f:
+                f.write(b.encode())
         u = usage.get(name, "")
         reg = re.search(r"REG:(\d+)", u)
         stack = re.search(r"STACK:(\d+)", u)
