@@ -254,13 +254,16 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
 }
 
 // ---- FAST_VGICP with DIRECT1 lookup (the only mode mrg_slam reaches: registrations.cpp:76-84 calls no search-method setter):
-// same arithmetic as lsq_eval_kernel<B2R_FAST_VGICP>, software-pipelined.  A point costs three DEPENDENT memory round
-// trips (point -> table cell -> voxel record) and the 28 f64 accumulators leave room for only 16 warps per SM, so the plain
-// loop is bound by that latency chain.  Here every thread keeps three points in flight:
-//   i + 3s : point load issued                       (s = stride of the thread's points)
-//   i + 2s : point has arrived -> transform, voxel coordinate, table probe issued
-//   i + 1s : probe has arrived -> voxel record and the point's covariance prefetched into L1 (CCTL.PF1, no registers)
-//   i      : Mahalanobis + accumulation, every operand an L1 hit
+// same arithmetic as lsq_eval_kernel<B2R_FAST_VGICP>, software-pipelined and compacted per warp.  A point costs three
+// DEPENDENT memory round trips (point -> table cell -> voxel record) and the 28 f64 accumulators leave room for only 16 warps
+// per SM, so the plain loop is bound by that latency chain; and with a far initial guess (loop-closure candidates) half of the
+// source points fall into empty voxels, whose lanes would idle through the Mahalanobis / Hessian arithmetic.  Every thread
+// keeps three points in flight (s = points per round of the grid):
+//   i + 2s : point load issued
+//   i + 1s : point has arrived -> transform, voxel coordinate, table probe issued
+//   i      : probe has arrived -> a hit is appended to the WARP's ring in shared memory (ballot + popc, point order, no block
+//            barrier); its voxel record and the point's covariance are prefetched into L1 (CCTL.PF1, no registers)
+//   ring   : as soon as it holds 32 hits: Mahalanobis + accumulation, one hit per lane, every operand an L1 hit
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int vgicp_probe(const CloudView& tgt, const double* x, const float4& p) {
@@ -278,6 +281,38 @@ __device__ __forceinline__ int vgicp_probe(const CloudView& tgt, const double* x
   return __ldg(&tgt.v_table[(cz * tgt.vd[1] + cy) * tgt.vd[0] + cx]);
 }
 
+// One correspondence of the VGICP cost: source point i of the pair against voxel record rec.
+__device__ __forceinline__ void vgicp_point(double* acc, const CloudView& src, const CloudView& tgt, const double* sx0, const double* sxi,
+                                            int i, int rec, bool lin) {
+  const float4 p = __ldg(&src.pts[i]);
+  const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+  double ax, ay, az;
+  apply_pose(sx0, px, py, pz, ax, ay, az);
+  double CA[6];
+  {
+    const double* pc = src.cov + (size_t)i * 6;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) CA[t] = __ldg(&pc[t]);
+  }
+  double RCR[6];
+  rsrt(sx0, CA, RCR);
+  const VoxRec& v = tgt.vrec[rec];
+  double S[6], M[6];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) S[t] = __ldg(&v.cov[t]) + RCR[t];
+  sym3_inverse(S, M);
+  const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
+  const double w = sqrt((double)__ldg(&v.n));
+  if (lin) {
+    accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
+  } else {
+    double bx, by, bz;
+    apply_pose(sxi, px, py, pz, bx, by, bz);
+    accumulate(acc, M, bx, by, bz, m0 - bx, m1 - by, m2 - bz, w, false);
+  }
+}
+
+constexpr int kVgRing = 64;  // per warp: <= 31 left over + 32 new
 __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                           const LsqState* __restrict__ states, double* __restrict__ partials) {
   const int pair = blockIdx.y;
@@ -288,6 +323,7 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
   const CloudView& tgt = views[pairs[pair].tgt];
   __shared__ double sx0[12], sxi[12];
   __shared__ double red[kAcc * 8];
+  __shared__ int2 s_ring[8][kVgRing];  // (source point, voxel record) hits of each warp
   if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
   __syncthreads();
   const bool lin = phase == PH_LINEARIZE;
@@ -296,53 +332,45 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
   for (int t = 0; t < kAcc; ++t) acc[t] = 0.0;
   int ncorr = 0;
   const int n = src.n, s = gridDim.x * blockDim.x;
-  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int2* ring = s_ring[threadIdx.x >> 5];
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int head = 0, tail = 0;  // ring positions (warp-uniform)
   // prologue: fill the pipeline
-  float4 p0 = i0 < n ? __ldg(&src.pts[i0]) : zero4;
-  float4 p1 = i0 + s < n ? __ldg(&src.pts[i0 + s]) : zero4;
-  float4 p2 = i0 + 2 * s < n ? __ldg(&src.pts[i0 + 2 * s]) : zero4;
-  int rec0 = i0 < n ? vgicp_probe(tgt, sx0, p0) : -1;
-  int rec1 = i0 + s < n ? vgicp_probe(tgt, sx0, p1) : -1;
-  for (int i = i0; i < n; i += s) {
-    const float4 p3 = i + 3 * s < n ? __ldg(&src.pts[i + 3 * s]) : zero4;
-    const int rec2 = i + 2 * s < n ? vgicp_probe(tgt, sx0, p2) : -1;
-    if (rec1 >= 0) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 p2 = i0 + s < n ? __ldg(&src.pts[i0 + s]) : zero4;
+  int rec1 = i0 < n ? vgicp_probe(tgt, sx0, __ldg(&src.pts[i0])) : -1;
+  const int wbase0 = i0 - lane;  // first point of the warp: the trip count below is the same for all its lanes
+  for (int wbase = wbase0; wbase < n; wbase += s) {
+    const int i = wbase + lane;
+    const float4 p3 = i + 2 * s < n ? __ldg(&src.pts[i + 2 * s]) : zero4;
+    const int rec2 = i + s < n ? vgicp_probe(tgt, sx0, p2) : -1;
+    // ---- append this round's hits of the warp
+    const bool hit = rec1 >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      ring[(tail + __popc(m & ((1u << lane) - 1u))) & (kVgRing - 1)] = make_int2(i, rec1);
       const char* vr = (const char*)&tgt.vrec[rec1];
       prefetch_l1(vr); prefetch_l1(vr + 32); prefetch_l1(vr + 64); prefetch_l1(vr + sizeof(VoxRec) - 1);
-      const char* pc = (const char*)(src.cov + (size_t)(i + s) * 6);
+      const char* pc = (const char*)(src.cov + (size_t)i * 6);
       prefetch_l1(pc); prefetch_l1(pc + 32); prefetch_l1(pc + 47);
     }
-    if (rec0 >= 0) {
-      const double px = (double)p0.x, py = (double)p0.y, pz = (double)p0.z;
-      double ax, ay, az;
-      apply_pose(sx0, px, py, pz, ax, ay, az);
-      double CA[6];
-      {
-        const double* pc = src.cov + (size_t)i * 6;
-#pragma unroll
-        for (int t = 0; t < 6; ++t) CA[t] = __ldg(&pc[t]);
+    tail += __popc(m);
+    __syncwarp();
+    // ---- drain: 32 hits at a time (and the remainder after the warp's last points)
+    const bool last = wbase + s >= n;
+    while (tail - head >= 32 || (last && tail - head > 0)) {
+      const int pos = head + lane;
+      if (pos < tail) {
+        const int2 it = ring[pos & (kVgRing - 1)];
+        vgicp_point(acc, src, tgt, sx0, sxi, it.x, it.y, lin);
+        ++ncorr;
       }
-      double RCR[6];
-      rsrt(sx0, CA, RCR);
-      const VoxRec& v = tgt.vrec[rec0];
-      double S[6], M[6];
-#pragma unroll
-      for (int t = 0; t < 6; ++t) S[t] = __ldg(&v.cov[t]) + RCR[t];
-      sym3_inverse(S, M);
-      const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
-      const double w = sqrt((double)__ldg(&v.n));
-      ++ncorr;
-      if (lin) {
-        accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
-      } else {
-        double bx, by, bz;
-        apply_pose(sxi, px, py, pz, bx, by, bz);
-        accumulate(acc, M, bx, by, bz, m0 - bx, m1 - by, m2 - bz, w, false);
-      }
+      head = min(head + 32, tail);
+      __syncwarp();
     }
-    p0 = p1; p1 = p2; p2 = p3;
-    rec0 = rec1; rec1 = rec2;
+    p2 = p3;
+    rec1 = rec2;
   }
   double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kPart;
   if (lin) {
