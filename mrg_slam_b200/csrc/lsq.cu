@@ -732,6 +732,7 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, 
   }
   B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(dg.p, guesses_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_CUDA(cudaMemsetAsync(ds.p, 0, sizeof(LsqState) * np, ctx.stream));  // H, b, d and the padding are copied back before every pair has written them
   B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, dg.p, cfg.maximum_iterations,
              cfg.method == B2R_SMALL_GICP ? 1e-3 : -1.0, done.p);
   const dim3 ge(chunks, np);

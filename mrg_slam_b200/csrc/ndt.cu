@@ -89,7 +89,8 @@ __device__ __forceinline__ float mad2(float a1, float b1, float a2, float b2) {
 }
 
 // updateDerivatives for one (point, leaf) hit.  xt: transformed point; pg / ph: the point's computePointDerivatives rows.
-__device__ __forceinline__ void ndt_hit(double* acc, const NdtRec& L, float xt0, float xt1, float xt2, const float* pg, const float* ph,
+template <bool SPLIT>
+__device__ __forceinline__ void ndt_hit(double* acc, double* sacc, const NdtRec& L, float xt0, float xt1, float xt2, const float* pg, const float* ph,
                                         float gd2, double gd1, bool do_grad, bool do_hess) {
   // updateDerivatives (float inner math)
   const float x0 = (float)((double)xt0 - __ldg(&L.mean[0]));
@@ -151,7 +152,8 @@ __device__ __forceinline__ void ndt_hit(double* acc, const NdtRec& L, float xt0,
         float v = __fmul_rn(ti, xcg[j]);
         if (i2_ >= 3 && j >= 3) v = __fadd_rn(v, XH[i2_ - 3][j - 3]);  // elsewhere the block of point_hessian is 0
         v = __fadd_rn(v, G);
-        acc[7 + i2_ * 6 + j] += (double)__fmul_rn(e, v);
+        if (SPLIT && i2_ >= 3) sacc[((i2_ - 3) * 6 + j) * 128] += (double)__fmul_rn(e, v);  // stride = kNdtThreads
+        else acc[7 + i2_ * 6 + j] += (double)__fmul_rn(e, v);
       }
     }
   }
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* 
       }
     }
     for (int hh = 0; hh < hits; ++hh) {
-      ndt_hit(acc, tgt.nrec[s_rec[hh * kNdtThreads + threadIdx.x]], xt0, xt1, xt2, pg, ph, gd2, gd1, do_grad, do_hess);
+      ndt_hit<false>(acc, nullptr, tgt.nrec[s_rec[hh * kNdtThreads + threadIdx.x]], xt0, xt1, xt2, pg, ph, gd2, gd1, do_grad, do_hess);
     }
     if (hits_out) hits_out[i] = hits;
     nhits += hits;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* 
 // points.  The point's own derivative rows are recomputed per hit (23 dot products against ~800 instructions per hit).
 constexpr int kNdtQueueOff = 7;  // DIRECT1 / DIRECT7 (registrations.cpp:140-146); DIRECT27 keeps ndt_eval_kernel
 constexpr int kNdtQueue = 1024;   // >= (kNdtThreads - 1) left over + kNdtQueueOff * kNdtThreads new hits
-__global__ void __launch_bounds__(kNdtThreads, 3) ndt_eval_queue_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+__global__ void __launch_bounds__(kNdtThreads, 4) ndt_eval_queue_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                               const NdtState* __restrict__ states, NdtParams prm,
                                                               double* __restrict__ partials, int32_t* __restrict__ hits_out) {
   const int pair = blockIdx.y;
@@ -253,14 +255,19 @@ __global__ void __launch_bounds__(kNdtThreads, 3) ndt_eval_queue_kernel(const Cl
   __shared__ double red[kNdtAcc * 4];
   __shared__ int2 s_q[kNdtQueue];  // (source point, leaf record)
   __shared__ int s_wsum[kNdtThreads / 32];
+  // rows 3..5 of the Hessian are accumulated in shared memory (one column per thread): 36 registers less, which is what
+  // lets a fourth block (16 warps) fit on the SM
+  __shared__ double s_hess[18 * kNdtThreads];
   if (threadIdx.x == 0) ndt_angle_tables(st.p_eval, tab);
   if (threadIdx.x < 16) T[threadIdx.x] = st.M[threadIdx.x];
   __syncthreads();
   const float gd2 = (float)prm.gauss_d2;
   const double gd1 = prm.gauss_d1;
-  double acc[kNdtAcc];
+  double acc[25];  // score, g(6), H rows 0..2
 #pragma unroll
-  for (int t = 0; t < kNdtAcc; ++t) acc[t] = 0.0;
+  for (int t = 0; t < 25; ++t) acc[t] = 0.0;
+#pragma unroll
+  for (int t = 0; t < 18; ++t) s_hess[t * kNdtThreads + threadIdx.x] = 0.0;
   const int noff = prm.neighbor_search == B2R_DIRECT1 ? 1 : 7;
   const bool have_grid = tgt.ncell_ndt > 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -273,6 +280,8 @@ __global__ void __launch_bounds__(kNdtThreads, 3) ndt_eval_queue_kernel(const Cl
       // ---- list the usable leaves of this round's points
       const int i = base + threadIdx.x;
       int recs[kNdtQueueOff];
+#pragma unroll
+      for (int o = 0; o < kNdtQueueOff; ++o) recs[o] = -1;  // threads past the end of the cloud list nothing
       int hits = 0;
       if (i < n && have_grid) {
         const float4 xo = __ldg(&src.pts[i]);
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(kNdtThreads, 3) ndt_eval_queue_kernel(const Cl
 #pragma unroll
           for (int r = 0; r < 15; ++r) ph[r] = dot3f(tab.h[r], xo.x, xo.y, xo.z);
         }
-        ndt_hit(acc, tgt.nrec[it.y], xt0, xt1, xt2, pg, ph, gd2, gd1, do_grad, do_hess);
+        ndt_hit<true>(acc, s_hess + threadIdx.x, tgt.nrec[it.y], xt0, xt1, xt2, pg, ph, gd2, gd1, do_grad, do_hess);
       }
       head = min(head + kNdtThreads, tail);
     }
@@ -348,7 +357,12 @@ __global__ void __launch_bounds__(kNdtThreads, 3) ndt_eval_queue_kernel(const Cl
     if (!more) break;
   }
   double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kNdtPart;
-  block_reduce_to<kNdtAcc>(acc, red, out);
+  double all[kNdtAcc];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) all[t] = acc[t];
+#pragma unroll
+  for (int t = 0; t < 18; ++t) all[25 + t] = s_hess[t * kNdtThreads + threadIdx.x];
+  block_reduce_to<kNdtAcc>(all, red, out);
   const int bh = block_sum_int(nhits, (int*)red);
   if (threadIdx.x == 0) out[43] = (double)bh;
 }
