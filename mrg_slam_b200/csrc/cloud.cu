@@ -545,11 +545,11 @@ __device__ unsigned long long g_knn_list_overflows = 0;  // queries whose candid
 __device__ unsigned long long g_knn_hist[66];
 #endif
 constexpr int kKnnThreads = 128;
-constexpr int kKnnListCap = 56;     // logged candidates per query kept in shared memory (28 KB per block)
+constexpr int kKnnListCap = 48;     // logged candidates per query kept in shared memory (24 KB per block: 8 blocks of 64 registers per SM)
 constexpr int kKnnListSpill = 72;   // further ones in per-thread local memory (~5 % of the queries of a prefiltered HDL-64 scan)
 
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 7) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+__global__ void __launch_bounds__(kKnnThreads, 8) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
   __shared__ int s_list[kKnnListCap * kKnnThreads];
   const CloudView& c = views[blockIdx.y];
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
