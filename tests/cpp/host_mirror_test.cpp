@@ -2,12 +2,14 @@
 // the way the reference's callers drive a registration object:
 //   apps/scan_matching_odometry_component.cpp:203-275 (setInputTarget / setInputSource / align / hasConverged /
 //   getFinalTransformation, keyframe switch) and src/mrg_slam/loop_detector.cpp:126-145.
+// and the loop matcher (include/b2r/loop_matcher.hpp) against src/mrg_slam/loop_detector.cpp:97-303.
 // Usage: host_mirror_test [--expect-gpu]
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 
+#include <b2r/loop_matcher.hpp>
 #include <b2r/pcl_adapter.hpp>
 #include <b2r/registration.hpp>
 
@@ -36,8 +38,63 @@ static b2r::PointCloud::Ptr make_cloud(int scan_idx) {
   return c;
 }
 
+
+static b2r::Mat4d pose_colmajor(int scan_idx) {
+  double T[16];
+  b2r_synth_pose(0x5EED0000ull, scan_idx, T);  // row-major
+  b2r::Mat4d M;
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) M[c * 4 + r] = T[r * 4 + c];
+  return M;
+}
+static b2r::Mat4d mul_d(const b2r::Mat4d& A, const b2r::Mat4d& B) {
+  b2r::Mat4d C{};
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r)
+      for (int k = 0; k < 4; ++k) C[c * 4 + r] += A[k * 4 + r] * B[c * 4 + k];
+  return C;
+}
+static b2r::Mat4d inv_rigid(const b2r::Mat4d& A) {
+  b2r::Mat4d I{};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) I[c * 4 + r] = A[r * 4 + c];
+  for (int r = 0; r < 3; ++r) I[12 + r] = -(I[r] * A[12] + I[4 + r] * A[13] + I[8 + r] * A[14]);
+  I[15] = 1.0;
+  return I;
+}
+
+// pure host math of the loop matcher: runs everywhere
+static void loop_matcher_math() {
+  b2r::Mat4d T = pose_colmajor(7);
+  for (int i = 0; i < 12; ++i)
+    if (i % 4 != 3) T[i] *= 1.0 + 1e-6;  // slightly denormalised rotation, what normalize_estimate is for
+  const b2r::Mat4d N = b2r::normalize_estimate(T);
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += N[a * 4 + k] * N[b * 4 + k];
+      CHECK(std::fabs(s - (a == b ? 1.0 : 0.0)) < 1e-14);
+    }
+  CHECK(N[12] == T[12] && N[13] == T[13] && N[14] == T[14]);
+  const b2r::Mat4f g = b2r::registration_guess(pose_colmajor(3), pose_colmajor(4));
+  const b2r::Mat4d gd = mul_d(inv_rigid(pose_colmajor(3)), pose_colmajor(4));
+  for (int i = 0; i < 16; ++i) CHECK(std::fabs(g[i] - (float)gd[i]) < 1e-6f);
+  const b2r::Mat4f gi = b2r::detail::mul(b2r::detail::inverse(g), g);
+  for (int i = 0; i < 16; ++i) CHECK(std::fabs(gi[i] - (i % 5 == 0 ? 1.f : 0.f)) < 1e-5f);
+  b2r::Mat4f R = b2r::identity4();
+  const float ang = 0.05f;
+  R[0] = std::cos(ang); R[4] = -std::sin(ang); R[1] = std::sin(ang); R[5] = std::cos(ang); R[12] = 0.3f; R[13] = -0.4f;
+  float dt, da;
+  b2r::detail::identity_delta(R, dt, da);
+  CHECK(std::fabs(dt - 0.5f) < 1e-6f && std::fabs(da - ang) < 1e-5f);
+  b2r::KeyframeRef kf;
+  b2r::LoopMatch none = b2r::match_keyframe(nullptr, kf, {});
+  CHECK(!none.loop_found && none.best == -1 && none.aligns == 0);  // no candidates: nullptr (:99-101)
+}
+
 int main(int argc, char** argv) {
   const bool expect_gpu = argc > 1 && std::strcmp(argv[1], "--expect-gpu") == 0;
+  loop_matcher_math();
   // ---- factory dispatch (registrations.cpp:46-148)
   b2r::RegistrationParams prm;
   prm.registration_method = "FAST_VGICP";
@@ -107,6 +164,61 @@ int main(int argc, char** argv) {
     auto Tp = base->getFinalTransformation();
     for (int i = 0; i < 16; ++i) CHECK(Tp.data()[i] == T[i]);  // same engine, same bits
     CHECK(std::fabs(reg->fitness() - f) < 1e-12);
+    // ---- loop matcher (loop_detector.cpp:97-303): new keyframe = scan 4 seen again, candidates = scans 3 and 5
+    {
+      b2r_handle* h = vg->handle();
+      auto up = [&](const b2r::PointCloud::Ptr& pc) {
+        b2r_cloud* cl = nullptr;
+        CHECK(b2r_cloud_create(h, pc->points.data(), pc->size(), 32, B2R_HOST, &cl) == B2R_OK);
+        return cl;
+      };
+      auto d2 = make_cloud(2), d6 = make_cloud(6);
+      b2r::KeyframeRef k2, k3, k4, k5, k6;
+      b2r::KeyframeRef* all[5] = {&k2, &k3, &k4, &k5, &k6};
+      b2r::PointCloud::Ptr pcs[5] = {d2, a, b, c, d6};
+      for (int i = 0; i < 5; ++i) { all[i]->cloud = up(pcs[i]); all[i]->estimate = pose_colmajor(2 + i); }
+      auto rel = [&](int from, int to) { return mul_d(inv_rigid(pose_colmajor(from)), pose_colmajor(to)); };  // from <- to
+      k3.prev = &k2; k3.rel_pose_to_prev = rel(3, 2); k3.next = &k5; k3.rel_pose_from_next = rel(5, 3);
+      k5.prev = &k3; k5.rel_pose_to_prev = rel(5, 3); k5.next = &k6; k5.rel_pose_from_next = rel(6, 5);
+      const std::vector<const b2r::KeyframeRef*> cands = {&k3, &k5};
+      b2r::LoopMatch m = b2r::match_keyframe(h, k4, cands);
+      CHECK(m.status == B2R_OK && m.best >= 0 && m.best_score < 1.25);
+      CHECK(m.loop_found && m.consistency_passed && m.aligns == 3);  // two candidates + the prev check
+      CHECK(m.delta_trans[0] >= 0.f && m.delta_trans[0] < 0.3f && m.delta_trans[1] < 0.f);
+      // the best candidate's pose is the single-pair result, bit for bit
+      b2r_result r1;
+      const b2r::Mat4f g = b2r::registration_guess(k4.estimate, cands[m.best]->estimate);
+      CHECK(b2r_set_target_cloud(h, k4.cloud) == B2R_OK && b2r_set_source_cloud(h, cands[m.best]->cloud) == B2R_OK);
+      CHECK(b2r_align(h, g.data(), &r1) == B2R_OK);
+      for (int i = 0; i < 16; ++i) CHECK(r1.T[i] == m.rel_pose_new_to_best[i]);
+      // a prev edge that cannot close: the next keyframe is tried and accepts
+      b2r::KeyframeRef* best = all[m.best == 0 ? 1 : 3];
+      const b2r::Mat4d good_prev = best->rel_pose_to_prev, good_next = best->rel_pose_from_next;
+      best->rel_pose_to_prev[12] += 1.0;
+      m = b2r::match_keyframe(h, k4, cands);
+      CHECK(m.loop_found && m.aligns == 4 && m.delta_trans[0] > 0.3f && m.delta_trans[1] >= 0.f && m.delta_trans[1] < 0.3f);
+      // both edges wrong: rejected although the score is below the threshold (:162-166)
+      best->rel_pose_from_next[12] += 1.0;
+      m = b2r::match_keyframe(h, k4, cands);
+      CHECK(!m.loop_found && !m.consistency_passed && m.best >= 0 && m.best_score < 1.25);
+      // ... unless the candidate is a robot's first keyframe (:197-199) or the check is disabled
+      best->first_keyframe = true;
+      m = b2r::match_keyframe(h, k4, cands);
+      CHECK(m.loop_found && m.aligns == 2);
+      best->first_keyframe = false;
+      b2r::LoopMatchParams off;
+      off.enable_loop_closure_consistency_check = false;
+      m = b2r::match_keyframe(h, k4, cands, off);
+      CHECK(m.loop_found && m.aligns == 2);
+      // a threshold nobody meets: loop not found (:156-160)
+      b2r::LoopMatchParams strict;
+      strict.fitness_score_thresh = 1e-9;
+      m = b2r::match_keyframe(h, k4, cands, strict);
+      CHECK(!m.loop_found && m.best >= 0);
+      best->rel_pose_to_prev = good_prev; best->rel_pose_from_next = good_next;
+      for (auto* k : all) b2r_cloud_destroy(k->cloud);
+      std::printf("loop matcher: gpu path ok\n");
+    }
     std::printf("host mirror: gpu path ok, tx=%.4f (gt %.4f), fitness=%.5f\n", T[12], gt_dx, f);
   }
   std::printf(fails ? "FAILED (%d)\n" : "OK\n", fails);
