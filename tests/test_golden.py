@@ -143,3 +143,56 @@ def test_gpu_matches_golden_v2(golden2):
         te, re = pose_error(golden2["odo_traj"][i].astype(np.float64), p.astype(np.float64))
         assert te <= 1e-4 and re <= 1e-4
     assert odo.keyframe_switches == int(golden2["odo_switches"])
+
+
+# ------------------------------------------------------------------------------------------------ golden_v3: loop matching
+PATH3 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v3.npz")
+
+
+def _check_v3(now, golden, pose_tol, delta_tol, score_rtol):
+    assert set(now) == set(golden)
+    for k, v in golden.items():
+        if k.endswith("_pose"):
+            te, re = pose_error(now[k].astype(np.float64), v.astype(np.float64))
+            assert te <= pose_tol and re <= pose_tol, (k, te, re)
+        elif k.endswith("_deltas"):
+            assert np.array_equal(now[k] < 0, v < 0), k  # the same checks ran
+            np.testing.assert_allclose(now[k], v, rtol=0, atol=delta_tol, err_msg=k)
+        elif k.endswith("_score"):
+            np.testing.assert_allclose(now[k], v, rtol=score_rtol, err_msg=k)
+        else:  # best candidate, decision, cloud sizes
+            assert np.array_equal(now[k], v), k
+
+
+def test_oracle_reproduces_golden_v3():
+    from tests.golden import make_golden_v3 as G3
+
+    _check_v3(G3.build(), dict(np.load(PATH3, allow_pickle=False)), 1e-6, 1e-6, 1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_v3():
+    """LoopDetector::matching + consistency check through the product, against the committed decisions and deltas
+    (no oracle at run time): transforms within the north-star tolerance, decisions identical."""
+    from mrg_slam_b200 import lib as B
+    from tests.golden import make_golden_v3 as G3
+
+    class GpuBatch:
+        def __init__(self):
+            self.reg = B.Registration(B.default_config(B.FAST_GICP))
+
+        def align_batch(self, sources, targets, guesses, with_fitness=False, fitness_max_range=np.finfo(np.float64).max):
+            cache = {}
+
+            def up(c):
+                if id(c) not in cache:
+                    cache[id(c)] = B.Cloud(self.reg, c)
+                return cache[id(c)]
+
+            out = self.reg.align_batch([up(s) for s in sources], [up(t) for t in targets], guesses, with_fitness=with_fitness,
+                                       fitness_max_range=fitness_max_range)
+            for c in cache.values():
+                c.close()
+            return out
+
+    _check_v3(G3.build(GpuBatch), dict(np.load(PATH3, allow_pickle=False)), 1e-4, 2e-4, 1e-3)
