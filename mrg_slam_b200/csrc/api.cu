@@ -443,7 +443,12 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
     DevCloud cur;
     load_points(h.ctx, in, n, stride_bytes, memspace, cur.pts);
     cur.n = (int)n;
-    if (cfg->enable_distance_filter) {
+    // cloud_callback order (apps/prefiltering_component.cpp:149-151): distance_filter, downsample, outlier_removal.
+    // When VoxelGrid follows the distance filter, the filter is folded into VoxelGrid's own passes (no compaction,
+    // no count read-back in between); the result is identical.
+    const double range[2] = {cfg->distance_near_thresh, cfg->distance_far_thresh};
+    const bool fold = cfg->enable_distance_filter && cfg->downsample_method == 1;
+    if (cfg->enable_distance_filter && !fold) {
       DevCloud nxt;
       filter_distance(h.ctx, cur.pts.p, cur.n, cfg->distance_near_thresh, cfg->distance_far_thresh, nxt);
       cur = std::move(nxt);
@@ -451,7 +456,8 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
     if (cfg->downsample_method == 1) {
       DevCloud nxt;
       bool ovf = false;
-      filter_voxelgrid(h.ctx, cur.pts.p, cur.n, cfg->downsample_resolution, cfg->downsample_min_points_per_voxel, nxt, ovf);
+      filter_voxelgrid(h.ctx, cur.pts.p, cur.n, cfg->downsample_resolution, cfg->downsample_min_points_per_voxel, nxt, ovf,
+                       fold ? range : nullptr);
       cur = std::move(nxt);
     }
     if (cfg->outlier_removal_method == 1) {

@@ -1126,4 +1126,51 @@ void compute_bbox(Ctx& ctx, const float4* pts, int n, float mn[3], float mx[3]) 
   for (int d = 0; d < 3; ++d) { mn[d] = ordered_to_float(hb[d]); mx[d] = ordered_to_float(hb[3 + d]); }
 }
 
+// getMinMax3D over the points the distance filter keeps (near < |p| < far, same float norm as distance_flag_kernel): lets
+// b2r_prefilter fold the distance filter into VoxelGrid without compacting the cloud in between.  count = points kept.
+__global__ void bbox_range_kernel(const float4* __restrict__ pts, int n, double near_t, double far_t, int* __restrict__ bbox_out,
+                                  int* __restrict__ count_out) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(&pts[i]);
+    const float s = __fadd_rn(__fmul_rn(p.x, p.x), __fadd_rn(__fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z)));
+    const double d = (double)__fsqrt_rn(s);
+    if (d > near_t && d < far_t) {  // false for non-finite points
+      ++cnt;
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(&bbox_out[d], float_to_ordered(mn[d]));
+      atomicMax(&bbox_out[3 + d], float_to_ordered(mx[d]));
+    }
+    if (cnt) atomicAdd(count_out, cnt);
+  }
+}
+
+void compute_bbox_range(Ctx& ctx, const float4* pts, int n, double near_t, double far_t, float mn[3], float mx[3], int* count) {
+  DBuf<int> db; db.alloc(7, ctx.stream);
+  B2R_LAUNCH(ctx, bbox_init_kernel, 1, 32, 0, db.p, 1);
+  B2R_CUDA(cudaMemsetAsync(db.p + 6, 0, sizeof(int), ctx.stream));
+  B2R_LAUNCH(ctx, bbox_range_kernel, blocks_for(n, 256 * 8, 2 * ctx.num_sms), 256, 0, pts, n, near_t, far_t, db.p, db.p + 6);
+  int hb[7];
+  B2R_CUDA(cudaMemcpyAsync(hb, db.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int d = 0; d < 3; ++d) { mn[d] = ordered_to_float(hb[d]); mx[d] = ordered_to_float(hb[3 + d]); }
+  *count = hb[6];
+}
+
 }  // namespace b2r

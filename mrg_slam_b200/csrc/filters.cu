@@ -15,6 +15,7 @@
 namespace b2r {
 
 void compute_bbox(Ctx& ctx, const float4* pts, int n, float mn[3], float mx[3]);  // cloud.cu
+void compute_bbox_range(Ctx& ctx, const float4* pts, int n, double near_t, double far_t, float mn[3], float mx[3], int* count);  // cloud.cu
 
 // ------------------------------------------------------------------------------------------------ distance filter
 // keep iff near < |p| < far, norm in float as x^2 + (y^2 + z^2) (Eigen 3-vector reduction order), widened to double
@@ -43,12 +44,21 @@ struct VgParams {
 };
 
 // key = dense voxel index (pcl::VoxelGrid: float math, floor(p*inv_leaf) - min_b), value = point index
-__global__ void vg_key_kernel(const float4* __restrict__ in, int n, VgParams prm, unsigned* __restrict__ keys, int* __restrict__ vals) {
+// RANGE: the distance filter (near < |p| < far, distance_flag_kernel's arithmetic) is applied here instead of compacting first
+template <bool RANGE>
+__global__ void vg_key_kernel(const float4* __restrict__ in, int n, VgParams prm, double near_t, double far_t, unsigned* __restrict__ keys,
+                              int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = in[i];
-  unsigned key = 0xffffffffu;  // non-finite points sort last and are dropped
-  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+  unsigned key = 0xffffffffu;  // non-finite (and out-of-range) points sort last and are dropped
+  bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+  if (RANGE) {
+    const float s = __fadd_rn(__fmul_rn(p.x, p.x), __fadd_rn(__fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z)));
+    const double d = (double)__fsqrt_rn(s);
+    ok = d > near_t && d < far_t;
+  }
+  if (ok) {
     const int i0 = (int)(floorf(__fmul_rn(p.x, prm.inv_leaf)) - (float)prm.min_b[0]);
     const int i1 = (int)(floorf(__fmul_rn(p.y, prm.inv_leaf)) - (float)prm.min_b[1]);
     const int i2 = (int)(floorf(__fmul_rn(p.z, prm.inv_leaf)) - (float)prm.min_b[2]);
@@ -103,17 +113,30 @@ __global__ void count_valid_kernel(const unsigned* __restrict__ keys, int n, int
 
 void flags_block_offsets(Ctx& ctx, const uint8_t* flags, int n, int* block_off);  // cloud.cu
 
-void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow) {
+// range != nullptr: {near, far} of the distance filter that precedes VoxelGrid in the prefilter chain
+// (apps/prefiltering_component.cpp:149-151), folded into the bounding-box and key passes; the result is the one of
+// filter_distance followed by filter_voxelgrid (same points, same relative order => same float sums).
+void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow, const double* range) {
   overflow = false;
   out.n = 0;
   if (n == 0) return;
   float mn[3], mx[3];
-  compute_bbox(ctx, in, n, mn, mx);
+  if (range) {
+    int kept = 0;
+    compute_bbox_range(ctx, in, n, range[0], range[1], mn, mx, &kept);
+    if (kept == 0) return;
+  } else {
+    compute_bbox(ctx, in, n, mn, mx);
+  }
   const float inv_leaf = 1.0f / leaf;
   const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv_leaf) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv_leaf) + 1,
                 dz = (int64_t)((mx[2] - mn[2]) * inv_leaf) + 1;
   if (dx * dy * dz > (int64_t)INT32_MAX) {  // PCL: "Leaf size is too small ... Integer indices would overflow": output = input
     overflow = true;
+    if (range) {  // ... the input of VoxelGrid being the distance-filtered cloud
+      filter_distance(ctx, in, n, range[0], range[1], out);
+      return;
+    }
     out.pts.alloc(n, ctx.stream);
     B2R_CUDA(cudaMemcpyAsync(out.pts.p, in, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx.stream));
     out.n = n;
@@ -136,7 +159,8 @@ void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts
   DBuf<int> v0, v1;
   k0.alloc(n, ctx.stream); k1.alloc(n, ctx.stream); v0.alloc(n, ctx.stream); v1.alloc(n, ctx.stream);
   const int nb = (n + 255) / 256;
-  B2R_LAUNCH(ctx, vg_key_kernel, nb, 256, 0, in, n, prm, k0.p, v0.p);
+  if (range) B2R_LAUNCH(ctx, vg_key_kernel<true>, nb, 256, 0, in, n, prm, range[0], range[1], k0.p, v0.p);
+  else B2R_LAUNCH(ctx, vg_key_kernel<false>, nb, 256, 0, in, n, prm, 0.0, 0.0, k0.p, v0.p);
   // stable LSD radix sort (CUB, library primitive): ascending voxel index, ties keep ascending point index
   size_t tmp_bytes = 0;
   B2R_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, ctx.stream));

@@ -147,7 +147,8 @@ struct DevCloud {  // packed device points + count
   int n = 0;
 };
 void filter_distance(Ctx& ctx, const float4* in, int n, double near_t, double far_t, DevCloud& out);
-void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow);
+void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow,
+                      const double* range = nullptr);  // range: {near, far} of a preceding distance filter, folded in
 void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out);
 void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out);
 

@@ -462,3 +462,42 @@ def test_two_handles_on_two_threads(vlp16_pair):
             assert out[i][rep] == serial[i]
     for r in regs:
         r.close()
+
+
+def test_prefilter_chain_variants_match_separate_filters(reg):
+    """b2r_prefilter folds the distance filter into VoxelGrid's own passes (no compaction in between); every variant of
+    the chain must still equal the separate filters applied one after the other, which are bit-exact against the oracle
+    above — including the VoxelGrid overflow branch (output = the distance-filtered input) and a range nobody survives."""
+    raw = synth.scan(synth.VLP16, 12)
+    raw = raw.copy()
+    raw[7, 1] = np.nan
+    raw[99, 0] = np.inf
+
+    def cfg(**kw):
+        c = B.PrefilterConfig()
+        B.load().b2r_default_prefilter_config(ctypes.byref(c))
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def separate(c):
+        cur = raw
+        if c.enable_distance_filter:
+            cur = reg.distance_filter(cur, c.distance_near_thresh, c.distance_far_thresh)
+        if c.downsample_method == 1:
+            cur, _ = reg.voxelgrid(cur, c.downsample_resolution, c.downsample_min_points_per_voxel)
+        if c.outlier_removal_method == 2:
+            cur = reg.radius_outlier(cur, c.radius_radius, c.radius_min_neighbors)
+        elif c.outlier_removal_method == 1:
+            cur = reg.statistical_outlier(cur, c.statistical_mean_k, c.statistical_stddev)
+        return cur
+
+    variants = [cfg(), cfg(distance_near_thresh=2.0, distance_far_thresh=12.0), cfg(downsample_resolution=0.35, downsample_min_points_per_voxel=2),
+                cfg(enable_distance_filter=0), cfg(outlier_removal_method=1), cfg(outlier_removal_method=0),
+                cfg(downsample_resolution=0.001, outlier_removal_method=0),            # INT32 overflow: VoxelGrid passes its input through
+                cfg(distance_near_thresh=500.0, distance_far_thresh=600.0)]            # nothing survives
+    for c in variants:
+        want, got = separate(c), reg.prefilter(raw, c)
+        assert np.array_equal(want, got), (c.distance_near_thresh, c.downsample_resolution, c.outlier_removal_method, len(want), len(got))
+    assert len(reg.prefilter(raw, variants[-1])) == 0
+    assert len(reg.prefilter(raw, variants[-2])) == len(reg.distance_filter(raw, 0.1, 35.0))
