@@ -462,11 +462,11 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
     }
     if (cfg->outlier_removal_method == 1) {
       DevCloud nxt;
-      filter_statistical(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->statistical_mean_k, cfg->statistical_stddev, nxt);
+      filter_statistical(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->statistical_mean_k, cfg->statistical_stddev, nxt, &cur);
       cur = std::move(nxt);
     } else if (cfg->outlier_removal_method == 2) {
       DevCloud nxt;
-      filter_radius(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->radius_radius, cfg->radius_min_neighbors, nxt);
+      filter_radius(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->radius_radius, cfg->radius_min_neighbors, nxt, &cur);
       cur = std::move(nxt);
     }
     finish_filter(h, cur, out, m, memspace);

@@ -142,6 +142,12 @@ void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts
     out.n = n;
     return;
   }
+  // the centroids lie inside the box of the points they average (up to an ulp of float rounding: padded)
+  out.has_box = true;
+  for (int d = 0; d < 3; ++d) {
+    out.box_min[d] = mn[d] - 1e-5f * std::max(1.f, std::fabs(mn[d]));
+    out.box_max[d] = mx[d] + 1e-5f * std::max(1.f, std::fabs(mx[d]));
+  }
   VgParams prm;
   prm.inv_leaf = inv_leaf;
   int div_b[3];
@@ -211,17 +217,21 @@ __global__ void radius_keep_kernel(const CloudView* __restrict__ views, float r2
 }
 
 // a cloud object over the caller's device points (borrowed: the filters only need it for the duration of the call)
-static void with_temp_cloud(Ctx& ctx, const float4* in, int n, Cloud& tmp) {
+static void with_temp_cloud(Ctx& ctx, const float4* in, int n, Cloud& tmp, const DevCloud* box = nullptr) {
   tmp.device = ctx.device;
   tmp.n = n;
   tmp.pts.p = const_cast<float4*>(in);
+  if (box && box->has_box) {  // any box containing the points serves the exact search grid
+    for (int d = 0; d < 3; ++d) { tmp.bmin[d] = box->box_min[d]; tmp.bmax[d] = box->box_max[d]; }
+    tmp.has_bbox = true;
+  }
 }
 
-void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out) {
+void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out, const DevCloud* box) {
   out.n = 0;
   if (n == 0) return;
   Cloud tmp;
-  with_temp_cloud(ctx, in, n, tmp);
+  with_temp_cloud(ctx, in, n, tmp, box);
   b2r_config c2 = cfg;
   c2.nn_cell_size = radius;  // 3x3x3 cells of size >= r cover the search ball
   std::vector<Cloud*> cl{&tmp};
@@ -278,13 +288,14 @@ __global__ void sor_keep_kernel(const float* __restrict__ distances, int n, cons
   keep[i] = ((double)distances[i] > *thr) ? 0 : 1;
 }
 
-void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out) {
+void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out,
+                        const DevCloud* box) {
   out.n = 0;
   if (n == 0) return;
   if (mean_k < 1 || mean_k > 31) throw Error(B2R_ERR_INVALID_ARG, "statistical_mean_k must be in [1,31]");
   if (n < mean_k + 1) throw Error(B2R_ERR_INVALID_ARG, "cloud has fewer than mean_k+1 points");
   Cloud tmp;
-  with_temp_cloud(ctx, in, n, tmp);
+  with_temp_cloud(ctx, in, n, tmp, box);
   std::vector<Cloud*> cl{&tmp};
   std::vector<Needs> nd(1);
   nd[0].grid = true;

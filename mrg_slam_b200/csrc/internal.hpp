@@ -145,12 +145,18 @@ void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor,
 struct DevCloud {  // packed device points + count
   DBuf<float4> pts;
   int n = 0;
+  // a box known to contain every point (VoxelGrid leaves the box of its input: centroids lie inside it), so that the
+  // outlier filter that follows need not run (and wait for) another bounding-box pass for its search grid
+  bool has_box = false;
+  float box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};
 };
 void filter_distance(Ctx& ctx, const float4* in, int n, double near_t, double far_t, DevCloud& out);
 void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts, DevCloud& out, bool& overflow,
                       const double* range = nullptr);  // range: {near, far} of a preceding distance filter, folded in
-void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out);
-void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out);
+void filter_radius(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, double radius, int min_nb, DevCloud& out,
+                   const DevCloud* box = nullptr);
+void filter_statistical(Ctx& ctx, const b2r_config& cfg, const float4* in, int n, int mean_k, double stddev_mul, DevCloud& out,
+                        const DevCloud* box = nullptr);
 
 // MapCloudGenerator::generate + ApproximateMeanVoxelGrid; null_result mirrors the reference's nullptr returns
 void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe, size_t count,
