@@ -545,11 +545,20 @@ __device__ unsigned long long g_knn_list_overflows = 0;  // queries whose candid
 __device__ unsigned long long g_knn_hist[66];
 #endif
 constexpr int kKnnThreads = 128;
-constexpr int kKnnListCap = 48;     // logged candidates per query kept in shared memory (24 KB per block: 8 blocks of 64 registers per SM)
-constexpr int kKnnListSpill = 72;   // further ones in per-thread local memory (~5 % of the queries of a prefiltered HDL-64 scan)
+#ifndef B2R_KNN_CAP
+#define B2R_KNN_CAP 24
+#endif
+#ifndef B2R_KNN_BLOCKS
+#define B2R_KNN_BLOCKS 8
+#endif
+// logged candidates per query kept in shared memory (12 KB per block).  Measured 8..48: the more of the unified L1 / shared
+// memory array is left to L1 the better (the candidates are re-read from neighbouring queries): 48 -> 1.03 ms, 32 -> 0.97,
+// 24 -> 0.96, 8 -> 0.97 on the headline step (the overflow goes to L1-backed local memory and costs the same)
+constexpr int kKnnListCap = B2R_KNN_CAP;
+constexpr int kKnnListSpill = 120 - B2R_KNN_CAP;   // further ones in per-thread local memory
 
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 8) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+__global__ void __launch_bounds__(kKnnThreads, B2R_KNN_BLOCKS) knn_cov_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
   __shared__ int s_list[kKnnListCap * kKnnThreads];
   const CloudView& c = views[blockIdx.y];
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
