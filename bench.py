@@ -307,17 +307,23 @@ def run_b2r(args):
     counter = {"next": 0, "conv": 0}
     lock = threading.Lock()
 
+    errors = []
+
     def worker(r):
-        torch.cuda.set_device(local_rank)
-        while True:
-            with lock:
-                k = counter["next"]
-                if k >= args.steps:
-                    return
-                counter["next"] = k + 1
-            out = step_on(r)
-            with lock:
-                counter["conv"] += sum(x.converged for x in out)
+        try:
+            torch.cuda.set_device(local_rank)
+            while True:
+                with lock:
+                    k = counter["next"]
+                    if k >= args.steps:
+                        return
+                    counter["next"] = k + 1
+                out = step_on(r)
+                with lock:
+                    counter["conv"] += sum(x.converged for x in out)
+                    counter["done"] = counter.get("done", 0) + 1
+        except Exception as e:  # a failed step must fail the run, not shorten it
+            errors.append(e)
 
     barrier()
     t0 = time.perf_counter()
@@ -328,6 +334,8 @@ def run_b2r(args):
         t.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if errors or counter.get("done", 0) != args.steps:
+        raise RuntimeError(f"overlapped e2e leg: {counter.get('done', 0)} of {args.steps} steps completed, errors: {errors}")
     barrier()
     e2e_conv = counter["conv"]
     clocks = sampler.stop() if rank == 0 else None
