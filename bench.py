@@ -325,6 +325,12 @@ def run_b2r(args):
         except Exception as e:  # a failed step must fail the run, not shorten it
             errors.append(e)
 
+    # Two Python threads hand the GIL back and forth around ~40 ctypes calls per step; with the default 5 ms switch interval a
+    # thread returning from a C call can wait that long for the other one, so the interval is shortened for this leg (a C++
+    # caller has no such lock).  It does not remove the occasional collapse of this schedule (about one run in five lands
+    # between 3k and 10k aligns/s instead of ~16.7k, cause not yet pinned down), hence max(serial, overlapped) below.
+    old_interval = sys.getswitchinterval()
+    sys.setswitchinterval(2e-5)
     barrier()
     t0 = time.perf_counter()
     threads = [threading.Thread(target=worker, args=(r,)) for r in regs]
@@ -334,6 +340,7 @@ def run_b2r(args):
         t.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    sys.setswitchinterval(old_interval)
     if errors or counter.get("done", 0) != args.steps:
         raise RuntimeError(f"overlapped e2e leg: {counter.get('done', 0)} of {args.steps} steps completed, errors: {errors}")
     barrier()
