@@ -95,6 +95,28 @@ int orc_map_cloud(const float* const* clouds, const int* n, const double* poses_
                   float resolution, int min_points_per_voxel, float distance_far_thresh, int skip_first_cloud, float* out,
                   int* voxel_keys_out);
 
+/* ---- pcl::GeneralizedIterativeClosestPoint ("GICP" / "GICP_OMP", registrations.cpp:93-116) — gicp_pcl.cpp.
+ * Oracle only: the product has no engine for this method yet. */
+typedef struct orc_gicp_pcl_params {
+  double transformation_epsilon;       /* reg_transformation_epsilon */
+  int maximum_iterations;              /* reg_maximum_iterations */
+  int use_reciprocal_correspondences;  /* reg_use_reciprocal_correspondences (false in the YAML; not restated) */
+  double max_correspondence_distance;  /* reg_max_correspondence_distance */
+  int correspondence_randomness;       /* reg_correspondence_randomness */
+  int max_optimizer_iterations;        /* reg_max_optimizer_iterations (BFGS steps per outer iteration) */
+  double rotation_epsilon;             /* PCL default 2e-3 */
+  double gicp_epsilon;                 /* PCL default 1e-3 */
+} orc_gicp_pcl_params;
+void orc_gicp_pcl_default_params(orc_gicp_pcl_params* p);
+int orc_gicp_pcl_align(const float* target, int nt, const float* source, int ns, const orc_gicp_pcl_params* p, const float* guess_colmajor,
+                       orc_result* out);
+void orc_gicp_pcl_apply_state(const double* x6, float* T_colmajor);
+double orc_gicp_pcl_fdf(const float* src, const float* tgt, const int* idx_src, const int* idx_tgt, int m, const double* mahalanobis, int ns,
+                        const double* x6, double* grad6);
+int orc_gicp_pcl_bfgs(const float* src, const float* tgt, const int* idx_src, const int* idx_tgt, int m, const double* mahalanobis, int ns,
+                      double* x6, int max_inner, double gradient_tol, int* status, double* f_out, int* evals);
+void orc_gicp_pcl_covariances(const float* xyzi, int n, int k, double gicp_epsilon, double* cov9_out);
+
 void orc_set_num_threads(int n);
 int orc_get_max_threads(void);
 

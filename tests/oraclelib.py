@@ -44,6 +44,19 @@ class Result(ctypes.Structure):
     ]
 
 
+class GicpPclParams(ctypes.Structure):
+    _fields_ = [
+        ("transformation_epsilon", ctypes.c_double),
+        ("maximum_iterations", ctypes.c_int),
+        ("use_reciprocal_correspondences", ctypes.c_int),
+        ("max_correspondence_distance", ctypes.c_double),
+        ("correspondence_randomness", ctypes.c_int),
+        ("max_optimizer_iterations", ctypes.c_int),
+        ("rotation_epsilon", ctypes.c_double),
+        ("gicp_epsilon", ctypes.c_double),
+    ]
+
+
 _lib = None
 
 
@@ -93,6 +106,15 @@ def lib():
         L.orc_knn.argtypes = [vp, ci, vp, ci, ci, vp, vp]
         L.orc_map_cloud.restype = ci
         L.orc_map_cloud.argtypes = [vp, vp, vp, vp, ci, ctypes.c_float, ci, ctypes.c_float, ci, vp, vp]
+        L.orc_gicp_pcl_default_params.argtypes = [ctypes.POINTER(GicpPclParams)]
+        L.orc_gicp_pcl_align.restype = ci
+        L.orc_gicp_pcl_align.argtypes = [vp, ci, vp, ci, ctypes.POINTER(GicpPclParams), vp, ctypes.POINTER(Result)]
+        L.orc_gicp_pcl_apply_state.argtypes = [vp, vp]
+        L.orc_gicp_pcl_fdf.restype = cd
+        L.orc_gicp_pcl_fdf.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp]
+        L.orc_gicp_pcl_bfgs.restype = ci
+        L.orc_gicp_pcl_bfgs.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, ci, cd, ctypes.POINTER(ci), ctypes.POINTER(cd), ctypes.POINTER(ci)]
+        L.orc_gicp_pcl_covariances.argtypes = [vp, ci, ci, cd, vp]
         L.orc_set_num_threads.argtypes = [ci]
         L.orc_get_max_threads.restype = ci
         _lib = L
@@ -361,3 +383,58 @@ def set_num_threads(n):
 
 def max_threads():
     return lib().orc_get_max_threads()
+
+
+# ---- pcl::GeneralizedIterativeClosestPoint ("GICP", registrations.cpp:93-103): oracle only, see oracle/gicp_pcl.cpp
+def gicp_pcl_params(**overrides):
+    p = GicpPclParams()
+    lib().orc_gicp_pcl_default_params(ctypes.byref(p))
+    for k, v in overrides.items():
+        assert hasattr(p, k), k
+        setattr(p, k, v)
+    return p
+
+
+def gicp_pcl_align(target, source, guess=None, params=None):
+    t, s = _pts(target), _pts(source)
+    g = colmajor(np.eye(4) if guess is None else guess)
+    r = Result()
+    p = params or gicp_pcl_params()
+    rc = lib().orc_gicp_pcl_align(_p(t), len(t), _p(s), len(s), ctypes.byref(p), _p(g), ctypes.byref(r))
+    assert rc == 0, rc
+    return r
+
+
+def gicp_pcl_apply_state(x6, base=None):
+    T = colmajor(np.eye(4) if base is None else base).copy()
+    x = np.ascontiguousarray(x6, dtype=np.float64)
+    lib().orc_gicp_pcl_apply_state(_p(x), _p(T))
+    return from_colmajor(T)
+
+
+def gicp_pcl_fdf(src, tgt, idx_src, idx_tgt, mahalanobis, x6, want_grad=True):
+    s, t = _pts(src), _pts(tgt)
+    a, b = np.ascontiguousarray(idx_src, dtype=np.int32), np.ascontiguousarray(idx_tgt, dtype=np.int32)
+    M = np.ascontiguousarray(mahalanobis, dtype=np.float64).reshape(len(s), 9)
+    x = np.ascontiguousarray(x6, dtype=np.float64)
+    g = np.zeros(6)
+    f = lib().orc_gicp_pcl_fdf(_p(s), _p(t), _p(a), _p(b), len(a), _p(M), len(s), _p(x), _p(g) if want_grad else None)
+    return f, g
+
+
+def gicp_pcl_bfgs(src, tgt, idx_src, idx_tgt, mahalanobis, x6, max_inner=20, gradient_tol=1e-2):
+    s, t = _pts(src), _pts(tgt)
+    a, b = np.ascontiguousarray(idx_src, dtype=np.int32), np.ascontiguousarray(idx_tgt, dtype=np.int32)
+    M = np.ascontiguousarray(mahalanobis, dtype=np.float64).reshape(len(s), 9)
+    x = np.ascontiguousarray(x6, dtype=np.float64).copy()
+    st, ev, f = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    inner = lib().orc_gicp_pcl_bfgs(_p(s), _p(t), _p(a), _p(b), len(a), _p(M), len(s), _p(x), max_inner, gradient_tol, ctypes.byref(st),
+                                    ctypes.byref(f), ctypes.byref(ev))
+    return x, inner, st.value, f.value, ev.value
+
+
+def gicp_pcl_covariances(cloud, k=20, gicp_epsilon=1e-3):
+    c = _pts(cloud)
+    out = np.zeros((len(c), 9))
+    lib().orc_gicp_pcl_covariances(_p(c), len(c), k, gicp_epsilon, _p(out))
+    return out.reshape(len(c), 3, 3)
