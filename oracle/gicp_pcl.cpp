@@ -501,8 +501,11 @@ struct GicpPcl {
     return false;
   }
 
-  int align(const float* guess_colmajor, orc_result* out) {
-    M4f guess;
+  M4f guess;
+  std::vector<float> output;   // guess * input (pcl::transformPointCloud, float)
+  std::vector<int> is, it;     // correspondences of the current outer iteration
+
+  int prepare(const float* guess_colmajor) {
     std::memcpy(guess.m, guess_colmajor, sizeof(guess.m));
     tree.build(target, nt);
     tree_src.build(source, ns);
@@ -512,45 +515,55 @@ struct GicpPcl {
     pcl_covariances(source, ns, tree_src, k, prm.gicp_epsilon, cov_s);
     mahalanobis.assign((size_t)ns * 9, 0.0);
     for (int i = 0; i < ns; ++i) mahalanobis[(size_t)i * 9] = mahalanobis[(size_t)i * 9 + 4] = mahalanobis[(size_t)i * 9 + 8] = 1.0;
-    // output = guess * input (pcl::transformPointCloud, float)
-    std::vector<float> output((size_t)ns * 4);
+    output.resize((size_t)ns * 4);
     for (int i = 0; i < ns; ++i) {
       m4f_point(guess, source + 4 * (size_t)i, &output[4 * (size_t)i]);
       output[4 * (size_t)i + 3] = source[4 * (size_t)i + 3];
     }
+    return 0;
+  }
+
+  // the correspondence pass of one outer iteration (gicp.hpp: the for loop over the source points)
+  int correspond(const M4f& transformation) {
+    is.clear(); it.clear();
+    is.reserve(ns); it.reserve(ns);
+    const double dist_threshold = prm.max_correspondence_distance * prm.max_correspondence_distance;
+    // transform_R = transformation_ * guess in double
+    double R[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double s = 0;
+        for (int kk = 0; kk < 4; ++kk) s += (double)transformation(i, kk) * (double)guess(kk, j);
+        R[i * 3 + j] = s;
+      }
+    for (int i = 0; i < ns; ++i) {
+      float q[4] = {0, 0, 0, 0};
+      m4f_point(transformation, &output[4 * (size_t)i], q);
+      int idx;
+      float d2;
+      if (tree.knn(q, 1, &idx, &d2) != 1) return -1;
+      if ((double)d2 < dist_threshold) {
+        double C1[9], C2[9], M[9], tmp[9];
+        std::memcpy(C1, &cov_s[(size_t)i * 9], sizeof(C1));
+        std::memcpy(C2, &cov_t[(size_t)idx * 9], sizeof(C2));
+        m3_mul(R, C1, M);          // M = R*C1
+        m3_mul_bt(M, R, tmp);      // temp = M*R'
+        for (int a = 0; a < 9; ++a) tmp[a] += C2[a];
+        m3_inverse(tmp, &mahalanobis[(size_t)i * 9]);
+        is.push_back(i);
+        it.push_back(idx);
+      }
+    }
+    return (int)is.size();
+  }
+
+  int align(const float* guess_colmajor, orc_result* out) {
+    if (prepare(guess_colmajor) != 0) return -1;
     M4f transformation = m4f_identity(), previous = m4f_identity();
     int nr_iterations = 0;
     bool converged = false;
-    const double dist_threshold = prm.max_correspondence_distance * prm.max_correspondence_distance;
     while (!converged) {
-      std::vector<int> is, it;
-      is.reserve(ns); it.reserve(ns);
-      // transform_R = transformation_ * guess in double
-      double R[9];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          double s = 0;
-          for (int kk = 0; kk < 4; ++kk) s += (double)transformation(i, kk) * (double)guess(kk, j);
-          R[i * 3 + j] = s;
-        }
-      for (int i = 0; i < ns; ++i) {
-        float q[4] = {0, 0, 0, 0};
-        m4f_point(transformation, &output[4 * (size_t)i], q);
-        int idx;
-        float d2;
-        if (tree.knn(q, 1, &idx, &d2) != 1) return -1;
-        if ((double)d2 < dist_threshold) {
-          double C1[9], C2[9], M[9], tmp[9];
-          std::memcpy(C1, &cov_s[(size_t)i * 9], sizeof(C1));
-          std::memcpy(C2, &cov_t[(size_t)idx * 9], sizeof(C2));
-          m3_mul(R, C1, M);          // M = R*C1
-          m3_mul_bt(M, R, tmp);      // temp = M*R'
-          for (int a = 0; a < 9; ++a) tmp[a] += C2[a];
-          m3_inverse(tmp, &mahalanobis[(size_t)i * 9]);
-          is.push_back(i);
-          it.push_back(idx);
-        }
-      }
+      if (correspond(transformation) < 0) return -1;
       previous = transformation;
       double delta = 0.;
       if (!estimate(output.data(), is, it, transformation)) break;  // upstream: exception caught, loop left, converged_ stays false
@@ -650,6 +663,33 @@ int orc_gicp_pcl_bfgs(const float* src, const float* tgt, const int* idx_src, co
   if (evals) *evals = pb.evals;
   return inner;
 }
+// ---- a persistent problem for the host test of the device state machine (mrg_slam_b200/csrc/gicp_pcl_sm.hpp)
+struct orc_gicp_pcl { GicpPcl g; };
+orc_gicp_pcl* orc_gicp_pcl_create(const float* target, int nt, const float* source, int ns, const orc_gicp_pcl_params* p,
+                                  const float* guess_colmajor) {
+  orc_gicp_pcl* o = new orc_gicp_pcl();
+  o->g.prm = *p;
+  o->g.target = target; o->g.nt = nt; o->g.source = source; o->g.ns = ns;
+  if (o->g.prepare(guess_colmajor) != 0) { delete o; return nullptr; }
+  return o;
+}
+void orc_gicp_pcl_destroy(orc_gicp_pcl* o) { delete o; }
+int orc_gicp_pcl_correspond(orc_gicp_pcl* o, const float* transformation_colmajor) {
+  M4f T;
+  std::memcpy(T.m, transformation_colmajor, sizeof(T.m));
+  return o->g.correspond(T);
+}
+double orc_gicp_pcl_eval(orc_gicp_pcl* o, const double* x6, double* grad6) {
+  Problem pb;
+  pb.src = o->g.output.data(); pb.tgt = o->g.target; pb.idx_src = &o->g.is; pb.idx_tgt = &o->g.it; pb.mahalanobis = &o->g.mahalanobis;
+  Vec6 x, g;
+  for (int i = 0; i < 6; ++i) x[i] = x6[i];
+  double f;
+  pb.fdf(x, &f, &g);
+  for (int i = 0; i < 6; ++i) grad6[i] = g[i];
+  return f;
+}
+
 void orc_gicp_pcl_covariances(const float* xyzi, int n, int k, double gicp_epsilon, double* cov9_out) {
   KdTree t;
   t.build(xyzi, n);

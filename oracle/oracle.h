@@ -116,6 +116,14 @@ double orc_gicp_pcl_fdf(const float* src, const float* tgt, const int* idx_src, 
 int orc_gicp_pcl_bfgs(const float* src, const float* tgt, const int* idx_src, const int* idx_tgt, int m, const double* mahalanobis, int ns,
                       double* x6, int max_inner, double gradient_tol, int* status, double* f_out, int* evals);
 void orc_gicp_pcl_covariances(const float* xyzi, int n, int k, double gicp_epsilon, double* cov9_out);
+/* a persistent problem: correspondences for a given transformation_, then the functor on them (host test of the device
+ * state machine in mrg_slam_b200/csrc/gicp_pcl_sm.hpp).  target / source must outlive the object. */
+typedef struct orc_gicp_pcl orc_gicp_pcl;
+orc_gicp_pcl* orc_gicp_pcl_create(const float* target, int nt, const float* source, int ns, const orc_gicp_pcl_params* p,
+                                  const float* guess_colmajor);
+void orc_gicp_pcl_destroy(orc_gicp_pcl* o);
+int orc_gicp_pcl_correspond(orc_gicp_pcl* o, const float* transformation_colmajor);
+double orc_gicp_pcl_eval(orc_gicp_pcl* o, const double* x6, double* grad6);
 
 void orc_set_num_threads(int n);
 int orc_get_max_threads(void);
