@@ -38,7 +38,8 @@ typedef enum b2r_method {
   B2R_NDT_OMP = 0,   /* "NDT_OMP"    registrations.cpp:130-147 -> pclomp::NormalDistributionsTransform */
   B2R_FAST_GICP = 1, /* "FAST_GICP"  registrations.cpp:55-63   -> fast_gicp::FastGICP ("GICP" row) */
   B2R_FAST_VGICP = 2, /* "FAST_VGICP" registrations.cpp:76-84   -> fast_gicp::FastVGICP */
-  B2R_SMALL_GICP = 3  /* "SMALL_GICP" registrations.cpp:46-54   -> small_gicp::RegistrationPCL (GICP), the YAML default */
+  B2R_SMALL_GICP = 3, /* "SMALL_GICP" registrations.cpp:46-54   -> small_gicp::RegistrationPCL (GICP), the YAML default */
+  B2R_GICP_PCL = 4    /* "GICP" / "GICP_OMP" registrations.cpp:93-116 -> pcl / pclomp GeneralizedIterativeClosestPoint (BFGS) */
 } b2r_method;
 
 typedef enum b2r_neighbor_search { B2R_DIRECT1 = 0, B2R_DIRECT7 = 1, B2R_DIRECT27 = 2 } b2r_neighbor_search;
@@ -61,6 +62,8 @@ typedef struct b2r_config {
   double ndt_step_size;               /* ndt_omp default 0.1 */
   double ndt_outlier_ratio;           /* ndt_omp default 0.55 */
   double nn_cell_size;                /* uniform-grid cell for exact kNN / 1-NN; 0 = auto from density */
+  int max_optimizer_iterations;       /* reg_max_optimizer_iterations (20): BFGS steps per outer iteration, GICP_PCL only */
+  double gicp_epsilon;                /* PCL default 1e-3: the regularised smallest singular value, GICP_PCL only */
 } b2r_config;
 
 typedef struct b2r_result {

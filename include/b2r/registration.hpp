@@ -60,6 +60,10 @@ class Registration {
   void setMaxCorrespondenceDistance(double d) { cfg_.max_correspondence_distance = d; dirty_ = true; }
   void setCorrespondenceRandomness(int k) { cfg_.correspondence_randomness = k; dirty_ = true; }
   void setResolution(double r) { cfg_.resolution = r; dirty_ = true; }
+  void setMaximumOptimizerIterations(int n) { cfg_.max_optimizer_iterations = n; dirty_ = true; }  // GICP (BFGS) only
+  void setUseReciprocalCorrespondences(bool on) {
+    if (on) std::fprintf(stderr, "b2r: reciprocal correspondences are not implemented (config/mrg_slam.yaml:106 sets false)\n");
+  }
   void setNeighborhoodSearchMethod(NeighborSearchMethod m) {
     cfg_.neighbor_search = m == NeighborSearchMethod::DIRECT1 ? B2R_DIRECT1 : (m == NeighborSearchMethod::DIRECT26 ? B2R_DIRECT27 : B2R_DIRECT7);
     if (m == NeighborSearchMethod::KDTREE) std::fprintf(stderr, "b2r: KDTREE neighbourhood search is not implemented, using DIRECT7\n");
@@ -212,7 +216,18 @@ inline Registration::Ptr select_registration_method(const RegistrationParams& p)
     r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
     return r;
   }
-  if (m == "FAST_VGICP_CUDA" || m == "ICP" || m.find("GICP") != std::string::npos || m == "NDT") {
+  if (m != "ICP" && m != "FAST_VGICP_CUDA" && m.find("GICP") != std::string::npos) {
+    // registrations.cpp:93-116: "GICP" -> pcl::GeneralizedIterativeClosestPoint, "GICP_OMP" -> pclomp's copy (BFGS inner loop)
+    auto r = std::make_shared<Registration>(B2R_GICP_PCL, p.device);
+    r->setTransformationEpsilon(p.reg_transformation_epsilon);
+    r->setMaximumIterations(p.reg_maximum_iterations);
+    r->setUseReciprocalCorrespondences(p.reg_use_reciprocal_correspondences);
+    r->setMaxCorrespondenceDistance(p.reg_max_correspondence_distance);
+    r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
+    r->setMaximumOptimizerIterations(p.reg_max_optimizer_iterations);
+    return r;
+  }
+  if (m == "FAST_VGICP_CUDA" || m == "ICP" || m == "NDT") {
     std::fprintf(stderr, "b2r: registration_method %s is outside this engine's scope\n", m.c_str());
     return nullptr;
   }

@@ -27,6 +27,11 @@ Needs needs_for(const b2r_config& cfg, bool is_target, bool want_fitness) {
       nd.cov_k = cfg.correspondence_randomness;
       if (is_target) nd.grid = true;
       break;
+    case B2R_GICP_PCL:  // PCL's own covariance arithmetic (float products, E[xx^T] - mean mean^T)
+      nd.cov_k = cfg.correspondence_randomness;
+      nd.cov_mode = 1;
+      if (is_target) nd.grid = true;
+      break;
     default:  // NDT_OMP
       if (is_target) nd.leaf = (float)cfg.resolution;
       break;
@@ -54,7 +59,7 @@ b2r_status guarded(b2r_handle* hh, F&& f) {
 }
 
 void check_cfg(const b2r_config& cfg) {
-  if (cfg.method < B2R_NDT_OMP || cfg.method > B2R_SMALL_GICP) throw Error(B2R_ERR_INVALID_ARG, "unknown method");
+  if (cfg.method < B2R_NDT_OMP || cfg.method > B2R_GICP_PCL) throw Error(B2R_ERR_INVALID_ARG, "unknown method");
   if (cfg.resolution <= 0) throw Error(B2R_ERR_INVALID_ARG, "resolution must be > 0");
   if (cfg.method != B2R_NDT_OMP && (cfg.correspondence_randomness < 4 || cfg.correspondence_randomness > 32))
     throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be in [4,32]");
@@ -86,6 +91,7 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<
     Needs& cur = needs[id];
     cur.grid = cur.grid || nd.grid;
     cur.cov_k = std::max(cur.cov_k, nd.cov_k);
+    cur.cov_mode = std::max(cur.cov_mode, nd.cov_mode);
     if (nd.vres > 0) cur.vres = nd.vres;
     if (nd.leaf > 0) cur.leaf = nd.leaf;
     return id;
@@ -101,6 +107,7 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<
   clouds_prepare(ctx, h.cfg, uniq, needs, dv);
   B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
   if (h.cfg.method == B2R_NDT_OMP) ndt_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
+  else if (h.cfg.method == B2R_GICP_PCL) gicp_pcl_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
   else lsq_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
   B2R_CUDA(cudaEventRecord(h.ev[2], ctx.stream));
   if (with_fitness) {
@@ -149,6 +156,8 @@ b2r_status b2r_default_config(int method, b2r_config* cfg) {
   cfg->ndt_step_size = 0.1;
   cfg->ndt_outlier_ratio = 0.55;
   cfg->nn_cell_size = 0.0;
+  cfg->max_optimizer_iterations = 20;      // config/mrg_slam.yaml:105
+  cfg->gicp_epsilon = 1e-3;
   return B2R_OK;
 }
 

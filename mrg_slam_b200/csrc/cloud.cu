@@ -617,6 +617,45 @@ __global__ void __launch_bounds__(kKnnThreads, B2R_KNN_BLOCKS) knn_cov_kernel(co
   for (int t = 0; t < 6; ++t) dst[t] = o[t];
 }
 
+// pcl::GeneralizedIterativeClosestPoint::computeCovariances (registrations.cpp:93-116 "GICP" / "GICP_OMP") from the
+// neighbour lists knn_cov_kernel writes: raw moments with FLOAT products widened to double, E[x x^T] - mean mean^T, the direction
+// of the smallest singular value (|eigenvalue|: the float products can make the matrix slightly indefinite) gets gicp_epsilon,
+// the other two 1.  One thread per point (original order); overwrites the fast_gicp covariance knn_cov_kernel left there.
+__global__ void pcl_cov_kernel(const CloudView* __restrict__ views, const int32_t* __restrict__ knn, int k, double eps) {
+  const CloudView& c = views[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  double mean[3] = {0, 0, 0}, m[6] = {0, 0, 0, 0, 0, 0};  // xx, yx, yy, zx, zy, zz
+  for (int j = 0; j < k; ++j) {
+    const float4 p = __ldg(&c.pts[knn[(size_t)i * k + j]]);
+    mean[0] += (double)p.x; mean[1] += (double)p.y; mean[2] += (double)p.z;
+    m[0] += (double)__fmul_rn(p.x, p.x);
+    m[1] += (double)__fmul_rn(p.y, p.x); m[2] += (double)__fmul_rn(p.y, p.y);
+    m[3] += (double)__fmul_rn(p.z, p.x); m[4] += (double)__fmul_rn(p.z, p.y); m[5] += (double)__fmul_rn(p.z, p.z);
+  }
+  const double kk = (double)k;
+  for (int a = 0; a < 3; ++a) mean[a] /= kk;
+  const double cxx = m[0] / kk - mean[0] * mean[0], cyx = m[1] / kk - mean[1] * mean[0], cyy = m[2] / kk - mean[1] * mean[1];
+  const double czx = m[3] / kk - mean[2] * mean[0], czy = m[4] / kk - mean[2] * mean[1], czz = m[5] / kk - mean[2] * mean[2];
+  double S[9] = {cxx, cyx, czx, cyx, cyy, czy, czx, czy, czz};
+  double ev[3], V[9];
+  sym3_eigen_dev(S, ev, V);
+  int small = 0;
+  if (fabs(ev[1]) < fabs(ev[small])) small = 1;
+  if (fabs(ev[2]) < fabs(ev[small])) small = 2;
+  double o[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double v = j == small ? eps : 1.0;
+    const double a = V[0 * 3 + j], b = V[1 * 3 + j], cc = V[2 * 3 + j];
+    o[0] += v * a * a; o[1] += v * a * b; o[2] += v * a * cc;
+    o[3] += v * b * b; o[4] += v * b * cc; o[5] += v * cc * cc;
+  }
+  double* dst = c.cov + (size_t)i * 6;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) dst[t] = o[t];
+}
+
 // arbitrary queries (debug / tests): one thread per query, neighbours as (distance, position) keys
 __global__ void __launch_bounds__(64) knn_query_kernel(const CloudView* __restrict__ views, const float4* __restrict__ queries, int nq, int k,
                                                         int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
@@ -833,7 +872,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
   // ---- plan: dimensions of everything that is missing, and ONE allocation for all of it
   std::vector<int> todo_grid, todo_cov, todo_vox, todo_ndt;
   ArenaPlan plan;
-  int cov_k = 0;
+  int cov_k = 0, cov_mode = 0;
   for (size_t i = 0; i < clouds.size(); ++i) {
     Cloud* c = clouds[i];
     const Needs& nd = needs[i];
@@ -846,12 +885,14 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       plan.want(c->spts.p, (size_t)c->n);
       todo_grid.push_back((int)i);
     }
-    const bool new_cov = nd.cov_k > 0 && c->cov_k != nd.cov_k;
+    const bool new_cov = nd.cov_k > 0 && (c->cov_k != nd.cov_k || c->cov_mode != nd.cov_mode);
     if (new_cov) {
       if (nd.cov_k > 32) throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be <= 32");
       if (c->n < nd.cov_k) throw Error(B2R_ERR_INVALID_ARG, "cloud has fewer points than correspondence_randomness");
       if (cov_k && cov_k != nd.cov_k) throw Error(B2R_ERR_INVALID_ARG, "one correspondence_randomness per call");
+      if (cov_k && cov_mode != nd.cov_mode) throw Error(B2R_ERR_INVALID_ARG, "one covariance mode per call");
       cov_k = nd.cov_k;
+      cov_mode = nd.cov_mode;
       plan.want(c->cov.p, (size_t)c->n * 6);
       c->vres = 0.0;  // a voxel map built from older covariances is stale
       todo_cov.push_back((int)i);
@@ -912,7 +953,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
   }
   // the flags go up now: the views below must describe the finished structures
   for (int i : todo_grid) clouds[i]->has_grid = true;
-  for (int i : todo_cov) clouds[i]->cov_k = cov_k;
+  for (int i : todo_cov) { clouds[i]->cov_k = cov_k; clouds[i]->cov_mode = cov_mode; }
   for (int i : todo_vox) clouds[i]->vres = needs[i].vres;
   for (int i : todo_ndt) clouds[i]->leaf = needs[i].leaf;
 
@@ -955,7 +996,18 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     std::vector<Cloud*> cl;
     int maxn = 1;
     for (int i : todo_cov) { cl.push_back(clouds[i]); maxn = std::max(maxn, clouds[i]->n); }
-    launch_knn_cov(ctx, dviews.p + off_cov, cl, cov_k, maxn, nullptr);
+    if (cov_mode == 0) {
+      launch_knn_cov(ctx, dviews.p + off_cov, cl, cov_k, maxn, nullptr);
+    } else {
+      // pcl::GeneralizedIterativeClosestPoint covariances: the same exact kNN, cloud by cloud with the neighbour lists written
+      // out, then PCL's own moment arithmetic over those lists
+      DBuf<int32_t> knn; knn.alloc((size_t)maxn * cov_k, ctx.stream);
+      for (size_t j = 0; j < cl.size(); ++j) {
+        std::vector<Cloud*> one{cl[j]};
+        launch_knn_cov(ctx, dviews.p + off_cov + j, one, cov_k, cl[j]->n, knn.p);
+        B2R_LAUNCH(ctx, pcl_cov_kernel, (cl[j]->n + 127) / 128, 128, 0, dviews.p + off_cov + j, knn.p, cov_k, cfg.gicp_epsilon);
+      }
+    }
   }
   if (!todo_vox.empty()) {
     const int nc = (int)todo_vox.size();

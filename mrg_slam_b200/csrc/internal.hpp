@@ -67,6 +67,7 @@ struct Cloud {
   Ref<float4> spts;
   // covariances
   int cov_k = 0;  // k the covariances were built with (0 = none)
+  int cov_mode = 0;  // Needs::cov_mode they were built with
   Ref<double> cov;
   // VGICP voxel map
   double vres = 0.0;  // resolution the map was built with (0 = none)
@@ -89,6 +90,7 @@ struct Cloud {
 struct Needs {
   bool grid = false;
   int cov_k = 0;
+  int cov_mode = 0;  // 0: fast_gicp / small_gicp covariances, 1: pcl::GeneralizedIterativeClosestPoint::computeCovariances
   double vres = 0.0;
   float leaf = 0.f;
 };
@@ -131,6 +133,8 @@ void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_vie
                          bool trial, double* H, double* b, double* err, int32_t* corr_out, uint8_t* corr_valid);
 
 // ---- ndt.cu ----
+void gicp_pcl_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
+                          const float* guesses_colmajor, b2r_result* out);
 void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
                      const float* guesses_colmajor, b2r_result* out);
 void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, int n_src, const double* p6, double* score,

@@ -15,11 +15,12 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2R_LIB_PATH") or os.path.join(_DIR, "libb2r.so")  # override: kernel experiments only
 
-NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP = 0, 1, 2, 3
+NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP, GICP_PCL = 0, 1, 2, 3, 4
 DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
 HOST, DEVICE = 0, 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_STATE = range(6)
-METHOD_BY_NAME = {"NDT_OMP": NDT_OMP, "FAST_GICP": FAST_GICP, "FAST_VGICP": FAST_VGICP}
+METHOD_BY_NAME = {"NDT_OMP": NDT_OMP, "FAST_GICP": FAST_GICP, "FAST_VGICP": FAST_VGICP, "SMALL_GICP": SMALL_GICP, "GICP": GICP_PCL,
+                  "GICP_OMP": GICP_PCL}
 
 
 class Config(ctypes.Structure):
@@ -38,6 +39,8 @@ class Config(ctypes.Structure):
         ("ndt_step_size", ctypes.c_double),
         ("ndt_outlier_ratio", ctypes.c_double),
         ("nn_cell_size", ctypes.c_double),
+        ("max_optimizer_iterations", ctypes.c_int),
+        ("gicp_epsilon", ctypes.c_double),
     ]
 
 
@@ -521,7 +524,11 @@ def select_registration_method(params):
     elif name == "SMALL_GICP":  # registrations.cpp:46-54: epsilon, iterations, correspondence distance and randomness are set
         cfg = default_config(SMALL_GICP, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
                              correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
-    elif name in ("FAST_VGICP_CUDA", "ICP", "GICP", "GICP_OMP", "NDT"):
+    elif name in ("GICP", "GICP_OMP"):  # registrations.cpp:93-116: pcl / pclomp GeneralizedIterativeClosestPoint (BFGS)
+        cfg = default_config(GICP_PCL, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
+                             correspondence_randomness=params.get("reg_correspondence_randomness", 20),
+                             max_optimizer_iterations=params.get("reg_max_optimizer_iterations", 20), **common)
+    elif name in ("FAST_VGICP_CUDA", "ICP", "NDT"):
         raise NotImplementedError(f"registration_method {name} is outside this engine's scope (see DESIGN.md)")
     else:
         if "NDT" not in name:

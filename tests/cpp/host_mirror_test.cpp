@@ -111,7 +111,11 @@ int main(int argc, char** argv) {
   prm.reg_max_correspondence_distance = 1.5;
   auto sg = b2r::select_registration_method(prm);
   CHECK(sg && sg->config().method == B2R_SMALL_GICP && sg->config().max_correspondence_distance == 1.5);
-  prm.registration_method = "GICP_OMP";  // PCL's BFGS GICP: outside the engine
+  prm.registration_method = "GICP_OMP";  // pclomp's BFGS GICP (registrations.cpp:104-116)
+  prm.reg_max_optimizer_iterations = 7;
+  auto pg = b2r::select_registration_method(prm);
+  CHECK(pg && pg->config().method == B2R_GICP_PCL && pg->config().max_optimizer_iterations == 7 && pg->config().gicp_epsilon == 1e-3);
+  prm.registration_method = "ICP";  // outside the engine
   CHECK(b2r::select_registration_method(prm) == nullptr);
 
   auto a = make_cloud(3), b = make_cloud(4), c = make_cloud(5);

@@ -102,8 +102,12 @@ def test_factory_string_dispatch(monkeypatch, capsys):
     assert made[-1].method == B.NDT_OMP and "unknown registration type(BOGUS)" in capsys.readouterr().err
     B.select_registration_method({"registration_method": "SMALL_GICP", "reg_max_correspondence_distance": 1.5})  # the YAML default
     assert made[-1].method == B.SMALL_GICP and made[-1].max_correspondence_distance == 1.5
+    B.select_registration_method({"registration_method": "GICP_OMP", "reg_max_optimizer_iterations": 9})  # registrations.cpp:104-116
+    assert made[-1].method == B.GICP_PCL and made[-1].max_optimizer_iterations == 9 and made[-1].gicp_epsilon == 1e-3
+    B.select_registration_method({"registration_method": "GICP"})                                          # :93-103
+    assert made[-1].method == B.GICP_PCL and made[-1].max_optimizer_iterations == 20 and made[-1].max_correspondence_distance == 2.0
     with pytest.raises(NotImplementedError):
-        B.select_registration_method({"registration_method": "GICP_OMP"})
+        B.select_registration_method({"registration_method": "ICP"})
 
 
 def test_synth_is_deterministic_and_shaped():

@@ -1,0 +1,71 @@
+"""registration_method GICP / GICP_OMP (pcl / pclomp GeneralizedIterativeClosestPoint, /root/reference/src/mrg_slam/registrations.cpp:93-116;
+SURVEY 8a row G) on the device, against the oracle restatement (oracle/gicp_pcl.cpp).
+
+The state machine behind it is verified on the host bit for bit (tests/test_gicp_pcl_sm.py).  The two CUDA kernels that answer
+its requests and PCL's covariance kernel are checked here.  Tolerances: BFGS with PCL's coarse stopping rule
+(|delta T| < transformation_epsilon = 0.1 m / rotation_epsilon = 2e-3 per outer iteration) stops wherever the last outer iteration
+happens to land, so the default configuration is compared at centimetre level and the north-star tolerance (1e-4 m / 1e-4 rad) is
+applied with a tight stopping rule, where both implementations reach the same minimum."""
+import numpy as np
+import pytest
+
+from mrg_slam_b200 import lib as B
+from tests import oraclelib as O
+from tests.conftest import pose_error
+
+# Not yet run on a GPU when this file was written (the round's GPU budget was spent): until the first green run on a B200 the
+# tests are expected-to-fail-or-pass (non-strict), so that they can neither hide nor fake a result.  Remove the marker then.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="GICP_PCL kernels not yet verified on a GPU")]
+
+
+def _align(method_cfg, a, b, guess):
+    g = B.Registration(method_cfg)
+    g.setInputTarget(a)
+    g.setInputSource(b)
+    r = g.align(guess)
+    T = g.getFinalTransformation()
+    fit = g.getFitnessScore()
+    g.close()
+    return r, T, fit
+
+
+def test_gicp_pcl_default_parameters(small_pair):
+    a, b, gt = small_pair
+    want = O.gicp_pcl_align(a, b, np.eye(4))
+    r, T, fit = _align(B.default_config(B.GICP_PCL), a, b, np.eye(4))
+    assert r.converged == want.converged == 1
+    te, re = pose_error(O.from_colmajor(list(want.T)), T)
+    assert te < 0.03 and re < 5e-3, (te, re)
+    assert abs(r.iterations - want.iterations) <= 1
+    te_gt, _ = pose_error(gt, T)
+    assert te_gt < 0.15 and fit > 0
+
+
+@pytest.mark.parametrize("guess_offset", [(0.0, 0.0), (0.3, -0.2)])
+def test_gicp_pcl_tight_stopping_rule_matches_oracle(small_pair, guess_offset):
+    a, b, gt = small_pair
+    guess = np.eye(4)
+    guess[0, 3], guess[1, 3] = gt[0, 3] + guess_offset[0], gt[1, 3] + guess_offset[1]
+    kw = dict(transformation_epsilon=2e-5, rotation_epsilon=2e-6, maximum_iterations=40)
+    want = O.gicp_pcl_align(a, b, guess, O.gicp_pcl_params(**kw))
+    r, T, _ = _align(B.default_config(B.GICP_PCL, **kw), a, b, guess)
+    te, re = pose_error(O.from_colmajor(list(want.T)), T)
+    assert te <= 1e-4 and re <= 1e-4, (te, re, r.iterations, want.iterations)
+
+
+def test_gicp_pcl_batch_and_factory(small_pair):
+    a, b, gt = small_pair
+    reg = B.select_registration_method({"registration_method": "GICP", "reg_max_optimizer_iterations": 20})
+    ca, cb = B.Cloud(reg, a), B.Cloud(reg, b)
+    far = np.eye(4)
+    far[0, 3] = 500.0
+    res = reg.align_batch([cb, cb, ca], [ca, ca, ca], [np.eye(4), far, np.eye(4)], with_fitness=True)
+    reg.setInputTarget(ca); reg.setInputSource(cb)
+    single = reg.align(np.eye(4))
+    assert list(res[0].T) == list(single.T) and res[0].iterations == single.iterations  # batch == single, bit for bit
+    assert res[1].converged == 0 and res[1].iterations == 0                              # no correspondences: BFGS "throws"
+    assert np.allclose(np.array(list(res[1].T)).reshape(4, 4).T, far, atol=1e-6)        # final = previous * guess = guess
+    assert res[2].converged == 1                                                         # a cloud against itself
+    te, re = pose_error(np.eye(4), B.from_colmajor(list(res[2].T)))
+    assert te < 1e-3 and re < 1e-3
+    ca.close(); cb.close(); reg.close()
