@@ -39,6 +39,7 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
     this->reg_name_ = method == B2R_NDT_OMP      ? "b2r::NDT_OMP"
                       : method == B2R_FAST_GICP  ? "b2r::FAST_GICP"
                       : method == B2R_SMALL_GICP ? "b2r::SMALL_GICP"
+                      : method == B2R_GICP_PCL   ? "b2r::GICP"
                                                  : "b2r::FAST_VGICP";
     static_assert(sizeof(PointT) == sizeof(::b2r::PointXYZI), "pcl::PointXYZI layout changed");
   }
@@ -50,6 +51,8 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
   void setMaxCorrespondenceDistance(double d) { Base::setMaxCorrespondenceDistance(d); impl_.setMaxCorrespondenceDistance(d); }
   void setCorrespondenceRandomness(int k) { impl_.setCorrespondenceRandomness(k); }
   void setResolution(double r) { impl_.setResolution(r); }
+  void setUseReciprocalCorrespondences(bool on) { impl_.setUseReciprocalCorrespondences(on); }  // GICP / GICP_OMP (:99, :110)
+  void setMaximumOptimizerIterations(int n) { impl_.setMaximumOptimizerIterations(n); }         // GICP / GICP_OMP (:102, :113)
   void setNeighborhoodSearchMethod(NeighborSearchMethod m) { impl_.setNeighborhoodSearchMethod(m); }
 
   // ---- virtuals of pcl::Registration
