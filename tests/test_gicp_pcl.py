@@ -142,3 +142,22 @@ def test_align_recovers_a_known_transform(small_pair, offset):
     fg.align(np.eye(4))
     d3 = np.linalg.inv(fg.getFinalTransformation()) @ O.from_colmajor(list(r3.T))
     assert r3.converged and np.linalg.norm(d3[:3, 3]) < 0.05
+
+
+def test_result_is_reproducible_only_to_about_a_millimetre(small_pair):
+    """Why the device engine is compared with this oracle at 2e-3 m rather than the north star's 1e-4 m: even with a tight outer
+    stopping rule the answer moves by a fraction of a millimetre when the initial guess moves by 1e-7 m — the inner BFGS stops at
+    |g| < 1e-2 and the outer rule stops wherever an iteration happens to land ("1e-4 parity fragile")."""
+    a, b, gt = small_pair
+    kw = dict(transformation_epsilon=2e-5, rotation_epsilon=2e-6, maximum_iterations=40)
+    guess = np.eye(4)
+    guess[0, 3], guess[1, 3] = gt[0, 3], gt[1, 3]
+    base = O.from_colmajor(list(O.gicp_pcl_align(a, b, guess, O.gicp_pcl_params(**kw)).T))
+    worst = 0.0
+    for eps in (1e-7, 1e-6, 1e-5):
+        g2 = guess.copy()
+        g2[0, 3] += eps
+        T = O.from_colmajor(list(O.gicp_pcl_align(a, b, g2, O.gicp_pcl_params(**kw)).T))
+        d = np.linalg.inv(base) @ T
+        worst = max(worst, float(np.linalg.norm(d[:3, 3])))
+    assert 1e-5 < worst < 2e-3, worst
