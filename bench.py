@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2r", choices=["b2r", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP)
-    ap.add_argument("--method", default="FAST_VGICP", choices=["FAST_VGICP", "FAST_GICP", "NDT_OMP"])
+    ap.add_argument("--method", default="FAST_VGICP", choices=["FAST_VGICP", "FAST_GICP", "NDT_OMP", "SMALL_GICP"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-handles", type=int, default=2, help="registration handles (streams + host threads) of the overlapped e2e leg")
     return ap.parse_args()

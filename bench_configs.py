@@ -314,20 +314,29 @@ def run_loop_closure(args):
         if args.cpu and world == 1:
             from tests import oraclelib as O
             O.set_num_threads(0)
-            o = O.Registration(O.default_params(getattr(O, args.method)))
+            pcl_gicp = args.method == "GICP_PCL"  # pcl::GeneralizedIterativeClosestPoint: its own oracle entry point (oracle/gicp_pcl.cpp)
+            o = None if pcl_gicp else O.Registration(O.default_params(getattr(O, args.method)))
             t0 = time.perf_counter()
             done, same = 0, 0
             ns = min(args.cpu_pairs, len(pairs))
             for i in range(ns):
                 ti, ci = pairs[i]
-                if i == 0 or pairs[i - 1][0] != ti:
-                    o.setInputTarget(pool_np[ti])
-                o.setInputSource(pool_np[ci])
-                r = o.align(guesses[i])
-                fo = o.getFitnessScore()
+                if pcl_gicp:
+                    r = O.gicp_pcl_align(pool_np[ti], pool_np[ci], guesses[i])
+                    To = O.from_colmajor(list(r.T))
+                    fo = O.fitness_score(pool_np[ti], pool_np[ci], To)[0]
+                    tol = 2e-3  # the method's own reproducibility (tests/test_gicp_pcl.py)
+                else:
+                    if i == 0 or pairs[i - 1][0] != ti:
+                        o.setInputTarget(pool_np[ti])
+                    o.setInputSource(pool_np[ci])
+                    r = o.align(guesses[i])
+                    fo = o.getFitnessScore()
+                    To = o.getFinalTransformation()
+                    tol = 1e-4
                 done += 1
-                d = np.linalg.inv(o.getFinalTransformation()) @ B.from_colmajor(table[i, :16])
-                if bool(r.converged) == bool(conv[i]) and np.linalg.norm(d[:3, 3]) < 1e-4 and (not conv[i] or abs(fo - table[i, 20]) <= 1e-3 * abs(fo)):
+                d = np.linalg.inv(To) @ B.from_colmajor(table[i, :16])
+                if bool(r.converged) == bool(conv[i]) and np.linalg.norm(d[:3, 3]) < tol and (fo is None or not conv[i] or abs(fo - table[i, 20]) <= 1e-3 * abs(fo)):
                     same += 1
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": done / dt, "unit": "aligns/s", "cores": O.max_threads(), "kind": "port",
@@ -397,7 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a bounded sample")
-    ap.add_argument("--method", default="FAST_GICP", choices=["FAST_VGICP", "FAST_GICP", "NDT_OMP"])
+    ap.add_argument("--method", default="FAST_GICP", choices=["FAST_VGICP", "FAST_GICP", "NDT_OMP", "SMALL_GICP", "GICP_PCL"])
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--candidates", type=int, default=16)
     ap.add_argument("--leaf", type=float, default=0.175)
