@@ -570,6 +570,7 @@ b2r_status b2r_debug_covariances(b2r_handle* hh, int which, double* cov6_out, in
       std::vector<Cloud*> cl{c};
       std::vector<Needs> nd(1);
       nd[0].cov_k = k;
+      nd[0].cov_mode = h.cfg.method == B2R_GICP_PCL ? 1 : 0;
       DBuf<CloudView> dvtmp;
       clouds_prepare(h.ctx, h.cfg, cl, nd, dvtmp);
     }

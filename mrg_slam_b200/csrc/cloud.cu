@@ -863,6 +863,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     const Needs& in = needs_in[i];
     nd.grid = nd.grid || in.grid || in.cov_k > 0;
     nd.cov_k = std::max(nd.cov_k, in.cov_k);
+    nd.cov_mode = std::max(nd.cov_mode, in.cov_mode);
     if (in.vres > 0) nd.vres = in.vres;
     if (in.leaf > 0) nd.leaf = in.leaf;
     if (nd.vres > 0 && nd.cov_k == 0) throw Error(B2R_ERR_STATE, "voxel map needs covariances");

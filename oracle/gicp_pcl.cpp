@@ -447,10 +447,15 @@ void pcl_covariances(const float* pts, int n, const KdTree& tree, int k, double 
           cov[b * 3 + a] = cov[a * 3 + b];
         }
       double ev[3], V[9];
-      sym3_eigen(cov, ev, V);  // ascending eigenvalues = descending singular-value order reversed: column 0 is the smallest
+      sym3_eigen(cov, ev, V);
+      // JacobiSVD orders by singular value = |eigenvalue|: the float products can leave the matrix slightly indefinite, and the
+      // regularised direction is the one of the smallest MAGNITUDE
+      int small = 0;
+      if (std::fabs(ev[1]) < std::fabs(ev[small])) small = 1;
+      if (std::fabs(ev[2]) < std::fabs(ev[small])) small = 2;
       double* out = &covs9[(size_t)i * 9];
       for (int c = 0; c < 3; ++c) {
-        const double v = c == 0 ? eps : 1.0;
+        const double v = c == small ? eps : 1.0;
         for (int a = 0; a < 3; ++a)
           for (int b = 0; b < 3; ++b) out[a * 3 + b] += v * V[a * 3 + c] * V[b * 3 + c];
       }

