@@ -13,6 +13,19 @@
 //
 // Arithmetic types follow upstream: float Matrix4f state and float point transforms, float products widened to double
 // in the covariance moments, double Mahalanobis matrices, double BFGS.
+//
+// Details restated from memory that a reader with the upstream sources should check first (none can be checked here):
+//   * gradient_tol = 1e-2 (local constant of estimateRigidTransformationBFGS) and the loop
+//     `do { inner++; result = minimizeOneStep(x); if (result) break; result = testGradient(tol); } while (Running && inner < max)`;
+//   * BFGS parameters set by gicp.hpp: sigma = rho = 0.01, tau1 = 9, tau2 = 0.05, tau3 = 0.5, order = 3; bfgs.h defaults
+//     step_size = 1, bracket_iters = sect_iters = 100;
+//   * the initial state from the matrix: x3 = atan2(T(2,1), T(2,2)), x4 = asin(-T(2,0)), x5 = atan2(T(1,0), T(0,0)), evaluated
+//     here with the float overloads (the arguments are Matrix4f entries);
+//   * applyState ADDS the translation (t.col(3) += T) and multiplies the rotation on the left, all in float;
+//   * the correspondence test `nn_dists[0] < corr_dist_threshold_^2`, mahalanobis_ reset to identity per align;
+//   * covariances: `cov(k,l) += pt[k] * pt[l]` are float products; JacobiSVD orders singular values (= |eigenvalues|), the
+//     smallest gets gicp_epsilon_;
+//   * use_reciprocal_correspondences (false in config/mrg_slam.yaml:106) is not restated.
 #include <cmath>
 #include <cstring>
 #include <limits>
