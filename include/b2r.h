@@ -30,7 +30,8 @@ typedef enum b2r_status {
   B2R_ERR_CUDA = 2,
   B2R_ERR_NO_DEVICE = 3,
   B2R_ERR_CAPACITY = 4, /* a dense voxel table would exceed its cap (cloud extent / resolution) */
-  B2R_ERR_STATE = 5     /* e.g. align before set_target */
+  B2R_ERR_STATE = 5,    /* e.g. align before set_target */
+  B2R_ERR_COMM = 6      /* NCCL missing / a collective failed */
 } b2r_status;
 
 /* registration_method strings handled by select_registration_method (src/mrg_slam/registrations.cpp:46-148) */
@@ -117,6 +118,53 @@ b2r_status b2r_fitness_pair(b2r_handle* h, b2r_cloud* target, b2r_cloud* source,
 b2r_status b2r_align_batch(b2r_handle* h, b2r_cloud* const* sources, b2r_cloud* const* targets, const float* guesses_colmajor,
                            size_t n_pairs, int with_fitness, double fitness_max_range, b2r_result* out);
 
+/* ScanMatchingOdometryComponent::publish_scan_matching_status (apps/scan_matching_odometry_component.cpp:403-415): the fraction of
+ * the aligned source points (T = the last final transformation) whose nearest target point is closer than
+ * max_correspondence_dist (0.5 there; k_sq_dists[0] < dist * dist), replacing the N host calls of
+ * getSearchMethodTarget()->nearestKSearch(pt, 1, ...).  fitness_out (optional) receives getFitnessScore() of the same pass (:403). */
+b2r_status b2r_inlier_fraction(b2r_handle* h, double max_correspondence_dist, double* fraction_out, double* fitness_out);
+
+/* ---- multi-GPU loop-closure batches: the candidate loops of LoopDetector::matching (loop_detector.cpp:97-180) of many
+ * new keyframes, sharded over the GPUs of one box, one process (or thread) per GPU.  The pairs are partitioned by target id (all
+ * candidates of a new keyframe on one rank: its target structures are built once), every rank aligns its slice, the fixed-size
+ * result rows are written on the device into the send buffer of ONE ncclAllGather (NVLink) and every rank receives the whole
+ * table in pair order.  There is no collective inside the optimiser.
+ *   - b2r_comm_unique_id: rank 0 creates the NCCL id; the launcher distributes the 128 bytes (MPI_Bcast, torch.distributed, a file).
+ *   - b2r_comm_init: ncclCommInitRank on the handle's device; collectives run on the handle's stream.  NCCL is dlopen'ed
+ *     (libnccl.so.2; a copy the host process already loaded is reused), B2R_ERR_COMM if absent.
+ *   - b2r_comm_init_host: the same entry points over a caller-provided HOST all-gather (MPI, gloo, tests): fn(user, send, recv,
+ *     bytes_per_rank) must fill recv[r * bytes_per_rank ...] with rank r's send block on every rank and return 0. ---- */
+#define B2R_UNIQUE_ID_BYTES 128
+typedef struct b2r_comm b2r_comm;
+typedef int (*b2r_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
+b2r_status b2r_comm_unique_id(void* id_out /* B2R_UNIQUE_ID_BYTES */);
+b2r_status b2r_comm_init(b2r_handle* h, const void* unique_id, int rank, int nranks, b2r_comm** out);
+b2r_status b2r_comm_init_host(b2r_allgather_fn fn, void* user, int rank, int nranks, b2r_comm** out);
+void b2r_comm_destroy(b2r_comm* c);
+int b2r_comm_rank(const b2r_comm* c);
+int b2r_comm_size(const b2r_comm* c);
+const char* b2r_comm_last_error(const b2r_comm* c);
+uint64_t b2r_comm_collectives(const b2r_comm* c); /* all-gathers issued so far */
+/* Static block partition by target id, optionally balanced by per-pair weights (e.g. source points): targets keep their order of
+ * first appearance, each rank gets a contiguous block of targets.  Pure host code, identical on every rank. */
+b2r_status b2r_partition_by_target(const int64_t* target_ids, const double* weights /* or NULL */, size_t n_pairs, int nranks,
+                                   int32_t* rank_of_pair);
+/* b2r_align_batch over the ranks of `comm`.  All ranks pass the same pair list (target_ids, weights, guesses); sources[i] /
+ * targets[i] must be valid on the rank that b2r_partition_by_target assigns pair i to and may be NULL elsewhere.  out receives all
+ * n_pairs rows on every rank.  A failure on one rank does not keep it out of the collective: its rows come back as
+ * converged = 0, T = guess, fitness = DBL_MAX and that rank returns the error status. */
+b2r_status b2r_align_batch_sharded(b2r_handle* h, b2r_comm* comm, b2r_cloud* const* sources, b2r_cloud* const* targets,
+                                   const int64_t* target_ids, const double* weights /* or NULL */, const float* guesses_colmajor,
+                                   size_t n_pairs, int with_fitness, double fitness_max_range, b2r_result* out);
+/* the gather step alone: local = this rank's rows in pair order; out = all n_pairs rows.  h may be NULL with a host transport. */
+b2r_status b2r_gather_results(b2r_handle* h, b2r_comm* comm, const int32_t* rank_of_pair, size_t n_pairs, const b2r_result* local,
+                              b2r_result* out);
+/* The candidate reduction of loop_detector.cpp:106-160 over a gathered table: per target (order of first appearance) the pair index
+ * of the best converged candidate — `score > best_score -> skip`, so equal scores go to the LATER candidate — or -1 when there is
+ * none or its score exceeds fitness_score_thresh.  best_pair_out / best_score_out: room for n_pairs entries. */
+b2r_status b2r_select_best_candidates(const b2r_result* results, const int64_t* target_ids, size_t n_pairs, double fitness_score_thresh,
+                                      int64_t* best_pair_out, double* best_score_out /* or NULL */, size_t* n_targets_out);
+
 /* ---- prefiltering (apps/prefiltering_component.cpp:149-151).  `out` has room for n points in `memspace`,
  * packed 16 B; *m receives the number written. ---- */
 /* distance_filter(), prefiltering_component.cpp:206-229 */
@@ -167,7 +215,9 @@ b2r_status b2r_map_cloud(b2r_handle* h, const void* const* clouds, const size_t*
                          float distance_far_thresh, int skip_first_cloud, void* out, size_t* m, int* is_null);
 
 /* ---- introspection for parity tests and benchmarks ---- */
-uint64_t b2r_kernel_launches(const b2r_handle* h); /* kernels launched by this handle so far */
+uint64_t b2r_kernel_launches(const b2r_handle* h); /* kernel + graph launches issued by this handle so far */
+uint64_t b2r_graph_launches(const b2r_handle* h);  /* of which optimiser loops launched as one CUDA graph (WHILE node; the {eval, step}
+                                                      rounds inside run without the host) */
 b2r_status b2r_synchronize(b2r_handle* h);
 /* kNN-covariance queries (on this device, since library load) whose in-kernel candidate log overflowed and took the
  * second-traversal path: a tuning counter for the exact-kNN grid, results are identical either way */

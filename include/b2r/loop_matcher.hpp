@@ -229,4 +229,110 @@ inline LoopMatch match_keyframe(b2r_handle* h, const KeyframeRef& new_keyframe, 
   return out;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// LoopDetector::matching (:97-180) for MANY new keyframes at once, sharded over the ranks of a b2r_comm (one process or thread per
+// GPU).  Every rank calls this with the same keyframe lists; a KeyframeRef's `cloud` only has to be valid on the rank
+// that b2r_partition_by_target assigns its target to (`cloud_of` is asked for exactly those).  Stages, as the reference orders them
+// per keyframe: (1) all candidate aligns + getFitnessScore as ONE sharded batch, best-candidate rule on the gathered table
+// (b2r_select_best_candidates); (2) perform_loop_closure_consistency_check: the `prev` aligns of all surviving loops as a second
+// (much smaller) sharded batch, then the `next` aligns of those that failed or have no prev edge as a third; (3) acceptance
+// (:156-166).  Every rank returns the same decisions.
+struct KeyframeJob {
+  const KeyframeRef* new_keyframe = nullptr;
+  std::vector<const KeyframeRef*> candidates;
+};
+
+inline std::vector<LoopMatch> match_keyframes_sharded(b2r_handle* h, b2r_comm* comm, const std::vector<KeyframeJob>& jobs,
+                                                      const LoopMatchParams& prm = LoopMatchParams()) {
+  std::vector<LoopMatch> out(jobs.size());
+  const int rank = b2r_comm_rank(comm), nranks = b2r_comm_size(comm);
+  // ---- stage 1: the candidate pairs of every job, in job order then candidate order (the tie rule depends on it)
+  struct PairRef { size_t job; int cand; };
+  std::vector<PairRef> ref;
+  std::vector<int64_t> ids;
+  std::vector<double> weights;
+  std::vector<float> guesses;
+  std::vector<const KeyframeRef*> src_kf, tgt_kf;
+  auto sharded = [&](std::vector<b2r_result>& res, int with_fitness) -> b2r_status {
+    const size_t n = ids.size();
+    res.assign(n, b2r_result());
+    if (n == 0) return B2R_OK;
+    std::vector<int32_t> rank_of(n);
+    b2r_status st = b2r_partition_by_target(ids.data(), weights.data(), n, nranks, rank_of.data());
+    if (st != B2R_OK) return st;
+    std::vector<b2r_cloud*> s(n, nullptr), t(n, nullptr);
+    for (size_t i = 0; i < n; ++i)
+      if (rank_of[i] == rank) { s[i] = src_kf[i]->cloud; t[i] = tgt_kf[i]->cloud; }
+    return b2r_align_batch_sharded(h, comm, s.data(), t.data(), ids.data(), weights.data(), guesses.data(), n, with_fitness,
+                                   prm.fitness_score_max_range, res.data());
+  };
+  auto push_pair = [&](size_t job, int cand, const KeyframeRef* target, const KeyframeRef* source) {
+    ref.push_back(PairRef{job, cand});
+    ids.push_back((int64_t)job);
+    weights.push_back(source->cloud ? (double)b2r_cloud_size(source->cloud) : 1.0);
+    const Mat4f g = registration_guess(target->estimate, source->estimate, prm.use_planar_registration_guess);
+    guesses.insert(guesses.end(), g.begin(), g.end());
+    src_kf.push_back(source);
+    tgt_kf.push_back(target);
+  };
+  for (size_t j = 0; j < jobs.size(); ++j)
+    for (size_t c = 0; c < jobs[j].candidates.size(); ++c) push_pair(j, (int)c, jobs[j].new_keyframe, jobs[j].candidates[c]);
+  std::vector<b2r_result> res;
+  b2r_status st = sharded(res, 1);
+  for (size_t i = 0; i < ref.size(); ++i) out[ref[i].job].aligns++;
+  if (st != B2R_OK) {
+    for (LoopMatch& m : out) m.status = st;
+    return out;
+  }
+  for (size_t i = 0; i < ref.size(); ++i) {  // :137-144 per job, candidates in order; DBL_MAX threshold: acceptance comes later
+    LoopMatch& m = out[ref[i].job];
+    if (!res[i].converged || res[i].fitness > m.best_score) continue;
+    m.best_score = res[i].fitness;
+    m.best = ref[i].cand;
+    for (int t = 0; t < 16; ++t) m.rel_pose_new_to_best[t] = res[i].T[t];
+  }
+  // ---- stage 2: consistency checks (:190-303), prev first, next for those that did not pass
+  std::vector<size_t> todo;
+  for (size_t j = 0; j < jobs.size(); ++j) {
+    LoopMatch& m = out[j];
+    const KeyframeRef* best = m.best >= 0 ? jobs[j].candidates[m.best] : nullptr;
+    if (best && (best->first_keyframe || best->static_keyframe)) { m.consistency_passed = true; continue; }  // :197-199
+    if (!best || !prm.enable_loop_closure_consistency_check || m.best_score > prm.fitness_score_thresh) continue;  // :201-204
+    todo.push_back(j);
+  }
+  for (int stage = 0; stage < 2; ++stage) {
+    ref.clear(); ids.clear(); weights.clear(); guesses.clear(); src_kf.clear(); tgt_kf.clear();
+    for (size_t j : todo) {
+      const KeyframeRef* best = jobs[j].candidates[out[j].best];
+      if (out[j].consistency_passed) continue;
+      const KeyframeRef* other = stage == 0 ? best->prev : best->next;
+      if (other) push_pair(j, stage, jobs[j].new_keyframe, other);
+    }
+    st = sharded(res, 0);
+    for (size_t i = 0; i < ref.size(); ++i) {
+      const size_t j = ref[i].job;
+      LoopMatch& m = out[j];
+      ++m.aligns;
+      const KeyframeRef* best = jobs[j].candidates[m.best];
+      Mat4f T;
+      for (int t = 0; t < 16; ++t) T[t] = st == B2R_OK ? res[i].T[t] : guesses[i * 16 + t];
+      const Mat4f M = stage == 0 ? detail::mul(detail::mul(detail::inverse(T), m.rel_pose_new_to_best), detail::to_float(best->rel_pose_to_prev))
+                                 : detail::mul(detail::mul(detail::inverse(m.rel_pose_new_to_best), T), detail::to_float(best->rel_pose_from_next));
+      detail::identity_delta(M, m.delta_trans[stage], m.delta_angle[stage]);
+      m.consistency_passed = !(m.delta_trans[stage] > prm.loop_closure_consistency_max_delta_trans ||
+                               m.delta_angle[stage] > prm.loop_closure_consistency_max_delta_angle);
+    }
+  }
+  // ---- stage 3: acceptance (:156-166)
+  for (size_t j = 0; j < jobs.size(); ++j) {
+    LoopMatch& m = out[j];
+    const KeyframeRef* best = m.best >= 0 ? jobs[j].candidates[m.best] : nullptr;
+    if (m.best_score > prm.fitness_score_thresh) continue;
+    if (prm.enable_loop_closure_consistency_check && best && !best->first_keyframe && !m.consistency_passed) continue;
+    m.loop_found = best != nullptr;
+  }
+  return out;
+}
+
 }  // namespace b2r

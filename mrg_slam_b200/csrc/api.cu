@@ -2,16 +2,40 @@
 // call, the prefilter chain and introspection entry points.  All work is delegated to the CUDA modules; there is
 // no CPU code path for any computation.
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <cstring>
 
 #include "internal.hpp"
 
 using namespace b2r;
 
-struct b2r_handle { Handle h; };
-struct b2r_cloud { Cloud c; };
+namespace b2r {
+// One private pool per device, shared by every handle of the process, never trimmed (release threshold = max): a batch
+// re-uses the blocks of the previous one without going back to the driver.
+cudaMemPool_t device_pool() {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) throw Error(B2R_ERR_CUDA, "cudaGetDevice failed");
+  std::lock_guard<std::mutex> lk(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    B2R_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+    uint64_t thr = UINT64_MAX;
+    B2R_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  return pools[dev];
+}
+}  // namespace b2r
+
 
 namespace {
 
@@ -65,18 +89,47 @@ void check_cfg(const b2r_config& cfg) {
     throw Error(B2R_ERR_INVALID_ARG, "correspondence_randomness must be in [4,32]");
 }
 
-// runs the optimiser on a list of (source, target, guess) triples; clouds are prepared (batched) first
-void run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<Cloud*>& targets, const float* guesses, int with_fitness,
-               double fitness_max_range, b2r_result* out) {
-  const int np = (int)sources.size();
+// A pair the configured method cannot run on: an empty cloud, or (GICP family) fewer points than the covariance neighbourhood.
+// The reference aligns candidates one by one (loop_detector.cpp:126-145), so a degenerate candidate only loses itself: such a
+// pair comes back as converged = 0, T = guess, fitness = DBL_MAX and the rest of the batch runs.
+bool degenerate_pair(const b2r_config& cfg, const Cloud* s, const Cloud* t) {
+  const int need = cfg.method == B2R_NDT_OMP ? 1 : cfg.correspondence_randomness;
+  return s->n < need || t->n < need;
+}
+void fail_result(const float* guess, b2r_result& r) {
+  memcpy(r.T, guess, 64);
+  r.converged = 0; r.iterations = 0; r.error = 0.0; r.evals = 0; r.fitness = DBL_MAX;
+}
+
+// Runs the optimiser on a list of (source, target, guess) triples; clouds are prepared (batched) first.  Everything between
+// the upload of the pair table and the final copy of the result rows is stream-ordered device work: structure builds, the
+// optimiser loop (one graph launch), result rows, fitness.
+//   out_all   host array of n rows, or nullptr
+//   rows_dev  device array of n rows the results are (also) left in, or nullptr — the all-gather send buffer of a sharded batch
+// With out_all == nullptr the call returns without synchronising.
+void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vector<Cloud*>& targets_in, const float* guesses_in, int with_fitness,
+               double fitness_max_range, b2r_result* out_all, b2r_result* rows_dev) {
   Ctx& ctx = h.ctx;
   B2R_CUDA(cudaEventRecord(h.ev[0], ctx.stream));
+  h.timings_pending = true;
+  const size_t n_all = sources_in.size();
+  // ---- per-pair validation: only the usable pairs go to the device
+  std::vector<int> live;
+  std::vector<Cloud*> sources, targets;
+  std::vector<b2r_result> failed;  // rows of the pairs that did not run (only materialised when there are any)
+  for (size_t i = 0; i < n_all; ++i) {
+    if (!sources_in[i] || !targets_in[i]) throw Error(B2R_ERR_INVALID_ARG, "null cloud");
+    if (degenerate_pair(h.cfg, sources_in[i], targets_in[i])) continue;
+    live.push_back((int)i);
+    sources.push_back(sources_in[i]);
+    targets.push_back(targets_in[i]);
+  }
+  const int np = (int)live.size();
+  const bool all_live = (size_t)np == n_all;
   std::vector<Cloud*> uniq;
   std::vector<Needs> needs;
   std::map<Cloud*, int> index;
   auto add = [&](Cloud* c, bool is_target) {
-    if (!c) throw Error(B2R_ERR_INVALID_ARG, "null cloud");
-    if (c->n == 0) throw Error(B2R_ERR_INVALID_ARG, "empty cloud");
     auto it = index.find(c);
     int id;
     if (it == index.end()) {
@@ -96,33 +149,71 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<
     if (nd.leaf > 0) cur.leaf = nd.leaf;
     return id;
   };
-  std::vector<PairDesc> pairs(np);
-  std::vector<int> src_sizes(np);
+  // ---- one host block [pairs | source sizes | guesses] -> one H2D copy
+  const size_t off_n = sizeof(PairDesc) * (size_t)np, off_g = off_n + sizeof(int) * (size_t)np, tot = off_g + 64 * (size_t)np;
+  std::vector<uint8_t> blk(std::max<size_t>(tot, 1));
+  PairDesc* pairs = reinterpret_cast<PairDesc*>(blk.data());
+  int* src_sizes = reinterpret_cast<int*>(blk.data() + off_n);
+  float* guesses = reinterpret_cast<float*>(blk.data() + off_g);
+  int maxn = 1;
   for (int i = 0; i < np; ++i) {
     pairs[i].src = add(sources[i], false);
     pairs[i].tgt = add(targets[i], true);
     src_sizes[i] = sources[i]->n;
+    maxn = std::max(maxn, sources[i]->n);
+    memcpy(guesses + (size_t)i * 16, guesses_in + (size_t)live[i] * 16, 64);
   }
-  DBuf<CloudView> dv;
-  clouds_prepare(ctx, h.cfg, uniq, needs, dv);
-  B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
-  if (h.cfg.method == B2R_NDT_OMP) ndt_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
-  else if (h.cfg.method == B2R_GICP_PCL) gicp_pcl_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
-  else lsq_align_batch(ctx, h.cfg, dv.p, pairs, src_sizes.data(), guesses, out);
-  B2R_CUDA(cudaEventRecord(h.ev[2], ctx.stream));
-  if (with_fitness) {
-    std::vector<float> Ts((size_t)np * 16);
-    std::vector<double> fit(np);
-    for (int i = 0; i < np; ++i) memcpy(&Ts[(size_t)i * 16], out[i].T, 64);
-    fitness_batch(ctx, dv.p, pairs, src_sizes.data(), Ts.data(), fitness_max_range, fit.data());
-    for (int i = 0; i < np; ++i) out[i].fitness = fit[i];
+  DBuf<uint8_t> dblk;
+  DBuf<b2r_result> rows_tmp;
+  b2r_result* d_rows = nullptr;
+  if (np > 0) {
+    dblk.alloc(tot, ctx.stream);
+    B2R_CUDA(cudaMemcpyAsync(dblk.p, blk.data(), tot, cudaMemcpyHostToDevice, ctx.stream));
+    if (rows_dev && all_live) d_rows = rows_dev;
+    else { rows_tmp.alloc(np, ctx.stream); d_rows = rows_tmp.p; }
+    DBuf<CloudView> dv;
+    clouds_prepare(ctx, h.cfg, uniq, needs, dv);
+    B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
+    BatchArgs b;
+    b.d_views = dv.p;
+    b.d_pairs = reinterpret_cast<const PairDesc*>(dblk.p);
+    b.d_src_n = reinterpret_cast<const int*>(dblk.p + off_n);
+    b.d_guesses = reinterpret_cast<const float*>(dblk.p + off_g);
+    b.guesses = guesses;
+    b.d_rows = d_rows;
+    b.np = np;
+    b.maxn = maxn;
+    b.src_sizes = src_sizes;
+    if (h.cfg.method == B2R_NDT_OMP) ndt_align_batch(ctx, h.cfg, b);
+    else if (h.cfg.method == B2R_GICP_PCL) gicp_pcl_align_batch(ctx, h.cfg, b);
+    else lsq_align_batch(ctx, h.cfg, b);
+    B2R_CUDA(cudaEventRecord(h.ev[2], ctx.stream));
+    if (with_fitness) fitness_batch(ctx, b, fitness_max_range);
+    B2R_CUDA(cudaEventRecord(h.ev[3], ctx.stream));
+    // dv, dblk and the optimisers' buffers are released stream-ordered: after everything enqueued above
+    if (all_live) {
+      if (out_all) {
+        B2R_CUDA(cudaMemcpyAsync(out_all, d_rows, sizeof(b2r_result) * np, cudaMemcpyDeviceToHost, ctx.stream));
+        B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+      }
+      return;
+    }
+  } else {
+    for (int e = 1; e < 4; ++e) B2R_CUDA(cudaEventRecord(h.ev[e], ctx.stream));
   }
-  B2R_CUDA(cudaEventRecord(h.ev[3], ctx.stream));
-  B2R_CUDA(cudaEventSynchronize(h.ev[3]));
-  cudaEventElapsedTime(&h.timings[0], h.ev[0], h.ev[1]);
-  cudaEventElapsedTime(&h.timings[1], h.ev[1], h.ev[2]);
-  cudaEventElapsedTime(&h.timings[2], h.ev[2], h.ev[3]);
-  cudaEventElapsedTime(&h.timings[3], h.ev[0], h.ev[3]);
+  // ---- some pairs were degenerate: merge on the host (rare path)
+  std::vector<b2r_result> merged(n_all), got(np);
+  if (np > 0) {
+    B2R_CUDA(cudaMemcpyAsync(got.data(), d_rows, sizeof(b2r_result) * np, cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  for (size_t i = 0; i < n_all; ++i) fail_result(guesses_in + i * 16, merged[i]);
+  for (int j = 0; j < np; ++j) merged[live[j]] = got[j];
+  if (out_all) memcpy(out_all, merged.data(), sizeof(b2r_result) * n_all);
+  if (rows_dev) {
+    B2R_CUDA(cudaMemcpyAsync(rows_dev, merged.data(), sizeof(b2r_result) * n_all, cudaMemcpyHostToDevice, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));  // `merged` goes out of scope
+  }
 }
 
 // two-entry view array {source, target} of the handle's current clouds, prepared for the configured method
@@ -135,9 +226,16 @@ void prepare_current(Handle& h, DBuf<CloudView>& dv, bool want_fitness) {
 
 }  // namespace
 
+namespace b2r {
+void b2r_run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<Cloud*>& targets, const float* guesses_colmajor,
+                   int with_fitness, double fitness_max_range, b2r_result* out_all, b2r_result* rows_dev) {
+  run_align(h, sources, targets, guesses_colmajor, with_fitness, fitness_max_range, out_all, rows_dev);
+}
+}  // namespace b2r
+
 extern "C" {
 
-const char* b2r_version(void) { return "b2r 0.1 (sm_100a)"; }
+const char* b2r_version(void) { return "b2r 0.2 (sm_100a)"; }
 
 b2r_status b2r_default_config(int method, b2r_config* cfg) {
   if (!cfg) return B2R_ERR_INVALID_ARG;
@@ -184,10 +282,7 @@ b2r_status b2r_create(const b2r_config* cfg, b2r_handle** out) {
     int sms = 0;
     B2R_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     h.ctx.num_sms = sms > 0 ? sms : 148;
-    cudaMemPool_t pool;
-    B2R_CUDA(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
-    uint64_t thr = UINT64_MAX;
-    B2R_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    (void)device_pool();  // the library's private memory pool of this device (the process's default pool is not touched)
     for (int i = 0; i < 4; ++i) B2R_CUDA(cudaEventCreate(&h.ev[i]));
     for (int i = 0; i < 16; ++i) h.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   } catch (const Error& e) {
@@ -304,8 +399,10 @@ b2r_status b2r_align(b2r_handle* hh, const float guess[16], b2r_result* out) {
     // pcl::Registration::align: converged_ = false, final_transformation_ = I before computeTransformation
     h.converged = false;
     for (int i = 0; i < 16; ++i) h.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    if (degenerate_pair(h.cfg, h.source, h.target))  // a single align reports it as an error (converged_ stays false)
+      throw Error(B2R_ERR_INVALID_ARG, h.source->n == 0 || h.target->n == 0 ? "empty cloud" : "cloud has fewer points than correspondence_randomness");
     std::vector<Cloud*> s{h.source}, t{h.target};
-    run_align(h, s, t, guess, 0, 0.0, out);
+    run_align(h, s, t, guess, 0, 0.0, out, nullptr);
     memcpy(h.final_T, out->T, sizeof(h.final_T));
     h.converged = out->converged != 0;
     h.has_result = true;
@@ -328,36 +425,76 @@ b2r_status b2r_align_batch(b2r_handle* hh, b2r_cloud* const* sources, b2r_cloud*
       s[i] = &sources[i]->c;
       t[i] = &targets[i]->c;
     }
-    run_align(h, s, t, guesses, with_fitness, fitness_max_range, out);
+    run_align(h, s, t, guesses, with_fitness, fitness_max_range, out, nullptr);
   });
+}
+
+// getFitnessScore / calc_fitness_score / inlier fraction of one (source, target, T) triple
+static void fitness_single(Handle& h, Cloud* source, Cloud* target, const float* T, double max_range, double* fitness_out, float inlier_d2,
+                           double* inlier_fraction_out) {
+  if (source->n == 0 || target->n == 0) {  // PCL: no correspondences -> max(); 0 / 0 inliers is reported as 0
+    if (fitness_out) *fitness_out = DBL_MAX;
+    if (inlier_fraction_out) *inlier_fraction_out = 0.0;
+    return;
+  }
+  Ctx& ctx = h.ctx;
+  std::vector<Cloud*> cl{source, target};
+  std::vector<Needs> nd(2);
+  nd[1].grid = true;
+  DBuf<CloudView> dv;
+  clouds_prepare(ctx, h.cfg, cl, nd, dv);
+  struct Block { PairDesc pair; int n; int pad; b2r_result row; } hb;
+  memset(&hb, 0, sizeof(hb));
+  hb.pair = PairDesc{0, 1};
+  hb.n = source->n;
+  memcpy(hb.row.T, T, 64);
+  DBuf<Block> db; db.alloc(1, ctx.stream);
+  DBuf<int> din; din.alloc(1, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(db.p, &hb, sizeof(hb), cudaMemcpyHostToDevice, ctx.stream));
+  BatchArgs b;
+  memset(&b, 0, sizeof(b));
+  b.d_views = dv.p;
+  b.d_pairs = &db.p->pair;
+  b.d_src_n = &db.p->n;
+  b.d_rows = &db.p->row;
+  b.np = 1;
+  b.maxn = source->n;
+  b.src_sizes = &hb.n;
+  fitness_batch(ctx, b, max_range, inlier_d2, inlier_fraction_out ? din.p : nullptr);
+  int inl = 0;
+  B2R_CUDA(cudaMemcpyAsync(&hb.row, &db.p->row, sizeof(b2r_result), cudaMemcpyDeviceToHost, ctx.stream));
+  if (inlier_fraction_out) B2R_CUDA(cudaMemcpyAsync(&inl, din.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  if (fitness_out) *fitness_out = hb.row.fitness;
+  // static_cast<float>(num_inliers) / aligned->size()  (scan_matching_odometry_component.cpp:415)
+  if (inlier_fraction_out) *inlier_fraction_out = (double)((float)inl / (float)source->n);
 }
 
 b2r_status b2r_fitness(b2r_handle* hh, double max_range, double* out) {
   return guarded(hh, [&](Handle& h) {
     if (!out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
     if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set first");
-    std::vector<Cloud*> cl{h.source, h.target};
-    std::vector<Needs> nd(2);
-    nd[1].grid = true;
-    DBuf<CloudView> dv;
-    clouds_prepare(h.ctx, h.cfg, cl, nd, dv);
-    std::vector<PairDesc> pairs{PairDesc{0, 1}};
-    int ns = h.source->n;
-    fitness_batch(h.ctx, dv.p, pairs, &ns, h.final_T, max_range, out);
+    fitness_single(h, h.source, h.target, h.final_T, max_range, out, 0.f, nullptr);
   });
 }
 
 b2r_status b2r_fitness_pair(b2r_handle* hh, b2r_cloud* target, b2r_cloud* source, const float T[16], double max_range, double* out) {
   return guarded(hh, [&](Handle& h) {
     if (!out || !target || !source || !T) throw Error(B2R_ERR_INVALID_ARG, "null argument");
-    std::vector<Cloud*> cl{&source->c, &target->c};
-    std::vector<Needs> nd(2);
-    nd[1].grid = true;
-    DBuf<CloudView> dv;
-    clouds_prepare(h.ctx, h.cfg, cl, nd, dv);
-    std::vector<PairDesc> pairs{PairDesc{0, 1}};
-    int ns = source->c.n;
-    fitness_batch(h.ctx, dv.p, pairs, &ns, T, max_range, out);
+    fitness_single(h, &source->c, &target->c, T, max_range, out, 0.f, nullptr);
+  });
+}
+
+b2r_status b2r_inlier_fraction(b2r_handle* hh, double max_correspondence_dist, double* fraction_out, double* fitness_out) {
+  return guarded(hh, [&](Handle& h) {
+    if (!fraction_out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    if (!(max_correspondence_dist > 0)) throw Error(B2R_ERR_INVALID_ARG, "max_correspondence_dist must be > 0");
+    if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set first");
+    // k_sq_dists[0] < max_correspondence_dist * max_correspondence_dist: a float against a double product (:413)
+    const double thr = max_correspondence_dist * max_correspondence_dist;
+    float thr_f = (float)thr;                    // smallest float t with (d2 < t) == ((double)d2 < thr) for every float d2:
+    if ((double)thr_f < thr) thr_f = std::nextafterf(thr_f, INFINITY);  // round the double threshold UP to a float
+    fitness_single(h, h.source, h.target, h.final_T, DBL_MAX, fitness_out, thr_f, fraction_out);
   });
 }
 
@@ -512,6 +649,7 @@ b2r_status b2r_map_cloud(b2r_handle* hh, const void* const* clouds, const size_t
 
 // ------------------------------------------------------------------------------------------------ introspection
 uint64_t b2r_kernel_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.launches : 0; }
+uint64_t b2r_graph_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.graph_launches : 0; }
 
 b2r_status b2r_debug_knn_list_overflows(b2r_handle* hh, uint64_t* out) {
   if (!out) return B2R_ERR_INVALID_ARG;
@@ -524,7 +662,19 @@ b2r_status b2r_synchronize(b2r_handle* hh) {
 
 b2r_status b2r_last_timings(const b2r_handle* hh, float ms_out[4]) {
   if (!hh || !ms_out) return B2R_ERR_INVALID_ARG;
-  for (int i = 0; i < 4; ++i) ms_out[i] = hh->h.timings[i];
+  Handle& h = const_cast<Handle&>(hh->h);
+  if (h.timings_pending) {  // the stage events of the last align call are read on demand (the call itself does not wait for them)
+    cudaSetDevice(h.ctx.device);
+    if (cudaEventSynchronize(h.ev[3]) == cudaSuccess) {
+      cudaEventElapsedTime(&h.timings[0], h.ev[0], h.ev[1]);
+      cudaEventElapsedTime(&h.timings[1], h.ev[1], h.ev[2]);
+      cudaEventElapsedTime(&h.timings[2], h.ev[2], h.ev[3]);
+      cudaEventElapsedTime(&h.timings[3], h.ev[0], h.ev[3]);
+    }
+    cudaGetLastError();
+    h.timings_pending = false;
+  }
+  for (int i = 0; i < 4; ++i) ms_out[i] = h.timings[i];
   return B2R_OK;
 }
 

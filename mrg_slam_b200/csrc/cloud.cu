@@ -816,7 +816,7 @@ void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, co
   std::vector<Cloud*> all;
   for (size_t i = 0; i < count; ++i) {
     Cloud& c = *clouds[i];
-    c.mem.push_back(arena);
+    c.mem_pts = arena;
     all.push_back(&c);
     if (n[i] == 0 || fused_copy) continue;
     if (stride_bytes == 16) {
@@ -948,9 +948,10 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
   }
   if (!plan.empty()) {
     std::shared_ptr<Arena> arena = plan.commit(ctx);
-    for (const std::vector<int>* t : {&todo_grid, &todo_cov, &todo_vox, &todo_ndt})
-      for (int i : *t)
-        if (clouds[i]->mem.empty() || clouds[i]->mem.back() != arena) clouds[i]->mem.push_back(arena);
+    for (int i : todo_grid) clouds[i]->mem_grid = arena;
+    for (int i : todo_cov) clouds[i]->mem_cov = arena;
+    for (int i : todo_vox) clouds[i]->mem_vox = arena;
+    for (int i : todo_ndt) clouds[i]->mem_ndt = arena;
   }
   // the flags go up now: the views below must describe the finished structures
   for (int i : todo_grid) clouds[i]->has_grid = true;
@@ -1068,7 +1069,7 @@ void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* kn
   if (!c.cov.p || c.cov_k == 0) {
     ArenaPlan plan;
     plan.want(c.cov.p, (size_t)c.n * 6);
-    c.mem.push_back(plan.commit(ctx));
+    c.mem_cov = plan.commit(ctx);
   }
   CloudView hv = c.view();
   DBuf<CloudView> dv; dv.alloc(1, ctx.stream);

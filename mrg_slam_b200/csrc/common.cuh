@@ -28,6 +28,11 @@ struct Error : std::runtime_error {
     }                                                                                                        \
   } while (0)
 
+// Private stream-ordered memory pool of the current device (created on first use, release threshold = keep everything): the
+// process's default pool and its attributes are left alone.
+cudaMemPool_t device_pool();
+inline cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t s) { return cudaMallocFromPoolAsync(p, bytes, device_pool(), s); }
+
 enum { PROF_KNN_COV = 0, PROF_LSQ_EVAL, PROF_NDT_EVAL, PROF_GRID_BUILD, PROF_VOXEL_REDUCE, PROF_FITNESS, PROF_COUNT };
 
 struct ProfRec {
@@ -51,7 +56,8 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::shared_ptr<StreamOwner> stream_owner;
-  uint64_t launches = 0;
+  uint64_t launches = 0;        // kernel launches + graph launches issued by this handle
+  uint64_t graph_launches = 0;  // of which: optimiser loops launched as one CUDA graph (the rounds inside are not counted)
   int num_sms = 148;
   bool profile = false;
   std::vector<ProfRec> prof_pending;
@@ -85,8 +91,8 @@ struct ProfScope {
   int id;
   double bytes;
   cudaEvent_t a = nullptr;
-  ProfScope(Ctx& ctx, int kernel_id, double algorithmic_bytes) : c(ctx), id(kernel_id), bytes(algorithmic_bytes) {
-    if (c.profile) { a = c.get_event(); cudaEventRecord(a, c.stream); }
+  ProfScope(Ctx& ctx, int kernel_id, double algorithmic_bytes, bool enabled = true) : c(ctx), id(kernel_id), bytes(algorithmic_bytes) {
+    if (c.profile && enabled) { a = c.get_event(); cudaEventRecord(a, c.stream); }
   }
   ~ProfScope() {
     if (a) {
@@ -125,7 +131,7 @@ struct DBuf {
     release();
     s = stream;
     n = count;
-    if (count) B2R_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+    if (count) B2R_CUDA(pool_malloc((void**)&p, count * sizeof(T), stream));
   }
   void release() {
     if (p) cudaFreeAsync(p, s);
@@ -191,6 +197,42 @@ struct CloudView {
   int* n_nrec;
   int* n_reccell;
 };
+
+// ------------------------------------------------------------------------------------------------
+// Optimiser loops that never leave the device.  Every method's alignment is { evaluate the cost over the source cloud ;
+// advance each pair's state machine } repeated until every pair of the batch has finished.  The pair of kernels is the body
+// of a CUDA-graph WHILE node: the step kernel's last block decides whether another round is needed and sets the node's
+// condition itself (cudaGraphSetConditional), so a whole alignment — whatever its iteration count — is ONE graph launch
+// with no host polling in between (north star: "the Gauss-Newton/Newton update and convergence test stay on the device").
+struct LoopCtl {        // device memory, zero-initialised before the loop
+  int done;             // pairs that reached their final state
+  int blocks_finished;  // step-kernel blocks of the current round that are through (last-block detection)
+  int rounds;           // rounds executed
+  int pad;
+};
+struct LoopArgs {       // passed by value to the step kernels
+  LoopCtl* ctl;
+  int npairs;
+  int max_rounds;
+  int use_graph;        // 0: the host polls ctl->done between groups of rounds (profiling / fallback path)
+  cudaGraphConditionalHandle handle;
+};
+// Called by EVERY thread of a step kernel after its work (no early returns before it).
+__device__ __forceinline__ void loop_tail(const LoopArgs& la) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned nblocks = gridDim.x * gridDim.y;
+    const int t = atomicAdd(&la.ctl->blocks_finished, 1);
+    if (t == (int)nblocks - 1) {  // last block of this round: every pair's state (and ctl->done) is final
+      __threadfence();
+      la.ctl->blocks_finished = 0;
+      const int rounds = atomicAdd(&la.ctl->rounds, 1) + 1;
+      const int done = atomicAdd(&la.ctl->done, 0);
+      if (la.use_graph) cudaGraphSetConditional(la.handle, (done < la.npairs && rounds < la.max_rounds) ? 1u : 0u);
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

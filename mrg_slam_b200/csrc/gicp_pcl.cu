@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256, 2) gicp_pcl_eval_kernel(const CloudView* 
   }
 }
 
-__global__ void gicp_pcl_step_kernel(gp::State* __restrict__ states, int npairs, gp::Params prm, const double* __restrict__ partials, int chunks,
-                                     int* __restrict__ m_arr, int* __restrict__ done_count) {
+__device__ void gicp_pcl_step_body(gp::State* __restrict__ states, int npairs, const gp::Params& prm, const double* __restrict__ partials,
+                                   int chunks, int* __restrict__ m_arr, int* __restrict__ done_count) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= npairs) return;
   gp::State s = states[pair];
@@ -146,69 +146,79 @@ __global__ void gicp_pcl_step_kernel(gp::State* __restrict__ states, int npairs,
   states[pair] = s;
 }
 
-void gicp_pcl_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
-                          const float* guesses_colmajor, b2r_result* out) {
-  const int np = (int)pairs.size();
+__global__ void gicp_pcl_step_kernel(gp::State* __restrict__ states, gp::Params prm, const double* __restrict__ partials, int chunks,
+                                     int* __restrict__ m_arr, LoopArgs la) {
+  gicp_pcl_step_body(states, la.npairs, prm, partials, chunks, m_arr, &la.ctl->done);
+  loop_tail(la);
+}
+// the first request of every pair (REQ_NONE -> REQ_CORRESPOND), before the loop
+__global__ void gicp_pcl_first_kernel(gp::State* __restrict__ states, int npairs, gp::Params prm, const double* __restrict__ partials, int chunks,
+                                      int* __restrict__ m_arr, int* __restrict__ done_count) {
+  gicp_pcl_step_body(states, npairs, prm, partials, chunks, m_arr, done_count);
+}
+__global__ void gicp_pcl_rows_kernel(const gp::State* __restrict__ states, int npairs, b2r_result* __restrict__ rows) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= npairs) return;
+  const gp::State& s = states[pair];
+  b2r_result& r = rows[pair];
+  gp::final_transformation(s, r.T);
+  r.converged = s.request == gp::REQ_DONE ? s.converged : 0;
+  r.iterations = s.nr_iterations;
+  r.error = s.f;
+  r.evals = s.evals;
+  r.fitness = 0.0;
+}
+
+void gicp_pcl_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
+  const int np = b.np;
   if (np == 0) return;
-  int maxn = 1;
-  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
-  const int chunks = std::max(1, std::min((maxn + 1023) / 1024, std::max(1, (32 * ctx.num_sms + np - 1) / np)));
+  const int chunks = std::max(1, std::min((b.maxn + 1023) / 1024, std::max(1, (32 * ctx.num_sms + np - 1) / np)));
   gp::Params prm;
   gp::default_params(prm);
   prm.transformation_epsilon = cfg.transformation_epsilon;
   prm.rotation_epsilon = cfg.rotation_epsilon;
   prm.maximum_iterations = cfg.maximum_iterations;
   prm.max_optimizer_iterations = cfg.max_optimizer_iterations;
-  const double thr2 = cfg.max_correspondence_distance * cfg.max_correspondence_distance;
-  const float max_d2 = thr2 >= (double)FLT_MAX ? INFINITY : (float)(thr2 * 1.0001);
+  double thr2 = cfg.max_correspondence_distance * cfg.max_correspondence_distance;
+  float max_d2 = thr2 >= (double)FLT_MAX ? INFINITY : (float)(thr2 * 1.0001);
   std::vector<gp::State> hs(np);
-  for (int i = 0; i < np; ++i) gp::init(hs[i], guesses_colmajor + (size_t)i * 16);
+  for (int i = 0; i < np; ++i) gp::init(hs[i], b.guesses + (size_t)i * 16);
   std::vector<long long> hoff(np);
   long long tot = 0;
-  for (int i = 0; i < np; ++i) { hoff[i] = tot; tot += src_sizes[i]; }
-  DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
+  for (int i = 0; i < np; ++i) { hoff[i] = tot; tot += b.src_sizes[i]; }
   DBuf<gp::State> ds; ds.alloc(np, ctx.stream);
   DBuf<double> part; part.alloc((size_t)np * chunks * kGpPart, ctx.stream);
   DBuf<int32_t> corr; corr.alloc((size_t)std::max(1ll, tot), ctx.stream);
   DBuf<long long> coff; coff.alloc(np, ctx.stream);
   DBuf<int> marr; marr.alloc(np, ctx.stream);
-  DBuf<int> done; done.alloc(1, ctx.stream);
-  done.zero(ctx.stream);
+  DBuf<LoopCtl> ctl; ctl.alloc(1, ctx.stream);
+  ctl.zero(ctx.stream);
   B2R_CUDA(cudaMemsetAsync(marr.p, 0, sizeof(int) * np, ctx.stream));
   B2R_CUDA(cudaMemsetAsync(part.p, 0, sizeof(double) * (size_t)np * chunks * kGpPart, ctx.stream));
-  B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, hs.data(), sizeof(gp::State) * np, cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(coff.p, hoff.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, ctx.stream));
-  const dim3 ge(chunks, np);
   const int step_blocks = (np + 63) / 64;
   // the first step only issues the first request (REQ_NONE -> REQ_CORRESPOND)
-  B2R_LAUNCH(ctx, gicp_pcl_step_kernel, step_blocks, 64, 0, ds.p, np, prm, part.p, chunks, marr.p, done.p);
+  B2R_LAUNCH(ctx, gicp_pcl_first_kernel, step_blocks, 64, 0, ds.p, np, prm, part.p, chunks, marr.p, &ctl.p->done);
   // per outer iteration: 1 correspondence pass + per BFGS step (<= max_optimizer_iterations) a line search of a few evaluations
   const long max_rounds = 4 + (long)std::max(1, cfg.maximum_iterations) * (2 + (long)std::max(1, cfg.max_optimizer_iterations) * 210);
-  long rounds = 0;
-  int hdone = 0;
-  int rounds_per_check = 16;
-  while (hdone < np && rounds < max_rounds) {
-    for (int r = 0; r < rounds_per_check; ++r) {
-      B2R_LAUNCH(ctx, gicp_pcl_eval_kernel, ge, 256, 0, d_views, dp.p, ds.p, thr2, max_d2, part.p, corr.p, coff.p);
-      B2R_LAUNCH(ctx, gicp_pcl_step_kernel, step_blocks, 64, 0, ds.p, np, prm, part.p, chunks, marr.p, done.p);
-    }
-    rounds += rounds_per_check;
-    B2R_CUDA(cudaMemcpyAsync(&hdone, done.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-  }
-  B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(gp::State) * np, cudaMemcpyDeviceToHost, ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-  for (int i = 0; i < np; ++i) {
-    const gp::State& s = hs[i];
-    b2r_result& r = out[i];
-    gp::final_transformation(s, r.T);
-    r.converged = s.request == gp::REQ_DONE ? s.converged : 0;
-    r.iterations = s.nr_iterations;
-    r.error = s.f;
-    r.evals = s.evals;
-    r.fitness = 0.0;
-  }
+  const CloudView* a_views = b.d_views;
+  const PairDesc* a_pairs = b.d_pairs;
+  const gp::State* a_states_c = ds.p;
+  gp::State* a_states = ds.p;
+  double* a_part = part.p;
+  const double* a_part_c = part.p;
+  int32_t* a_corr = corr.p;
+  const long long* a_coff = coff.p;
+  int* a_marr = marr.p;
+  int a_chunks = chunks;
+  LoopArgs la;
+  memset(&la, 0, sizeof(la));
+  void* eval_args[] = {&a_views, &a_pairs, &a_states_c, &thr2, &max_d2, &a_part, &a_corr, &a_coff};
+  void* step_args[] = {&a_states, &prm, &a_part_c, &a_chunks, &a_marr, &la};
+  run_device_loop(ctx, (const void*)gicp_pcl_eval_kernel, dim3(chunks, np), dim3(256), eval_args, (const void*)gicp_pcl_step_kernel,
+                  dim3(step_blocks), dim3(64), step_args, la, ctl.p, np, max_rounds, -1);
+  B2R_LAUNCH(ctx, gicp_pcl_rows_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_rows);
 }
 
 }  // namespace b2r

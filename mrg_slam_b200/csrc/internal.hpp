@@ -36,7 +36,7 @@ struct ArenaPlan {
     a->keep = ctx.stream_owner;
     a->bytes = zbytes + bytes;
     if (a->bytes) {
-      B2R_CUDA(cudaMallocAsync(&a->p, a->bytes, stream));
+      B2R_CUDA(pool_malloc(&a->p, a->bytes, stream));
       if (zbytes) B2R_CUDA(cudaMemsetAsync(a->p, 0, zbytes, stream));
     }
     for (const Slot& sl : slots) *sl.dst = (char*)a->p + (sl.zeroed ? sl.off : zbytes + sl.off);
@@ -53,7 +53,10 @@ struct Ref {  // non-owning device pointer into one of the cloud's arenas
 struct Cloud {
   int device = 0;
   int n = 0;
-  std::vector<std::shared_ptr<Arena>> mem;  // keeps every buffer below alive
+  // The allocation each group of buffers below was carved out of (shared with the other structures / clouds of the same build
+  // step).  Rebuilding a structure with other parameters (k, covariance mode, resolution, leaf) replaces its entry, so the
+  // superseded allocation is released as soon as no other structure uses it: device memory does not grow with alternating use.
+  std::shared_ptr<Arena> mem_pts, mem_grid, mem_cov, mem_vox, mem_ndt;
   Ref<float4> pts;
   bool has_bbox = false;
   float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
@@ -107,9 +110,23 @@ struct Handle {
   bool converged = false;
   bool has_result = false;
   float timings[4] = {0, 0, 0, 0};
+  bool timings_pending = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+}  // namespace b2r
+struct b2r_handle { b2r::Handle h; };
+struct b2r_cloud { b2r::Cloud c; };
+namespace b2r {
+inline Handle* b2r_handle_impl(b2r_handle* h) { return &h->h; }
+inline Cloud* b2r_cloud_impl(b2r_cloud* c) { return &c->c; }
+
+// ---- api.cu: the batch path behind b2r_align / b2r_align_batch / b2r_align_batch_sharded ----
+//   out_all   host array of n rows, or nullptr (then the call returns without synchronising)
+//   rows_dev  device array of n rows the results are (also) left in, or nullptr
+void b2r_run_align(Handle& h, const std::vector<Cloud*>& sources, const std::vector<Cloud*>& targets, const float* guesses_colmajor,
+                   int with_fitness, double fitness_max_range, b2r_result* out_all, b2r_result* rows_dev);
 
 // ---- cloud.cu ----
 // uploads `count` clouds into one shared allocation and computes their bounding boxes; one synchronisation at the end
@@ -122,27 +139,43 @@ void debug_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, const float* queries, 
 unsigned long long debug_knn_list_overflows(Ctx& ctx);  // per device, since library load
 void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* knn_out);
 
-// ---- lsq.cu (FAST_GICP / FAST_VGICP) ----
+// ---- the batch every optimiser works on: all of it in device memory, results included (api.cu: run_align) ----
 struct PairDesc {
   int src;  // index into the views array
   int tgt;
 };
-void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
-                     const float* guesses_colmajor, b2r_result* out);
+struct BatchArgs {
+  const CloudView* d_views;
+  const PairDesc* d_pairs;
+  const int* d_src_n;       // source points per pair
+  const float* d_guesses;   // 16 floats per pair, column-major
+  const float* guesses;     // host copy of d_guesses (NDT / GICP_PCL initialise their state machines on the host)
+  b2r_result* d_rows;       // one result row per pair; the optimisers fill everything but `fitness`
+  int np;
+  int maxn;                 // largest source cloud of the batch
+  const int* src_sizes;     // host copy of d_src_n
+};
+
+// ---- loop.cu: { eval ; step } until every pair is done, as one CUDA-graph launch (WHILE node) or, when per-kernel profiling is
+// on or B2R_GRAPH_LOOP=0, as a host-polled loop.  `la` must be the LoopArgs object the step kernel's argument array points at;
+// prof_id < 0: the evaluation launches are not bracketed.  Stream-ordered: returns without synchronising in graph mode.
+void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_block, void** eval_args, const void* step_fn, dim3 step_grid,
+                     dim3 step_block, void** step_args, LoopArgs& la, LoopCtl* d_ctl, int npairs, long max_rounds, int prof_id);
+
+// ---- lsq.cu (FAST_GICP / FAST_VGICP / SMALL_GICP) ----
+void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b);
 void lsq_debug_linearize(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, int n_src, const double* T_lin, const double* T_trial,
                          bool trial, double* H, double* b, double* err, int32_t* corr_out, uint8_t* corr_valid);
 
-// ---- ndt.cu ----
-void gicp_pcl_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
-                          const float* guesses_colmajor, b2r_result* out);
-void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
-                     const float* guesses_colmajor, b2r_result* out);
+// ---- gicp_pcl.cu / ndt.cu ----
+void gicp_pcl_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b);
+void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b);
 void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, int n_src, const double* p6, double* score,
                            double* grad6, double* hess36, int32_t* hits_out);
 
-// ---- fitness (in lsq.cu) ----
-void fitness_batch(Ctx& ctx, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes, const float* T_colmajor,
-                   double max_range, double* out);
+// ---- fitness / inlier fraction (in lsq.cu): reads T from the rows, writes rows[i].fitness.  inlier_d2 > 0 additionally counts the
+// source points whose nearest target point is closer than sqrt(inlier_d2) into inlier_out[i] (device, np ints) ----
+void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_d2 = 0.f, int* d_inlier_out = nullptr);
 void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor, float4* out);
 
 // ---- filters.cu ----

@@ -1,0 +1,87 @@
+// The optimiser loop of every registration method as ONE CUDA-graph launch (common.cuh: LoopCtl / loop_tail).
+//
+// Replaces the host loops of fast_gicp LsqRegistration::computeTransformation, pclomp NDT::computeTransformation and
+// pcl GICP::computeTransformation (selected at /root/reference/src/mrg_slam/registrations.cpp:46-148): there the host runs
+// "linearise, solve, test convergence" iteration by iteration; here the graph's WHILE node repeats {eval kernel, step kernel}
+// and the step kernel's last block clears the condition when every pair of the batch has finished.
+#include <cstdlib>
+
+#include "internal.hpp"
+
+namespace b2r {
+
+static bool graph_loop_enabled() {
+  static const bool on = [] { const char* e = getenv("B2R_GRAPH_LOOP"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
+#define B2R_GRAPH(expr, g, ge)                                                                              \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      if (ge) cudaGraphExecDestroy(ge);                                                                     \
+      if (g) cudaGraphDestroy(g);                                                                           \
+      char _b[512];                                                                                         \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw ::b2r::Error(B2R_ERR_CUDA, _b);                                                                 \
+    }                                                                                                       \
+  } while (0)
+
+void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_block, void** eval_args, const void* step_fn, dim3 step_grid,
+                     dim3 step_block, void** step_args, LoopArgs& la, LoopCtl* d_ctl, int npairs, long max_rounds, int prof_id) {
+  la.ctl = d_ctl;
+  la.npairs = npairs;
+  la.max_rounds = (int)std::min<long>(max_rounds, 1l << 30);
+  la.handle = 0;
+  B2R_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(LoopCtl), ctx.stream));
+  if (graph_loop_enabled() && !ctx.profile) {
+    la.use_graph = 1;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    B2R_GRAPH(cudaGraphCreate(&g, 0), g, ge);
+    B2R_GRAPH(cudaGraphConditionalHandleCreate(&la.handle, g, 1, cudaGraphCondAssignDefault), g, ge);
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = la.handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t wnode = nullptr;
+    B2R_GRAPH(cudaGraphAddNode(&wnode, g, nullptr, 0, &cp), g, ge);
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    cudaKernelNodeParams ke = {}, ks = {};
+    ke.func = const_cast<void*>(eval_fn); ke.gridDim = eval_grid; ke.blockDim = eval_block; ke.kernelParams = eval_args;
+    ks.func = const_cast<void*>(step_fn); ks.gridDim = step_grid; ks.blockDim = step_block; ks.kernelParams = step_args;
+    cudaGraphNode_t ne = nullptr, ns = nullptr;
+    B2R_GRAPH(cudaGraphAddKernelNode(&ne, body, nullptr, 0, &ke), g, ge);
+    B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, &ne, 1, &ks), g, ge);
+    B2R_GRAPH(cudaGraphInstantiate(&ge, g, 0), g, ge);
+    B2R_GRAPH(cudaGraphLaunch(ge, ctx.stream), g, ge);
+    ctx.launches += 1;  // one graph launch; the rounds it ran are read from LoopCtl by whoever wants them
+    ++ctx.graph_launches;
+    // the executable graph may be destroyed while a launch is in flight: the runtime defers the release until it completes
+    cudaGraphExecDestroy(ge);
+    cudaGraphDestroy(g);
+    return;
+  }
+  // ---- host-polled loop: groups of rounds, then one read of the done counter
+  la.use_graph = 0;
+  int rounds_per_check = 6;
+  long rounds = 0;
+  int hdone = 0;
+  while (hdone < npairs && rounds < max_rounds) {
+    for (int r = 0; r < rounds_per_check; ++r) {
+      {
+        ProfScope ps(ctx, prof_id >= 0 ? prof_id : 0, 0.0, prof_id >= 0);  // bytes are added by the caller from the work the device did
+        B2R_CUDA(cudaLaunchKernel(eval_fn, eval_grid, eval_block, eval_args, 0, ctx.stream));
+        ++ctx.launches;
+      }
+      B2R_CUDA(cudaLaunchKernel(step_fn, step_grid, step_block, step_args, 0, ctx.stream));
+      ++ctx.launches;
+    }
+    rounds += rounds_per_check;
+    B2R_CUDA(cudaMemcpyAsync(&hdone, &d_ctl->done, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    rounds_per_check = 4;
+  }
+}
+
+}  // namespace b2r

@@ -498,10 +498,26 @@ __device__ void lsq_finish(LsqState& s, int* done_count) {
   atomicAdd(done_count, 1);
 }
 
+// getFinalTransformation / hasConverged / nr_iterations_ of a finished pair, as the row the C ABI hands out (written on the
+// device: for a sharded batch the row array IS the all-gather send buffer)
+__device__ void lsq_write_row(const LsqState& s, b2r_result& r) {
+  for (int rr = 0; rr < 3; ++rr) {
+    for (int c = 0; c < 3; ++c) r.T[c * 4 + rr] = (float)s.x0[rr * 3 + c];
+    r.T[12 + rr] = (float)s.x0[9 + rr];
+    r.T[rr * 4 + 3] = 0.f;
+  }
+  r.T[15] = 1.f;
+  r.converged = s.converged;
+  r.iterations = s.nr_iterations;
+  r.error = s.y0;
+  r.evals = s.evals;
+  r.fitness = 0.0;
+}
+
 // One warp per pair: fixed-order sum of the chunk partials, then the LM state machine of
 // LsqRegistration::computeTransformation / step_lm advanced by one evaluation.
-__global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqParams prm, const double* __restrict__ partials, int chunks,
-                                const int* __restrict__ src_n, int* __restrict__ done_count) {
+__device__ void lsq_step_body(LsqState* __restrict__ states, int npairs, const LsqParams& prm, const double* __restrict__ partials, int chunks,
+                              const int* __restrict__ src_n, int* __restrict__ done_count) {
   const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= npairs) return;
@@ -640,6 +656,16 @@ __global__ void lsq_step_kernel(LsqState* __restrict__ states, int npairs, LsqPa
   s.phase = PH_LINEARIZE;
 }
 
+__global__ void lsq_step_kernel(LsqState* __restrict__ states, LsqParams prm, const double* __restrict__ partials, int chunks,
+                                const int* __restrict__ src_n, LoopArgs la) {
+  lsq_step_body(states, la.npairs, prm, partials, chunks, src_n, &la.ctl->done);
+  loop_tail(la);
+}
+__global__ void lsq_rows_kernel(const LsqState* __restrict__ states, int npairs, b2r_result* __restrict__ rows) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair < npairs) lsq_write_row(states[pair], rows[pair]);
+}
+
 __global__ void lsq_init_kernel(LsqState* __restrict__ states, int npairs, const float* __restrict__ guesses, int max_iterations,
                                 double init_lambda, int* __restrict__ done_count) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
@@ -702,82 +728,66 @@ static int pick_chunks(const Ctx& ctx, int npairs, int maxn) {
   return std::max(1, std::min(by_size, by_fill));
 }
 
-void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
-                     const float* guesses_colmajor, b2r_result* out) {
-  const int np = (int)pairs.size();
+void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
+  const int np = b.np;
   if (np == 0) return;
-  int maxn = 1;
-  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
-  const int chunks = pick_chunks(ctx, np, maxn);
-  const LsqParams prm = make_params(cfg);
-  DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
+  const int chunks = pick_chunks(ctx, np, b.maxn);
+  LsqParams prm = make_params(cfg);
   DBuf<LsqState> ds; ds.alloc(np, ctx.stream);
-  DBuf<float> dg; dg.alloc((size_t)np * 16, ctx.stream);
   DBuf<double> part; part.alloc((size_t)np * chunks * kPart, ctx.stream);
-  DBuf<int> done; done.alloc(1, ctx.stream);
-  done.zero(ctx.stream);
-  DBuf<int> dn; dn.alloc(np, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dn.p, src_sizes, sizeof(int) * np, cudaMemcpyHostToDevice, ctx.stream));
-  // FAST_GICP: correspondence cache, one int per source point of every pair
+  DBuf<LoopCtl> ctl; ctl.alloc(1, ctx.stream);
+  ctl.zero(ctx.stream);
+  // FAST_GICP / SMALL_GICP: correspondence cache, one int per source point of every pair
   DBuf<int32_t> corr;
   DBuf<long long> coff;
   std::vector<long long> hoff;
   if (cfg.method == B2R_FAST_GICP || cfg.method == B2R_SMALL_GICP) {
     hoff.resize(np);
     long long tot = 0;
-    for (int i = 0; i < np; ++i) { hoff[i] = tot; tot += src_sizes[i]; }
+    for (int i = 0; i < np; ++i) { hoff[i] = tot; tot += b.src_sizes[i]; }
     corr.alloc((size_t)std::max(1ll, tot), ctx.stream);
     coff.alloc(np, ctx.stream);
     B2R_CUDA(cudaMemcpyAsync(coff.p, hoff.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, ctx.stream));
   }
-  B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
-  B2R_CUDA(cudaMemcpyAsync(dg.p, guesses_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
-  B2R_CUDA(cudaMemsetAsync(ds.p, 0, sizeof(LsqState) * np, ctx.stream));  // H, b, d and the padding are copied back before every pair has written them
-  B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, dg.p, cfg.maximum_iterations,
-             cfg.method == B2R_SMALL_GICP ? 1e-3 : -1.0, done.p);
-  const dim3 ge(chunks, np);
-  const int step_blocks = (np + 3) / 4;
-  int rounds_per_check = 6;
-  int hdone = 0;
+  B2R_CUDA(cudaMemsetAsync(ds.p, 0, sizeof(LsqState) * np, ctx.stream));
+  B2R_LAUNCH(ctx, lsq_init_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_guesses, cfg.maximum_iterations,
+             cfg.method == B2R_SMALL_GICP ? 1e-3 : -1.0, &ctl.p->done);
   const long max_rounds = (long)std::max(1, cfg.maximum_iterations) * (1 + std::max(1, cfg.lm_max_iterations)) + 2;
-  long rounds = 0;
-  while (hdone < np && rounds < max_rounds) {
-    for (int r = 0; r < rounds_per_check; ++r) {
-      {
-        ProfScope ps(ctx, PROF_LSQ_EVAL, 0.0);  // bytes are added below from the work the device actually did
-        launch_lsq_eval(ctx, cfg.method, ge, d_views, dp.p, ds.p, prm, part.p, corr.p, coff.p, nullptr, nullptr);
-      }
-      B2R_LAUNCH(ctx, lsq_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, dn.p, done.p);
-    }
-    rounds += rounds_per_check;
-    B2R_CUDA(cudaMemcpyAsync(&hdone, done.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-    rounds_per_check = 4;
-  }
-  std::vector<LsqState> hs(np);
-  B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(LsqState) * np, cudaMemcpyDeviceToHost, ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  // ---- the whole LM iteration as one device-side loop
+  const CloudView* a_views = b.d_views;
+  const PairDesc* a_pairs = b.d_pairs;
+  const LsqState* a_states_c = ds.p;
+  LsqState* a_states = ds.p;
+  double* a_part = part.p;
+  const double* a_part_c = part.p;
+  int32_t* a_corr = corr.p;
+  const long long* a_coff = coff.p;
+  int32_t* a_null_i = nullptr;
+  uint8_t* a_null_b = nullptr;
+  int a_chunks = chunks;
+  const int* a_src_n = b.d_src_n;
+  LoopArgs la;
+  memset(&la, 0, sizeof(la));
+  static const bool pipelined = [] { const char* e = getenv("B2R_VGICP_PIPE"); return !e || atoi(e) != 0; }();
+  const bool pipe = cfg.method == B2R_FAST_VGICP && prm.neighbor_search == B2R_DIRECT1 && pipelined;
+  void* eval_args_pipe[] = {&a_views, &a_pairs, &a_states_c, &a_part};
+  void* eval_args_gen[] = {&a_views, &a_pairs, &a_states_c, &prm, &a_part, &a_corr, &a_coff, &a_null_i, &a_null_b};
+  void* step_args[] = {&a_states, &prm, &a_part_c, &a_chunks, &a_src_n, &la};
+  const void* eval_fn = pipe ? (const void*)vgicp_eval_kernel
+                             : (cfg.method == B2R_FAST_VGICP ? (const void*)lsq_eval_kernel<B2R_FAST_VGICP>
+                                : (cfg.method == B2R_FAST_GICP ? (const void*)lsq_eval_kernel<B2R_FAST_GICP> : (const void*)lsq_eval_kernel<B2R_SMALL_GICP>));
+  run_device_loop(ctx, eval_fn, dim3(chunks, np), dim3(256), pipe ? eval_args_pipe : eval_args_gen, (const void*)lsq_step_kernel,
+                  dim3((np + 3) / 4), dim3(128), step_args, la, ctl.p, np, max_rounds, PROF_LSQ_EVAL);
+  B2R_LAUNCH(ctx, lsq_rows_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_rows);
   if (ctx.profile) {
     // per evaluation pass 40 B per source point + one 64 B voxel record (VGICP) or 40 B target
     // point + covariance (GICP) per correspondence, summed over the passes each pair actually ran
+    std::vector<LsqState> hs(np);
+    B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(LsqState) * np, cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
     double wp = 0.0, wc = 0.0;
     for (int i = 0; i < np; ++i) { wp += hs[i].work_pts; wc += hs[i].work_corr; }
     ctx.prof_bytes[PROF_LSQ_EVAL] += 40.0 * wp + (cfg.method == B2R_FAST_VGICP ? 64.0 : 40.0) * wc;
-  }
-  for (int i = 0; i < np; ++i) {
-    const LsqState& s = hs[i];
-    b2r_result& r = out[i];
-    for (int rr = 0; rr < 3; ++rr) {
-      for (int c = 0; c < 3; ++c) r.T[c * 4 + rr] = (float)s.x0[rr * 3 + c];
-      r.T[12 + rr] = (float)s.x0[9 + rr];
-      r.T[rr * 4 + 3] = 0.f;
-    }
-    r.T[15] = 1.f;
-    r.converged = s.converged;
-    r.iterations = s.nr_iterations;
-    r.error = s.y0;
-    r.evals = s.evals;
-    r.fitness = 0.0;
   }
 }
 
@@ -862,17 +872,20 @@ void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor,
 }
 
 // grid = (chunks, pairs): per source point exact 1-NN squared distance into the target; sum of those <= max_range
+// (getFitnessScore, A13) and, when inlier_d2 > 0, the number of points whose nearest neighbour is closer than that (A15: the
+// inlier fraction of ScanMatchingOdometryComponent::publish_scan_matching_status, scan_matching_odometry_component.cpp:403-415).
+// The transform is the pair's result row (written on the device by the optimiser: no host round trip in between).
 __global__ void __launch_bounds__(256) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
-                                                       const float* __restrict__ Ts, double max_range, float max_d2,
+                                                       const b2r_result* __restrict__ rows, double max_range, float max_d2, float inlier_d2,
                                                        double* __restrict__ partials) {
   const int pair = blockIdx.y;
   const CloudView& src = views[pairs[pair].src];
   const CloudView& tgt = views[pairs[pair].tgt];
   __shared__ float T[16];
-  __shared__ double red[2 * 8];
-  if (threadIdx.x < 16) T[threadIdx.x] = Ts[(size_t)pair * 16 + threadIdx.x];
+  __shared__ double red[3 * 8];
+  if (threadIdx.x < 16) T[threadIdx.x] = rows[pair].T[threadIdx.x];
   __syncthreads();
-  double acc[2] = {0.0, 0.0};
+  double acc[3] = {0.0, 0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(&src.pts[i]);
     float qx, qy, qz;
@@ -880,40 +893,37 @@ __global__ void __launch_bounds__(256) fitness_kernel(const CloudView* __restric
     float d2;
     const int pos = nn1_search(tgt, qx, qy, qz, max_d2, d2);
     if (pos >= 0 && (double)d2 <= max_range) { acc[0] += (double)d2; acc[1] += 1.0; }
+    if (pos >= 0 && d2 < inlier_d2) acc[2] += 1.0;
   }
-  block_reduce_to<2>(acc, red, partials + ((size_t)pair * gridDim.x + blockIdx.x) * 2);
+  block_reduce_to<3>(acc, red, partials + ((size_t)pair * gridDim.x + blockIdx.x) * 3);
 }
-__global__ void fitness_finish_kernel(const double* __restrict__ partials, int npairs, int chunks, double* __restrict__ out) {
+__global__ void fitness_finish_kernel(const double* __restrict__ partials, int npairs, int chunks, b2r_result* __restrict__ rows,
+                                      int* __restrict__ inliers) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= npairs) return;
-  double s = 0.0, c = 0.0;
-  for (int k = 0; k < chunks; ++k) { s += partials[((size_t)pair * chunks + k) * 2]; c += partials[((size_t)pair * chunks + k) * 2 + 1]; }
-  out[pair] = c > 0.0 ? s / c : DBL_MAX;
+  double s = 0.0, c = 0.0, in = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const double* p = partials + ((size_t)pair * chunks + k) * 3;
+    s += p[0]; c += p[1]; in += p[2];
+  }
+  rows[pair].fitness = c > 0.0 ? s / c : DBL_MAX;
+  if (inliers) inliers[pair] = (int)in;
 }
 
-void fitness_batch(Ctx& ctx, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes, const float* T_colmajor,
-                   double max_range, double* out) {
-  const int np = (int)pairs.size();
+void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_d2, int* d_inlier_out) {
+  const int np = b.np;
   if (np == 0) return;
-  int maxn = 1;
-  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
-  const int chunks = pick_chunks(ctx, np, maxn);
-  DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
-  DBuf<float> dT; dT.alloc((size_t)np * 16, ctx.stream);
-  DBuf<double> part; part.alloc((size_t)np * chunks * 2, ctx.stream);
-  DBuf<double> dout; dout.alloc(np, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
-  B2R_CUDA(cudaMemcpyAsync(dT.p, T_colmajor, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, ctx.stream));
-  const float max_d2 = max_range >= (double)FLT_MAX ? INFINITY : (float)(max_range * 1.0001);
+  const int chunks = pick_chunks(ctx, np, b.maxn);
+  DBuf<double> part; part.alloc((size_t)np * chunks * 3, ctx.stream);
+  float max_d2 = max_range >= (double)FLT_MAX ? INFINITY : (float)(max_range * 1.0001);
+  if (inlier_d2 > 0.f) max_d2 = fmaxf(max_d2, inlier_d2 * 1.0001f);
   {
     double pts = 0.0;  // 16 B source point + one gathered 16 B neighbour
-    for (int i = 0; i < np; ++i) pts += src_sizes[i];
+    for (int i = 0; i < np; ++i) pts += b.src_sizes[i];
     ProfScope ps(ctx, PROF_FITNESS, 32.0 * pts);
-    B2R_LAUNCH(ctx, fitness_kernel, dim3(chunks, np), 256, 0, d_views, dp.p, dT.p, max_range, max_d2, part.p);
+    B2R_LAUNCH(ctx, fitness_kernel, dim3(chunks, np), 256, 0, b.d_views, b.d_pairs, b.d_rows, max_range, max_d2, inlier_d2, part.p);
   }
-  B2R_LAUNCH(ctx, fitness_finish_kernel, (np + 127) / 128, 128, 0, part.p, np, chunks, dout.p);
-  B2R_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * np, cudaMemcpyDeviceToHost, ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  B2R_LAUNCH(ctx, fitness_finish_kernel, (np + 127) / 128, 128, 0, part.p, np, chunks, b.d_rows, d_inlier_out);
 }
 
 }  // namespace b2r

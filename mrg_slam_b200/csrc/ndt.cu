@@ -587,8 +587,8 @@ __device__ bool ndt_mt_continue(NdtState& s, const NdtParams& prm) {
   return ndt_mt_end(s, prm);
 }
 
-__global__ void ndt_step_kernel(NdtState* __restrict__ states, int npairs, NdtParams prm, const double* __restrict__ partials, int chunks,
-                                const int* __restrict__ src_n, int* __restrict__ done_count) {
+__device__ void ndt_step_body(NdtState* __restrict__ states, int npairs, const NdtParams& prm, const double* __restrict__ partials, int chunks,
+                              const int* __restrict__ src_n, int* __restrict__ done_count) {
   const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= npairs) return;
@@ -647,6 +647,24 @@ __global__ void ndt_step_kernel(NdtState* __restrict__ states, int npairs, NdtPa
     s.phase = NP_DONE;
     atomicAdd(done_count, 1);
   }
+}
+
+__global__ void ndt_step_kernel(NdtState* __restrict__ states, NdtParams prm, const double* __restrict__ partials, int chunks,
+                                const int* __restrict__ src_n, LoopArgs la) {
+  ndt_step_body(states, la.npairs, prm, partials, chunks, src_n, &la.ctl->done);
+  loop_tail(la);
+}
+__global__ void ndt_rows_kernel(const NdtState* __restrict__ states, int npairs, b2r_result* __restrict__ rows) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= npairs) return;
+  const NdtState& s = states[pair];
+  b2r_result& r = rows[pair];
+  for (int t = 0; t < 16; ++t) r.T[t] = s.M[t];
+  r.converged = s.converged;
+  r.iterations = s.nr_iterations;
+  r.error = s.score;
+  r.evals = s.evals;
+  r.fitness = 0.0;
 }
 
 // Eigen::Matrix3f::eulerAngles(0,1,2) (Eigen >= 3.3), float
@@ -708,63 +726,44 @@ static void ndt_init_state(NdtState& s, const float* g) {
   s.eval_mode = EV_GRAD_HESS;
 }
 
-void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const CloudView* d_views, const std::vector<PairDesc>& pairs, const int* src_sizes,
-                     const float* guesses_colmajor, b2r_result* out) {
-  const int np = (int)pairs.size();
+void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
+  const int np = b.np;
   if (np == 0) return;
-  int maxn = 1;
-  for (int i = 0; i < np; ++i) maxn = std::max(maxn, src_sizes[i]);
-  const int chunks = ndt_chunks(ctx, np, maxn);
-  const NdtParams prm = make_ndt_params(cfg);
+  const int chunks = ndt_chunks(ctx, np, b.maxn);
+  NdtParams prm = make_ndt_params(cfg);
   std::vector<NdtState> hs(np);
-  for (int i = 0; i < np; ++i) ndt_init_state(hs[i], guesses_colmajor + (size_t)i * 16);
-  DBuf<PairDesc> dp; dp.alloc(np, ctx.stream);
+  for (int i = 0; i < np; ++i) ndt_init_state(hs[i], b.guesses + (size_t)i * 16);
   DBuf<NdtState> ds; ds.alloc(np, ctx.stream);
   DBuf<double> part; part.alloc((size_t)np * chunks * kNdtPart, ctx.stream);
-  DBuf<int> done; done.alloc(1, ctx.stream);
-  done.zero(ctx.stream);
-  DBuf<int> dn; dn.alloc(np, ctx.stream);
-  B2R_CUDA(cudaMemcpyAsync(dn.p, src_sizes, sizeof(int) * np, cudaMemcpyHostToDevice, ctx.stream));
-  B2R_CUDA(cudaMemcpyAsync(dp.p, pairs.data(), sizeof(PairDesc) * np, cudaMemcpyHostToDevice, ctx.stream));
+  DBuf<LoopCtl> ctl; ctl.alloc(1, ctx.stream);
+  ctl.zero(ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(ds.p, hs.data(), sizeof(NdtState) * np, cudaMemcpyHostToDevice, ctx.stream));
-  const dim3 ge(chunks, np);
-  const int step_blocks = (np + 3) / 4;
-  int hdone = 0;
-  int rounds_per_check = 6;
   // each outer iteration evaluates at most 1 + 10 + 1 times
   const long max_rounds = 2 + (long)(std::max(0, cfg.maximum_iterations) + 3) * (kMtMaxIter + 2);
-  long rounds = 0;
-  while (hdone < np && rounds < max_rounds) {
-    for (int r = 0; r < rounds_per_check; ++r) {
-      {
-        ProfScope ps(ctx, PROF_NDT_EVAL, 0.0);  // bytes are added below from the work the device actually did
-        if (ndt_use_queue() && prm.neighbor_search != B2R_DIRECT27) B2R_LAUNCH(ctx, ndt_eval_queue_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
-        else B2R_LAUNCH(ctx, ndt_eval_kernel, ge, 128, 0, d_views, dp.p, ds.p, prm, part.p, (int32_t*)nullptr);
-      }
-      B2R_LAUNCH(ctx, ndt_step_kernel, step_blocks, 128, 0, ds.p, np, prm, part.p, chunks, dn.p, done.p);
-    }
-    rounds += rounds_per_check;
-    B2R_CUDA(cudaMemcpyAsync(&hdone, done.p, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-    rounds_per_check = 4;
-  }
-  B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(NdtState) * np, cudaMemcpyDeviceToHost, ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  const CloudView* a_views = b.d_views;
+  const PairDesc* a_pairs = b.d_pairs;
+  const NdtState* a_states_c = ds.p;
+  NdtState* a_states = ds.p;
+  double* a_part = part.p;
+  const double* a_part_c = part.p;
+  int32_t* a_null = nullptr;
+  int a_chunks = chunks;
+  const int* a_src_n = b.d_src_n;
+  LoopArgs la;
+  memset(&la, 0, sizeof(la));
+  void* eval_args[] = {&a_views, &a_pairs, &a_states_c, &prm, &a_part, &a_null};
+  void* step_args[] = {&a_states, &prm, &a_part_c, &a_chunks, &a_src_n, &la};
+  const bool queue = ndt_use_queue() && prm.neighbor_search != B2R_DIRECT27;
+  run_device_loop(ctx, queue ? (const void*)ndt_eval_queue_kernel : (const void*)ndt_eval_kernel, dim3(chunks, np), dim3(kNdtThreads), eval_args,
+                  (const void*)ndt_step_kernel, dim3((np + 3) / 4), dim3(128), step_args, la, ctl.p, np, max_rounds, PROF_NDT_EVAL);
+  B2R_LAUNCH(ctx, ndt_rows_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_rows);
   if (ctx.profile) {
     // per derivative pass 16 B per source point + 64 B per voxel hit, over the passes each pair ran
+    B2R_CUDA(cudaMemcpyAsync(hs.data(), ds.p, sizeof(NdtState) * np, cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
     double wp = 0.0, wh = 0.0;
     for (int i = 0; i < np; ++i) { wp += hs[i].work_pts; wh += hs[i].work_hits; }
     ctx.prof_bytes[PROF_NDT_EVAL] += 16.0 * wp + 64.0 * wh;
-  }
-  for (int i = 0; i < np; ++i) {
-    const NdtState& s = hs[i];
-    b2r_result& r = out[i];
-    memcpy(r.T, s.M, sizeof(r.T));
-    r.converged = s.converged;
-    r.iterations = s.nr_iterations;
-    r.error = s.score;
-    r.evals = s.evals;
-    r.fitness = 0.0;
   }
 }
 

@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("B2R_LIB_PATH") or os.path.join(_DIR, "libb2r.so")  # 
 NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP, GICP_PCL = 0, 1, 2, 3, 4
 DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
 HOST, DEVICE = 0, 1
-OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_STATE = range(6)
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_STATE, ERR_COMM = range(7)
+UNIQUE_ID_BYTES = 128
 METHOD_BY_NAME = {"NDT_OMP": NDT_OMP, "FAST_GICP": FAST_GICP, "FAST_VGICP": FAST_VGICP, "SMALL_GICP": SMALL_GICP, "GICP": GICP_PCL,
                   "GICP_OMP": GICP_PCL}
 
@@ -90,7 +91,11 @@ EXPORTED_SYMBOLS = [
     "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_knn_list_overflows", "b2r_debug_covariances", "b2r_debug_voxelmap",
     "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
     "b2r_debug_knn", "b2r_last_timings", "b2r_event_record", "b2r_event_elapsed_ms", "b2r_profile_enable", "b2r_profile_read",
+    "b2r_inlier_fraction", "b2r_comm_unique_id", "b2r_comm_init", "b2r_comm_init_host", "b2r_comm_destroy", "b2r_comm_rank",
+    "b2r_comm_size", "b2r_comm_last_error", "b2r_comm_collectives", "b2r_partition_by_target", "b2r_align_batch_sharded",
+    "b2r_gather_results", "b2r_select_best_candidates", "b2r_graph_launches",
 ]
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 PROFILE_KERNELS = {"knn_cov": 0, "lsq_eval": 1, "ndt_eval": 2, "grid_build": 3, "voxel_reduce": 4, "fitness": 5}
 
 _lib = None
@@ -158,6 +163,24 @@ def load():
     L.b2r_event_elapsed_ms.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_float)]
     L.b2r_profile_enable.argtypes = [vp, ci]
     L.b2r_profile_read.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(cd)]
+    L.b2r_inlier_fraction.argtypes = [vp, cd, ctypes.POINTER(cd), ctypes.POINTER(cd)]
+    L.b2r_graph_launches.argtypes = [vp]
+    L.b2r_graph_launches.restype = ctypes.c_uint64
+    L.b2r_comm_unique_id.argtypes = [vp]
+    L.b2r_comm_init.argtypes = [vp, vp, ci, ci, ctypes.POINTER(vp)]
+    L.b2r_comm_init_host.argtypes = [ALLGATHER_FN, vp, ci, ci, ctypes.POINTER(vp)]
+    L.b2r_comm_destroy.argtypes = [vp]
+    L.b2r_comm_destroy.restype = None
+    L.b2r_comm_rank.argtypes = [vp]
+    L.b2r_comm_size.argtypes = [vp]
+    L.b2r_comm_last_error.argtypes = [vp]
+    L.b2r_comm_last_error.restype = ctypes.c_char_p
+    L.b2r_comm_collectives.argtypes = [vp]
+    L.b2r_comm_collectives.restype = ctypes.c_uint64
+    L.b2r_partition_by_target.argtypes = [vp, vp, sz, ci, vp]
+    L.b2r_align_batch_sharded.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, ci, cd, vp]
+    L.b2r_gather_results.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.b2r_select_best_candidates.argtypes = [vp, vp, sz, cd, vp, vp, ctypes.POINTER(sz)]
     _lib = L
     return L
 
@@ -235,6 +258,126 @@ def create_clouds(reg, pointers, sizes, memspace, stride=16):
         c._reg, c._lib, c._h = reg, load(), ctypes.c_void_p(H[i])
         out.append(c)
     return out
+
+
+def partition_by_target(target_ids, world_size, weights=None):
+    """b2r_partition_by_target: rank of every pair (numpy int32).  Pure host code in libb2r.so (runs without a GPU)."""
+    t = np.ascontiguousarray(target_ids, dtype=np.int64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    out = np.zeros(len(t), dtype=np.int32)
+    st = load().b2r_partition_by_target(t.ctypes.data, None if w is None else w.ctypes.data, len(t), int(world_size), out.ctypes.data)
+    if st != OK:
+        raise B2RError(st, "b2r_partition_by_target failed")
+    return out
+
+
+def select_best_candidates(table, target_ids, fitness_score_thresh=1.25):
+    """b2r_select_best_candidates over a RESULT_DTYPE table: (best pair index per target or -1, best score per target)."""
+    t = np.ascontiguousarray(target_ids, dtype=np.int64)
+    tab = np.ascontiguousarray(table)
+    assert tab.dtype == RESULT_DTYPE and len(tab) == len(t)
+    best = np.zeros(max(len(t), 1), dtype=np.int64)
+    score = np.zeros(max(len(t), 1), dtype=np.float64)
+    nt = ctypes.c_size_t()
+    st = load().b2r_select_best_candidates(tab.ctypes.data, t.ctypes.data, len(t), fitness_score_thresh, best.ctypes.data, score.ctypes.data,
+                                           ctypes.byref(nt))
+    if st != OK:
+        raise B2RError(st, "b2r_select_best_candidates failed")
+    return best[: nt.value].copy(), score[: nt.value].copy()
+
+
+class Comm:
+    """b2r_comm: the ranks of a sharded loop-closure batch.  Comm.nccl(...) runs the all-gather over NCCL / NVLink on the
+    handle's stream; Comm.host(...) takes a host all-gather (e.g. torch.distributed gloo) — CPU tests and single-GPU boxes."""
+
+    def __init__(self, h, keep=None):
+        self._h = h
+        self._keep = keep
+        self._lib = load()
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(UNIQUE_ID_BYTES)
+        st = load().b2r_comm_unique_id(buf)
+        if st != OK:
+            raise B2RError(st, "b2r_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf.raw)
+
+    @classmethod
+    def nccl(cls, reg, unique_id, rank, world_size):
+        h = ctypes.c_void_p()
+        reg._check(load().b2r_comm_init(reg._h, ctypes.c_char_p(unique_id), rank, world_size, ctypes.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def host(cls, allgather, rank, world_size):
+        """allgather(send: bytes) -> list of world_size bytes objects (rank order)."""
+        def tramp(user, send, recv, nbytes):
+            try:
+                parts = allgather(ctypes.string_at(send, nbytes))
+                for r, blk in enumerate(parts):
+                    ctypes.memmove(recv + r * nbytes, blk, nbytes)
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+                traceback.print_exc()
+                return 1
+        fn = ALLGATHER_FN(tramp) if world_size > 1 or allgather is not None else ALLGATHER_FN(0)
+        h = ctypes.c_void_p()
+        st = load().b2r_comm_init_host(fn, None, rank, world_size, ctypes.byref(h))
+        if st != OK:
+            raise B2RError(st, "b2r_comm_init_host failed")
+        return cls(h, keep=fn)
+
+    @classmethod
+    def torch_host(cls, group=None):
+        """Host transport over torch.distributed (gloo on CPU, or any backend with CPU tensors)."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return cls.host(None, 0, 1)
+        ws, rk = dist.get_world_size(group), dist.get_rank(group)
+
+        def allgather(blob):
+            t = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+            outs = [torch.empty_like(t) for _ in range(ws)]
+            dist.all_gather(outs, t, group=group)
+            return [o.numpy().tobytes() for o in outs]
+        return cls.host(allgather, rk, ws)
+
+    @property
+    def rank(self):
+        return int(self._lib.b2r_comm_rank(self._h))
+
+    @property
+    def size(self):
+        return int(self._lib.b2r_comm_size(self._h))
+
+    def collectives(self):
+        return int(self._lib.b2r_comm_collectives(self._h))
+
+    def gather_results(self, rank_of_pair, local_table, reg=None):
+        """b2r_gather_results: local_table = this rank's rows (RESULT_DTYPE) in pair order -> all rows in pair order."""
+        rp = np.ascontiguousarray(rank_of_pair, dtype=np.int32)
+        loc = np.ascontiguousarray(local_table)
+        assert loc.dtype == RESULT_DTYPE
+        out = np.zeros(len(rp), dtype=RESULT_DTYPE)
+        st = self._lib.b2r_gather_results(reg._h if reg is not None else None, self._h, rp.ctypes.data, len(rp),
+                                          loc.ctypes.data if len(loc) else None, out.ctypes.data)
+        if st != OK:
+            raise B2RError(st, self._lib.b2r_comm_last_error(self._h).decode())
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b2r_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Registration:
@@ -332,6 +475,32 @@ class Registration:
         R = (Result * max(n, 1))()
         self._check(self._lib.b2r_align_batch(self._h, S, T, G.ctypes.data, n, int(with_fitness), fitness_max_range, R))
         return np.frombuffer(R, dtype=RESULT_DTYPE, count=n).copy()
+
+    def align_batch_sharded(self, comm, sources, targets, target_ids, guesses, weights=None, with_fitness=False,
+                            fitness_max_range=np.finfo(np.float64).max):
+        """b2r_align_batch_sharded: every rank passes the same pair list; sources[i] / targets[i] may be None on ranks that do not
+        own pair i.  Returns the whole table (RESULT_DTYPE, pair order) on every rank."""
+        n = len(sources)
+        S = (ctypes.c_void_p * max(n, 1))(*[c._h if c is not None else None for c in sources])
+        T = (ctypes.c_void_p * max(n, 1))(*[c._h if c is not None else None for c in targets])
+        ids = np.ascontiguousarray(target_ids, dtype=np.int64)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        G = np.ascontiguousarray(np.asarray(guesses, dtype=np.float64).reshape(n, 4, 4).transpose(0, 2, 1).reshape(n, 16).astype(np.float32))
+        R = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
+        st = self._lib.b2r_align_batch_sharded(self._h, comm._h, S, T, ids.ctypes.data, None if w is None else w.ctypes.data, G.ctypes.data, n,
+                                               int(with_fitness), fitness_max_range, R.ctypes.data)
+        if st != OK:
+            raise B2RError(st, self._lib.b2r_comm_last_error(comm._h).decode())
+        return R[:n]
+
+    def inlier_fraction(self, max_correspondence_dist=0.5):
+        """(inlier fraction, fitness score) of the last alignment: scan_matching_odometry_component.cpp:403-415."""
+        frac, fit = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.b2r_inlier_fraction(self._h, max_correspondence_dist, ctypes.byref(frac), ctypes.byref(fit)))
+        return frac.value, fit.value
+
+    def graph_launches(self):
+        return int(self._lib.b2r_graph_launches(self._h))
 
     def fitness_pair(self, target, source, T, max_range=np.finfo(np.float64).max):
         out = ctypes.c_double()

@@ -23,30 +23,26 @@ DBL_MAX = float(np.finfo(np.float64).max)
 RESULT_WIDTH = 24  # T(16) converged iterations error evals fitness pair_index pad pad
 
 
+def _int_ids(ids):
+    """Arbitrary hashable target ids -> int64 labels in order of first appearance."""
+    seen = {}
+    return np.array([seen.setdefault(t, len(seen)) for t in ids], dtype=np.int64)
+
+
 def partition_by_target(target_ids: Sequence[int], world_size: int, weights: Optional[Sequence[float]] = None) -> List[List[int]]:
     """Static block partition of pair indices by target id, balanced by pair count or, if given, by per-pair `weights`
     (e.g. the source cloud sizes: an alignment's cost is proportional to the points it evaluates).
 
     Targets keep their order of first appearance; each rank gets a contiguous block of targets.  Every pair of
-    a given target lands on exactly one rank.
+    a given target lands on exactly one rank.  The partition itself is libb2r's (b2r_partition_by_target, the one
+    b2r_align_batch_sharded applies on every rank); this wrapper only reshapes it into per-rank index lists.
     """
-    order, groups = [], {}
-    for i, t in enumerate(target_ids):
-        if t not in groups:
-            groups[t] = []
-            order.append(t)
-        groups[t].append(i)
-    w = [1.0] * len(target_ids) if weights is None else [float(x) for x in weights]
-    total = sum(w)
+    from .lib import partition_by_target as c_partition
+
+    rank_of = c_partition(_int_ids(target_ids), world_size, weights)
     shards: List[List[int]] = [[] for _ in range(world_size)]
-    rank, acc = 0, 0.0
-    for t in order:
-        gw = sum(w[i] for i in groups[t])
-        # move on when this rank holds its share (a group goes where most of it falls); never starve the later ranks
-        while rank < world_size - 1 and acc + 0.5 * gw >= (rank + 1) * total / world_size:
-            rank += 1
-        shards[rank].extend(groups[t])
-        acc += gw
+    for i, r in enumerate(rank_of):
+        shards[int(r)].append(i)
     return shards
 
 
@@ -99,39 +95,69 @@ def pack_results(results, pair_indices) -> np.ndarray:
     return out
 
 
-def gather_results(local: np.ndarray, n_pairs: int, device=None, group=None, counts: Optional[Sequence[int]] = None) -> np.ndarray:
-    """All-gathers the per-rank result rows into an (n_pairs, RESULT_WIDTH) array ordered by pair index.
+def table_from_results(tab) -> np.ndarray:
+    """RESULT_DTYPE rows (pair order) -> the (n, RESULT_WIDTH) float64 table used by the host logic below."""
+    return pack_table(tab, np.arange(len(tab)))
 
-    counts: rows per rank when every rank already knows them (detect_loops: all ranks compute the same partition), which
-    saves the size exchange; one collective and one device-to-host copy then carry the whole table."""
-    import torch
+
+def results_from_table(local: np.ndarray):
+    """(n, RESULT_WIDTH) float64 rows -> RESULT_DTYPE rows (the wire format of b2r_gather_results)."""
+    from .lib import RESULT_DTYPE
+
+    out = np.zeros(len(local), dtype=RESULT_DTYPE)
+    if len(local):
+        out["T"] = local[:, :16].astype(np.float32)
+        out["converged"] = local[:, 16].astype(np.int32)
+        out["iterations"] = local[:, 17].astype(np.int32)
+        out["error"] = local[:, 18]
+        out["evals"] = local[:, 19].astype(np.int32)
+        out["fitness"] = local[:, 20]
+    return out
+
+
+def make_comm(reg=None, rank=0, world_size=1, group=None, nccl=False):
+    """The communicator of a sharded batch.  nccl=True: ncclCommInitRank on reg's device (the unique id is created by rank 0 and
+    broadcast over torch.distributed); otherwise a host all-gather over torch.distributed (gloo) or, for one rank, none at all."""
+    from .lib import Comm
+
+    if world_size == 1 and not nccl:
+        return Comm.host(None, 0, 1)
+    import torch.distributed as dist
+    if nccl:
+        box = [Comm.unique_id() if rank == 0 else None]
+        if world_size > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        return Comm.nccl(reg, box[0], rank, world_size)
+    return Comm.torch_host(group)
+
+
+def gather_results(local: np.ndarray, n_pairs: int, device=None, group=None, counts: Optional[Sequence[int]] = None, comm=None,
+                   rank_of_pair=None) -> np.ndarray:
+    """All-gathers the per-rank result rows into an (n_pairs, RESULT_WIDTH) array ordered by pair index, through
+    b2r_gather_results (libb2r's own gather step; host transport over torch.distributed unless `comm` says otherwise).
+    local[:, 21] carries the global pair index of each row."""
     import torch.distributed as dist
 
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        full = np.zeros((n_pairs, RESULT_WIDTH))
-        full[local[:, 21].astype(np.int64)] = local
-        return full
-    ws = dist.get_world_size(group)
-    dev = device if device is not None else torch.device("cpu")
-    if counts is None:
-        cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-        cnts = [torch.zeros_like(cnt) for _ in range(ws)]
-        dist.all_gather(cnts, cnt, group=group)
-        counts = [int(c.item()) for c in cnts]
-    assert len(counts) == ws and counts[dist.get_rank(group)] == local.shape[0]
-    mx = max(1, int(max(counts)))
-    buf = torch.zeros((mx, RESULT_WIDTH), dtype=torch.float64, device=dev)
-    if local.shape[0]:
-        buf[: local.shape[0]] = torch.from_numpy(local).to(dev)
-    allbuf = torch.empty((ws, mx, RESULT_WIDTH), dtype=torch.float64, device=dev)
-    dist.all_gather(list(allbuf.unbind(0)), buf, group=group)
-    rows_all = allbuf.cpu().numpy()
-    full = np.zeros((n_pairs, RESULT_WIDTH))
-    for r, k in enumerate(counts):
-        if k:
-            rows = rows_all[r, :k]
-            full[rows[:, 21].astype(np.int64)] = rows
-    return full
+    own = comm is None
+    if own:
+        ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rk = dist.get_rank(group) if ws > 1 else 0
+        comm = make_comm(None, rk, ws, group)
+    if rank_of_pair is None:  # reconstruct who owns which pair from the indices every rank holds
+        import torch
+        mine = np.zeros(n_pairs, dtype=np.int32)
+        mine[local[:, 21].astype(np.int64)] = 1
+        if comm.size > 1:
+            t = torch.from_numpy(mine * (comm.rank + 1))
+            dist.all_reduce(t, group=group)
+            rank_of_pair = t.numpy() - 1
+        else:
+            rank_of_pair = np.zeros(n_pairs, dtype=np.int32)
+    order = np.argsort(local[:, 21], kind="stable") if len(local) else np.zeros(0, dtype=np.int64)
+    tab = comm.gather_results(rank_of_pair, results_from_table(local[order]))
+    if own:
+        comm.close()
+    return table_from_results(tab)
 
 
 LAST_TIMINGS = {}  # host wall clock of the last detect_loops call on this rank: align_ms (partition + batch), gather_ms
@@ -151,34 +177,51 @@ def _cloud(clouds, i):
 
 
 def sharded_align(reg, clouds, pairs, guesses, with_fitness=True, fitness_score_max_range=DBL_MAX, rank=0, world_size=1, device=None,
-                  group=None, pair_weights=None) -> np.ndarray:
-    """One batch of (target, source) pairs: partition by target, this rank's slice through reg.align_batch, all-gather.
-    Returns the full (len(pairs), RESULT_WIDTH) table on every rank.  `clouds` is a list or a callable index -> cloud."""
+                  group=None, pair_weights=None, comm=None) -> np.ndarray:
+    """One batch of (target, source) pairs through b2r_align_batch_sharded: partition by target, this rank's slice aligned, one
+    all-gather, the full (len(pairs), RESULT_WIDTH) table on every rank.  `clouds` is a list or a callable index -> cloud (only
+    the clouds of this rank's slice need to exist).  `comm`: a lib.Comm (NCCL on GPUs); by default a host transport over
+    torch.distributed.  A registration stand-in with only the plain align_batch surface (CPU tests) runs its slice itself and
+    the rows go through b2r_gather_results."""
     import time
 
     t_start = time.perf_counter()
-    target_ids = [p[0] for p in pairs]
-    shards = partition_by_target(target_ids, world_size, pair_weights)  # every rank computes the same partition
-    mine = shards[rank]
-    if mine and not hasattr(reg, "align_batch_table"):  # any object with the plain align_batch surface
-        local = pack_results(reg.align_batch([_cloud(clouds, pairs[i][1]) for i in mine], [_cloud(clouds, pairs[i][0]) for i in mine],
-                                             [guesses[i] for i in mine], with_fitness=with_fitness,
-                                             fitness_max_range=fitness_score_max_range), mine)
-    elif mine:
-        res = reg.align_batch_table([_cloud(clouds, pairs[i][1]) for i in mine], [_cloud(clouds, pairs[i][0]) for i in mine],
-                                    [guesses[i] for i in mine], with_fitness=with_fitness, fitness_max_range=fitness_score_max_range)
-        local = pack_table(res, mine)
-    else:
-        local = np.zeros((0, RESULT_WIDTH))
-    t_aligned = time.perf_counter()
-    table = gather_results(local, len(pairs), device=device, group=group, counts=[len(x) for x in shards])
-    t_gathered = time.perf_counter()
+    ids = _int_ids([p[0] for p in pairs])
+    own = comm is None
+    if own:
+        comm = make_comm(None, rank, world_size, group)
+    try:
+        if hasattr(reg, "align_batch_sharded"):
+            from .lib import partition_by_target as c_partition
+            rank_of = c_partition(ids, comm.size, pair_weights)
+            src = [_cloud(clouds, p[1]) if rank_of[i] == comm.rank else None for i, p in enumerate(pairs)]
+            tgt = [_cloud(clouds, p[0]) if rank_of[i] == comm.rank else None for i, p in enumerate(pairs)]
+            tab = reg.align_batch_sharded(comm, src, tgt, ids, guesses, weights=pair_weights, with_fitness=with_fitness,
+                                          fitness_max_range=fitness_score_max_range)
+            t_aligned = t_gathered = time.perf_counter()
+            table = table_from_results(tab)
+        else:
+            from .lib import partition_by_target as c_partition
+            rank_of = c_partition(ids, comm.size, pair_weights)
+            mine = [i for i in range(len(pairs)) if rank_of[i] == comm.rank]
+            if mine:
+                local = pack_results(reg.align_batch([_cloud(clouds, pairs[i][1]) for i in mine], [_cloud(clouds, pairs[i][0]) for i in mine],
+                                                     [guesses[i] for i in mine], with_fitness=with_fitness,
+                                                     fitness_max_range=fitness_score_max_range), mine)
+            else:
+                local = np.zeros((0, RESULT_WIDTH))
+            t_aligned = time.perf_counter()
+            table = table_from_results(comm.gather_results(rank_of, results_from_table(local)))
+            t_gathered = time.perf_counter()
+    finally:
+        if own:
+            comm.close()
     LAST_TIMINGS.update(align_ms=1e3 * (t_aligned - t_start), gather_ms=1e3 * (t_gathered - t_aligned))
     return table
 
 
 def detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range=DBL_MAX, fitness_score_thresh=1.25, rank=0, world_size=1,
-                 device=None, group=None, pair_weights=None):
+                 device=None, group=None, pair_weights=None, comm=None):
     """Batched LoopDetector::matching over many new keyframes.
 
     clouds: list of mrg_slam_b200.lib.Cloud (only those this rank needs may be non-None)
@@ -189,30 +232,19 @@ def detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range=DBL_MAX, f
     from .lib import from_colmajor
 
     target_ids = [p[0] for p in pairs]
-    table = sharded_align(reg, clouds, pairs, guesses, True, fitness_score_max_range, rank, world_size, device, group, pair_weights)
+    table = sharded_align(reg, clouds, pairs, guesses, True, fitness_score_max_range, rank, world_size, device, group, pair_weights, comm)
+    # the candidate reduction of loop_detector.cpp:106-160 is libb2r's (b2r_select_best_candidates), the same call a C++ host makes
+    from .lib import select_best_candidates
+
+    best_pair, best_score = select_best_candidates(results_from_table(table), _int_ids(target_ids), fitness_score_thresh)
     loops, seen = [], {}
     for i, t in enumerate(target_ids):
         seen.setdefault(t, []).append(i)
-    sizes = {len(v) for v in seen.values()}
-    contiguous = all(v == list(range(v[0], v[0] + len(v))) for v in seen.values())
-    if len(sizes) == 1 and contiguous and list(seen) == sorted(seen, key=lambda t: seen[t][0]):
-        # the usual shape (every keyframe has the same number of candidates, stored contiguously): one vectorised reduction
-        k = sizes.pop()
-        first = np.array([v[0] for v in seen.values()])
-        rows = first[:, None] + np.arange(k)[None, :]
-        best, score = select_best_grouped(table[rows, 20], table[rows, 16] != 0)
-        for (t, idxs), b, sc in zip(seen.items(), best, score):
-            if b < 0 or sc > fitness_score_thresh:
-                loops.append(Loop(t, None, float(sc), None))
-            else:
-                loops.append(Loop(t, int(b), float(sc), from_colmajor(table[idxs[int(b)], :16]), pairs[idxs[int(b)]][1]))
-        return loops, table
-    for t, idxs in seen.items():
-        best, score = select_best(table[idxs, 20], table[idxs, 16] != 0)
-        if best is None or score > fitness_score_thresh:
-            loops.append(Loop(t, None, score, None))
+    for (t, idxs), bp, sc in zip(seen.items(), best_pair, best_score):
+        if bp < 0:
+            loops.append(Loop(t, None, float(sc), None))
         else:
-            loops.append(Loop(t, best, score, from_colmajor(table[idxs[best], :16]), pairs[idxs[best]][1]))
+            loops.append(Loop(t, idxs.index(int(bp)), float(sc), from_colmajor(table[int(bp), :16]), pairs[int(bp)][1]))
     return loops, table
 
 
@@ -304,7 +336,7 @@ def identity_check_next(T_new_next, T_new_best, T_next_cand):
 
 
 def check_consistency(reg, clouds, loops: Sequence[Loop], estimates, links, max_delta_trans=0.3, max_delta_angle=0.0523599,
-                      use_planar_registration_guess=False, enable=True, rank=0, world_size=1, device=None, group=None):
+                      use_planar_registration_guess=False, enable=True, rank=0, world_size=1, device=None, group=None, comm=None):
     """perform_loop_closure_consistency_check (:190-218) for every loop of detect_loops at once.
 
     estimates: cloud index -> 4x4 graph estimate of that keyframe (node->estimate()); links: cloud index -> KeyframeLinks.
@@ -338,7 +370,7 @@ def check_consistency(reg, clouds, loops: Sequence[Loop], estimates, links, max_
             other = getattr(links[loops[i].source], key)
             pairs.append((loops[i].target, other))  # the target is still the new keyframe (:104)
             guesses.append(registration_guess(estimates[loops[i].target], estimates[other], use_planar_registration_guess).astype(np.float64))
-        table = sharded_align(reg, clouds, pairs, guesses, False, DBL_MAX, rank, world_size, device, group)
+        table = sharded_align(reg, clouds, pairs, guesses, False, DBL_MAX, rank, world_size, device, group, None, comm)
         out = {}
         for row, i in zip(table, sel):
             lk = links[loops[i].source]
@@ -363,13 +395,14 @@ def check_consistency(reg, clouds, loops: Sequence[Loop], estimates, links, max_
 
 def match_keyframes(reg, clouds, pairs, guesses, estimates, links, fitness_score_max_range=DBL_MAX, fitness_score_thresh=1.25,
                     enable_loop_closure_consistency_check=True, max_delta_trans=0.3, max_delta_angle=0.0523599,
-                    use_planar_registration_guess=False, rank=0, world_size=1, device=None, group=None, pair_weights=None):
+                    use_planar_registration_guess=False, rank=0, world_size=1, device=None, group=None, pair_weights=None, comm=None):
     """LoopDetector::matching (:97-180) for many new keyframes at once: candidate batch, best-candidate rule, consistency
     check, acceptance.  Returns (accepted loops, all loops, consistency details, result table)."""
     loops, table = detect_loops(reg, clouds, pairs, guesses, fitness_score_max_range, fitness_score_thresh, rank, world_size, device,
-                                group, pair_weights)
+                                group, pair_weights, comm)
     passed, details = check_consistency(reg, clouds, loops, estimates, links, max_delta_trans, max_delta_angle,
-                                        use_planar_registration_guess, enable_loop_closure_consistency_check, rank, world_size, device, group)
+                                        use_planar_registration_guess, enable_loop_closure_consistency_check, rank, world_size, device, group,
+                                        comm)
     accepted = []
     for lp, ok in zip(loops, passed):
         if lp.best_candidate is None:

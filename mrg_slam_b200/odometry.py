@@ -23,7 +23,7 @@ class OdometryParams:
     enable_transform_thresholding: bool = False
     max_acceptable_translation: float = 1.0
     max_acceptable_angle: float = 1.0
-    max_consecutive_rejections: int = 3
+    max_consecutive_rejections: int = 5  # scan_matching_odometry_component.cpp:110, config/mrg_slam.yaml
 
 
 def _quat_w(R):

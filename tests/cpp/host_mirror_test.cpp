@@ -5,13 +5,18 @@
 // and the loop matcher (include/b2r/loop_matcher.hpp) against src/mrg_slam/loop_detector.cpp:97-303.
 // Usage: host_mirror_test [--expect-gpu]
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include <b2r/loop_matcher.hpp>
 #include <b2r/pcl_adapter.hpp>
 #include <b2r/registration.hpp>
+
+#include <cfloat>
 
 extern "C" int b2r_synth_num_rays(int sensor);
 extern "C" int b2r_synth_scan(int sensor, uint64_t seed, int scan_idx, float* out_xyzi);
@@ -92,9 +97,116 @@ static void loop_matcher_math() {
   CHECK(!none.loop_found && none.best == -1 && none.aligns == 0);  // no candidates: nullptr (:99-101)
 }
 
+// ---- an in-process "world" of N ranks (one thread each) for the host transport of b2r_comm: every rank deposits its block,
+// the last one in releases all of them.  What MPI_Allgather / a gloo all_gather would do between processes.
+struct ThreadWorld {
+  int n;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<std::vector<char>> blocks;
+  int arrived = 0, generation = 0;
+  explicit ThreadWorld(int n_) : n(n_), blocks(n_) {}
+};
+struct ThreadRank { ThreadWorld* w; int rank; };
+static int thread_allgather(void* user, const void* send, void* recv, size_t bytes) {
+  ThreadRank* r = static_cast<ThreadRank*>(user);
+  ThreadWorld& w = *r->w;
+  std::unique_lock<std::mutex> lk(w.mu);
+  w.blocks[r->rank].assign((const char*)send, (const char*)send + bytes);
+  const int gen = w.generation;
+  if (++w.arrived == w.n) {
+    w.arrived = 0;
+    ++w.generation;
+    w.cv.notify_all();
+  } else {
+    w.cv.wait(lk, [&] { return w.generation != gen; });
+  }
+  for (int i = 0; i < w.n; ++i) std::memcpy((char*)recv + (size_t)i * bytes, w.blocks[i].data(), bytes);
+  // nobody may overwrite a block before everyone has copied it: second rendezvous
+  const int gen2 = w.generation;
+  if (++w.arrived == w.n) {
+    w.arrived = 0;
+    ++w.generation;
+    w.cv.notify_all();
+  } else {
+    w.cv.wait(lk, [&] { return w.generation != gen2; });
+  }
+  return 0;
+}
+
+// host-side logic of the sharded batch (no GPU needed): partition, gather through the C entry point at world size 2, best-candidate rule
+static void sharding_host_logic() {
+  const size_t n_targets = 9, k = 5, n = n_targets * k;
+  std::vector<int64_t> ids(n);
+  std::vector<double> w(n);
+  for (size_t i = 0; i < n; ++i) { ids[i] = 100 + (int64_t)(i / k); w[i] = 1.0 + (double)(i % 3); }
+  std::vector<int32_t> rank_of(n, -1);
+  CHECK(b2r_partition_by_target(ids.data(), w.data(), n, 2, rank_of.data()) == B2R_OK);
+  size_t c0 = 0;
+  for (size_t i = 0; i < n; ++i) {
+    CHECK(rank_of[i] == 0 || rank_of[i] == 1);
+    CHECK(rank_of[i] == rank_of[(i / k) * k]);           // a target never straddles two ranks
+    if (i) CHECK(rank_of[i] >= rank_of[i - 1]);          // contiguous blocks of targets
+    c0 += rank_of[i] == 0;
+  }
+  CHECK(c0 >= 2 * k && c0 <= n - 2 * k);                 // both ranks get a real share
+  auto fake = [&](size_t i) {
+    b2r_result r;
+    std::memset(&r, 0, sizeof(r));
+    for (int t = 0; t < 16; ++t) r.T[t] = (float)(i * 16 + t);
+    r.converged = (i % 7) != 3;
+    r.iterations = (int)(i % 5);
+    r.error = 0.5 * (double)i;
+    r.evals = 2 + (int)(i % 3);
+    r.fitness = 0.25 * (double)((i * 2654435761u >> 7) % 4);  // coarse values: ties occur
+    return r;
+  };
+  ThreadWorld world(2);
+  std::vector<b2r_result> table[2];
+  std::thread th[2];
+  for (int rk = 0; rk < 2; ++rk) {
+    th[rk] = std::thread([&, rk] {
+      ThreadRank me{&world, rk};
+      b2r_comm* comm = nullptr;
+      CHECK(b2r_comm_init_host(thread_allgather, &me, rk, 2, &comm) == B2R_OK);
+      CHECK(b2r_comm_rank(comm) == rk && b2r_comm_size(comm) == 2);
+      std::vector<b2r_result> local;
+      for (size_t i = 0; i < n; ++i)
+        if (rank_of[i] == rk) local.push_back(fake(i));
+      table[rk].resize(n);
+      CHECK(b2r_gather_results(nullptr, comm, rank_of.data(), n, local.data(), table[rk].data()) == B2R_OK);
+      CHECK(b2r_comm_collectives(comm) == 1);
+      b2r_comm_destroy(comm);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < n; ++i) {
+    const b2r_result want = fake(i);
+    CHECK(std::memcmp(&table[0][i], &want, sizeof(want)) == 0 && std::memcmp(&table[1][i], &want, sizeof(want)) == 0);
+  }
+  std::vector<int64_t> best(n);
+  std::vector<double> score(n);
+  size_t nt = 0;
+  CHECK(b2r_select_best_candidates(table[0].data(), ids.data(), n, 0.5, best.data(), score.data(), &nt) == B2R_OK && nt == n_targets);
+  for (size_t t = 0; t < n_targets; ++t) {  // the reference's loop (:106-145) followed by the threshold (:156)
+    double bs = DBL_MAX;
+    int64_t bi = -1;
+    for (size_t c = 0; c < k; ++c) {
+      const b2r_result& r = table[0][t * k + c];
+      if (!r.converged || r.fitness > bs) continue;
+      bs = r.fitness;
+      bi = (int64_t)(t * k + c);
+    }
+    CHECK(score[t] == bs && best[t] == (bs > 0.5 ? -1 : bi));
+  }
+  CHECK(b2r_comm_init_host(nullptr, nullptr, 0, 2, nullptr) == B2R_ERR_INVALID_ARG);
+  std::printf("sharding host logic ok\n");
+}
+
 int main(int argc, char** argv) {
   const bool expect_gpu = argc > 1 && std::strcmp(argv[1], "--expect-gpu") == 0;
   loop_matcher_math();
+  sharding_host_logic();
   // ---- factory dispatch (registrations.cpp:46-148)
   b2r::RegistrationParams prm;
   prm.registration_method = "FAST_VGICP";
@@ -220,6 +332,55 @@ int main(int argc, char** argv) {
       m = b2r::match_keyframe(h, k4, cands, strict);
       CHECK(!m.loop_found && m.best >= 0);
       best->rel_pose_to_prev = good_prev; best->rel_pose_from_next = good_next;
+      // ---- the sharded multi-keyframe matcher (b2r_align_batch_sharded) must take the same decisions
+      {
+        const b2r::LoopMatch single4 = b2r::match_keyframe(h, k4, cands);
+        const std::vector<const b2r::KeyframeRef*> cands3 = {&k2, &k4};
+        const b2r::LoopMatch single3 = b2r::match_keyframe(h, k3, cands3);
+        std::vector<b2r::KeyframeJob> jobs(2);
+        jobs[0].new_keyframe = &k4; jobs[0].candidates = cands;
+        jobs[1].new_keyframe = &k3; jobs[1].candidates = cands3;
+        auto same = [&](const b2r::LoopMatch& a, const b2r::LoopMatch& b) {
+          bool ok = a.best == b.best && a.best_score == b.best_score && a.loop_found == b.loop_found &&
+                    a.consistency_passed == b.consistency_passed && a.aligns == b.aligns;
+          for (int i = 0; i < 16; ++i) ok = ok && a.rel_pose_new_to_best[i] == b.rel_pose_new_to_best[i];
+          for (int i = 0; i < 2; ++i) ok = ok && a.delta_trans[i] == b.delta_trans[i] && a.delta_angle[i] == b.delta_angle[i];
+          return ok;
+        };
+        // (a) NCCL transport, one rank: ncclCommInitRank + ncclAllGather on this GPU
+        unsigned char id[B2R_UNIQUE_ID_BYTES];
+        b2r_comm* nc = nullptr;
+        CHECK(b2r_comm_unique_id(id) == B2R_OK);
+        CHECK(b2r_comm_init(h, id, 0, 1, &nc) == B2R_OK);
+        if (nc) {
+          const std::vector<b2r::LoopMatch> got = b2r::match_keyframes_sharded(h, nc, jobs);
+          CHECK(got.size() == 2 && got[0].status == B2R_OK && same(got[0], single4) && same(got[1], single3));
+          CHECK(b2r_comm_collectives(nc) >= 1);
+          b2r_comm_destroy(nc);
+        }
+        // (b) host transport, two ranks = two threads with one handle (stream) each on this GPU; every rank must end up with
+        // the decisions of the single-rank run although each aligned only its own keyframe's candidates
+        ThreadWorld world(2);
+        std::vector<b2r::LoopMatch> res2[2];
+        std::thread th[2];
+        for (int rk = 0; rk < 2; ++rk) {
+          th[rk] = std::thread([&, rk] {
+            b2r_config cfg;
+            b2r_default_config(B2R_FAST_VGICP, &cfg);
+            b2r_handle* hr = nullptr;
+            CHECK(b2r_create(&cfg, &hr) == B2R_OK);
+            ThreadRank me{&world, rk};
+            b2r_comm* comm = nullptr;
+            CHECK(b2r_comm_init_host(thread_allgather, &me, rk, 2, &comm) == B2R_OK);
+            res2[rk] = b2r::match_keyframes_sharded(hr, comm, jobs);
+            b2r_comm_destroy(comm);
+            b2r_destroy(hr);
+          });
+        }
+        for (auto& t : th) t.join();
+        for (int rk = 0; rk < 2; ++rk) CHECK(res2[rk].size() == 2 && same(res2[rk][0], single4) && same(res2[rk][1], single3));
+        std::printf("sharded matcher: nccl(1 rank) and host transport (2 ranks) ok\n");
+      }
       for (auto* k : all) b2r_cloud_destroy(k->cloud);
       std::printf("loop matcher: gpu path ok\n");
     }

@@ -13,7 +13,7 @@ def _build(tmp_path):
     exe = str(tmp_path / "host_mirror_test")
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", f"-I{ROOT}/include", f"-I{ROOT}/tests/cpp/pcl_stub",
            f"{ROOT}/tests/cpp/host_mirror_test.cpp", "-o", exe, f"-L{ROOT}/mrg_slam_b200", "-lb2r", "-lb2r_synth",
-           f"-Wl,-rpath,{ROOT}/mrg_slam_b200", "-L/usr/local/cuda/lib64", "-lcudart"]
+           f"-Wl,-rpath,{ROOT}/mrg_slam_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return exe

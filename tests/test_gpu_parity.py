@@ -383,6 +383,17 @@ def test_error_behaviour():
     with pytest.raises(B.B2RError) as e:  # fewer points than correspondence_randomness
         g.align(np.eye(4))
     assert e.value.status == B.ERR_INVALID_ARG
+    # ... but inside a batch a degenerate candidate only loses itself (the reference aligns candidates one by one,
+    # loop_detector.cpp:126-145): converged = 0, T = guess, fitness = DBL_MAX, and the other pairs run
+    ok = synth.scan(synth.VLP16, 3)[::4]
+    c_ok, c_tiny = B.Cloud(g, ok), B.Cloud(g, tiny)
+    shifted = np.eye(4); shifted[0, 3] = 0.25
+    res = g.align_batch([c_ok, c_tiny, c_ok], [c_ok, c_ok, c_tiny], [np.eye(4), shifted, np.eye(4)], with_fitness=True)
+    assert res[0].converged == 1 and res[0].fitness < 1e-6
+    for r_bad, g_bad in ((res[1], shifted), (res[2], np.eye(4))):
+        assert r_bad.converged == 0 and r_bad.iterations == 0 and r_bad.fitness == np.finfo(np.float64).max
+        assert list(r_bad.T) == list(B.colmajor(g_bad))
+    c_ok.close(); c_tiny.close()
     with pytest.raises(B.B2RError):
         g.setInputSource(np.zeros((0, 4), np.float32))
     with pytest.raises(B.B2RError):

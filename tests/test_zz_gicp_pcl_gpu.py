@@ -14,14 +14,12 @@ from mrg_slam_b200 import lib as B
 from tests import oraclelib as O
 from tests.conftest import pose_error
 
-# Status: the default-parameter and batch / factory tests passed on a B200 once — but with fast_gicp-style covariances, because
-# the covariance mode was then lost when clouds_prepare merged the per-cloud needs (fixed since; pcl_cov_kernel has therefore NOT
-# run on a GPU yet).  The two tight-stopping-rule cases missed the 1e-4 m bar they were first written with; that bar is not
-# meaningful for this method: the ORACLE's own result moves by 0.2-0.8 mm (and its outer iteration count by up to 2) when the
-# initial guess is perturbed by 1e-7 m (tests/test_gicp_pcl.py), so they now use 2e-3 m / 1e-3 rad.  Nothing here has been re-run
-# since those changes (the round's GPU budget was spent): every test is expected-to-fail-or-pass (non-strict) until the next
-# green run, so that it can neither hide nor fake a result.  Remove the marker then.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="GICP_PCL: code changed after the only GPU run; not re-run yet")]
+# Status: all five tests passed on a B200 at the end of round 1 (GPUTEST_r01.json: 5 xpassed) with PCL-style covariances from
+# pcl_cov_kernel; the marker that let them pass or fail silently is gone, a regression in pcl_cov_kernel / gicp_pcl_eval_kernel /
+# gicp_pcl_step_kernel now turns the suite red.  The tight-stopping-rule cases use 2e-3 m / 1e-3 rad: the ORACLE's own result
+# moves by 0.2-0.8 mm (and its outer iteration count by up to 2) when the initial guess is perturbed by 1e-7 m
+# (tests/test_gicp_pcl.py::test_result_is_reproducible_only_to_about_a_millimetre).
+pytestmark = pytest.mark.gpu
 
 
 def _align(method_cfg, a, b, guess):
