@@ -282,6 +282,8 @@ b2r_status b2r_create(const b2r_config* cfg, b2r_handle** out) {
     int sms = 0;
     B2R_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     h.ctx.num_sms = sms > 0 ? sms : 148;
+    B2R_CUDA(cudaMalloc((void**)&h.ctx.d_graph_rounds, sizeof(unsigned long long)));
+    B2R_CUDA(cudaMemset(h.ctx.d_graph_rounds, 0, sizeof(unsigned long long)));
     (void)device_pool();  // the library's private memory pool of this device (the process's default pool is not touched)
     for (int i = 0; i < 4; ++i) B2R_CUDA(cudaEventCreate(&h.ev[i]));
     for (int i = 0; i < 16; ++i) h.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -306,6 +308,7 @@ void b2r_destroy(b2r_handle* hh) {
   for (int i = 0; i < 8; ++i)
     if (h.user_ev[i]) cudaEventDestroy(h.user_ev[i]);
   h.ctx.prof_resolve();
+  if (h.ctx.d_graph_rounds) cudaFree(h.ctx.d_graph_rounds);
   for (cudaEvent_t e : h.ctx.ev_pool) cudaEventDestroy(e);
   h.ctx.ev_pool.clear();
   if (h.ctx.stream) cudaStreamSynchronize(h.ctx.stream);
@@ -648,7 +651,18 @@ b2r_status b2r_map_cloud(b2r_handle* hh, const void* const* clouds, const size_t
 }
 
 // ------------------------------------------------------------------------------------------------ introspection
-uint64_t b2r_kernel_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.launches : 0; }
+// kernels launched by the host + the kernels executed inside the optimiser graphs (two per round, counted on the device)
+uint64_t b2r_kernel_launches(const b2r_handle* hh) {
+  if (!hh) return 0;
+  const Ctx& c = hh->h.ctx;
+  unsigned long long rounds = 0;
+  if (c.d_graph_rounds) {
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    if (cudaMemcpy(&rounds, c.d_graph_rounds, sizeof(rounds), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); rounds = 0; }
+  }
+  return c.launches - c.graph_launches + 2ull * rounds;
+}
 uint64_t b2r_graph_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.graph_launches : 0; }
 
 b2r_status b2r_debug_knn_list_overflows(b2r_handle* hh, uint64_t* out) {

@@ -57,7 +57,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   std::shared_ptr<StreamOwner> stream_owner;
   uint64_t launches = 0;        // kernel launches + graph launches issued by this handle
-  uint64_t graph_launches = 0;  // of which: optimiser loops launched as one CUDA graph (the rounds inside are not counted)
+  uint64_t graph_launches = 0;  // of which: optimiser loops launched as one CUDA graph
+  unsigned long long* d_graph_rounds = nullptr;  // device counter: {eval, step} rounds executed inside those graphs
   int num_sms = 148;
   bool profile = false;
   std::vector<ProfRec> prof_pending;
@@ -216,6 +217,7 @@ struct LoopArgs {       // passed by value to the step kernels
   int max_rounds;
   int use_graph;        // 0: the host polls ctl->done between groups of rounds (profiling / fallback path)
   cudaGraphConditionalHandle handle;
+  unsigned long long* rounds_total;  // per-handle counter of rounds run inside graphs (kernel-launch accounting), or nullptr
 };
 // Called by EVERY thread of a step kernel after its work (no early returns before it).
 __device__ __forceinline__ void loop_tail(const LoopArgs& la) {
@@ -229,6 +231,7 @@ __device__ __forceinline__ void loop_tail(const LoopArgs& la) {
       la.ctl->blocks_finished = 0;
       const int rounds = atomicAdd(&la.ctl->rounds, 1) + 1;
       const int done = atomicAdd(&la.ctl->done, 0);
+      if (la.use_graph && la.rounds_total) atomicAdd(la.rounds_total, 1ull);
       if (la.use_graph) cudaGraphSetConditional(la.handle, (done < la.npairs && rounds < la.max_rounds) ? 1u : 0u);
     }
   }

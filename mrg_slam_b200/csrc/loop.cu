@@ -33,7 +33,7 @@ void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_bl
   la.npairs = npairs;
   la.max_rounds = (int)std::min<long>(max_rounds, 1l << 30);
   la.handle = 0;
-  B2R_CUDA(cudaMemsetAsync(d_ctl, 0, sizeof(LoopCtl), ctx.stream));
+  la.rounds_total = ctx.d_graph_rounds;
   if (graph_loop_enabled() && !ctx.profile) {
     la.use_graph = 1;
     cudaGraph_t g = nullptr;
