@@ -97,6 +97,7 @@ bool degenerate_pair(const b2r_config& cfg, const Cloud* s, const Cloud* t) {
   return s->n < need || t->n < need;
 }
 void fail_result(const float* guess, b2r_result& r) {
+  memset(&r, 0, sizeof(r));
   memcpy(r.T, guess, 64);
   r.converged = 0; r.iterations = 0; r.error = 0.0; r.evals = 0; r.fitness = DBL_MAX;
 }

@@ -237,6 +237,10 @@ __device__ __forceinline__ void loop_tail(const LoopArgs& la) {
   }
 }
 
+// b2r_result has 4 bytes of padding after `evals`; rows are all-gathered and compared as bytes, so the writers clear it
+static_assert(sizeof(b2r_result) == 96, "b2r_result layout");
+__host__ __device__ inline void clear_row_padding(b2r_result& r) { reinterpret_cast<int*>(&r)[21] = 0; }
+
 // ------------------------------------------------------------------------------------------------
 // device helpers
 __device__ __forceinline__ double warp_sum(double v) {

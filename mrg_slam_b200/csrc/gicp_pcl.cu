@@ -166,6 +166,7 @@ __global__ void gicp_pcl_rows_kernel(const gp::State* __restrict__ states, int n
   r.iterations = s.nr_iterations;
   r.error = s.f;
   r.evals = s.evals;
+  clear_row_padding(r);
   r.fitness = 0.0;
 }
 

@@ -511,6 +511,7 @@ __device__ void lsq_write_row(const LsqState& s, b2r_result& r) {
   r.iterations = s.nr_iterations;
   r.error = s.y0;
   r.evals = s.evals;
+  clear_row_padding(r);
   r.fitness = 0.0;
 }
 

@@ -664,6 +664,7 @@ __global__ void ndt_rows_kernel(const NdtState* __restrict__ states, int npairs,
   r.iterations = s.nr_iterations;
   r.error = s.score;
   r.evals = s.evals;
+  clear_row_padding(r);
   r.fitness = 0.0;
 }
 
