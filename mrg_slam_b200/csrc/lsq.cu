@@ -876,6 +876,13 @@ void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor,
 // (getFitnessScore, A13) and, when inlier_d2 > 0, the number of points whose nearest neighbour is closer than that (A15: the
 // inlier fraction of ScanMatchingOdometryComponent::publish_scan_matching_status, scan_matching_odometry_component.cpp:403-415).
 // The transform is the pair's result row (written on the device by the optimiser: no host round trip in between).
+// Measured and rejected for the far queries (4 % of the source points of a loop-closure pair have their nearest target point
+// beyond one grid cell; 73 % of the warps hold at least one): (a) abandoning a query after a budget of candidate tests and
+// searching it warp-cooperatively (32 rows per step, strips swept with coalesced loads): 10.1 -> 14.5-38 ms per 4096-pair batch,
+// the strips of a far query are many and short; (b) queueing the abandoned queries per block / per warp and draining them one per
+// lane: 12.1-20 ms — ncu shows the budgeted first phase alone costs what the plain kernel costs (7.0 G of 7.4 G warp
+// instructions): the time is in the ORDINARY queries' short, divergent sweeps (5-6 of 32 lanes in the distance tests), not in a
+// few expensive ones (profiles/r2/ncu_fitness_batch4096_*.md).
 __global__ void __launch_bounds__(256) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                        const b2r_result* __restrict__ rows, double max_range, float max_d2, float inlier_d2,
                                                        double* __restrict__ partials) {
