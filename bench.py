@@ -301,14 +301,24 @@ def run_b2r(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     comm = LC.make_comm(reg, rank, world, nccl=True)  # libb2r's own NCCL communicator (ncclCommInitRank on the handle's device)
 
+    # what a host keeps per keyframe store: buffer addresses and sizes of the clouds this rank needs, and the pair table as index
+    # arrays (built once; a step only fills in the handles of the clouds it has just created)
+    needed_a = np.array(needed, dtype=np.int64)
+    sizes = np.array([len(pool_np[c]) for c in needed], dtype=np.uint64)
+    ptrs = {id(bufs): np.array([bufs[c].data_ptr() for c in needed], dtype=np.uint64) for bufs in (dev_bufs, pin_bufs)}
+    pair_t = np.array([p[0] for p in pairs], dtype=np.int64)
+    pair_s = np.array([p[1] for p in pairs], dtype=np.int64)
+    own = rank_of == rank
+    guesses32 = np.ascontiguousarray(guesses.transpose(0, 2, 1).reshape(n_pairs, 16).astype(np.float32))  # column-major
+
     def step(bufs, memspace):
-        cl = B.create_clouds(reg, [bufs[c].data_ptr() for c in needed], [bufs[c].shape[0] for c in needed], memspace)
-        byid = dict(zip(needed, cl))
-        src = [byid.get(p[1]) if rank_of[i] == rank else None for i, p in enumerate(pairs)]
-        tgt = [byid.get(p[0]) if rank_of[i] == rank else None for i, p in enumerate(pairs)]
-        table = reg.align_batch_sharded(comm, src, tgt, ids, guesses, weights=weights, with_fitness=True)
-        for c in cl:
-            c.close()
+        cl = B.CloudBatch(reg, ptrs[id(bufs)], sizes, memspace)
+        handle_of = np.zeros(len(pool_np), dtype=np.uint64)
+        handle_of[needed_a] = cl.handles[:len(needed)]
+        src = np.where(own, handle_of[pair_s], 0).astype(np.uint64)
+        tgt = np.where(own, handle_of[pair_t], 0).astype(np.uint64)
+        table = reg.align_batch_sharded(comm, src, tgt, ids, guesses32, weights=weights, with_fitness=True)
+        cl.close()
         return table
 
     def barrier():

@@ -43,7 +43,9 @@ typedef enum b2r_method {
   B2R_GICP_PCL = 4    /* "GICP" / "GICP_OMP" registrations.cpp:93-116 -> pcl / pclomp GeneralizedIterativeClosestPoint (BFGS) */
 } b2r_method;
 
-typedef enum b2r_neighbor_search { B2R_DIRECT1 = 0, B2R_DIRECT7 = 1, B2R_DIRECT27 = 2 } b2r_neighbor_search;
+/* reg_nn_search_method (registrations.cpp:140-146).  KDTREE (NDT only): pclomp's radius search over the leaf centroids with
+ * radius = resolution, which is also what pcl::NormalDistributionsTransform (method string "NDT") always does. */
+typedef enum b2r_neighbor_search { B2R_DIRECT1 = 0, B2R_DIRECT7 = 1, B2R_DIRECT27 = 2, B2R_KDTREE = 3 } b2r_neighbor_search;
 typedef enum b2r_memspace { B2R_HOST = 0, B2R_DEVICE = 1 } b2r_memspace;
 
 /* The 10 reg_* ROS parameters read at registrations.cpp:34-43 plus the upstream
@@ -73,6 +75,7 @@ typedef struct b2r_result {
   int iterations; /* nr_iterations_ as the upstream class leaves it */
   double error;   /* last LM error (GICP/VGICP) or NDT score */
   int evals;      /* cost-function passes over the source cloud */
+  int reserved;   /* 0 (explicit padding: result rows are all-gathered and compared as bytes) */
   double fitness; /* getFitnessScore(max_range) when requested by a batch call, else 0 */
 } b2r_result;
 
@@ -94,6 +97,7 @@ b2r_status b2r_cloud_create(b2r_handle* h, const void* points, size_t n, size_t 
 b2r_status b2r_cloud_create_batch(b2r_handle* h, const void* const* points, const size_t* n, size_t count, size_t stride_bytes, int memspace,
                                   b2r_cloud** out);
 void b2r_cloud_destroy(b2r_cloud* c);
+void b2r_cloud_destroy_batch(b2r_cloud* const* clouds, size_t count); /* NULL entries are skipped */
 size_t b2r_cloud_size(const b2r_cloud* c);
 
 /* ---- pcl::Registration surface (apps/scan_matching_odometry_component.cpp:203,208,266,270,275;

@@ -61,12 +61,14 @@ class Registration {
   void setCorrespondenceRandomness(int k) { cfg_.correspondence_randomness = k; dirty_ = true; }
   void setResolution(double r) { cfg_.resolution = r; dirty_ = true; }
   void setMaximumOptimizerIterations(int n) { cfg_.max_optimizer_iterations = n; dirty_ = true; }  // GICP (BFGS) only
-  void setUseReciprocalCorrespondences(bool on) {
-    if (on) std::fprintf(stderr, "b2r: reciprocal correspondences are not implemented (config/mrg_slam.yaml:106 sets false)\n");
-  }
+  // registrations.cpp:99,110 pass reg_use_reciprocal_correspondences to pcl / pclomp GeneralizedIterativeClosestPoint, which
+  // inherit the flag from pcl::IterativeClosestPoint but never read it: GICP::computeTransformation searches tree_ directly.  So
+  // for every method this engine covers the flag has no effect upstream, and none here (only "ICP", outside the engine, uses it).
+  void setUseReciprocalCorrespondences(bool on) { use_reciprocal_ = on; }
+  bool getUseReciprocalCorrespondences() const { return use_reciprocal_; }
   void setNeighborhoodSearchMethod(NeighborSearchMethod m) {
-    cfg_.neighbor_search = m == NeighborSearchMethod::DIRECT1 ? B2R_DIRECT1 : (m == NeighborSearchMethod::DIRECT26 ? B2R_DIRECT27 : B2R_DIRECT7);
-    if (m == NeighborSearchMethod::KDTREE) std::fprintf(stderr, "b2r: KDTREE neighbourhood search is not implemented, using DIRECT7\n");
+    cfg_.neighbor_search = m == NeighborSearchMethod::DIRECT1 ? B2R_DIRECT1
+                           : (m == NeighborSearchMethod::DIRECT26 ? B2R_DIRECT27 : (m == NeighborSearchMethod::KDTREE ? B2R_KDTREE : B2R_DIRECT7));
     dirty_ = true;
   }
   const b2r_config& config() const { return cfg_; }
@@ -159,6 +161,7 @@ class Registration {
   b2r_config cfg_;
   b2r_handle* h_ = nullptr;
   bool dirty_ = true;
+  bool use_reciprocal_ = false;
   PointCloud::ConstPtr source_ptr_, target_ptr_;
   CloudHandle source_, target_;
   Matrix4f final_ = identity4();
@@ -184,9 +187,17 @@ struct RegistrationParams {
   int device = 0;
 };
 
-// Mirror of mrg_slam::select_registration_method (registrations.cpp:46-148) for the methods this engine covers.
-// Method strings that map to classes outside the engine return nullptr (the reference's trailing `return nullptr`),
-// unknown strings warn and fall back to NDT exactly like :117-120 (NDT_OMP, the engine's NDT).
+// Mirror of mrg_slam::select_registration_method (registrations.cpp:46-148): the same chain of string tests in the same order.
+//   "ICP"              pcl::IterativeClosestPoint: outside this engine -> nullptr (the reference's trailing `return nullptr`)
+//   "FAST_VGICP_CUDA"  exists upstream only under USE_VGICP_CUDA (fast_gicp's own CUDA VGICP); here the request for a CUDA VGICP
+//                      gets this engine's FAST_VGICP (without that build flag the reference's chain would fall through to the
+//                      "GICP" substring test and hand out pcl::GeneralizedIterativeClosestPoint)
+//   *GICP* / *GICP*OMP pcl / pclomp GeneralizedIterativeClosestPoint (BFGS)                                   (:93-116)
+//   anything else      NDT; a string without "NDT" warns first (:117-120); without "OMP" the reference hands out
+//                      pcl::NormalDistributionsTransform (:122-128: epsilon, iterations, resolution only), whose neighbourhood search
+//                      is the kd-tree radius search that pclomp calls KDTREE; with "OMP" pclomp's NDT with reg_nn_search_method.
+//                      Both run on this engine's NDT kernels (pclomp's float inner arithmetic; pcl::NDT's double arithmetic in
+//                      updateDerivatives is a stated deviation for the non-OMP string).
 inline Registration::Ptr select_registration_method(const RegistrationParams& p) {
   const std::string& m = p.registration_method;
   if (m == "SMALL_GICP") {  // registrations.cpp:46-54, the shipped YAML default (config/mrg_slam.yaml:100)
@@ -207,17 +218,21 @@ inline Registration::Ptr select_registration_method(const RegistrationParams& p)
     r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
     return r;
   }
-  if (m == "FAST_VGICP") {
+  if (m == "FAST_VGICP" || m == "FAST_VGICP_CUDA") {
     auto r = std::make_shared<Registration>(B2R_FAST_VGICP, p.device);
-    r->setNumThreads(p.reg_num_threads);
+    if (m == "FAST_VGICP") r->setNumThreads(p.reg_num_threads);
     r->setResolution(p.reg_resolution);
     r->setTransformationEpsilon(p.reg_transformation_epsilon);
     r->setMaximumIterations(p.reg_maximum_iterations);
     r->setCorrespondenceRandomness(p.reg_correspondence_randomness);
     return r;
   }
-  if (m != "ICP" && m != "FAST_VGICP_CUDA" && m.find("GICP") != std::string::npos) {
-    // registrations.cpp:93-116: "GICP" -> pcl::GeneralizedIterativeClosestPoint, "GICP_OMP" -> pclomp's copy (BFGS inner loop)
+  if (m == "ICP") {
+    std::fprintf(stderr, "b2r: registration_method ICP (pcl::IterativeClosestPoint) is outside this engine's scope\n");
+    return nullptr;
+  }
+  if (m.find("GICP") != std::string::npos) {
+    // registrations.cpp:93-116: without "OMP" pcl::GeneralizedIterativeClosestPoint, with it pclomp's copy — the same algorithm
     auto r = std::make_shared<Registration>(B2R_GICP_PCL, p.device);
     r->setTransformationEpsilon(p.reg_transformation_epsilon);
     r->setMaximumIterations(p.reg_maximum_iterations);
@@ -227,14 +242,17 @@ inline Registration::Ptr select_registration_method(const RegistrationParams& p)
     r->setMaximumOptimizerIterations(p.reg_max_optimizer_iterations);
     return r;
   }
-  if (m == "FAST_VGICP_CUDA" || m == "ICP" || m == "NDT") {
-    std::fprintf(stderr, "b2r: registration_method %s is outside this engine's scope\n", m.c_str());
-    return nullptr;
-  }
   if (m.find("NDT") == std::string::npos) {
     std::fprintf(stderr, "warning: unknown registration type(%s)\n       : use NDT\n", m.c_str());
   }
   auto r = std::make_shared<Registration>(B2R_NDT_OMP, p.device);
+  if (m.find("OMP") == std::string::npos) {  // pcl::NormalDistributionsTransform (:122-128)
+    r->setTransformationEpsilon(p.reg_transformation_epsilon);
+    r->setMaximumIterations(p.reg_maximum_iterations);
+    r->setResolution(p.reg_resolution);
+    r->setNeighborhoodSearchMethod(NeighborSearchMethod::KDTREE);
+    return r;
+  }
   if (p.reg_num_threads > 0) r->setNumThreads(p.reg_num_threads);
   r->setTransformationEpsilon(p.reg_transformation_epsilon);
   r->setMaximumIterations(p.reg_maximum_iterations);

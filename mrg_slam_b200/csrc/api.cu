@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <cstring>
@@ -57,7 +58,7 @@ Needs needs_for(const b2r_config& cfg, bool is_target, bool want_fitness) {
       if (is_target) nd.grid = true;
       break;
     default:  // NDT_OMP
-      if (is_target) nd.leaf = (float)cfg.resolution;
+      if (is_target) { nd.leaf = (float)cfg.resolution; nd.leaf_centroids = cfg.neighbor_search == B2R_KDTREE; }
       break;
   }
   if (is_target && want_fitness) nd.grid = true;
@@ -83,6 +84,8 @@ b2r_status guarded(b2r_handle* hh, F&& f) {
 }
 
 void check_cfg(const b2r_config& cfg) {
+  if (cfg.neighbor_search < B2R_DIRECT1 || cfg.neighbor_search > B2R_KDTREE) throw Error(B2R_ERR_INVALID_ARG, "unknown neighbor_search");
+  if (cfg.neighbor_search == B2R_KDTREE && cfg.method != B2R_NDT_OMP) throw Error(B2R_ERR_INVALID_ARG, "KDTREE search is an NDT mode");
   if (cfg.method < B2R_NDT_OMP || cfg.method > B2R_GICP_PCL) throw Error(B2R_ERR_INVALID_ARG, "unknown method");
   if (cfg.resolution <= 0) throw Error(B2R_ERR_INVALID_ARG, "resolution must be > 0");
   if (cfg.method != B2R_NDT_OMP && (cfg.correspondence_randomness < 4 || cfg.correspondence_randomness > 32))
@@ -111,6 +114,7 @@ void fail_result(const float* guess, b2r_result& r) {
 void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vector<Cloud*>& targets_in, const float* guesses_in, int with_fitness,
                double fitness_max_range, b2r_result* out_all, b2r_result* rows_dev) {
   Ctx& ctx = h.ctx;
+  HostTrace tr;
   B2R_CUDA(cudaEventRecord(h.ev[0], ctx.stream));
   h.timings_pending = true;
   const size_t n_all = sources_in.size();
@@ -129,25 +133,27 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vect
   const bool all_live = (size_t)np == n_all;
   std::vector<Cloud*> uniq;
   std::vector<Needs> needs;
-  std::map<Cloud*, int> index;
+  static std::atomic<uint64_t> epoch_counter{0};
+  const uint64_t epoch = ++epoch_counter;  // marks the clouds already listed in this call (O(1) per pair, no map)
+  const Needs nd_src = needs_for(h.cfg, false, with_fitness != 0), nd_tgt = needs_for(h.cfg, true, with_fitness != 0);
   auto add = [&](Cloud* c, bool is_target) {
-    auto it = index.find(c);
     int id;
-    if (it == index.end()) {
-      id = (int)uniq.size();
-      index[c] = id;
+    if (c->batch_epoch != epoch) {
+      c->batch_epoch = epoch;
+      c->batch_slot = id = (int)uniq.size();
       uniq.push_back(c);
       needs.push_back(Needs());
     } else {
-      id = it->second;
+      id = c->batch_slot;
     }
-    Needs nd = needs_for(h.cfg, is_target, with_fitness != 0);
+    const Needs& nd = is_target ? nd_tgt : nd_src;
     Needs& cur = needs[id];
     cur.grid = cur.grid || nd.grid;
     cur.cov_k = std::max(cur.cov_k, nd.cov_k);
     cur.cov_mode = std::max(cur.cov_mode, nd.cov_mode);
     if (nd.vres > 0) cur.vres = nd.vres;
     if (nd.leaf > 0) cur.leaf = nd.leaf;
+    cur.leaf_centroids = cur.leaf_centroids || nd.leaf_centroids;
     return id;
   };
   // ---- one host block [pairs | source sizes | guesses] -> one H2D copy
@@ -167,6 +173,7 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vect
   DBuf<uint8_t> dblk;
   DBuf<b2r_result> rows_tmp;
   b2r_result* d_rows = nullptr;
+  tr.mark("pairs");
   if (np > 0) {
     dblk.alloc(tot, ctx.stream);
     B2R_CUDA(cudaMemcpyAsync(dblk.p, blk.data(), tot, cudaMemcpyHostToDevice, ctx.stream));
@@ -174,6 +181,7 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vect
     else { rows_tmp.alloc(np, ctx.stream); d_rows = rows_tmp.p; }
     DBuf<CloudView> dv;
     clouds_prepare(ctx, h.cfg, uniq, needs, dv);
+    tr.mark("prepare");
     B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
     BatchArgs b;
     b.d_views = dv.p;
@@ -189,14 +197,18 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vect
     else if (h.cfg.method == B2R_GICP_PCL) gicp_pcl_align_batch(ctx, h.cfg, b);
     else lsq_align_batch(ctx, h.cfg, b);
     B2R_CUDA(cudaEventRecord(h.ev[2], ctx.stream));
+    tr.mark("optimise");
     if (with_fitness) fitness_batch(ctx, b, fitness_max_range);
     B2R_CUDA(cudaEventRecord(h.ev[3], ctx.stream));
+    tr.mark("fitness");
     // dv, dblk and the optimisers' buffers are released stream-ordered: after everything enqueued above
     if (all_live) {
       if (out_all) {
         B2R_CUDA(cudaMemcpyAsync(out_all, d_rows, sizeof(b2r_result) * np, cudaMemcpyDeviceToHost, ctx.stream));
         B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+        tr.mark("rows_d2h+sync");
       }
+      tr.print("run_align (host ms; device work is asynchronous)");
       return;
     }
   } else {
@@ -309,6 +321,7 @@ void b2r_destroy(b2r_handle* hh) {
   for (int i = 0; i < 8; ++i)
     if (h.user_ev[i]) cudaEventDestroy(h.user_ev[i]);
   h.ctx.prof_resolve();
+  h.ctx.reap_graphs(true);
   if (h.ctx.d_graph_rounds) cudaFree(h.ctx.d_graph_rounds);
   for (cudaEvent_t e : h.ctx.ev_pool) cudaEventDestroy(e);
   h.ctx.ev_pool.clear();
@@ -360,6 +373,15 @@ void b2r_cloud_destroy(b2r_cloud* c) {
   if (!c) return;
   cudaSetDevice(c->c.device);
   delete c;
+}
+void b2r_cloud_destroy_batch(b2r_cloud* const* clouds, size_t count) {
+  if (!clouds) return;
+  int dev = -1;
+  for (size_t i = 0; i < count; ++i) {
+    if (!clouds[i]) continue;
+    if (clouds[i]->c.device != dev) { dev = clouds[i]->c.device; cudaSetDevice(dev); }
+    delete clouds[i];
+  }
 }
 size_t b2r_cloud_size(const b2r_cloud* c) { return c ? (size_t)c->c.n : 0; }
 

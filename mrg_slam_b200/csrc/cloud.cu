@@ -33,7 +33,7 @@ CloudView Cloud::view() const {
   v.v_nrec = v_nrec.p; v.v_reccell = v_reccell.p;
   v.leaf = leaf; v.inv_leaf = leaf > 0 ? 1.0f / leaf : 0.f;
   for (int d = 0; d < 3; ++d) { v.min_b[d] = min_b[d]; v.max_b[d] = max_b[d]; v.div_b[d] = div_b[d]; }
-  v.ncell_ndt = ncell_ndt; v.n_start = n_start.p; v.n_cnt = n_cnt.p; v.n_order = n_order.p; v.n_table = n_table.p; v.nrec = nrec.p;
+  v.ncell_ndt = ncell_ndt; v.ndt_centroids = ndt_centroids ? 1 : 0; v.n_start = n_start.p; v.n_cnt = n_cnt.p; v.n_order = n_order.p; v.n_table = n_table.p; v.nrec = nrec.p;
   v.n_nrec = n_nrec.p; v.n_reccell = n_reccell.p;
   return v;
 }
@@ -410,6 +410,15 @@ __global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __rest
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
     if (lane != 0) continue;
+    float cen[3] = {0.f, 0.f, 0.f};
+    if (c.ndt_centroids) {  // the kd-tree's points: sequential FLOAT sums in point order, divided by the float count
+      for (int j = 0; j < e - s; ++j) {
+        const float4 p = __ldg(&c.pts[idx[j]]);
+        cen[0] = __fadd_rn(cen[0], p.x); cen[1] = __fadd_rn(cen[1], p.y); cen[2] = __fadd_rn(cen[2], p.z);
+      }
+      const float fn = (float)(e - s);
+      cen[0] = __fdiv_rn(cen[0], fn); cen[1] = __fdiv_rn(cen[1], fn); cen[2] = __fdiv_rn(cen[2], fn);
+    }
     double sum[3] = {acc[0], acc[1], acc[2]};
     double cov[9] = {acc[3], acc[4], acc[5], acc[4], acc[6], acc[7], acc[5], acc[7], acc[8]};
     NdtRec r;
@@ -419,6 +428,7 @@ __global__ void __launch_bounds__(256) ndt_reduce_kernel(const CloudView* __rest
     r.mean[0] = mean[0]; r.mean[1] = mean[1]; r.mean[2] = mean[2];
     r.n = npts;
     r.cell = cell;
+    r.centroid[0] = cen[0]; r.centroid[1] = cen[1]; r.centroid[2] = cen[2]; r.pad = 0.f;
 #pragma unroll
     for (int a = 0; a < 9; ++a) { r.icov[a] = 0.f; r.icov_d[a] = 0.0; }
     if (npts >= 6) {
@@ -866,6 +876,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
     nd.cov_mode = std::max(nd.cov_mode, in.cov_mode);
     if (in.vres > 0) nd.vres = in.vres;
     if (in.leaf > 0) nd.leaf = in.leaf;
+    nd.leaf_centroids = nd.leaf_centroids || in.leaf_centroids;
     if (nd.vres > 0 && nd.cov_k == 0) throw Error(B2R_ERR_STATE, "voxel map needs covariances");
   }
   clouds_compute_bbox(ctx, clouds);  // the only synchronisation (skipped when the clouds came through clouds_upload)
@@ -919,7 +930,8 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       plan.want(c->v_nrec.p, 1);
       todo_vox.push_back((int)i);
     }
-    if (nd.leaf > 0 && c->leaf != nd.leaf) {
+    if (nd.leaf > 0 && (c->leaf != nd.leaf || (nd.leaf_centroids && !c->ndt_centroids))) {
+      c->ndt_centroids = nd.leaf_centroids;
       const float leaf = nd.leaf, inv_leaf = 1.0f / leaf;
       int64_t dx = (int64_t)((c->bmax[0] - c->bmin[0]) * inv_leaf) + 1, dy = (int64_t)((c->bmax[1] - c->bmin[1]) * inv_leaf) + 1,
               dz = (int64_t)((c->bmax[2] - c->bmin[2]) * inv_leaf) + 1;

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -51,6 +53,35 @@ struct StreamOwner {
   }
 };
 
+// Host-side stage timer (B2R_TRACE=1): wall-clock milliseconds between marks, printed to stderr by the caller.
+struct HostTrace {
+  bool on;
+  std::vector<std::pair<const char*, double>> marks;
+  double t0;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  HostTrace() {
+    static const bool enabled = [] { const char* e = getenv("B2R_TRACE"); return e && atoi(e) != 0; }();
+    on = enabled;
+    t0 = on ? now() : 0.0;
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    const double t = now();
+    marks.emplace_back(name, t - t0);
+    t0 = t;
+  }
+  void print(const char* what) const {
+    if (!on) return;
+    fprintf(stderr, "[b2r trace] %s:", what);
+    for (const auto& m : marks) fprintf(stderr, " %s %.3f", m.first, m.second);
+    fprintf(stderr, "\n");
+  }
+};
+
 // Execution context of one handle: device, stream, launch counter, optional per-kernel event timing.
 struct Ctx {
   int device = 0;
@@ -59,6 +90,16 @@ struct Ctx {
   uint64_t launches = 0;        // kernel launches + graph launches issued by this handle
   uint64_t graph_launches = 0;  // of which: optimiser loops launched as one CUDA graph
   unsigned long long* d_graph_rounds = nullptr;  // device counter: {eval, step} rounds executed inside those graphs
+  // executable graphs of loops that may still be running: destroying one in flight makes the host wait for it, so they are
+  // released later, once the stream has drained (reap_graphs)
+  std::vector<std::pair<cudaGraphExec_t, cudaGraph_t>> graph_graveyard;
+  void reap_graphs(bool force) {
+    if (graph_graveyard.empty()) return;
+    if (!force && graph_graveyard.size() < 64 && cudaStreamQuery(stream) != cudaSuccess) { cudaGetLastError(); return; }
+    if (force || graph_graveyard.size() >= 64) cudaStreamSynchronize(stream);
+    for (auto& g : graph_graveyard) { cudaGraphExecDestroy(g.first); cudaGraphDestroy(g.second); }
+    graph_graveyard.clear();
+  }
   int num_sms = 148;
   bool profile = false;
   std::vector<ProfRec> prof_pending;
@@ -157,6 +198,8 @@ struct NdtRec {      // NDT leaf (pclomp::VoxelGridCovariance)
   int n;             // nr_points, -1 if unusable
   int cell;
   double icov_d[9];  // full-precision copy for export
+  float centroid[3]; // leaf.centroid of VoxelGridCovariance: float sum in point order / float count (KDTREE search only)
+  float pad;
 };
 
 struct CloudView {
@@ -190,6 +233,7 @@ struct CloudView {
   float leaf, inv_leaf;
   int min_b[3], max_b[3], div_b[3];
   int ncell_ndt;
+  int ndt_centroids;  // the leaves carry their float centroids (needed by the KDTREE neighbourhood search)
   int* n_start;
   int* n_cnt;
   int* n_order;
@@ -237,9 +281,8 @@ __device__ __forceinline__ void loop_tail(const LoopArgs& la) {
   }
 }
 
-// b2r_result has 4 bytes of padding after `evals`; rows are all-gathered and compared as bytes, so the writers clear it
 static_assert(sizeof(b2r_result) == 96, "b2r_result layout");
-__host__ __device__ inline void clear_row_padding(b2r_result& r) { reinterpret_cast<int*>(&r)[21] = 0; }
+__host__ __device__ inline void clear_row_padding(b2r_result& r) { r.reserved = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -269,6 +312,37 @@ __device__ __forceinline__ void block_reduce_to(double* v, double* smem, double*
     double s = warp_sum(v[k]);
     if (lane == 0) smem[warp * K + k] = s;
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nwarp; ++w) s += smem[w * K + k];
+    out[k] = s;
+  }
+  __syncthreads();
+}
+
+// The same block-wide sum for K <= 32 values per thread with a transposing butterfly inside each warp: at every step a lane
+// keeps one half of its values and hands the other half to its partner, so 32 x 32 partial sums collapse in 31 exchanges per lane
+// (16 + 8 + 4 + 2 + 1) instead of K x 5; lane l ends up with the warp's total of value l.  Fixed tree order => deterministic.
+// (ncu on the 4096-pair batch: the K x 5 shuffle reduction was 15 % of vgicp_eval_kernel's instructions.)
+template <int K>
+__device__ __forceinline__ void block_reduce_butterfly(const double* v_in, double* smem /* K * nwarp */, double* out /*global, K values*/) {
+  static_assert(K <= 32, "at most one value per lane");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i < K ? v_in[i] : 0.0;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;  // this lane keeps the upper half of its remaining values
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = up ? v[i] : v[i + half];
+      const double keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  if (lane < K) smem[warp * K + lane] = v[0];
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     double s = 0.0;
@@ -320,7 +394,7 @@ __device__ __forceinline__ void neighbor_offset(int mode, int o, int& ox, int& o
   ox = oy = oz = 0;
   if (mode == B2R_DIRECT7) {
     if (o == 1) ox = 1; else if (o == 2) ox = -1; else if (o == 3) oy = 1; else if (o == 4) oy = -1; else if (o == 5) oz = 1; else if (o == 6) oz = -1;
-  } else if (mode == B2R_DIRECT27) {
+  } else if (mode == B2R_DIRECT27 || mode == B2R_KDTREE) {
     ox = o / 9 - 1; oy = (o / 3) % 3 - 1; oz = o % 3 - 1;
   }
 }

@@ -53,6 +53,9 @@ struct Ref {  // non-owning device pointer into one of the cloud's arenas
 struct Cloud {
   int device = 0;
   int n = 0;
+  // scratch of run_align: this cloud's slot in the current batch's list of distinct clouds (valid while batch_epoch matches)
+  int batch_slot = 0;
+  uint64_t batch_epoch = 0;
   // The allocation each group of buffers below was carved out of (shared with the other structures / clouds of the same build
   // step).  Rebuilding a structure with other parameters (k, covariance mode, resolution, leaf) replaces its entry, so the
   // superseded allocation is released as soon as no other structure uses it: device memory does not grow with alternating use.
@@ -83,6 +86,7 @@ struct Cloud {
   int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0};
   int ncell_ndt = 0;
   bool ndt_overflow = false;
+  bool ndt_centroids = false;  // the grid was built with the leaves' float centroids
   Ref<int> n_start, n_cnt, n_order, n_table, n_nrec, n_reccell;
   Ref<NdtRec> nrec;
 
@@ -96,6 +100,7 @@ struct Needs {
   int cov_mode = 0;  // 0: fast_gicp / small_gicp covariances, 1: pcl::GeneralizedIterativeClosestPoint::computeCovariances
   double vres = 0.0;
   float leaf = 0.f;
+  bool leaf_centroids = false;  // NDT KDTREE search: the leaves' float centroids as well
 };
 
 struct Handle {

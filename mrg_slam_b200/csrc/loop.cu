@@ -36,6 +36,7 @@ void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_bl
   la.rounds_total = ctx.d_graph_rounds;
   if (graph_loop_enabled() && !ctx.profile) {
     la.use_graph = 1;
+    ctx.reap_graphs(false);
     cudaGraph_t g = nullptr;
     cudaGraphExec_t ge = nullptr;
     B2R_GRAPH(cudaGraphCreate(&g, 0), g, ge);
@@ -57,9 +58,7 @@ void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_bl
     B2R_GRAPH(cudaGraphLaunch(ge, ctx.stream), g, ge);
     ctx.launches += 1;  // one graph launch; the rounds it ran are read from LoopCtl by whoever wants them
     ++ctx.graph_launches;
-    // the executable graph may be destroyed while a launch is in flight: the runtime defers the release until it completes
-    cudaGraphExecDestroy(ge);
-    cudaGraphDestroy(g);
+    ctx.graph_graveyard.emplace_back(ge, g);  // released once the stream has drained (destroying it now would wait for the launch)
     return;
   }
   // ---- host-polled loop: groups of rounds, then one read of the done counter

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
   }
   double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kPart;
   if (lin) {
-    block_reduce_to<kAcc>(acc, red, out);
+    block_reduce_butterfly<kAcc>(acc, red, out);
     const int bc = block_sum_int(ncorr, (int*)red);
     if (threadIdx.x == 0) out[28] = (double)bc;
   } else {
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
   }
   double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kPart;
   if (lin) {
-    block_reduce_to<kAcc>(acc, red, out);
+    block_reduce_butterfly<kAcc>(acc, red, out);
     const int bc = block_sum_int(ncorr, (int*)red);
     if (threadIdx.x == 0) out[28] = (double)bc;
   } else {
@@ -718,21 +718,23 @@ static LsqParams make_params(const b2r_config& cfg) {
   return p;
 }
 
-static int pick_chunks(const Ctx& ctx, int npairs, int maxn) {
+static int pick_chunks(const Ctx& ctx, int npairs, int maxn, bool uniform_cost = false) {
   int by_size = std::max(1, (maxn + 1023) / 1024);
   static const int fill = [] { const char* e = getenv("B2R_FILL_PER_SM"); return e ? atoi(e) : 32; }();  // blocks per SM a launch should offer: short tails when few pairs are active
   int by_fill = std::max(1, (fill * ctx.num_sms + npairs - 1) / npairs);
   // large batches: still split every pair into blocks of <= ~8k points, so that a pair whose correspondence search is slow
   // (far guess) cannot leave the last wave of the launch to a few long-running blocks
   static const int tail_pts = [] { const char* e = getenv("B2R_CHUNK_POINTS"); return e ? atoi(e) : 8192; }();
-  by_fill = std::max(by_fill, (maxn + tail_pts - 1) / tail_pts);
+  // (a VGICP pass costs the same for every point — one table probe — so its blocks may be 4x larger: fewer block reductions)
+  const int tp = uniform_cost ? 4 * tail_pts : tail_pts;
+  by_fill = std::max(by_fill, (maxn + tp - 1) / tp);
   return std::max(1, std::min(by_size, by_fill));
 }
 
 void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
   const int np = b.np;
   if (np == 0) return;
-  const int chunks = pick_chunks(ctx, np, b.maxn);
+  const int chunks = pick_chunks(ctx, np, b.maxn, cfg.method == B2R_FAST_VGICP);
   LsqParams prm = make_params(cfg);
   DBuf<LsqState> ds; ds.alloc(np, ctx.stream);
   DBuf<double> part; part.alloc((size_t)np * chunks * kPart, ctx.stream);

@@ -185,6 +185,11 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* 
   for (int t = 0; t < kNdtAcc; ++t) acc[t] = 0.0;
   const int noff = prm.neighbor_search == B2R_DIRECT1 ? 1 : (prm.neighbor_search == B2R_DIRECT7 ? 7 : 27);
   const bool have_grid = tgt.ncell_ndt > 0;
+  // KDTREE (pclomp::KDTREE, registrations.cpp:140-141; also what pcl::NormalDistributionsTransform does): radius search over the
+  // leaves' float centroids, FLANN L2_Simple distance < (float)(resolution^2).  A centroid lies inside its own cell, so the 27
+  // cells around the query's hold every centroid within one leaf size: probe them, keep those that pass the distance test.
+  const bool kdtree = prm.neighbor_search == B2R_KDTREE;
+  const float kd_r2 = (float)((double)tgt.leaf * (double)tgt.leaf);
   int nhits = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
     const float4 xo = __ldg(&src.pts[i]);
@@ -207,6 +212,10 @@ __global__ void __launch_bounds__(kNdtThreads) ndt_eval_kernel(const CloudView* 
       const int rec = __ldg(&tgt.n_table[idx]);
       if (rec < 0) continue;
       if (__ldg(&tgt.nrec[rec].n) < 6) continue;
+      if (kdtree) {
+        const float* cen = tgt.nrec[rec].centroid;
+        if (!(dist2_flann(xt0, xt1, xt2, __ldg(&cen[0]), __ldg(&cen[1]), __ldg(&cen[2])) < kd_r2)) continue;
+      }
       s_rec[hits * kNdtThreads + threadIdx.x] = rec;
       ++hits;
     }
@@ -754,7 +763,7 @@ void ndt_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
   memset(&la, 0, sizeof(la));
   void* eval_args[] = {&a_views, &a_pairs, &a_states_c, &prm, &a_part, &a_null};
   void* step_args[] = {&a_states, &prm, &a_part_c, &a_chunks, &a_src_n, &la};
-  const bool queue = ndt_use_queue() && prm.neighbor_search != B2R_DIRECT27;
+  const bool queue = ndt_use_queue() && (prm.neighbor_search == B2R_DIRECT1 || prm.neighbor_search == B2R_DIRECT7);
   run_device_loop(ctx, queue ? (const void*)ndt_eval_queue_kernel : (const void*)ndt_eval_kernel, dim3(chunks, np), dim3(kNdtThreads), eval_args,
                   (const void*)ndt_step_kernel, dim3((np + 3) / 4), dim3(128), step_args, la, ctl.p, np, max_rounds, PROF_NDT_EVAL);
   B2R_LAUNCH(ctx, ndt_rows_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_rows);
@@ -786,7 +795,7 @@ void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_v
   if (hits_out) dh.alloc(n_src, ctx.stream);
   B2R_CUDA(cudaMemcpyAsync(dp.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, ctx.stream));
   B2R_CUDA(cudaMemcpyAsync(ds.p, &s, sizeof(s), cudaMemcpyHostToDevice, ctx.stream));
-  if (ndt_use_queue() && prm.neighbor_search != B2R_DIRECT27) B2R_LAUNCH(ctx, ndt_eval_queue_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
+  if (ndt_use_queue() && (prm.neighbor_search == B2R_DIRECT1 || prm.neighbor_search == B2R_DIRECT7)) B2R_LAUNCH(ctx, ndt_eval_queue_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
   else B2R_LAUNCH(ctx, ndt_eval_kernel, dim3(chunks, 1), 128, 0, d_views, dp.p, ds.p, prm, part.p, hits_out ? dh.p : nullptr);
   std::vector<double> hp((size_t)chunks * kNdtPart);
   B2R_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, ctx.stream));

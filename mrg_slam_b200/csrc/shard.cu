@@ -254,6 +254,7 @@ b2r_status b2r_align_batch_sharded(b2r_handle* hh, b2r_comm* comm, b2r_cloud* co
   return comm_guarded(comm, [&] {
     B2R_CUDA(cudaSetDevice(h.ctx.device));
     Ctx& ctx = h.ctx;
+    HostTrace tr;
     // ---- the same partition on every rank
     std::vector<int32_t> rank_of(n_pairs);
     partition_pairs(target_ids, weights, n_pairs, comm->nranks, rank_of.data());
@@ -274,6 +275,7 @@ b2r_status b2r_align_batch_sharded(b2r_handle* hh, b2r_comm* comm, b2r_cloud* co
       memcpy(&g[j * 16], guesses + i * 16, 64);
       ++j;
     }
+    tr.mark("partition+slice");
     // ---- align: the result rows are written on the device straight into the all-gather send buffer.  A failure on this rank must
     // not keep it out of the collective (the others would wait forever): its rows become failure rows and the error is reported
     // after the gather.
@@ -311,15 +313,19 @@ b2r_status b2r_align_batch_sharded(b2r_handle* hh, b2r_comm* comm, b2r_cloud* co
         B2R_CUDA(cudaStreamSynchronize(ctx.stream));
       }
     }
+    tr.mark("run_align");
     // ---- one all-gather of fixed-size rows; every rank ends up with the whole table in pair order
     std::vector<b2r_result> all;
     if (comm->nranks == 1 && host_transport) all = host_rows;
     else gather_rows(&h, comm, send.p, host_rows.data(), cnt_max, all);
+    tr.mark("allgather+d2h+sync");
     std::vector<size_t> cur(comm->nranks, 0);
     for (size_t i = 0; i < n_pairs; ++i) {
       const int r = rank_of[i];
       out[i] = all[(size_t)r * cnt_max + cur[r]++];
     }
+    tr.mark("scatter");
+    tr.print("align_batch_sharded");
     if (local_status != B2R_OK) throw Error(local_status, local_error);
   });
 }

@@ -16,7 +16,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2R_LIB_PATH") or os.path.join(_DIR, "libb2r.so")  # override: kernel experiments only
 
 NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP, GICP_PCL = 0, 1, 2, 3, 4
-DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
+DIRECT1, DIRECT7, DIRECT27, KDTREE = 0, 1, 2, 3
 HOST, DEVICE = 0, 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY, ERR_STATE, ERR_COMM = range(7)
 UNIQUE_ID_BYTES = 128
@@ -52,15 +52,16 @@ class Result(ctypes.Structure):
         ("iterations", ctypes.c_int),
         ("error", ctypes.c_double),
         ("evals", ctypes.c_int),
+        ("reserved", ctypes.c_int),
         ("fitness", ctypes.c_double),
     ]
 
 
 # numpy view of b2r_result (natural C alignment, matches ctypes' layout of Result)
-RESULT_DTYPE = np.dtype({"names": ["T", "converged", "iterations", "error", "evals", "fitness"],
-                         "formats": [("<f4", 16), "<i4", "<i4", "<f8", "<i4", "<f8"],
+RESULT_DTYPE = np.dtype({"names": ["T", "converged", "iterations", "error", "evals", "reserved", "fitness"],
+                         "formats": [("<f4", 16), "<i4", "<i4", "<f8", "<i4", "<i4", "<f8"],
                          "offsets": [Result.T.offset, Result.converged.offset, Result.iterations.offset, Result.error.offset,
-                                     Result.evals.offset, Result.fitness.offset],
+                                     Result.evals.offset, Result.reserved.offset, Result.fitness.offset],
                          "itemsize": ctypes.sizeof(Result)})
 
 
@@ -83,7 +84,7 @@ class PrefilterConfig(ctypes.Structure):
 # every symbol include/b2r.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "b2r_default_config", "b2r_create", "b2r_destroy", "b2r_last_error", "b2r_version",
-    "b2r_cloud_create", "b2r_cloud_create_batch", "b2r_cloud_destroy", "b2r_cloud_size",
+    "b2r_cloud_create", "b2r_cloud_create_batch", "b2r_cloud_destroy", "b2r_cloud_destroy_batch", "b2r_cloud_size",
     "b2r_set_target", "b2r_set_source", "b2r_set_target_cloud", "b2r_set_source_cloud",
     "b2r_align", "b2r_fitness", "b2r_transform_source", "b2r_fitness_pair", "b2r_align_batch",
     "b2r_distance_filter", "b2r_voxelgrid", "b2r_radius_outlier", "b2r_statistical_outlier",
@@ -127,6 +128,8 @@ def load():
     L.b2r_cloud_create_batch.argtypes = [vp, vp, vp, sz, sz, ci, vp]
     L.b2r_cloud_destroy.argtypes = [vp]
     L.b2r_cloud_destroy.restype = None
+    L.b2r_cloud_destroy_batch.argtypes = [vp, sz]
+    L.b2r_cloud_destroy_batch.restype = None
     L.b2r_cloud_size.argtypes = [vp]
     L.b2r_cloud_size.restype = sz
     for name in ("b2r_set_target", "b2r_set_source"):
@@ -380,6 +383,40 @@ class Comm:
             pass
 
 
+class CloudBatch:
+    """The clouds of one b2r_cloud_create_batch call as an array of handles (numpy uint64): no per-cloud Python objects, one
+    destroy call — for hosts that move thousands of handles per batch (bench.py)."""
+
+    def __init__(self, reg, pointers, sizes, memspace, stride=16):
+        n = len(pointers)
+        P = np.ascontiguousarray(pointers, dtype=np.uint64)
+        N = np.ascontiguousarray(sizes, dtype=np.uint64)
+        self.handles = np.zeros(max(n, 1), dtype=np.uint64)
+        self.n = n
+        reg._check(load().b2r_cloud_create_batch(reg._h, P.ctypes.data, N.ctypes.data, n, stride, memspace, self.handles.ctypes.data))
+
+    def close(self):
+        if self.handles is not None:
+            load().b2r_cloud_destroy_batch(self.handles.ctypes.data, self.n)
+            self.handles = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _handle_array(clouds):
+    """list of Cloud / None, or a numpy uint64 array of b2r_cloud handles (0 = NULL) -> (pointer, keep-alive object)"""
+    if isinstance(clouds, np.ndarray):
+        a = np.ascontiguousarray(clouds, dtype=np.uint64)
+        return a.ctypes.data, a
+    n = len(clouds)
+    arr = (ctypes.c_void_p * max(n, 1))(*[c._h if c is not None else None for c in clouds])
+    return ctypes.cast(arr, ctypes.c_void_p), arr
+
+
 class Registration:
     """pcl::Registration-shaped front end over one b2r_handle."""
 
@@ -481,11 +518,14 @@ class Registration:
         """b2r_align_batch_sharded: every rank passes the same pair list; sources[i] / targets[i] may be None on ranks that do not
         own pair i.  Returns the whole table (RESULT_DTYPE, pair order) on every rank."""
         n = len(sources)
-        S = (ctypes.c_void_p * max(n, 1))(*[c._h if c is not None else None for c in sources])
-        T = (ctypes.c_void_p * max(n, 1))(*[c._h if c is not None else None for c in targets])
+        S, _ks = _handle_array(sources)
+        T, _kt = _handle_array(targets)
         ids = np.ascontiguousarray(target_ids, dtype=np.int64)
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
-        G = np.ascontiguousarray(np.asarray(guesses, dtype=np.float64).reshape(n, 4, 4).transpose(0, 2, 1).reshape(n, 16).astype(np.float32))
+        if isinstance(guesses, np.ndarray) and guesses.dtype == np.float32 and guesses.shape == (n, 16):
+            G = np.ascontiguousarray(guesses)  # already column-major float32 (e.g. prepared once for a repeated batch)
+        else:
+            G = np.ascontiguousarray(np.asarray(guesses, dtype=np.float64).reshape(n, 4, 4).transpose(0, 2, 1).reshape(n, 16).astype(np.float32))
         R = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
         st = self._lib.b2r_align_batch_sharded(self._h, comm._h, S, T, ids.ctypes.data, None if w is None else w.ctypes.data, G.ctypes.data, n,
                                                int(with_fitness), fitness_max_range, R.ctypes.data)
@@ -670,11 +710,18 @@ class Registration:
 
 
 def select_registration_method(params):
-    """Python mirror of select_registration_method() (/root/reference/src/mrg_slam/registrations.cpp:28-152).
+    """Python mirror of select_registration_method() (/root/reference/src/mrg_slam/registrations.cpp:28-152): the same chain of
+    string tests in the same order as the C++ mirror (include/b2r/registration.hpp), so one parameter set gives one engine
+    whatever the entry point.
 
-    `params` is a dict carrying the same ROS parameter names the reference reads at :34-43.  Method strings the
-    reference maps to classes outside this engine's scope raise; an unknown string warns and falls back to NDT
-    exactly like :117-120 does (NDT_OMP here, the engine's NDT).
+    `params` is a dict carrying the ROS parameter names the reference reads at :34-43.
+      "ICP"                      outside the engine -> None (the C++ mirror's nullptr)
+      "FAST_VGICP_CUDA"          this engine's FAST_VGICP (it IS a CUDA VGICP; upstream only under USE_VGICP_CUDA)
+      *GICP* (with/without OMP)  pcl / pclomp GeneralizedIterativeClosestPoint (BFGS)                       (:93-116)
+      anything else              NDT; strings without "NDT" warn first (:117-120); without "OMP" ->
+                                 pcl::NormalDistributionsTransform = kd-tree radius search (KDTREE); with "OMP" -> pclomp NDT with
+                                 reg_nn_search_method KDTREE / DIRECT1 / else DIRECT7                      (:121-146)
+    reg_use_reciprocal_correspondences is accepted and has no effect, as upstream: pcl / pclomp GICP never read the flag.
     """
     import sys
 
@@ -684,26 +731,28 @@ def select_registration_method(params):
         transformation_epsilon=params.get("reg_transformation_epsilon", 0.1),
         maximum_iterations=params.get("reg_maximum_iterations", 64),
     )
-    if name == "FAST_GICP":
-        cfg = default_config(FAST_GICP, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
-                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
-    elif name == "FAST_VGICP":
-        cfg = default_config(FAST_VGICP, resolution=params.get("reg_resolution", 1.0),
-                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
-    elif name == "SMALL_GICP":  # registrations.cpp:46-54: epsilon, iterations, correspondence distance and randomness are set
+    if name == "SMALL_GICP":  # registrations.cpp:46-54: epsilon, iterations, correspondence distance and randomness are set
         cfg = default_config(SMALL_GICP, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
                              correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
-    elif name in ("GICP", "GICP_OMP"):  # registrations.cpp:93-116: pcl / pclomp GeneralizedIterativeClosestPoint (BFGS)
+    elif name == "FAST_GICP":
+        cfg = default_config(FAST_GICP, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
+                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
+    elif name in ("FAST_VGICP", "FAST_VGICP_CUDA"):
+        cfg = default_config(FAST_VGICP, resolution=params.get("reg_resolution", 1.0),
+                             correspondence_randomness=params.get("reg_correspondence_randomness", 20), **common)
+    elif name == "ICP":
+        print("b2r: registration_method ICP (pcl::IterativeClosestPoint) is outside this engine's scope", file=sys.stderr)
+        return None
+    elif "GICP" in name:  # registrations.cpp:93-116: pcl / pclomp GeneralizedIterativeClosestPoint (BFGS)
         cfg = default_config(GICP_PCL, max_correspondence_distance=params.get("reg_max_correspondence_distance", 2.0),
                              correspondence_randomness=params.get("reg_correspondence_randomness", 20),
                              max_optimizer_iterations=params.get("reg_max_optimizer_iterations", 20), **common)
-    elif name in ("FAST_VGICP_CUDA", "ICP", "NDT"):
-        raise NotImplementedError(f"registration_method {name} is outside this engine's scope (see DESIGN.md)")
     else:
         if "NDT" not in name:
             print(f"warning: unknown registration type({name})\n       : use NDT", file=sys.stderr)
-        nn = {"KDTREE": None, "DIRECT1": DIRECT1}.get(params.get("reg_nn_search_method", "DIRECT7"), DIRECT7)
-        if nn is None:
-            raise NotImplementedError("reg_nn_search_method KDTREE is not implemented (DIRECT1 / DIRECT7 only)")
+        if "OMP" not in name:  # pcl::NormalDistributionsTransform (:122-128)
+            nn = KDTREE
+        else:
+            nn = {"KDTREE": KDTREE, "DIRECT1": DIRECT1}.get(params.get("reg_nn_search_method", "DIRECT7"), DIRECT7)
         cfg = default_config(NDT_OMP, resolution=params.get("reg_resolution", 1.0), neighbor_search=nn, **common)
     return Registration(cfg)

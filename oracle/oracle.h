@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 enum { ORC_NDT_OMP = 0, ORC_FAST_GICP = 1, ORC_FAST_VGICP = 2, ORC_SMALL_GICP = 3 };
-enum { ORC_DIRECT1 = 0, ORC_DIRECT7 = 1, ORC_DIRECT27 = 2 };
+enum { ORC_DIRECT1 = 0, ORC_DIRECT7 = 1, ORC_DIRECT27 = 2, ORC_KDTREE = 3 };
 
 typedef struct orc_params {
   int method;                     /* ORC_* */

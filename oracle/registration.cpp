@@ -230,6 +230,8 @@ inline double accumulate_hb(const double* a, const double* e, const double* M, d
 // ---- NDT target cells: pclomp::VoxelGridCovariance (App. A.4) -----------------
 struct NdtLeaf {
   int nr_points = 0;
+  int idx = 0;                    // dense cell index (deterministic tie-break of the KDTREE neighbour order)
+  float centroid[3] = {0, 0, 0};  // VoxelGridCovariance leaf.centroid: FLOAT sum in point order / float count (the kd-tree's points)
   double mean[3] = {0, 0, 0};
   double cov[9] = {0};
   double icov[9] = {0};
@@ -268,6 +270,8 @@ struct NdtGrid {
       int ijk1 = (int)(std::floor(p[1] * inv_leaf) - (float)min_b[1]);
       int ijk2 = (int)(std::floor(p[2] * inv_leaf) - (float)min_b[2]);
       NdtLeaf& L = leaves[ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2]];
+      L.idx = ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2];
+      for (int a = 0; a < 3; ++a) L.centroid[a] += p[a];  // leaf.centroid.head<4>() += Vector4f(x, y, z, 0)
       double q[3] = {(double)p[0], (double)p[1], (double)p[2]};
       for (int a = 0; a < 3; ++a) {
         L.mean[a] += q[a];
@@ -280,6 +284,7 @@ struct NdtGrid {
       double pt_sum[3] = {L.mean[0], L.mean[1], L.mean[2]};
       double npt = (double)L.nr_points;
       for (int a = 0; a < 3; ++a) L.mean[a] /= npt;
+      for (int a = 0; a < 3; ++a) L.centroid[a] /= (float)L.nr_points;  // leaf.centroid /= static_cast<float>(nr_points)
       if (L.nr_points < kMinPts) continue;
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
@@ -331,6 +336,30 @@ struct NdtGrid {
       for (int ox = -1; ox <= 1; ++ox)
         for (int oy = -1; oy <= 1; ++oy)
           for (int oz = -1; oz <= 1; ++oz) probe(ox, oy, oz);
+    if (mode == ORC_KDTREE) {
+      // pclomp KDTREE (registrations.cpp:140-141) = pcl::NormalDistributionsTransform's own search:
+      //   target_cells_.radiusSearch(x_trans_pt, resolution_, neighborhood, distances)
+      // i.e. a FLANN radius search (float L2_Simple distance, dist < (float)(radius * radius), results sorted by distance) over
+      // the float centroids of the leaves with >= min_points_per_voxel points.  A centroid lies inside its own cell, so every
+      // centroid closer than one leaf size sits in the 27 cells around the query's: the probe above followed by the distance
+      // test returns the same set.  Equal distances are ordered by cell index here (FLANN leaves that order unspecified).
+      const float r2 = (float)((double)leaf * (double)leaf);
+      std::pair<float, const NdtLeaf*> hit[27];
+      int m = 0;
+      for (int i = 0; i < cnt; ++i) {
+        const float* c = out[i]->centroid;
+        const float dx = p[0] - c[0], dy = p[1] - c[1], dz = p[2] - c[2];
+        float d = dx * dx;
+        d = d + dy * dy;
+        d = d + dz * dz;
+        if (d < r2) hit[m++] = {d, out[i]};
+      }
+      std::sort(hit, hit + m, [](const std::pair<float, const NdtLeaf*>& a, const std::pair<float, const NdtLeaf*>& b) {
+        return a.first != b.first ? a.first < b.first : a.second->idx < b.second->idx;
+      });
+      for (int i = 0; i < m; ++i) out[i] = hit[i].second;
+      cnt = m;
+    }
     return cnt;
   }
 };

@@ -216,9 +216,16 @@ int main(int argc, char** argv) {
   prm.registration_method = "NDT_OMP"; prm.reg_nn_search_method = "DIRECT1"; prm.reg_resolution = 0.5;
   auto ndt = b2r::select_registration_method(prm);
   CHECK(ndt && ndt->config().method == B2R_NDT_OMP && ndt->config().neighbor_search == B2R_DIRECT1 && ndt->config().resolution == 0.5);
-  prm.registration_method = "BOGUS";
+  prm.registration_method = "NDT_OMP"; prm.reg_nn_search_method = "KDTREE";
+  auto ndtk = b2r::select_registration_method(prm);
+  CHECK(ndtk && ndtk->config().neighbor_search == B2R_KDTREE);  // registrations.cpp:140-141
+  prm.registration_method = "BOGUS"; prm.reg_nn_search_method = "DIRECT1";
   auto fb = b2r::select_registration_method(prm);
-  CHECK(fb && fb->config().method == B2R_NDT_OMP);  // unknown -> warning + NDT
+  // unknown -> warning + NDT; no "OMP" in the string -> pcl::NormalDistributionsTransform (:122-128) = kd-tree radius search
+  CHECK(fb && fb->config().method == B2R_NDT_OMP && fb->config().neighbor_search == B2R_KDTREE);
+  prm.registration_method = "FAST_VGICP_CUDA";
+  auto vc = b2r::select_registration_method(prm);
+  CHECK(vc && vc->config().method == B2R_FAST_VGICP);
   prm.registration_method = "SMALL_GICP";  // the YAML default (registrations.cpp:46-54)
   prm.reg_max_correspondence_distance = 1.5;
   auto sg = b2r::select_registration_method(prm);

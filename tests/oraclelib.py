@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 
 NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP = 0, 1, 2, 3
-DIRECT1, DIRECT7, DIRECT27 = 0, 1, 2
+DIRECT1, DIRECT7, DIRECT27, KDTREE = 0, 1, 2, 3
 
 
 class Params(ctypes.Structure):

@@ -98,16 +98,30 @@ def test_factory_string_dispatch(monkeypatch, capsys):
     assert made[-1].method == B.NDT_OMP and made[-1].neighbor_search == B.DIRECT1 and made[-1].resolution == 0.5
     B.select_registration_method({"registration_method": "NDT_OMP", "reg_nn_search_method": "whatever"})
     assert made[-1].neighbor_search == B.DIRECT7  # registrations.cpp:144-146: anything else -> DIRECT7
-    B.select_registration_method({"registration_method": "BOGUS"})
-    assert made[-1].method == B.NDT_OMP and "unknown registration type(BOGUS)" in capsys.readouterr().err
+    B.select_registration_method({"registration_method": "NDT_OMP", "reg_nn_search_method": "KDTREE"})   # :140-141
+    assert made[-1].method == B.NDT_OMP and made[-1].neighbor_search == B.KDTREE
+    # :117-129: a string without "NDT" warns; without "OMP" the reference hands out pcl::NormalDistributionsTransform, whose search is
+    # the kd-tree radius search (KDTREE), whatever reg_nn_search_method says
+    B.select_registration_method({"registration_method": "BOGUS", "reg_nn_search_method": "DIRECT1"})
+    assert made[-1].method == B.NDT_OMP and made[-1].neighbor_search == B.KDTREE
+    assert "unknown registration type(BOGUS)" in capsys.readouterr().err
+    B.select_registration_method({"registration_method": "NDT", "reg_resolution": 2.0})
+    assert made[-1].method == B.NDT_OMP and made[-1].neighbor_search == B.KDTREE and made[-1].resolution == 2.0
+    assert "unknown" not in capsys.readouterr().err
+    B.select_registration_method({"registration_method": "BOGUS_OMP"})  # unknown but "OMP": pclomp NDT, DIRECT7
+    assert made[-1].method == B.NDT_OMP and made[-1].neighbor_search == B.DIRECT7
     B.select_registration_method({"registration_method": "SMALL_GICP", "reg_max_correspondence_distance": 1.5})  # the YAML default
     assert made[-1].method == B.SMALL_GICP and made[-1].max_correspondence_distance == 1.5
     B.select_registration_method({"registration_method": "GICP_OMP", "reg_max_optimizer_iterations": 9})  # registrations.cpp:104-116
     assert made[-1].method == B.GICP_PCL and made[-1].max_optimizer_iterations == 9 and made[-1].gicp_epsilon == 1e-3
     B.select_registration_method({"registration_method": "GICP"})                                          # :93-103
     assert made[-1].method == B.GICP_PCL and made[-1].max_optimizer_iterations == 20 and made[-1].max_correspondence_distance == 2.0
-    with pytest.raises(NotImplementedError):
-        B.select_registration_method({"registration_method": "ICP"})
+    B.select_registration_method({"registration_method": "MY_GICP_VARIANT", "reg_use_reciprocal_correspondences": True})  # find("GICP")
+    assert made[-1].method == B.GICP_PCL
+    B.select_registration_method({"registration_method": "FAST_VGICP_CUDA", "reg_resolution": 0.5})
+    assert made[-1].method == B.FAST_VGICP and made[-1].resolution == 0.5
+    n = len(made)
+    assert B.select_registration_method({"registration_method": "ICP"}) is None and len(made) == n  # outside the engine
 
 
 def test_synth_is_deterministic_and_shaped():

@@ -213,6 +213,8 @@ def test_align_matches_oracle(vlp16_pair, method):
     (B.NDT_OMP, dict(resolution=0.5)),
     (B.NDT_OMP, dict(neighbor_search=B.DIRECT1, transformation_epsilon=0.01)),
     (B.NDT_OMP, dict(resolution=2.0, neighbor_search=B.DIRECT27, maximum_iterations=5)),
+    (B.NDT_OMP, dict(neighbor_search=B.KDTREE)),                                          # registrations.cpp:140-141
+    (B.NDT_OMP, dict(resolution=2.0, neighbor_search=B.KDTREE, transformation_epsilon=0.01, maximum_iterations=8)),
 ])
 def test_align_parameter_variants(vlp16_pair, method, over):
     a, b, gt = vlp16_pair
@@ -250,6 +252,19 @@ def test_ndt_intermediates(vlp16_pair):
             assert np.abs(og - gg).max() <= 1e-6 * np.abs(og).max()
             assert np.abs(oH - gH).max() <= 1e-6 * np.abs(oH).max()
         g.close()
+        # KDTREE neighbourhoods (radius search over the leaves' float centroids): the same per-point hit counts
+        gk = B.Registration(B.default_config(B.NDT_OMP, resolution=res, neighbor_search=B.KDTREE))
+        ok = O.Registration(O.default_params(O.NDT_OMP, resolution=res, neighbor_search=O.KDTREE))
+        gk.setInputTarget(a); gk.setInputSource(b)
+        ok.setInputTarget(a); ok.setInputSource(b)
+        for p in (np.zeros(6), np.array([0.4, 0.01, 0.0, 0.001, -0.002, 0.01])):
+            os_, og, oH, ohits = ok.ndt_derivatives(p)
+            gs_, gg, gH, ghits = gk.debug_ndt_derivatives(p)
+            assert np.array_equal(ohits, ghits) and ohits.max() >= 3
+            assert abs(os_ - gs_) <= 1e-7 * abs(os_)
+            assert np.abs(og - gg).max() <= 1e-6 * np.abs(og).max()
+            assert np.abs(oH - gH).max() <= 1e-6 * np.abs(oH).max()
+        gk.close()
 
 
 def test_small_gicp_intermediates(vlp16_pair):

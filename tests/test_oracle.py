@@ -282,3 +282,43 @@ def test_lm_reports_iterations_and_convergence(vlp16_pair):
     r2 = O.Registration(O.default_params(O.FAST_VGICP, maximum_iterations=1, transformation_epsilon=1e-6, rotation_epsilon=1e-9))
     r2.setInputTarget(a); r2.setInputSource(b)
     assert not r2.align(g).converged
+
+
+def test_ndt_kdtree_neighbourhood_is_a_radius_search_over_float_centroids(vlp16_pair):
+    """pclomp KDTREE / pcl::NormalDistributionsTransform (registrations.cpp:121-141): the neighbourhood of a point is the set of
+    leaves (>= 6 points) whose FLOAT centroid — sequential float sum in point order / float count — lies closer than the
+    resolution (FLANN float distance, strict).  Checked against scipy's kd-tree over independently computed centroids."""
+    from scipy.spatial import cKDTree
+    a, b, _ = vlp16_pair
+    res = 1.0
+    o = O.Registration(O.default_params(O.NDT_OMP, resolution=res, neighbor_search=O.KDTREE))
+    o.setInputTarget(a); o.setInputSource(b)
+    _, _, _, hits = o.ndt_derivatives(np.zeros(6))  # identity: the transformed cloud is the source itself
+    inv = np.float32(1.0) / np.float32(res)
+    key = np.floor(a[:, :3] * inv).astype(np.int64)
+    order = np.lexsort((np.arange(len(a)), key[:, 0], key[:, 1], key[:, 2]))  # voxels, point order inside a voxel
+    ks = key[order]
+    starts = np.flatnonzero(np.r_[True, (ks[1:] != ks[:-1]).any(axis=1)])
+    ends = np.r_[starts[1:], len(a)]
+    cen = []
+    for s, e in zip(starts, ends):
+        if e - s >= 6:
+            pts = a[order[s:e], :3]
+            cen.append(np.cumsum(pts, axis=0, dtype=np.float32)[-1] / np.float32(e - s))  # sequential float32 sums
+    cen = np.array(cen, dtype=np.float32)
+    tree = cKDTree(cen.astype(np.float64))
+    want = np.zeros(len(b), dtype=np.int32)
+    r2 = np.float32(np.float64(np.float32(res)) ** 2)
+    for i, cand in enumerate(tree.query_ball_point(b[:, :3].astype(np.float64), res * 1.001)):
+        if cand:
+            d = b[i, :3] - cen[cand]
+            d2 = (d[:, 0] * d[:, 0]).astype(np.float32)
+            d2 = (d2 + (d[:, 1] * d[:, 1]).astype(np.float32)).astype(np.float32)
+            d2 = (d2 + (d[:, 2] * d[:, 2]).astype(np.float32)).astype(np.float32)
+            want[i] = int((d2 < r2).sum())
+    # leaves whose covariance turned out unusable are dropped by the oracle (nr_points = -1): allow for those few
+    assert (hits <= want).all() and (hits == want).mean() > 0.98 and hits.max() >= 3
+    d7 = O.Registration(O.default_params(O.NDT_OMP, resolution=res))
+    d7.setInputTarget(a); d7.setInputSource(b)
+    _, _, _, hits7 = d7.ndt_derivatives(np.zeros(6))
+    assert not np.array_equal(hits, hits7)  # a different neighbourhood from DIRECT7's face neighbours
