@@ -90,6 +90,18 @@ struct Ctx {
   uint64_t launches = 0;        // kernel launches + graph launches issued by this handle
   uint64_t graph_launches = 0;  // of which: optimiser loops launched as one CUDA graph
   unsigned long long* d_graph_rounds = nullptr;  // device counter: {eval, step} rounds executed inside those graphs
+  // One instantiated loop graph per (eval kernel, step kernel) pair of this handle: later alignments only rewrite the two kernel
+  // nodes' parameters (cudaGraphExecKernelNodeSetParams) instead of building and instantiating a new graph (~0.26 ms each).
+  struct LoopGraph {
+    const void* eval_fn;
+    const void* step_fn;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    cudaGraphNode_t eval_node, step_node;
+    cudaGraphConditionalHandle handle;
+  };
+  std::vector<LoopGraph> loop_graphs;
+  bool loop_graph_cache_ok = true;  // cleared if the driver refuses to update nodes inside a conditional body
   // executable graphs of loops that may still be running: destroying one in flight makes the host wait for it, so they are
   // released later, once the stream has drained (reap_graphs)
   std::vector<std::pair<cudaGraphExec_t, cudaGraph_t>> graph_graveyard;
@@ -99,6 +111,10 @@ struct Ctx {
     if (force || graph_graveyard.size() >= 64) cudaStreamSynchronize(stream);
     for (auto& g : graph_graveyard) { cudaGraphExecDestroy(g.first); cudaGraphDestroy(g.second); }
     graph_graveyard.clear();
+    if (force) {
+      for (auto& g : loop_graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); }
+      loop_graphs.clear();
+    }
   }
   int num_sms = 148;
   bool profile = false;

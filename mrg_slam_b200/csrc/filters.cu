@@ -7,7 +7,6 @@
 #include <climits>
 #include <cmath>
 #include <algorithm>
-#include <cub/device/device_radix_sort.cuh>
 
 #include "internal.hpp"
 #include "knn.cuh"
@@ -41,13 +40,15 @@ struct VgParams {
   float inv_leaf;
   int min_b[3];
   int mul[3];
+  int div[3];     // voxels per axis
+  int shift, cx;  // coarse cells of the sort: runs of 2^shift x-voxels, cx of them per (y, z) row
 };
 
 // key = dense voxel index (pcl::VoxelGrid: float math, floor(p*inv_leaf) - min_b), value = point index
 // RANGE: the distance filter (near < |p| < far, distance_flag_kernel's arithmetic) is applied here instead of compacting first
 template <bool RANGE>
 __global__ void vg_key_kernel(const float4* __restrict__ in, int n, VgParams prm, double near_t, double far_t, unsigned* __restrict__ keys,
-                              int* __restrict__ vals) {
+                              int* __restrict__ coarse, int* __restrict__ cell_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = in[i];
@@ -58,20 +59,24 @@ __global__ void vg_key_kernel(const float4* __restrict__ in, int n, VgParams prm
     const double d = (double)__fsqrt_rn(s);
     ok = d > near_t && d < far_t;
   }
+  int cc = 0;
   if (ok) {
     const int i0 = (int)(floorf(__fmul_rn(p.x, prm.inv_leaf)) - (float)prm.min_b[0]);
     const int i1 = (int)(floorf(__fmul_rn(p.y, prm.inv_leaf)) - (float)prm.min_b[1]);
     const int i2 = (int)(floorf(__fmul_rn(p.z, prm.inv_leaf)) - (float)prm.min_b[2]);
     key = (unsigned)(i0 * prm.mul[0] + i1 * prm.mul[1] + i2 * prm.mul[2]);
+    cc = (i2 * prm.div[1] + i1) * prm.cx + (i0 >> prm.shift);
+    atomicAdd(&cell_cnt[cc], 1);  // the sort's counting pass (VoxelSort)
   }
   keys[i] = key;
-  vals[i] = i;
+  coarse[i] = cc;
 }
-__global__ void vg_head_kernel(const unsigned* __restrict__ keys, int n, uint8_t* __restrict__ head) {
+// sorted keys [0, *n_valid): 1 where a new voxel starts; 0 beyond the valid entries
+template <typename KeyT>
+__global__ void vg_head_kernel(const KeyT* __restrict__ keys, int n, const int* __restrict__ n_valid, uint8_t* __restrict__ head) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const unsigned k = keys[i];
-  head[i] = (k != 0xffffffffu && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+  head[i] = (i < n_valid[0] && (i == 0 || keys[i - 1] != keys[i])) ? 1 : 0;
 }
 // counts per block of 256 -> (after scan) offsets; then each head writes its position
 __global__ void vg_seg_kernel(const uint8_t* __restrict__ head, int n, const int* __restrict__ block_off, int* __restrict__ seg_start) {
@@ -86,32 +91,239 @@ __global__ void vg_seg_kernel(const uint8_t* __restrict__ head, int n, const int
   for (int w = 0; w < warp; ++w) woff += wsum[w];
   if (v) seg_start[block_off[blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u))] = i;
 }
-// one thread per voxel: pcl::CentroidPoint<PointXYZI> — float sums in (stable-sorted = ascending point index) order,
-// divided by float(count)
-__global__ void vg_centroid_kernel(const float4* __restrict__ in, const int* __restrict__ vals, const int* __restrict__ seg_start, int nseg,
-                                   int n_valid, int min_pts, float4* __restrict__ out, uint8_t* __restrict__ keep) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per voxel: pcl::CentroidPoint<PointXYZI> — float sums in (stable-sorted = ascending point index) order, divided by
+// float(count).  The order of the additions is fixed, so they stay sequential, but the points of a voxel are gathered 32 at a
+// time by the lanes (the loads are the expensive part: a thread per voxel spent its time waiting for them one by one, and a
+// voxel near the sensor holds hundreds of points) and handed to the running sums through shuffles.
+__global__ void __launch_bounds__(256) vg_centroid_kernel(const float4* __restrict__ in, const int* __restrict__ vals, const int* __restrict__ seg_start,
+                                                          int nseg, int n_valid, int min_pts, float4* __restrict__ out, uint8_t* __restrict__ keep) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (s >= nseg) return;
   const int b = seg_start[s], e = (s + 1 < nseg) ? seg_start[s + 1] : n_valid;
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-  for (int j = b; j < e; ++j) {
-    const float4 p = __ldg(&in[vals[j]]);
-    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+  for (int j0 = b; j0 < e; j0 += 32) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j0 + lane < e) p = __ldg(&in[__ldg(&vals[j0 + lane])]);
+    const int m = min(32, e - j0);
+    for (int l = 0; l < m; ++l) {
+      sx = __fadd_rn(sx, __shfl_sync(0xffffffffu, p.x, l)); sy = __fadd_rn(sy, __shfl_sync(0xffffffffu, p.y, l));
+      sz = __fadd_rn(sz, __shfl_sync(0xffffffffu, p.z, l)); si = __fadd_rn(si, __shfl_sync(0xffffffffu, p.w, l));
+    }
   }
+  if (lane != 0) return;
   const float cnt = (float)(e - b);
   out[s] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), __fdiv_rn(si, cnt));
   if (keep) keep[s] = (e - b) >= min_pts ? 1 : 0;
 }
-__global__ void count_valid_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ n_valid) {
-  // keys sorted ascending: the first 0xffffffff marks the end of the finite points
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const bool valid = keys[i] != 0xffffffffu;
-  const bool next_valid = (i + 1 < n) ? keys[i + 1] != 0xffffffffu : false;
-  if (valid && !next_valid) *n_valid = i + 1;
-}
 
 void flags_block_offsets(Ctx& ctx, const uint8_t* flags, int n, int* block_off);  // cloud.cu
+
+// ------------------------------------------------------------------------------------------------ voxel sort
+// Stable sort of (voxel key, point index) pairs by key — the std::sort of pcl::VoxelGrid::applyFilter and the
+// accumulation order of ApproximateMeanVoxelGrid's hash map — WITHOUT a general radix sort.  The key is a dense voxel index
+// x + DX * (y + DY * z), so ascending key = ascending (z, y, x): the points are counting-sorted in ONE pass into coarse cells
+// that are runs of 2^shift consecutive x-voxels of one (y, z) row (coarse cell order = key order), and every entry then finds
+// its rank inside its coarse cell by (key, point index).  Whatever the number of key bits this is one pass over the data:
+//   vs_count     cell counts (atomics)                     vs_scan      exclusive scan (tile scans; the last block to finish
+//   vs_scatter   entries into their cell (atomic cursor)                scans the tile totals: one launch)
+//   vs_rank      in-cell rank -> final position, keys and point indices written sorted
+// (replaces cub::DeviceRadixSort::SortPairs, which needs 4 digit passes for a 32-bit key and 8 for a 64-bit one).
+// shift is chosen so that the table has at most max(4 M, 32 n) cells: a coarse cell holds a handful of entries, and the quadratic
+// in-cell ranking stays cheap.  A cell with more than kVsHeavy entries (a leaf size of many metres: thousands of points per
+// voxel) is not ranked; the call then falls back to a plain bitonic sort of the (key, index) pairs (vs_bitonic_*): slow,
+// O(n log^2 n), but only reached by inputs no mrg_slam configuration produces.
+constexpr int kVsTile = 2048;   // cells per scan tile (256 threads x 8)
+constexpr int kVsHeavy = 8192;  // entries per coarse cell beyond which the in-cell ranking is refused
+
+// start[c] = exclusive scan of cnt inside its tile; tile_off[t] = exclusive scan of the tile totals (written by the last block);
+// cnt is reset to 0 (it becomes the scatter cursor); total[0] = number of valid entries
+__global__ void __launch_bounds__(256) vs_scan_kernel(int* __restrict__ cnt, int ncell, int* __restrict__ start, int* __restrict__ tile_tot,
+                                                      int* __restrict__ tile_off, int ntiles, unsigned* __restrict__ blocks_done, int* __restrict__ total) {
+  __shared__ int wsum[8];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = blockIdx.x * kVsTile + threadIdx.x * 8;  // the table is padded to whole tiles (zero counts beyond ncell)
+  int v[8], run = 0;
+  {
+    const int4 a = *reinterpret_cast<const int4*>(cnt + base), b = *reinterpret_cast<const int4*>(cnt + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) run += v[k];
+  }
+  int incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { woff += w < warp ? wsum[w] : 0; tot += wsum[w]; }
+  int ex = woff + incl - run;
+  int o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { o[k] = ex; ex += v[k]; }
+  *reinterpret_cast<int4*>(start + base) = make_int4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<int4*>(start + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+  *reinterpret_cast<int4*>(cnt + base) = make_int4(0, 0, 0, 0);
+  *reinterpret_cast<int4*>(cnt + base + 4) = make_int4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    tile_tot[blockIdx.x] = tot;
+    __threadfence();
+    last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // the last block: exclusive scan of the tile totals (sequential chunks of 256)
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b = 0; b < ntiles; b += 256) {
+    const int i = b + threadIdx.x;
+    const int x = i < ntiles ? ((volatile int*)tile_tot)[i] : 0;
+    int in2 = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, in2, o);
+      if (lane >= o) in2 += t;
+    }
+    if (lane == 31) wsum[warp] = in2;
+    __syncthreads();
+    int wo = 0, tt = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { wo += w < warp ? wsum[w] : 0; tt += wsum[w]; }
+    if (i < ntiles) tile_off[i] = carry + wo + in2 - x;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tt;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { total[0] = carry; *blocks_done = 0u; }
+}
+template <typename KeyT>
+__global__ void vs_scatter_kernel(const KeyT* __restrict__ keys, const int* __restrict__ coarse, int n, const int* __restrict__ start,
+                                  const int* __restrict__ tile_off, int* __restrict__ cur, int* __restrict__ tmp_idx, KeyT* __restrict__ tmp_key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const KeyT k = keys[i];
+  if (k == (KeyT)~(KeyT)0) return;
+  const int c = coarse[i];
+  const int pos = start[c] + tile_off[c / kVsTile] + atomicAdd(&cur[c], 1);
+  tmp_idx[pos] = i;
+  tmp_key[pos] = k;
+}
+// one thread per entry (scatter order inside a cell is arbitrary): rank by (key, point index) among the cell's entries
+template <typename KeyT>
+__global__ void vs_rank_kernel(const KeyT* __restrict__ tmp_key, const int* __restrict__ coarse, const int* __restrict__ tmp_idx,
+                               const int* __restrict__ total, const int* __restrict__ start, const int* __restrict__ tile_off,
+                               const int* __restrict__ cur /* = cell counts after the scatter */, KeyT* __restrict__ keys_out,
+                               int* __restrict__ vals_out, int* __restrict__ heavy_flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total[0]) return;
+  const int i = tmp_idx[j];
+  const KeyT k = tmp_key[j];
+  const int c = coarse[i];
+  const int s = start[c] + tile_off[c / kVsTile], e = s + cur[c];
+  if (e - s > kVsHeavy) { *heavy_flag = 1; return; }
+  int rank = 0;
+#pragma unroll 8
+  for (int t = s; t < e; ++t) {  // the cell's entries: read by all of its threads (L1 broadcast)
+    const int it = __ldg(&tmp_idx[t]);
+    const KeyT kt = __ldg(&tmp_key[t]);
+    rank += (kt < k || (kt == k && it < i)) ? 1 : 0;
+  }
+  keys_out[s + rank] = k;
+  vals_out[s + rank] = i;
+}
+
+// keys[i]: dense voxel index of point i or all-ones (dropped); coarse[i]: its coarse cell (any value for dropped points).
+// On return keys_out / vals_out[0 .. *d_total) hold the valid pairs in ascending (key, point index) order.
+// ---- fallback: bitonic sort of (key, point index) pairs, padded to a power of two with all-ones keys (which sort last)
+template <typename KeyT>
+__global__ void vs_bitonic_init_kernel(const KeyT* __restrict__ keys, int n, int npad, KeyT* __restrict__ k, int* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  k[i] = i < n ? keys[i] : (KeyT)~(KeyT)0;
+  v[i] = i;
+}
+template <typename KeyT>
+__global__ void vs_bitonic_step_kernel(KeyT* __restrict__ k, int* __restrict__ v, int npad, int jj, int kk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = i ^ jj;
+  if (i >= npad || p <= i) return;
+  const KeyT ka = k[i], kb = k[p];
+  const int va = v[i], vb = v[p];
+  const bool gt = ka > kb || (ka == kb && va > vb);
+  if (((i & kk) == 0) == gt) { k[i] = kb; k[p] = ka; v[i] = vb; v[p] = va; }
+}
+template <typename KeyT>
+__global__ void vs_count_valid_kernel(const KeyT* __restrict__ k, int n, int* __restrict__ total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool valid = k[i] != (KeyT)~(KeyT)0;
+  const bool next_valid = (i + 1 < n) ? k[i + 1] != (KeyT)~(KeyT)0 : false;
+  if (valid && !next_valid) total[0] = i + 1;
+  if (i == 0 && !valid) total[0] = 0;
+}
+template <typename KeyT>
+static void voxel_sort_fallback(Ctx& ctx, const KeyT* keys, int n, KeyT* keys_out, int* vals_out, int* d_total) {
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  DBuf<KeyT> k; k.alloc(npad, ctx.stream);
+  DBuf<int> v; v.alloc(npad, ctx.stream);
+  const int nb = (npad + 255) / 256;
+  B2R_LAUNCH(ctx, vs_bitonic_init_kernel<KeyT>, nb, 256, 0, keys, n, npad, k.p, v.p);
+  for (int kk = 2; kk <= npad; kk <<= 1)
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) B2R_LAUNCH(ctx, vs_bitonic_step_kernel<KeyT>, nb, 256, 0, k.p, v.p, npad, jj, kk);
+  B2R_CUDA(cudaMemcpyAsync(keys_out, k.p, sizeof(KeyT) * n, cudaMemcpyDeviceToDevice, ctx.stream));
+  B2R_CUDA(cudaMemcpyAsync(vals_out, v.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, vs_count_valid_kernel<KeyT>, (n + 255) / 256, 256, 0, keys_out, n, d_total);
+}
+
+// The sort in two calls around the caller's key kernel, which counts the cells itself (cnt[coarse] += 1 per valid point):
+//   VoxelSort vs; vs.begin(ctx, n, ncoarse);  <key kernel writing keys / coarse and counting into vs.cnt.p>;  vs.finish(...)
+// d_heavy (device int, zeroed by begin): set when a coarse cell was too crowded to rank — the caller reads it at its next
+// synchronisation and, if set, calls voxel_sort_fallback and repeats what it derived from the sorted arrays.
+struct VoxelSort {
+  DBuf<int> cnt, start, tile, tmp;
+  int n = 0, ncoarse = 0, ntiles = 0;
+  void begin(Ctx& ctx, int n_, int ncoarse_, int* d_heavy) {
+    n = n_; ncoarse = ncoarse_;
+    ntiles = (ncoarse + kVsTile - 1) / kVsTile;
+    cnt.alloc((size_t)ntiles * kVsTile, ctx.stream);
+    start.alloc((size_t)ntiles * kVsTile, ctx.stream);
+    tile.alloc((size_t)2 * ntiles + 1, ctx.stream);
+    tmp.alloc((size_t)n, ctx.stream);
+    cnt.zero(ctx.stream);
+    B2R_CUDA(cudaMemsetAsync(tile.p + 2 * ntiles, 0, sizeof(unsigned), ctx.stream));
+    B2R_CUDA(cudaMemsetAsync(d_heavy, 0, sizeof(int), ctx.stream));
+  }
+  template <typename KeyT>
+  void finish(Ctx& ctx, const KeyT* keys, const int* coarse, KeyT* keys_out, int* vals_out, int* d_total, int* d_heavy) {
+    DBuf<KeyT> tmpk;
+    tmpk.alloc((size_t)n, ctx.stream);
+    unsigned* done = reinterpret_cast<unsigned*>(tile.p + 2 * ntiles);
+    const int nb = (n + 255) / 256;
+    B2R_LAUNCH(ctx, vs_scan_kernel, ntiles, 256, 0, cnt.p, ncoarse, start.p, tile.p, tile.p + ntiles, ntiles, done, d_total);
+    B2R_LAUNCH(ctx, vs_scatter_kernel<KeyT>, nb, 256, 0, keys, coarse, n, start.p, tile.p + ntiles, cnt.p, tmp.p, tmpk.p);
+    B2R_LAUNCH(ctx, vs_rank_kernel<KeyT>, nb, 256, 0, tmpk.p, coarse, tmp.p, d_total, start.p, tile.p + ntiles, cnt.p, keys_out, vals_out, d_heavy);
+  }
+};
+// x-voxels per coarse cell (a power of two) and the table size for a DX x DY x DZ voxel grid holding n points
+static void voxel_sort_dims(long long DX, long long DY, long long DZ, int n, int& shift, long long& cx, long long& ncoarse) {
+  const long long want = std::max<long long>(1 << 22, 32ll * n);
+  shift = 0;
+  for (;;) {
+    cx = ((DX - 1) >> shift) + 1;
+    ncoarse = cx * DY * DZ;
+    if (ncoarse <= want || cx == 1) break;
+    ++shift;
+  }
+  if (ncoarse > (1ll << 27)) throw Error(B2R_ERR_CAPACITY, "voxel grid has too many (y, z) rows for the sort table");
+}
 
 // range != nullptr: {near, far} of the distance filter that precedes VoxelGrid in the prefilter chain
 // (apps/prefiltering_component.cpp:149-151), folded into the bounding-box and key passes; the result is the one of
@@ -156,45 +368,45 @@ void filter_voxelgrid(Ctx& ctx, const float4* in, int n, float leaf, int min_pts
     div_b[d] = (int)std::floor(mx[d] * inv_leaf) - prm.min_b[d] + 1;
   }
   prm.mul[0] = 1; prm.mul[1] = div_b[0]; prm.mul[2] = div_b[0] * div_b[1];
-  const int64_t max_idx = (int64_t)div_b[0] * div_b[1] * div_b[2];
-  int end_bit = 1;
-  while (end_bit < 32 && ((int64_t)1 << end_bit) <= max_idx) ++end_bit;
-  end_bit = 32;  // the 0xffffffff sentinel of non-finite points needs all bits
+  for (int d = 0; d < 3; ++d) prm.div[d] = div_b[d];
+  long long cx = 1, ncoarse = 1;
+  voxel_sort_dims(div_b[0], div_b[1], div_b[2], n, prm.shift, cx, ncoarse);
+  prm.cx = (int)cx;
 
   DBuf<unsigned> k0, k1;
-  DBuf<int> v0, v1;
-  k0.alloc(n, ctx.stream); k1.alloc(n, ctx.stream); v0.alloc(n, ctx.stream); v1.alloc(n, ctx.stream);
+  DBuf<int> c0, v1;
+  k0.alloc(n, ctx.stream); k1.alloc(n, ctx.stream); c0.alloc(n, ctx.stream); v1.alloc(n, ctx.stream);
   const int nb = (n + 255) / 256;
-  if (range) B2R_LAUNCH(ctx, vg_key_kernel<true>, nb, 256, 0, in, n, prm, range[0], range[1], k0.p, v0.p);
-  else B2R_LAUNCH(ctx, vg_key_kernel<false>, nb, 256, 0, in, n, prm, 0.0, 0.0, k0.p, v0.p);
-  // stable LSD radix sort (CUB, library primitive): ascending voxel index, ties keep ascending point index
-  size_t tmp_bytes = 0;
-  B2R_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, ctx.stream));
-  DBuf<uint8_t> tmp; tmp.alloc(tmp_bytes, ctx.stream);
-  B2R_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k0.p, k1.p, v0.p, v1.p, n, 0, end_bit, ctx.stream));
-  ctx.launches += 5;  // CUB onesweep: histogram + 4 digit passes
-
+  DBuf<int> cnt; cnt.alloc((size_t)nb + 3, ctx.stream);  // block offsets | number of voxels | valid points | crowded-cell flag
+  // ascending voxel index, ties in ascending point index (what a stable sort gives): one-pass counting sort + in-cell ranks
+  VoxelSort vs;
+  vs.begin(ctx, n, (int)ncoarse, cnt.p + nb + 2);
+  if (range) B2R_LAUNCH(ctx, vg_key_kernel<true>, nb, 256, 0, in, n, prm, range[0], range[1], k0.p, c0.p, vs.cnt.p);
+  else B2R_LAUNCH(ctx, vg_key_kernel<false>, nb, 256, 0, in, n, prm, 0.0, 0.0, k0.p, c0.p, vs.cnt.p);
+  vs.finish<unsigned>(ctx, k0.p, c0.p, k1.p, v1.p, cnt.p + nb + 1, cnt.p + nb + 2);
   DBuf<uint8_t> head; head.alloc(n, ctx.stream);
-  DBuf<int> cnt; cnt.alloc((size_t)nb + 2, ctx.stream);
-  B2R_CUDA(cudaMemsetAsync(cnt.p + nb + 1, 0, sizeof(int), ctx.stream));
-  B2R_LAUNCH(ctx, vg_head_kernel, nb, 256, 0, k1.p, n, head.p);
-  B2R_LAUNCH(ctx, count_valid_kernel, nb, 256, 0, k1.p, n, cnt.p + nb + 1);
-  flags_block_offsets(ctx, head.p, n, cnt.p);
-  int h2[2] = {0, 0};
-  B2R_CUDA(cudaMemcpyAsync(h2, cnt.p + nb, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  int h2[3] = {0, 0, 0};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2R_LAUNCH(ctx, vg_head_kernel<unsigned>, nb, 256, 0, k1.p, n, cnt.p + nb + 1, head.p);
+    flags_block_offsets(ctx, head.p, n, cnt.p);
+    B2R_CUDA(cudaMemcpyAsync(h2, cnt.p + nb, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (!h2[2]) break;
+    voxel_sort_fallback<unsigned>(ctx, k0.p, n, k1.p, v1.p, cnt.p + nb + 1);  // a crowded cell was left unranked
+    B2R_CUDA(cudaMemsetAsync(cnt.p + nb + 2, 0, sizeof(int), ctx.stream));
+  }
   const int nseg = h2[0], n_valid = h2[1];
   if (nseg == 0) return;
   DBuf<int> seg; seg.alloc(nseg, ctx.stream);
   B2R_LAUNCH(ctx, vg_seg_kernel, nb, 256, 0, head.p, n, cnt.p, seg.p);
   if (min_pts <= 1) {
     out.pts.alloc(nseg, ctx.stream);
-    B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 127) / 128, 128, 0, in, v1.p, seg.p, nseg, n_valid, min_pts, out.pts.p, (uint8_t*)nullptr);
+    B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 7) / 8, 256, 0, in, v1.p, seg.p, nseg, n_valid, min_pts, out.pts.p, (uint8_t*)nullptr);
     out.n = nseg;
   } else {
     DBuf<float4> cen; cen.alloc(nseg, ctx.stream);
     DBuf<uint8_t> keep; keep.alloc(nseg, ctx.stream);
-    B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 127) / 128, 128, 0, in, v1.p, seg.p, nseg, n_valid, min_pts, cen.p, keep.p);
+    B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 7) / 8, 256, 0, in, v1.p, seg.p, nseg, n_valid, min_pts, cen.p, keep.p);
     compact_points(ctx, cen.p, keep.p, nseg, out);
   }
 }
@@ -365,10 +577,14 @@ struct AmvgParams {
   float inv_leaf;
   int min_b[3];
   long long mul[3];
+  long long cx;  // coarse cells of the sort per (y, z) row
+  long long ext1;
+  int shift;
 };
 // key = (ix - min) + nx * ((iy - min) + ny * (iz - min)), ixyz = (int)floor(p * inv_leaf) (hpp:88-90): one key per
 // ApproximateMeanVoxelGrid hash-map entry; sorting by it only fixes the (implementation-defined) output order
-__global__ void amvg_key_kernel(const float4* __restrict__ in, int n, AmvgParams prm, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+__global__ void amvg_key_kernel(const float4* __restrict__ in, int n, AmvgParams prm, unsigned long long* __restrict__ keys, int* __restrict__ coarse,
+                                int* __restrict__ cell_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = in[i];
@@ -376,12 +592,9 @@ __global__ void amvg_key_kernel(const float4* __restrict__ in, int n, AmvgParams
   const long long i1 = (long long)(int)floorf(__fmul_rn(p.y, prm.inv_leaf)) - prm.min_b[1];
   const long long i2 = (long long)(int)floorf(__fmul_rn(p.z, prm.inv_leaf)) - prm.min_b[2];
   keys[i] = (unsigned long long)(i0 * prm.mul[0] + i1 * prm.mul[1] + i2 * prm.mul[2]);
-  vals[i] = i;
-}
-__global__ void amvg_head_kernel(const unsigned long long* __restrict__ keys, int n, uint8_t* __restrict__ head) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  head[i] = (i == 0 || keys[i - 1] != keys[i]) ? 1 : 0;
+  const int cc = (int)((i2 * prm.ext1 + i1) * prm.cx + (i0 >> prm.shift));
+  coarse[i] = cc;
+  atomicAdd(&cell_cnt[cc], 1);  // the sort's counting pass (VoxelSort)
 }
 
 void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const double* poses_colmajor, const uint8_t* first_keyframe, size_t count,
@@ -448,32 +661,37 @@ void map_cloud(Ctx& ctx, const void* const* clouds, const size_t* n, const doubl
   }
   if ((double)ext[0] * (double)ext[1] * (double)ext[2] > 9.0e18) throw Error(B2R_ERR_CAPACITY, "map cloud: voxel index range exceeds 63 bits");
   prm.mul[0] = 1; prm.mul[1] = ext[0]; prm.mul[2] = ext[0] * ext[1];
-  const unsigned long long max_key = (unsigned long long)(ext[0] * ext[1] * ext[2]);
-  int end_bit = 1;
-  while (end_bit < 64 && (1ull << end_bit) <= max_key) ++end_bit;
+  long long ncoarse = 1;
+  prm.ext1 = ext[1];
+  voxel_sort_dims(ext[0], ext[1], ext[2], M, prm.shift, prm.cx, ncoarse);
   DBuf<unsigned long long> k0, k1;
-  DBuf<int> v0, v1;
-  k0.alloc(M, ctx.stream); k1.alloc(M, ctx.stream); v0.alloc(M, ctx.stream); v1.alloc(M, ctx.stream);
+  DBuf<int> c0, v1;
+  k0.alloc(M, ctx.stream); k1.alloc(M, ctx.stream); c0.alloc(M, ctx.stream); v1.alloc(M, ctx.stream);
   const int nb = (M + 255) / 256;
-  B2R_LAUNCH(ctx, amvg_key_kernel, nb, 256, 0, world.pts.p, M, prm, k0.p, v0.p);
-  size_t tmp_bytes = 0;  // stable LSD radix sort (CUB): equal keys keep ascending input order = the hash map's accumulation order
-  B2R_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0.p, k1.p, v0.p, v1.p, M, 0, end_bit, ctx.stream));
-  DBuf<uint8_t> tmp; tmp.alloc(tmp_bytes, ctx.stream);
-  B2R_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k0.p, k1.p, v0.p, v1.p, M, 0, end_bit, ctx.stream));
-  ctx.launches += 1 + (end_bit + 7) / 8;
+  DBuf<int> cnt; cnt.alloc((size_t)nb + 3, ctx.stream);
+  // equal keys keep ascending input order = the hash map's accumulation order
+  VoxelSort vs;
+  vs.begin(ctx, M, (int)ncoarse, cnt.p + nb + 2);
+  B2R_LAUNCH(ctx, amvg_key_kernel, nb, 256, 0, world.pts.p, M, prm, k0.p, c0.p, vs.cnt.p);
+  vs.finish<unsigned long long>(ctx, k0.p, c0.p, k1.p, v1.p, cnt.p + nb + 1, cnt.p + nb + 2);
   DBuf<uint8_t> head; head.alloc(M, ctx.stream);
-  DBuf<int> cnt; cnt.alloc((size_t)nb + 1, ctx.stream);
-  B2R_LAUNCH(ctx, amvg_head_kernel, nb, 256, 0, k1.p, M, head.p);
-  flags_block_offsets(ctx, head.p, M, cnt.p);
-  int nseg = 0;
-  B2R_CUDA(cudaMemcpyAsync(&nseg, cnt.p + nb, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
-  B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  int h3[3] = {0, 0, 0};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2R_LAUNCH(ctx, vg_head_kernel<unsigned long long>, nb, 256, 0, k1.p, M, cnt.p + nb + 1, head.p);
+    flags_block_offsets(ctx, head.p, M, cnt.p);
+    B2R_CUDA(cudaMemcpyAsync(h3, cnt.p + nb, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (!h3[2]) break;
+    voxel_sort_fallback<unsigned long long>(ctx, k0.p, M, k1.p, v1.p, cnt.p + nb + 1);
+    B2R_CUDA(cudaMemsetAsync(cnt.p + nb + 2, 0, sizeof(int), ctx.stream));
+  }
+  const int nseg = h3[0];
   DBuf<int> seg; seg.alloc(nseg, ctx.stream);
   B2R_LAUNCH(ctx, vg_seg_kernel, nb, 256, 0, head.p, M, cnt.p, seg.p);
   DBuf<float4> cen; cen.alloc(nseg, ctx.stream);
   DBuf<uint8_t> vkeep; vkeep.alloc(nseg, ctx.stream);
   // count_threshold_: keep iff count >= min_points_per_voxel (hpp:114)
-  B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 127) / 128, 128, 0, world.pts.p, v1.p, seg.p, nseg, M, min_points_per_voxel, cen.p, vkeep.p);
+  B2R_LAUNCH(ctx, vg_centroid_kernel, (nseg + 7) / 8, 256, 0, world.pts.p, v1.p, seg.p, nseg, M, min_points_per_voxel, cen.p, vkeep.p);
   compact_points(ctx, cen.p, vkeep.p, nseg, out);
 }
 

@@ -74,6 +74,11 @@ def test_filter_edge_cases(reg):
     # statistical with the code defaults of prefiltering_component.cpp:100-104 (k=20, 1.0)
     ks, _, _ = O.statistical_outlier(v, 20, 1.0)
     assert np.array_equal(v[ks], reg.statistical_outlier(v, 20, 1.0))
+    # a leaf of many metres: thousands of points per voxel — the sort's crowded-cell fallback (bitonic) must give the same cloud
+    for leaf in (8.0, 60.0):
+        o, _ = O.voxelgrid(c, leaf, 1)
+        g, _ = reg.voxelgrid(c, leaf, 1)
+        assert np.array_equal(o, g) and 0 < len(g) < 200
     # empty and tiny inputs
     empty = np.zeros((0, 4), np.float32)
     assert len(reg.distance_filter(empty, 0.1, 35.0)) == 0

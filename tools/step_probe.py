@@ -11,7 +11,7 @@ from mrg_slam_b200 import loop_closure as LC
 
 method = sys.argv[1] if len(sys.argv) > 1 else "FAST_VGICP"
 reg = B.Registration(B.default_config(getattr(B, method)))
-n_targets, n_cand = 256, 16
+n_targets, n_cand = (int(sys.argv[2]) if len(sys.argv) > 2 else 256), 16
 pool_np, poses = bench.keyframe_pool(reg.prefilter, lambda c, leaf: reg.voxelgrid(c, leaf)[0], n_targets + n_cand)
 pairs, guesses = bench.batch_pairs(n_targets, n_cand, poses)
 ids = np.array([p[0] for p in pairs], dtype=np.int64)
