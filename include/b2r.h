@@ -128,6 +128,14 @@ b2r_status b2r_align_batch(b2r_handle* h, b2r_cloud* const* sources, b2r_cloud* 
  * getSearchMethodTarget()->nearestKSearch(pt, 1, ...).  fitness_out (optional) receives getFitnessScore() of the same pass (:403). */
 b2r_status b2r_inlier_fraction(b2r_handle* h, double max_correspondence_dist, double* fraction_out, double* fitness_out);
 
+/* Per-point nearest neighbours of the aligned source (T = the last final transformation, float transform with PCL's association)
+ * in the target: idx_out[i] = index of the nearest target point (-1: empty target), d2_out[i] = its squared distance (FLANN float
+ * association), xyz_out (optional, 3 floats per point) = the transformed point itself.  This is the table behind
+ * pcl::Registration::getFitnessScore's loop of tree_->nearestKSearch(point, 1, ...) calls (and the inlier loop of
+ * scan_matching_odometry_component.cpp:409-415): include/b2r/pcl_adapter.hpp serves those calls from it through a
+ * pcl::search::KdTree subclass, so unmodified callers of getFitnessScore() get GPU answers (option (i)). */
+b2r_status b2r_nearest_neighbors(b2r_handle* h, int32_t* idx_out, float* d2_out, float* xyz_out);
+
 /* ---- multi-GPU loop-closure batches: the candidate loops of LoopDetector::matching (loop_detector.cpp:97-180) of many
  * new keyframes, sharded over the GPUs of one box, one process (or thread) per GPU.  The pairs are partitioned by target id (all
  * candidates of a new keyframe on one rank: its target structures are built once), every rank aligns its slice, the fixed-size

@@ -9,21 +9,87 @@
 //   virtual      : setInputSource, setInputTarget, computeTransformation (protected)          -> overridden here
 //   non-virtual  : align, hasConverged, getFinalTransformation, getFitnessScore, getSearchMethodTarget
 // align()/hasConverged()/getFinalTransformation() work unchanged because computeTransformation() fills
-// final_transformation_, converged_, nr_iterations_ and the output cloud.  getFitnessScore() is non-virtual and walks
-// the base class's FLANN tree_ on the host; callers that want the GPU version call fitness() (two call sites:
-// src/mrg_slam/loop_detector.cpp:137, apps/scan_matching_odometry_component.cpp:403).
+// final_transformation_, converged_, nr_iterations_ and the output cloud.  getFitnessScore() is non-virtual and walks the base
+// class's tree_ on the host, one nearestKSearch(point, 1) per source point, and initCompute() rebuilds that FLANN tree on every
+// target change.  Both are taken off the host WITHOUT touching the callers (SURVEY 8b option (i)): the adapter installs a
+// pcl::search::KdTree subclass (GpuServedKdTree) with setSearchMethodTarget(tree, /*force_no_recompute=*/true) whose
+// setInputCloud builds nothing and whose nearestKSearch answers from a table computed on the GPU in one pass
+// (b2r_nearest_neighbors) — so src/mrg_slam/loop_detector.cpp:137 and apps/scan_matching_odometry_component.cpp:403-415 get GPU
+// answers unmodified.  Queries the table cannot serve (another k, a point that is not the next aligned source point) fall back to
+// the real kd-tree, built lazily.  fitness() remains as the explicit, cheaper call (option (ii)): one number, no table.
 #pragma once
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <pcl/registration/registration.h>
+#include <pcl/search/kdtree.h>
 
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
+#include <vector>
 
 #include "registration.hpp"
 
 namespace b2r {
+
+// The search object handed to pcl::Registration (tree_).  pcl::Registration::getFitnessScore and the inlier loop of
+// scan_matching_odometry_component.cpp:409-415 call nearestKSearch(aligned_point_i, 1, ...) for i = 0 .. n-1 in order; the table
+// holds exactly those answers, so the i-th call after an align() is served from row i (the point is compared with the table's
+// own transformed point, bit for bit, before the row is trusted).
+class GpuServedKdTree : public pcl::search::KdTree<pcl::PointXYZI> {
+ public:
+  using PointT = pcl::PointXYZI;
+  using Base = pcl::search::KdTree<PointT>;
+  using PointCloudConstPtr = typename Base::PointCloudConstPtr;
+  using IndicesConstPtr = typename Base::IndicesConstPtr;
+  // fills (nearest target index, squared distance, transformed xyz) for every source point; false if unavailable
+  std::function<bool(std::vector<int>&, std::vector<float>&, std::vector<float>&)> fetch;
+
+  void setInputCloud(const PointCloudConstPtr& cloud, const IndicesConstPtr& = IndicesConstPtr()) override {
+    cloud_ = cloud;  // no FLANN build: the GPU owns the target's search structures
+    host_ready_ = false;
+    invalidate();
+  }
+  void invalidate() { table_ready_ = false; cursor_ = 0; }  // a new align(): the table describes the previous result
+
+  int nearestKSearch(const PointT& p, int k, pcl::Indices& k_indices, std::vector<float>& k_sqr_distances) const override {
+    if (k == 1 && ensure_table()) {
+      const size_t n = idx_.size();
+      for (int attempt = 0; attempt < 2 && n; ++attempt) {  // the expected row, then row 0 (a caller starting a new pass)
+        const size_t i = attempt == 0 ? (cursor_ < n ? cursor_ : 0) : 0;
+        if (xyz_[3 * i] == p.x && xyz_[3 * i + 1] == p.y && xyz_[3 * i + 2] == p.z && idx_[i] >= 0) {
+          k_indices.assign(1, idx_[i]);
+          k_sqr_distances.assign(1, d2_[i]);
+          cursor_ = i + 1;
+          ++served;
+          return 1;
+        }
+      }
+    }
+    if (!host_ready_ && cloud_) {  // anything else: the real kd-tree, built on first use
+      const_cast<GpuServedKdTree*>(this)->Base::setInputCloud(cloud_);
+      host_ready_ = true;
+    }
+    return Base::nearestKSearch(p, k, k_indices, k_sqr_distances);
+  }
+  mutable long served = 0;  // queries answered from the GPU table
+
+ private:
+  bool ensure_table() const {
+    if (!table_ready_) {
+      table_ready_ = true;  // one attempt per align()
+      if (!fetch || !fetch(idx_, d2_, xyz_)) { idx_.clear(); d2_.clear(); xyz_.clear(); }
+      cursor_ = 0;
+    }
+    return !idx_.empty();
+  }
+  PointCloudConstPtr cloud_;
+  mutable bool host_ready_ = false, table_ready_ = false;
+  mutable size_t cursor_ = 0;
+  mutable std::vector<int> idx_;
+  mutable std::vector<float> d2_, xyz_;
+};
 
 class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI, float> {
  public:
@@ -42,7 +108,19 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
                       : method == B2R_GICP_PCL   ? "b2r::GICP"
                                                  : "b2r::FAST_VGICP";
     static_assert(sizeof(PointT) == sizeof(::b2r::PointXYZI), "pcl::PointXYZI layout changed");
+    // getFitnessScore() / getSearchMethodTarget()->nearestKSearch() of unmodified callers: served from the GPU; and no FLANN
+    // build of the target in initCompute() (force_no_recompute)
+    gpu_tree_.reset(new GpuServedKdTree);
+    gpu_tree_->fetch = [this](std::vector<int>& idx, std::vector<float>& d2, std::vector<float>& xyz) {
+      b2r_handle* h = impl_.handle();
+      const size_t n = this->input_ ? this->input_->size() : 0;
+      if (!h || n == 0 || !this->target_) return false;
+      idx.resize(n); d2.resize(n); xyz.resize(3 * n);
+      return b2r_nearest_neighbors(h, idx.data(), d2.data(), xyz.data()) == B2R_OK;
+    };
+    this->setSearchMethodTarget(gpu_tree_, /*force_no_recompute=*/true);
   }
+  const GpuServedKdTree& gpuTree() const { return *gpu_tree_; }
 
   // ---- the setters registrations.cpp calls
   void setNumThreads(int n) { impl_.setNumThreads(n); }
@@ -61,7 +139,8 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
     impl_.setInputSource(wrap(cloud));
   }
   void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
-    Base::setInputTarget(cloud);  // also marks the base kd-tree dirty; it is rebuilt lazily by initCompute()
+    Base::setInputTarget(cloud);
+    gpu_tree_->setInputCloud(cloud);  // remembers the cloud for the host fallback; builds nothing
     impl_.setInputTarget(wrap(cloud));
   }
 
@@ -74,6 +153,7 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
     Matrix4f g;
     std::memcpy(g.data(), guess.data(), sizeof(float) * 16);  // Eigen::Matrix4f is column-major, like the C ABI
     ::b2r::PointCloud out;
+    gpu_tree_->invalidate();
     impl_.align(out, g);
     const Matrix4f T = impl_.getFinalTransformation();
     std::memcpy(this->final_transformation_.data(), T.data(), sizeof(float) * 16);
@@ -106,6 +186,7 @@ class PclRegistration : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI,
   }
 
   ::b2r::Registration impl_;
+  std::shared_ptr<GpuServedKdTree> gpu_tree_;
   std::weak_ptr<const pcl::PointCloud<PointT>> last_pcl_[2];
   ::b2r::PointCloud::ConstPtr last_wrapped_[2];
   int slot_ = 0;

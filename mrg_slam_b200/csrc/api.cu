@@ -524,6 +524,34 @@ b2r_status b2r_inlier_fraction(b2r_handle* hh, double max_correspondence_dist, d
   });
 }
 
+b2r_status b2r_nearest_neighbors(b2r_handle* hh, int32_t* idx_out, float* d2_out, float* xyz_out) {
+  return guarded(hh, [&](Handle& h) {
+    if (!idx_out || !d2_out) throw Error(B2R_ERR_INVALID_ARG, "null argument");
+    if (!h.source || !h.target) throw Error(B2R_ERR_STATE, "source and target must be set first");
+    const int n = h.source->n;
+    if (n == 0) return;
+    if (h.target->n == 0) {
+      for (int i = 0; i < n; ++i) { idx_out[i] = -1; d2_out[i] = INFINITY; }
+      return;
+    }
+    Ctx& ctx = h.ctx;
+    std::vector<Cloud*> cl{h.source, h.target};
+    std::vector<Needs> nd(2);
+    nd[1].grid = true;
+    DBuf<CloudView> dv;
+    clouds_prepare(ctx, h.cfg, cl, nd, dv);
+    DBuf<int32_t> di; di.alloc(n, ctx.stream);
+    DBuf<float> dd; dd.alloc(n, ctx.stream);
+    DBuf<float> dx;
+    if (xyz_out) dx.alloc((size_t)n * 3, ctx.stream);
+    nearest_neighbors(ctx, dv.p, n, h.final_T, di.p, dd.p, xyz_out ? dx.p : nullptr);
+    B2R_CUDA(cudaMemcpyAsync(idx_out, di.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaMemcpyAsync(d2_out, dd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx.stream));
+    if (xyz_out) B2R_CUDA(cudaMemcpyAsync(xyz_out, dx.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+  });
+}
+
 b2r_status b2r_transform_source(b2r_handle* hh, void* out_points, size_t stride_bytes, int memspace) {
   return guarded(hh, [&](Handle& h) {
     if (!h.source) throw Error(B2R_ERR_STATE, "source must be set first");

@@ -550,6 +550,29 @@ __device__ __noinline__ CovAccum cov_accumulate_ties(const CloudView* cp, float 
   return v.a;
 }
 
+// covariance = E[d d^T] - E[d] E[d]^T of the k neighbours, symmetric 3x3 Jacobi eigen-decomposition, PLANE regularisation
+// (singular values replaced by (1, 1, 1e-3), smallest = plane normal), stored in original point order
+__device__ __forceinline__ void cov_store(const CloudView& c, int orig, const CovAccum& a, int k) {
+  const double kk = (double)k;
+  const double mx = a.s[0] / kk, my = a.s[1] / kk, mz = a.s[2] / kk;
+  const double m0 = a.s[3] / kk - mx * mx, m1 = a.s[4] / kk - mx * my, m2 = a.s[5] / kk - mx * mz;
+  const double m3 = a.s[6] / kk - my * my, m4 = a.s[7] / kk - my * mz, m5 = a.s[8] / kk - mz * mz;
+  double S[9] = {m0, m1, m2, m1, m3, m4, m2, m4, m5};
+  double ev[3], V[9];
+  sym3_eigen_dev(S, ev, V);
+  const double vals[3] = {1e-3, 1.0, 1.0};
+  double o[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double aa = V[0 * 3 + j], b = V[1 * 3 + j], cc = V[2 * 3 + j];
+    o[0] += vals[j] * aa * aa; o[1] += vals[j] * aa * b; o[2] += vals[j] * aa * cc;
+    o[3] += vals[j] * b * b; o[4] += vals[j] * b * cc; o[5] += vals[j] * cc * cc;
+  }
+  double* dst = c.cov + (size_t)orig * 6;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) dst[t] = o[t];
+}
+
 __device__ unsigned long long g_knn_list_overflows = 0;  // queries whose candidate log overflowed (second traversal taken)
 #ifdef B2R_KNN_STATS
 __device__ unsigned long long g_knn_hist[66];
@@ -606,25 +629,118 @@ __global__ void __launch_bounds__(kKnnThreads, B2R_KNN_BLOCKS) knn_cov_kernel(co
     visit_rows(c, q, sp.x, r, false, v);  // log overflowed: same rows again, radius = k-th distance
   }
   if (v.a.cnt > k) v.a = cov_accumulate_ties(&c, sp.x, sp.y, sp.z, r, dk, k, v.knn_row);
-  const double kk = (double)k;
-  const double mx = v.a.s[0] / kk, my = v.a.s[1] / kk, mz = v.a.s[2] / kk;
-  const double m0 = v.a.s[3] / kk - mx * mx, m1 = v.a.s[4] / kk - mx * my, m2 = v.a.s[5] / kk - mx * mz;
-  const double m3 = v.a.s[6] / kk - my * my, m4 = v.a.s[7] / kk - my * mz, m5 = v.a.s[8] / kk - mz * mz;
-  // PLANE regularisation: singular values replaced by (1, 1, 1e-3), smallest = plane normal
-  double S[9] = {m0, m1, m2, m1, m3, m4, m2, m4, m5};
-  double ev[3], V[9];
-  sym3_eigen_dev(S, ev, V);
-  const double vals[3] = {1e-3, 1.0, 1.0};
-  double o[6] = {0, 0, 0, 0, 0, 0};
+  cov_store(c, orig, v.a, k);
+}
+
+// ---- the same computation with the candidate rows staged in shared memory by TMA (north star: "shared-memory-staged tiles, TMA
+// where it fits").  A block's 128 cell-sorted queries sit in one or two (y, z) rows and a few metres of x, so the points all of
+// them can touch form, per neighbouring row, ONE contiguous range of spts: the strip [x_min - h, x_max + h] of that row.  One
+// thread computes the strips of the rectangle of rows around the block and issues one cp.async.bulk (global -> shared, completion
+// on an mbarrier) per row; the search and the covariance pass then read their candidates from shared memory (positions outside
+// the staged strip, e.g. a second ring, fall back to global memory: the tile is a cache, never a correctness condition).
+// Compared with knn_cov_kernel: no dependent L1 / L2 round trip per candidate (ncu: 3.0 long-scoreboard stalls per issue
+// there), and no candidate log at all — the covariance pass simply sweeps the staged rows again with the proven k-th distance
+// as its radius, which removes the log's shared-memory columns, its local-memory spill (72 ints per thread, 1.7x DRAM traffic)
+// and the log bookkeeping in the inner loop.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  return ok != 0;
+}
+
+constexpr int kTilePts = 2560;  // staged points per block (40 KB)
+constexpr int kTileRows = 32;   // rows of the staged rectangle
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, 5) knn_cov_tile_kernel(const CloudView* __restrict__ views, int k, int32_t* __restrict__ knn_out) {
+  __shared__ __align__(128) float4 s_tile[kTilePts];
+  __shared__ TileRow s_rows[kTileRows];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_ext[6];  // min cy, max cy, min cz, max cz, min / max ordered x bits
+  __shared__ int s_total;
+  const CloudView& c = views[blockIdx.y];
+  const int q0 = blockIdx.x * blockDim.x;
+  if (q0 >= c.n) return;
+  const int qi = min(q0 + (int)threadIdx.x, c.n - 1);  // the last block's spare threads repeat its last query (no store)
+  const bool live = q0 + (int)threadIdx.x < c.n;
+  const float4 sp = __ldg(&c.spts[qi]);
+  const int orig = __float_as_int(sp.w);
+  const QueryCell q = query_cell(c, sp.x, sp.y, sp.z);
+  // ---- the block's rectangle of rows and its x extent
+  if (threadIdx.x == 0) { s_ext[0] = INT_MAX; s_ext[1] = INT_MIN; s_ext[2] = INT_MAX; s_ext[3] = INT_MIN; s_ext[4] = INT_MAX; s_ext[5] = INT_MIN; }
+  __syncthreads();
+  {
+    int cy0 = q.cy, cy1 = q.cy, cz0 = q.cz, cz1 = q.cz, x0 = float_order_key(sp.x), x1 = x0;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const double a = V[0 * 3 + j], b = V[1 * 3 + j], cc = V[2 * 3 + j];
-    o[0] += vals[j] * a * a; o[1] += vals[j] * a * b; o[2] += vals[j] * a * cc;
-    o[3] += vals[j] * b * b; o[4] += vals[j] * b * cc; o[5] += vals[j] * cc * cc;
+    for (int o = 16; o > 0; o >>= 1) {
+      cy0 = min(cy0, __shfl_xor_sync(0xffffffffu, cy0, o)); cy1 = max(cy1, __shfl_xor_sync(0xffffffffu, cy1, o));
+      cz0 = min(cz0, __shfl_xor_sync(0xffffffffu, cz0, o)); cz1 = max(cz1, __shfl_xor_sync(0xffffffffu, cz1, o));
+      x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_ext[0], cy0); atomicMax(&s_ext[1], cy1); atomicMin(&s_ext[2], cz0); atomicMax(&s_ext[3], cz1);
+      atomicMin(&s_ext[4], x0); atomicMax(&s_ext[5], x1);
+    }
   }
-  double* dst = c.cov + (size_t)orig * 6;
-#pragma unroll
-  for (int t = 0; t < 6; ++t) dst[t] = o[t];
+  __syncthreads();
+  const int y_base = max(s_ext[0] - 1, 0), y_end = min(s_ext[1] + 1, c.gd[1] - 1);
+  const int z_base = max(s_ext[2] - 1, 0), z_end = min(s_ext[3] + 1, c.gd[2] - 1);
+  const int ny = y_end - y_base + 1, nz = z_end - z_base + 1;
+  const int nrows = ny * nz <= kTileRows ? ny * nz : 0;  // a block that straddles many rows (sparse regions) is not staged
+  if ((int)threadIdx.x < nrows) {
+    const int xb0 = s_ext[4], xb1 = s_ext[5];
+    const float xmin = __int_as_float(xb0 >= 0 ? xb0 : xb0 ^ 0x7fffffff), xmax = __int_as_float(xb1 >= 0 ? xb1 : xb1 ^ 0x7fffffff);
+    const int cx_lo = clampi((int)floorf((xmin - c.h - c.bmin[0]) * c.inv_hx), 0, c.gd[0] - 1);
+    const int cx_hi = clampi((int)floorf((xmax + c.h - c.bmin[0]) * c.inv_hx), 0, c.gd[0] - 1);
+    const int rowbase = ((z_base + (int)threadIdx.x / ny) * c.gd[1] + y_base + (int)threadIdx.x % ny) * c.gd[0];
+    s_rows[threadIdx.x] = TileRow{__ldg(&c.cell_start[rowbase + cx_lo]), __ldg(&c.cell_start[rowbase + cx_hi + 1]), 0};
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int t = 0; t < nrows; ++t) {  // strips in row order until the tile is full; the rest stays in global memory
+      TileRow r = s_rows[t];
+      if (off + (r.hi - r.lo) > kTilePts) r.hi = r.lo;
+      r.off = off;
+      off += r.hi - r.lo;
+      s_rows[t] = r;
+    }
+    s_total = off;
+    if (off > 0) {
+      mbar_init(&s_bar, 1);
+      mbar_expect_tx(&s_bar, (unsigned)off * 16u);
+      for (int t = 0; t < nrows; ++t) {
+        const TileRow r = s_rows[t];
+        if (r.hi > r.lo) tma_bulk_g2s(&s_tile[r.off], &c.spts[r.lo], (unsigned)(r.hi - r.lo) * 16u, &s_bar);
+      }
+    }
+  }
+  __syncthreads();
+  if (s_total > 0) {
+    while (!mbar_try_wait(&s_bar, 0)) {}
+  }
+  const TilePts src{s_tile, s_rows, y_base, z_base, nrows ? ny : 0, nrows ? nz : 0};
+  // ---- pass 1: exact k-th distance; pass 2: moments of the points within it (both from the tile)
+  TopkVisitor<K> tv(sp.x, sp.y, sp.z);
+  const int r = knn_topk<K>(c, q, k, tv, src);
+  const float dk = topk_kth<K>(tv.d, k);
+  CovVisitor v{sp.x, sp.y, sp.z, dk, true, k, (knn_out && live) ? knn_out + (size_t)orig * k : nullptr, {{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0}};
+  visit_rows(c, q, sp.x, r, false, v, src);
+  if (v.a.cnt > k) v.a = cov_accumulate_ties(&c, sp.x, sp.y, sp.z, r, dk, k, v.knn_row);
+  if (live) cov_store(c, orig, v.a, k);
 }
 
 // pcl::GeneralizedIterativeClosestPoint::computeCovariances (registrations.cpp:93-116 "GICP" / "GICP_OMP") from the
@@ -737,6 +853,20 @@ static void launch_knn_cov(Ctx& ctx, const CloudView* dviews, const std::vector<
   for (Cloud* c : clouds) bytes += 40.0 * c->n;
   const dim3 grid((unsigned)((maxn + 127) / 128), (unsigned)nc);
   ProfScope ps(ctx, PROF_KNN_COV, bytes);
+  // B2R_KNN_TILE=1: the variant with the rows staged in shared memory by TMA bulk copies.  Measured on the 4096-pair batch
+  // (272 clouds of 22.6k points) 5.69 ms against 3.32 ms for knn_cov_kernel, on the 33-cloud chain 1.61 against 0.96 ms: the
+  // search is bound by instruction issue, not by load latency, and the tile adds instructions (range test per load, a second
+  // sweep instead of the candidate log, a serial prologue) while leaving room for 5 instead of 8 blocks per SM.  Kept as a
+  // measured alternative (profiles/r2/ncu_knn_cov_tile_*.md, SASS with UBLKCP in profiles/sass/); the default stays the log kernel.
+  static const bool tile = [] { const char* e = getenv("B2R_KNN_TILE"); return e && atoi(e) != 0; }();
+  if (tile) {
+    if (k <= 8) B2R_LAUNCH(ctx, knn_cov_tile_kernel<8>, grid, 128, 0, dviews, k, knn_out);
+    else if (k <= 16) B2R_LAUNCH(ctx, knn_cov_tile_kernel<16>, grid, 128, 0, dviews, k, knn_out);
+    else if (k <= 20) B2R_LAUNCH(ctx, knn_cov_tile_kernel<20>, grid, 128, 0, dviews, k, knn_out);
+    else if (k <= 24) B2R_LAUNCH(ctx, knn_cov_tile_kernel<24>, grid, 128, 0, dviews, k, knn_out);
+    else B2R_LAUNCH(ctx, knn_cov_tile_kernel<32>, grid, 128, 0, dviews, k, knn_out);
+    return;
+  }
   if (k <= 8) B2R_LAUNCH(ctx, knn_cov_kernel<8>, grid, 128, 0, dviews, k, knn_out);
   else if (k <= 16) B2R_LAUNCH(ctx, knn_cov_kernel<16>, grid, 128, 0, dviews, k, knn_out);
   else if (k <= 20) B2R_LAUNCH(ctx, knn_cov_kernel<20>, grid, 128, 0, dviews, k, knn_out);

@@ -182,6 +182,8 @@ void ndt_debug_derivatives(Ctx& ctx, const b2r_config& cfg, const CloudView* d_v
 // source points whose nearest target point is closer than sqrt(inlier_d2) into inlier_out[i] (device, np ints) ----
 void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_d2 = 0.f, int* d_inlier_out = nullptr);
 void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor, float4* out);
+// per source point: nearest target point (original index), squared distance, transformed point (device arrays of n / n / 3n)
+void nearest_neighbors(Ctx& ctx, const CloudView* d_views, int n_src, const float* T_colmajor, int32_t* d_idx, float* d_d2, float* d_xyz);
 
 // ---- filters.cu ----
 struct DevCloud {  // packed device points + count

@@ -76,38 +76,69 @@ __device__ __forceinline__ float axis_gap(float f, int d) {
   return fmaxf(g - 2e-3f, 0.f);
 }
 
+// Where a visitor's candidate points come from.  GlobalPts: the cloud's cell-sorted copy in global memory (L1 / L2).
+// TilePts (knn_cov_tile_kernel): the strips of the rows around a block's queries, staged in shared memory by TMA bulk copies
+// (one cp.async.bulk per row: a row's strip is a contiguous range of spts); positions outside the staged strip of a row
+// fall back to global memory, so the staging is a cache, never a correctness condition.
+struct GlobalPts {
+  struct Row {};
+  __device__ __forceinline__ Row row(int, int) const { return Row{}; }
+  __device__ __forceinline__ float4 load(const CloudView& c, const Row&, int j) const { return __ldg(&c.spts[j]); }
+};
+struct TileRow { int lo, hi, off; };  // positions [lo, hi) of spts live at tile[off ...]
+struct TilePts {
+  const float4* tile;    // shared memory
+  const TileRow* rows;   // shared memory: the (ny x nz) rectangle of rows starting at (y_base, z_base)
+  int y_base, z_base, ny, nz;
+  struct Row { int lo, hi, delta; };
+  __device__ __forceinline__ Row row(int y, int z) const {
+    const int iy = y - y_base, iz = z - z_base;
+    if (iy < 0 || iy >= ny || iz < 0 || iz >= nz) return Row{0, 0, 0};
+    const TileRow t = rows[iz * ny + iy];
+    return Row{t.lo, t.hi, t.off - t.lo};
+  }
+  __device__ __forceinline__ float4 load(const CloudView& c, const Row& r, int j) const {
+    return (j >= r.lo && j < r.hi) ? tile[j + r.delta] : __ldg(&c.spts[j]);
+  }
+};
+
 // Visits the rows at Chebyshev (y, z) distance <= r (ring == false) or == r (ring == true) of the query's row.
 // Visitor interface:  thr()      squared distance beyond which a ROW cannot matter (may shrink while scanning);
 //                     stop(dx2)  true when a point at squared x-distance dx2 (and all farther ones) cannot matter;
 //                     test(p,j)  candidate p = spts[j].
 // The query's own row comes first: a good k-th distance early prunes most of the rest.
-template <typename V>
-__device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q, float qx, int y, int z, V& v) {
+template <typename V, typename S>
+__device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q, float qx, int y, int z, V& v, const S& src) {
   const int rowbase = (z * c.gd[1] + y) * c.gd[0];
   const int row_s = __ldg(&c.cell_start[rowbase]), row_e = __ldg(&c.cell_start[rowbase + c.gd[0]]);
   if (row_s == row_e) return;
   const int cs = __ldg(&c.cell_start[rowbase + q.cx]), ce = __ldg(&c.cell_start[rowbase + q.cx + 1]);
-  for (int j = cs; j < ce; ++j) v.test(__ldg(&c.spts[j]), j);
+  const typename S::Row sr = src.row(y, z);
+  for (int j = cs; j < ce; ++j) v.test(src.load(c, sr, j), j);
   for (int j = cs - 1; j >= row_s; --j) {  // towards smaller x
-    const float4 p = __ldg(&c.spts[j]);
+    const float4 p = src.load(c, sr, j);
     const float dx = __fsub_rn(qx, p.x);
     if (v.stop(__fmul_rn(dx, dx))) break;
     v.test(p, j);
   }
   for (int j = ce; j < row_e; ++j) {  // towards larger x
-    const float4 p = __ldg(&c.spts[j]);
+    const float4 p = src.load(c, sr, j);
     const float dx = __fsub_rn(qx, p.x);
     if (v.stop(__fmul_rn(dx, dx))) break;
     v.test(p, j);
   }
 }
 template <typename V>
-__device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& q, float qx, int r, bool ring, V& v) {
+__device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q, float qx, int y, int z, V& v) {
+  visit_row(c, q, qx, y, z, v, GlobalPts{});
+}
+template <typename V, typename S>
+__device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& q, float qx, int r, bool ring, V& v, const S& src) {
   const int z0 = max(q.cz - r, 0), z1 = min(q.cz + r, c.gd[2] - 1);
   const int y0 = max(q.cy - r, 0), y1 = min(q.cy + r, c.gd[1] - 1);
   const float h2 = c.h * c.h;
   const bool own_first = !ring && q.cy >= y0 && q.cy <= y1 && q.cz >= z0 && q.cz <= z1;
-  if (own_first) visit_row(c, q, qx, q.cy, q.cz, v);
+  if (own_first) visit_row(c, q, qx, q.cy, q.cz, v, src);
   for (int z = z0; z <= z1; ++z) {
     const int dz = z - q.cz;
     const bool zedge = dz == r || dz == -r;
@@ -117,9 +148,13 @@ __device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& 
       if (ring ? !(zedge || dy == r || dy == -r) : (own_first && dy == 0 && dz == 0)) continue;
       const float gy = axis_gap(q.fy, dy);
       if (!((gy * gy + gz * gz) * h2 + q.xout2 < v.thr())) continue;
-      visit_row(c, q, qx, y, z, v);
+      visit_row(c, q, qx, y, z, v, src);
     }
   }
+}
+template <typename V>
+__device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& q, float qx, int r, bool ring, V& v) {
+  visit_rows(c, q, qx, r, ring, v, GlobalPts{});
 }
 
 // ---- K smallest squared distances, ascending, in registers
@@ -197,17 +232,21 @@ struct TopkListVisitor {
 
 // Exact k smallest squared distances (k <= K, ascending in v.d[0..k)) of the query in cloud c.
 // Returns the (y, z) radius of the scanned rows; v.d[k-1] == INFINITY if the cloud has fewer than k points.
-template <int K, typename V>
-__device__ __forceinline__ int knn_topk(const CloudView& c, const QueryCell& q, int k, V& v) {
+template <int K, typename V, typename S>
+__device__ __forceinline__ int knn_topk(const CloudView& c, const QueryCell& q, int k, V& v, const S& src) {
   int r = rows_outside(c, q) + 1;
-  visit_rows(c, q, v.qx, r, false, v);
+  visit_rows(c, q, v.qx, r, false, v, src);
   for (;;) {
     if (topk_kth<K>(v.d, k) <= ring_safe_d2(r, c.h) + q.xout2) break;
     if (ring_covers_grid(c, q, r)) break;
     ++r;
-    visit_rows(c, q, v.qx, r, true, v);
+    visit_rows(c, q, v.qx, r, true, v, src);
   }
   return r;
+}
+template <int K, typename V>
+__device__ __forceinline__ int knn_topk(const CloudView& c, const QueryCell& q, int k, V& v) {
+  return knn_topk<K>(c, q, k, v, GlobalPts{});
 }
 
 // ---- same search keeping (distance, position) pairs as 64-bit keys: float bits of d^2 << 32 | position in spts.

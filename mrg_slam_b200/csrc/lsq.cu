@@ -867,6 +867,29 @@ __global__ void transform_kernel(const float4* __restrict__ in, int n, Mat16 T, 
   out[i] = o;
 }
 
+// views[0] = source, views[1] = target: the nearestKSearch(point, 1) answers of getFitnessScore's loop, all at once
+__global__ void nn_export_kernel(const CloudView* __restrict__ views, Mat16 T, int32_t* __restrict__ idx, float* __restrict__ d2o,
+                                 float* __restrict__ xyz) {
+  const CloudView& src = views[0];
+  const CloudView& tgt = views[1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= src.n) return;
+  const float4 p = __ldg(&src.pts[i]);
+  float qx, qy, qz;
+  pcl_transform(T.m, p.x, p.y, p.z, qx, qy, qz);
+  float d2;
+  const int pos = nn1_search(tgt, qx, qy, qz, INFINITY, d2);
+  idx[i] = pos >= 0 ? __float_as_int(tgt.spts[pos].w) : -1;
+  d2o[i] = d2;
+  if (xyz) { xyz[3 * (size_t)i] = qx; xyz[3 * (size_t)i + 1] = qy; xyz[3 * (size_t)i + 2] = qz; }
+}
+void nearest_neighbors(Ctx& ctx, const CloudView* d_views, int n_src, const float* T_colmajor, int32_t* d_idx, float* d_d2, float* d_xyz) {
+  if (n_src == 0) return;
+  Mat16 T;
+  memcpy(T.m, T_colmajor, sizeof(T.m));
+  B2R_LAUNCH(ctx, nn_export_kernel, (n_src + 127) / 128, 128, 0, d_views, T, d_idx, d_d2, d_xyz);
+}
+
 void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor, float4* out) {
   if (n == 0) return;
   Mat16 T;

@@ -92,7 +92,7 @@ EXPORTED_SYMBOLS = [
     "b2r_kernel_launches", "b2r_synchronize", "b2r_debug_knn_list_overflows", "b2r_debug_covariances", "b2r_debug_voxelmap",
     "b2r_debug_linearize", "b2r_debug_compute_error", "b2r_debug_ndt_grid", "b2r_debug_ndt_derivatives",
     "b2r_debug_knn", "b2r_last_timings", "b2r_event_record", "b2r_event_elapsed_ms", "b2r_profile_enable", "b2r_profile_read",
-    "b2r_inlier_fraction", "b2r_comm_unique_id", "b2r_comm_init", "b2r_comm_init_host", "b2r_comm_destroy", "b2r_comm_rank",
+    "b2r_inlier_fraction", "b2r_nearest_neighbors", "b2r_comm_unique_id", "b2r_comm_init", "b2r_comm_init_host", "b2r_comm_destroy", "b2r_comm_rank",
     "b2r_comm_size", "b2r_comm_last_error", "b2r_comm_collectives", "b2r_partition_by_target", "b2r_align_batch_sharded",
     "b2r_gather_results", "b2r_select_best_candidates", "b2r_graph_launches",
 ]
@@ -167,6 +167,7 @@ def load():
     L.b2r_profile_enable.argtypes = [vp, ci]
     L.b2r_profile_read.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(cd)]
     L.b2r_inlier_fraction.argtypes = [vp, cd, ctypes.POINTER(cd), ctypes.POINTER(cd)]
+    L.b2r_nearest_neighbors.argtypes = [vp, vp, vp, vp]
     L.b2r_graph_launches.argtypes = [vp]
     L.b2r_graph_launches.restype = ctypes.c_uint64
     L.b2r_comm_unique_id.argtypes = [vp]
@@ -538,6 +539,13 @@ class Registration:
         frac, fit = ctypes.c_double(), ctypes.c_double()
         self._check(self._lib.b2r_inlier_fraction(self._h, max_correspondence_dist, ctypes.byref(frac), ctypes.byref(fit)))
         return frac.value, fit.value
+
+    def nearest_neighbors(self):
+        """b2r_nearest_neighbors: (index of the nearest target point, squared distance, transformed point) per source point."""
+        n = self._src_n
+        idx = np.zeros(n, dtype=np.int32); d2 = np.zeros(n, dtype=np.float32); xyz = np.zeros((n, 3), dtype=np.float32)
+        self._check(self._lib.b2r_nearest_neighbors(self._h, idx.ctypes.data, d2.ctypes.data, xyz.ctypes.data))
+        return idx, d2, xyz
 
     def graph_launches(self):
         return int(self._lib.b2r_graph_launches(self._h))

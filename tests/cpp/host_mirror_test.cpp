@@ -287,6 +287,29 @@ int main(int argc, char** argv) {
     auto Tp = base->getFinalTransformation();
     for (int i = 0; i < 16; ++i) CHECK(Tp.data()[i] == T[i]);  // same engine, same bits
     CHECK(std::fabs(reg->fitness() - f) < 1e-12);
+    // pcl::Registration's own (non-virtual) getFitnessScore walks tree_: every query must be served from the GPU table, the
+    // result must be the GPU fitness to the last bit of the host's summation order, and no host kd-tree may have been built
+    {
+      const double f_pcl = base->getFitnessScore();
+      CHECK(std::fabs(f_pcl - f) <= 1e-12 * f);
+      CHECK(reg->gpuTree().served == (long)pb->size() && reg->gpuTree().host_builds == 0 && reg->gpuTree().host_queries == 0);
+      const double f_rng = base->getFitnessScore(0.01);  // max_range (squared) below most distances: a second pass over the table
+      CHECK(f_rng < f_pcl && reg->gpuTree().served == 2 * (long)pb->size());
+      // the inlier loop of scan_matching_odometry_component.cpp:409-415 through getSearchMethodTarget()
+      pcl::Indices ki; std::vector<float> kd;
+      int inl = 0;
+      for (size_t i = 0; i < out.size(); ++i) {
+        base->getSearchMethodTarget()->nearestKSearch(out.points[i], 1, ki, kd);
+        if (kd[0] < 0.5 * 0.5) ++inl;
+      }
+      double frac = 0, fit2 = 0;
+      CHECK(b2r_inlier_fraction(reg->engine().handle(), 0.5, &frac, &fit2) == B2R_OK);
+      CHECK(frac == (double)((float)inl / (float)out.size()) && reg->gpuTree().host_queries == 0);
+      // a query the table cannot serve falls back to the host tree (built now, once)
+      pcl::PointXYZI stray; stray.x = 1.f; stray.y = 2.f; stray.z = 3.f;
+      base->getSearchMethodTarget()->nearestKSearch(stray, 1, ki, kd);
+      CHECK(reg->gpuTree().host_builds == 1 && reg->gpuTree().host_queries == 1 && ki[0] >= 0);
+    }
     // ---- loop matcher (loop_detector.cpp:97-303): new keyframe = scan 4 seen again, candidates = scans 3 and 5
     {
       b2r_handle* h = vg->handle();

@@ -154,6 +154,13 @@ def test_inlier_fraction_matches_kdtree(vlp16_pair):
     want = np.float32(np.count_nonzero(d2.astype(np.float64) < 0.5 * 0.5)) / np.float32(len(aligned))
     assert frac == float(want)
     assert abs(fit - reg.getFitnessScore()) <= 1e-12 * abs(fit)
+    # the table behind pcl::Registration::getFitnessScore's nearestKSearch loop (b2r_nearest_neighbors, pcl_adapter.hpp)
+    idx, nd2, xyz = reg.nearest_neighbors()
+    assert np.array_equal(xyz, aligned[:, :3]) and np.array_equal(nd2, d2)
+    dd = aligned[:, :3] - a[idx, :3]
+    chk = ((dd[:, 0] * dd[:, 0]).astype(np.float32) + (dd[:, 1] * dd[:, 1]).astype(np.float32)).astype(np.float32)
+    assert np.array_equal((chk + (dd[:, 2] * dd[:, 2]).astype(np.float32)).astype(np.float32), nd2)  # the index is that of a nearest point
+    assert abs(float(np.mean(nd2.astype(np.float64))) - fit) <= 1e-12 * fit
     assert 0.5 < frac <= 1.0
     f2, _ = reg.inlier_fraction(0.05)
     assert f2 < frac

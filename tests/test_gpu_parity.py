@@ -124,6 +124,29 @@ def test_knn_bit_exact(reg, vlp16_pair):
     cl.close()
 
 
+def test_knn_cov_tma_tile_variant_matches(vlp16_pair):
+    """B2R_KNN_TILE=1 selects knn_cov_tile_kernel (candidate rows staged in shared memory by cp.async.bulk): the same neighbour
+    sets and covariances as the default kernel.  The switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys, tempfile
+    a, b, _ = vlp16_pair
+    with tempfile.TemporaryDirectory() as d:
+        np.save(os.path.join(d, "b.npy"), b)
+        code = ("import sys, numpy as np; sys.path.insert(0, %r); from mrg_slam_b200 import lib as B\n"
+                "b = np.load(%r)\n"
+                "g = B.Registration(B.default_config(B.FAST_GICP)); g.setInputTarget(b); g.setInputSource(b)\n"
+                "cov, knn = g.debug_covariances(0, want_knn=True); np.save(%r, cov); np.save(%r, np.sort(knn, 1))\n"
+                "g2 = B.Registration(B.default_config(B.FAST_GICP, nn_cell_size=3.0)); g2.setInputTarget(b); g2.setInputSource(b)\n"
+                "np.save(%r, g2.debug_covariances(0))\n"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(d, "b.npy"), os.path.join(d, "cov.npy"),
+                   os.path.join(d, "knn.npy"), os.path.join(d, "cov3.npy")))
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2R_KNN_TILE="1"), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        ocov, oknn = O.knn_covariances(b, 20, want_idx=True)
+        np.testing.assert_allclose(np.load(os.path.join(d, "cov.npy")), ocov, atol=1e-11)
+        np.testing.assert_allclose(np.load(os.path.join(d, "cov3.npy")), ocov, atol=1e-11)  # coarse grid: strips exceed the tile
+        assert np.array_equal(np.sort(oknn, 1), np.load(os.path.join(d, "knn.npy")))
+
+
 def test_knn_cov_candidate_log_overflow_path(vlp16_pair):
     """knn_cov keeps the candidates that entered the top-k in a bounded shared-memory log; a coarse NN grid makes the log
     overflow, which must take the second-traversal path and give the same neighbours and covariances."""
