@@ -24,14 +24,19 @@
 
 using orc::KdTree;
 
+extern int g_variant[ORC_VAR_COUNT];  // registration.cpp
+
 extern "C" {
+
+void orc_set_variant(int id, int value) { if (id >= 0 && id < ORC_VAR_COUNT) g_variant[id] = value; }
+int orc_get_variant(int id) { return (id >= 0 && id < ORC_VAR_COUNT) ? g_variant[id] : 0; }
 
 // A.11 — keep iff near < |p| < far; norm evaluated in float as x^2 + (y^2 + z^2).
 int orc_distance_filter(const float* xyzi, int n, double near_thresh, double far_thresh, float* out) {
   int m = 0;
   for (int i = 0; i < n; ++i) {
     const float* p = xyzi + 4 * (size_t)i;
-    float s = p[0] * p[0] + (p[1] * p[1] + p[2] * p[2]);
+    float s = g_variant[ORC_VAR_NORM_LEFT_TO_RIGHT] ? (p[0] * p[0] + p[1] * p[1]) + p[2] * p[2] : p[0] * p[0] + (p[1] * p[1] + p[2] * p[2]);
     double d = (double)std::sqrt(s);
     if (d > near_thresh && d < far_thresh) {
       std::memcpy(out + 4 * (size_t)m, p, 16);
@@ -79,6 +84,10 @@ int orc_voxelgrid(const float* xyzi, int n, float leaf, int min_points_per_voxel
   // upstream std::sort is unstable => within-voxel order unspecified; the oracle
   // fixes ascending point index (pair ordering).
   std::sort(iv.begin(), iv.end());
+  if (g_variant[ORC_VAR_VOXELGRID_DESCENDING])  // "any other order an unstable sort may leave": descending index inside a voxel
+    std::sort(iv.begin(), iv.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      return a.first != b.first ? a.first < b.first : a.second > b.second;
+    });
   int m = 0;
   size_t first = 0;
   while (first < iv.size()) {
@@ -117,7 +126,7 @@ int orc_radius_outlier(const float* xyzi, int n, double radius, int min_neighbor
       k = tree.knn(q, 2, idx, d2);
       if (k == 2 && d2[1] > r2) k = 1;
     } else {
-      k = tree.radius_count(q, r2, min_neighbors);
+      k = tree.radius_count(q, g_variant[ORC_VAR_RADIUS_NONSTRICT] ? std::nextafter(r2, INFINITY) : r2, min_neighbors);
     }
     keep[i] = (k > min_neighbors) ? 1 : 0;
     kept += keep[i];
@@ -180,7 +189,7 @@ void orc_transform_cloud(const float* xyzi, int n, const float* T_colmajor, floa
       float a = x * c0[r];
       float b = y * c1[r];
       float c = z * c2[r];
-      o[r] = (a + b) + (c + c3[r]);
+      o[r] = g_variant[ORC_VAR_TRANSFORM_LEFT_TO_RIGHT] ? ((a + b) + c) + c3[r] : (a + b) + (c + c3[r]);
     }
     o[3] = p[3];
   }

@@ -125,6 +125,25 @@ void orc_gicp_pcl_destroy(orc_gicp_pcl* o);
 int orc_gicp_pcl_correspond(orc_gicp_pcl* o, const float* transformation_colmajor);
 double orc_gicp_pcl_eval(orc_gicp_pcl* o, const double* x6, double* grad6);
 
+/* ---- upstream-version variants: the alternative reading of every detail SURVEY.md Appendix A marks as version-dependent.
+ * Test infrastructure for tests/test_oracle_variants.py (how far does a result move if upstream differs?); 0 = documented choice. */
+enum {
+  ORC_VAR_VGICP_COORD_NO_HALF = 0, /* voxel_coord = floor(x / res) instead of floor(x / res - 0.5)                      (A.2) */
+  ORC_VAR_NDT_ANGLE_EPS_1E5 = 1,   /* small-angle cut-off 1e-5 instead of the literal 10e-5                              (A.3) */
+  ORC_VAR_NDT_INNER_DOUBLE = 2,    /* updateDerivatives / point derivatives in double (PCL, older ndt_omp) instead of float (A.3) */
+  ORC_VAR_MT_CLAMP_MAX_FIRST = 3,  /* a_t = min(max(a_t, step_min), step_max) instead of max(min(a_t, step_max), step_min)  (A.3) */
+  ORC_VAR_NDT_COV_NEWER_PCL = 4,   /* leaf covariance (cov - pt_sum mean^T) / (n - 1) instead of the older single-pass form  (A.4) */
+  ORC_VAR_NDT_LOOKUP_MUL = 5,      /* neighbourhood lookup key floor(p * inv_leaf) instead of floor(p / leaf)               (A.4) */
+  ORC_VAR_VOXELGRID_DESCENDING = 6,/* points of a voxel summed in descending instead of ascending index order (unstable sort) (A.6) */
+  ORC_VAR_RADIUS_NONSTRICT = 7,    /* radius search d2 <= r2 instead of d2 < r2                                             (A.7) */
+  ORC_VAR_TRANSFORM_LEFT_TO_RIGHT = 8, /* transformPointCloud ((x c0 + y c1) + z c2) + c3 instead of the SSE association      (A.10) */
+  ORC_VAR_NORM_LEFT_TO_RIGHT = 9,  /* distance filter norm (x^2 + y^2) + z^2 instead of x^2 + (y^2 + z^2)                    (A.11) */
+  ORC_VAR_EULER_NO_FIXUP = 10,     /* eulerAngles(0,1,2) without the first-angle fix-up of Eigen >= 3.3                     (A.3) */
+  ORC_VAR_COUNT = 11
+};
+void orc_set_variant(int id, int value);
+int orc_get_variant(int id);
+
 void orc_set_num_threads(int n);
 int orc_get_max_threads(void);
 

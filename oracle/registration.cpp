@@ -28,6 +28,14 @@
 
 using namespace orc;
 
+// ---- upstream-version variants (SURVEY Appendix A, items marked with a warning sign) ---------------------------------------
+// The reference pins none of PCL / ndt_omp / fast_gicp, and their sources are not available here, so a handful of details of
+// this restatement are "the surveyor's best knowledge of upstream master".  Each has a plausible alternative; orc_set_variant()
+// switches the oracle to it so that tests/test_oracle_variants.py can MEASURE how far an alignment moves if upstream differs
+// (the bound on the unpinned-parity risk).  0 is always the documented choice that the GPU engine reproduces.
+int g_variant[ORC_VAR_COUNT] = {0};
+
+
 namespace {
 
 struct Pose {  // Eigen::Isometry3d
@@ -169,8 +177,9 @@ struct GaussianVoxelMap {
   double resolution = 1.0;
   std::unordered_map<VoxKey, GaussVoxel, VoxHash> voxels;
   inline VoxKey coord(const double* x) const {
-    return VoxKey{(int)std::floor(x[0] / resolution - 0.5), (int)std::floor(x[1] / resolution - 0.5),
-                  (int)std::floor(x[2] / resolution - 0.5)};
+    const double half = g_variant[ORC_VAR_VGICP_COORD_NO_HALF] ? 0.0 : 0.5;  // fast_gicp: floor(x / resolution - 0.5)
+    return VoxKey{(int)std::floor(x[0] / resolution - half), (int)std::floor(x[1] / resolution - half),
+                  (int)std::floor(x[2] / resolution - half)};
   }
   void create(const float* pts, int n, const double* covs) {
     voxels.clear();
@@ -286,10 +295,15 @@ struct NdtGrid {
       for (int a = 0; a < 3; ++a) L.mean[a] /= npt;
       for (int a = 0; a < 3; ++a) L.centroid[a] /= (float)L.nr_points;  // leaf.centroid /= static_cast<float>(nr_points)
       if (L.nr_points < kMinPts) continue;
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b)
-          L.cov[a * 3 + b] = (L.cov[a * 3 + b] - 2 * (pt_sum[a] * L.mean[b])) / npt + L.mean[a] * L.mean[b];
-      for (int a = 0; a < 9; ++a) L.cov[a] *= (npt - 1.0) / npt;
+      if (g_variant[ORC_VAR_NDT_COV_NEWER_PCL]) {  // newer PCL: (cov - pt_sum * mean^T) / (n - 1)
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) L.cov[a * 3 + b] = (L.cov[a * 3 + b] - pt_sum[a] * L.mean[b]) / (npt - 1.0);
+      } else {
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b)
+            L.cov[a * 3 + b] = (L.cov[a * 3 + b] - 2 * (pt_sum[a] * L.mean[b])) / npt + L.mean[a] * L.mean[b];
+        for (int a = 0; a < 9; ++a) L.cov[a] *= (npt - 1.0) / npt;
+      }
       // the single-pass form above is not exactly symmetric; the eigen solver reads the lower triangle
       double S[9];
       for (int a = 0; a < 3; ++a)
@@ -320,6 +334,8 @@ struct NdtGrid {
     static const int off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
     if (leaves.empty()) return 0;
     int ijk[3] = {(int)std::floor(p[0] / leaf), (int)std::floor(p[1] / leaf), (int)std::floor(p[2] / leaf)};
+    if (g_variant[ORC_VAR_NDT_LOOKUP_MUL])  // multiplication by the inverse leaf size, as the build does
+      for (int d = 0; d < 3; ++d) ijk[d] = (int)std::floor(p[d] * inv_leaf);
     int cnt = 0;
     auto probe = [&](int ox, int oy, int oz) {
       int c[3] = {ijk[0] + ox, ijk[1] + oy, ijk[2] + oz};
@@ -405,7 +421,7 @@ void euler_angles_012(const float* R /*row-major 3x3*/, float* res) {
   auto c = [&](int r, int cc) { return R[r * 3 + cc]; };
   res[0] = std::atan2(c(j, k), c(k, k));
   float c2 = std::sqrt(c(i, i) * c(i, i) + c(i, j) * c(i, j));
-  if (res[0] > 0.f) {
+  if (res[0] > 0.f && !g_variant[ORC_VAR_EULER_NO_FIXUP]) {  // (Eigen 3.2 had no such branch: first angle in [-pi, pi])
     if (res[0] > 0.f) res[0] -= (float)M_PI; else res[0] += (float)M_PI;
     res[1] = std::atan2(-c(i, k), -c2);
   } else {
@@ -444,6 +460,7 @@ struct orc_reg {
   NdtGrid ndt;
   double gauss_d1 = 0, gauss_d2 = 0;
   float j_ang[8][3], h_ang[16][3];
+  double j_ang_d[8][3], h_ang_d[16][3];  // ORC_VAR_NDT_INNER_DOUBLE: PCL / older ndt_omp keep these (and the inner products) in double
   std::vector<float> trans_cloud;
 
   int threads() const { return prm.num_threads > 0 ? prm.num_threads : omp_get_max_threads(); }
@@ -793,9 +810,10 @@ struct orc_reg {
   // ------------------------------------------------------------------------ NDT
   void ndt_angle_derivatives(const double* p) {
     double cx, cy, cz, sx, sy, sz;
-    if (std::fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
-    if (std::fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
-    if (std::fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
+    const double aeps = g_variant[ORC_VAR_NDT_ANGLE_EPS_1E5] ? 1e-5 : 10e-5;  // upstream writes the literal 10e-5
+    if (std::fabs(p[3]) < aeps) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
+    if (std::fabs(p[4]) < aeps) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
+    if (std::fabs(p[5]) < aeps) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
     const double J[8][3] = {{-sx * sz + cx * sy * cz, -sx * cz - cx * sy * sz, -cx * cy},
                             {cx * sz + sx * sy * cz, cx * cz - sx * sy * sz, -sx * cy},
                             {-sy * cz, sy * sz, cy},
@@ -820,47 +838,49 @@ struct orc_reg {
                               {-cx * sz - sx * sy * cz, -cx * cz + sx * sy * sz, 0},         // f2
                               {-sx * sz + cx * sy * cz, -cx * sy * sz - sx * cz, 0}};        // f3
     for (int r = 0; r < 8; ++r)
-      for (int c = 0; c < 3; ++c) j_ang[r][c] = (float)J[r][c];
+      for (int c = 0; c < 3; ++c) { j_ang[r][c] = (float)J[r][c]; j_ang_d[r][c] = J[r][c]; }
     for (int r = 0; r < 15; ++r)
-      for (int c = 0; c < 3; ++c) h_ang[r][c] = (float)Hh[r][c];
-    for (int c = 0; c < 3; ++c) h_ang[15][c] = 0.f;
+      for (int c = 0; c < 3; ++c) { h_ang[r][c] = (float)Hh[r][c]; h_ang_d[r][c] = Hh[r][c]; }
+    for (int c = 0; c < 3; ++c) { h_ang[15][c] = 0.f; h_ang_d[15][c] = 0.0; }
   }
 
   // ndt_omp updateDerivatives / updateHessian, float inner math (App. A.3)
-  inline double ndt_update(double* g, double* H, const float pg[3][6], const float ph[18][6], const double* x_trans, const double* c_inv,
+  // S = float: current ndt_omp; S = double: pcl::NormalDistributionsTransform / older ndt_omp (variant ORC_VAR_NDT_INNER_DOUBLE)
+  template <typename S>
+  inline double ndt_update(double* g, double* H, const S pg[3][6], const S ph[18][6], const double* x_trans, const double* c_inv,
                            bool do_grad, bool do_hess) const {
-    float x4[3] = {(float)x_trans[0], (float)x_trans[1], (float)x_trans[2]};
-    float C[3][3];
+    S x4[3] = {(S)x_trans[0], (S)x_trans[1], (S)x_trans[2]};
+    S C[3][3];
     for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 3; ++b) C[a][b] = (float)c_inv[a * 3 + b];
-    float xC[3];  // x4 * C4 (row vector)
+      for (int b = 0; b < 3; ++b) C[a][b] = (S)c_inv[a * 3 + b];
+    S xC[3];  // x4 * C4 (row vector)
     for (int j = 0; j < 3; ++j) {
-      float s = x4[0] * C[0][j];
+      S s = x4[0] * C[0][j];
       s = s + x4[1] * C[1][j];
       s = s + x4[2] * C[2][j];
       xC[j] = s;
     }
-    float xCx = x4[0] * xC[0];
+    S xCx = x4[0] * xC[0];
     xCx = xCx + x4[1] * xC[1];
     xCx = xCx + x4[2] * xC[2];
-    float gd2 = (float)gauss_d2;
+    S gd2 = (S)gauss_d2;
     // exp taken in double and rounded to float: models a correctly rounded expf (glibc's is, in all but rare cases)
-    float e = (float)std::exp((double)(-gd2 * xCx * 0.5f));
-    float score_inc = (float)(-gauss_d1 * (double)e);
+    S e = (S)std::exp((double)(-gd2 * xCx * (S)0.5));
+    S score_inc = (S)(-gauss_d1 * (double)e);
     e = gd2 * e;
     if (e > 1 || e < 0 || e != e) return 0;
-    e = (float)((double)e * gauss_d1);
-    float cg[3][6];  // C4 * pg
+    e = (S)((double)e * gauss_d1);
+    S cg[3][6];  // C4 * pg
     for (int a = 0; a < 3; ++a)
       for (int c = 0; c < 6; ++c) {
-        float s = C[a][0] * pg[0][c];
+        S s = C[a][0] * pg[0][c];
         s = s + C[a][1] * pg[1][c];
         s = s + C[a][2] * pg[2][c];
         cg[a][c] = s;
       }
-    float xcg[6];
+    S xcg[6];
     for (int c = 0; c < 6; ++c) {
-      float s = x4[0] * cg[0][c];
+      S s = x4[0] * cg[0][c];
       s = s + x4[1] * cg[1][c];
       s = s + x4[2] * cg[2][c];
       xcg[c] = s;
@@ -868,20 +888,20 @@ struct orc_reg {
     if (do_grad)
       for (int c = 0; c < 6; ++c) g[c] += (double)(e * xcg[c]);
     if (do_hess) {
-      float G[6][6];  // pg^T * cg
+      S G[6][6];  // pg^T * cg
       for (int a = 0; a < 6; ++a)
         for (int c = 0; c < 6; ++c) {
-          float s = pg[0][a] * cg[0][c];
+          S s = pg[0][a] * cg[0][c];
           s = s + pg[1][a] * cg[1][c];
           s = s + pg[2][a] * cg[2][c];
           G[a][c] = s;
         }
       for (int i = 0; i < 6; ++i) {
-        float xh[6];
+        S xh[6];
         for (int j = 0; j < 6; ++j) {
-          if (i < 3) { xh[j] = 0.f; continue; }
+          if (i < 3) { xh[j] = (S)0; continue; }
           const int rb = (i - 3) * 3;  // three live rows of the 4-row block i
-          float s = xC[0] * ph[rb + 0][j];
+          S s = xC[0] * ph[rb + 0][j];
           s = s + xC[1] * ph[rb + 1][j];
           s = s + xC[2] * ph[rb + 2][j];
           xh[j] = s;
@@ -893,47 +913,53 @@ struct orc_reg {
   }
 
   // computeDerivatives / computeHessian over trans_cloud (App. A.3).  Per-point results summed in index order.
+  template <typename S>
+  void ndt_point(int i, const S (*jang)[3], const S (*hang)[3], bool do_grad, bool do_hess, int* hits_out, double* out) {
+    const float* xt = &trans_cloud[4 * (size_t)i];
+    const NdtLeaf* nb[27];
+    int cnt = ndt.neighbors(xt, prm.neighbor_search, nb);
+    if (hits_out) hits_out[i] = cnt;
+    if (!cnt) return;
+    const float* xo = &source[4 * (size_t)i];
+    // computePointDerivatives
+    S pg[3][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}};
+    auto dot3 = [&](const S* row) {
+      S s = row[0] * (S)xo[0];
+      s = s + row[1] * (S)xo[1];
+      s = s + row[2] * (S)xo[2];
+      return s;
+    };
+    pg[1][3] = dot3(jang[0]); pg[2][3] = dot3(jang[1]);
+    pg[0][4] = dot3(jang[2]); pg[1][4] = dot3(jang[3]); pg[2][4] = dot3(jang[4]);
+    pg[0][5] = dot3(jang[5]); pg[1][5] = dot3(jang[6]); pg[2][5] = dot3(jang[7]);
+    S ph[18][6];
+    std::memset(ph, 0, sizeof(ph));
+    if (do_hess) {
+      S xh[15];
+      for (int r = 0; r < 15; ++r) xh[r] = dot3(hang[r]);
+      S a[3] = {0, xh[0], xh[1]}, b[3] = {0, xh[2], xh[3]}, c[3] = {0, xh[4], xh[5]};
+      S d[3] = {xh[6], xh[7], xh[8]}, e[3] = {xh[9], xh[10], xh[11]}, f[3] = {xh[12], xh[13], xh[14]};
+      for (int r = 0; r < 3; ++r) {
+        ph[0 + r][3] = a[r]; ph[3 + r][3] = b[r]; ph[6 + r][3] = c[r];
+        ph[0 + r][4] = b[r]; ph[3 + r][4] = d[r]; ph[6 + r][4] = e[r];
+        ph[0 + r][5] = c[r]; ph[3 + r][5] = e[r]; ph[6 + r][5] = f[r];
+      }
+    }
+    for (int k = 0; k < cnt; ++k) {
+      double x_trans[3] = {(double)xt[0] - nb[k]->mean[0], (double)xt[1] - nb[k]->mean[1], (double)xt[2] - nb[k]->mean[2]};
+      out[0] += ndt_update<S>(out + 1, out + 7, pg, ph, x_trans, nb[k]->icov, do_grad, do_hess);
+    }
+  }
+
   double ndt_derivatives(const double* p, double* grad, double* hess, bool do_grad, bool do_hess, int* hits_out) {
     ++evals;
     ndt_angle_derivatives(p);
     std::vector<double> per((size_t)ns * 43, 0.0);
+    const bool inner_double = g_variant[ORC_VAR_NDT_INNER_DOUBLE] != 0;
 #pragma omp parallel for schedule(dynamic, 64) num_threads(threads())
     for (int i = 0; i < ns; ++i) {
-      const float* xt = &trans_cloud[4 * (size_t)i];
-      const NdtLeaf* nb[27];
-      int cnt = ndt.neighbors(xt, prm.neighbor_search, nb);
-      if (hits_out) hits_out[i] = cnt;
-      if (!cnt) continue;
-      const float* xo = &source[4 * (size_t)i];
-      // computePointDerivatives (float)
-      float pg[3][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}};
-      auto dot3 = [&](const float* row) {
-        float s = row[0] * xo[0];
-        s = s + row[1] * xo[1];
-        s = s + row[2] * xo[2];
-        return s;
-      };
-      pg[1][3] = dot3(j_ang[0]); pg[2][3] = dot3(j_ang[1]);
-      pg[0][4] = dot3(j_ang[2]); pg[1][4] = dot3(j_ang[3]); pg[2][4] = dot3(j_ang[4]);
-      pg[0][5] = dot3(j_ang[5]); pg[1][5] = dot3(j_ang[6]); pg[2][5] = dot3(j_ang[7]);
-      float ph[18][6];
-      std::memset(ph, 0, sizeof(ph));
-      if (do_hess) {
-        float xh[15];
-        for (int r = 0; r < 15; ++r) xh[r] = dot3(h_ang[r]);
-        float a[3] = {0, xh[0], xh[1]}, b[3] = {0, xh[2], xh[3]}, c[3] = {0, xh[4], xh[5]};
-        float d[3] = {xh[6], xh[7], xh[8]}, e[3] = {xh[9], xh[10], xh[11]}, f[3] = {xh[12], xh[13], xh[14]};
-        for (int r = 0; r < 3; ++r) {
-          ph[0 + r][3] = a[r]; ph[3 + r][3] = b[r]; ph[6 + r][3] = c[r];
-          ph[0 + r][4] = b[r]; ph[3 + r][4] = d[r]; ph[6 + r][4] = e[r];
-          ph[0 + r][5] = c[r]; ph[3 + r][5] = e[r]; ph[6 + r][5] = f[r];
-        }
-      }
-      double* out = &per[(size_t)i * 43];
-      for (int k = 0; k < cnt; ++k) {
-        double x_trans[3] = {(double)xt[0] - nb[k]->mean[0], (double)xt[1] - nb[k]->mean[1], (double)xt[2] - nb[k]->mean[2]};
-        out[0] += ndt_update(out + 1, out + 7, pg, ph, x_trans, nb[k]->icov, do_grad, do_hess);
-      }
+      if (inner_double) ndt_point<double>(i, j_ang_d, h_ang_d, do_grad, do_hess, hits_out, &per[(size_t)i * 43]);
+      else ndt_point<float>(i, j_ang, h_ang, do_grad, do_hess, hits_out, &per[(size_t)i * 43]);
     }
     double score = 0;
     if (do_grad) std::fill(grad, grad + 6, 0.0);
@@ -1017,8 +1043,8 @@ struct orc_reg {
     double f_u = psiMT(a_u, phi_0, phi_0, d_phi_0, mu), g_u = dpsiMT(d_phi_0, d_phi_0, mu);
     bool interval_converged = (step_max - step_min) < 0, open_interval = true;
     double a_t = step_init;
-    a_t = std::min(a_t, step_max);
-    a_t = std::max(a_t, step_min);
+    if (g_variant[ORC_VAR_MT_CLAMP_MAX_FIRST]) { a_t = std::max(a_t, step_min); a_t = std::min(a_t, step_max); }
+    else { a_t = std::min(a_t, step_max); a_t = std::max(a_t, step_min); }
     double x_t[6];
     for (int i = 0; i < 6; ++i) x_t[i] = x[i] + step_dir[i] * a_t;
     ndt_transform_source(x_t);
@@ -1030,8 +1056,8 @@ struct orc_reg {
     while (!interval_converged && step_iterations < max_step_iterations && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
       if (open_interval) a_t = trialValueSelectionMT(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
       else a_t = trialValueSelectionMT(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
-      a_t = std::min(a_t, step_max);
-      a_t = std::max(a_t, step_min);
+      if (g_variant[ORC_VAR_MT_CLAMP_MAX_FIRST]) { a_t = std::max(a_t, step_min); a_t = std::min(a_t, step_max); }
+      else { a_t = std::min(a_t, step_max); a_t = std::max(a_t, step_min); }
       for (int i = 0; i < 6; ++i) x_t[i] = x[i] + step_dir[i] * a_t;
       ndt_transform_source(x_t);
       score = ndt_derivatives(x_t, grad, hess, true, false, nullptr);

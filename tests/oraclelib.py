@@ -14,6 +14,23 @@ _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 
 NDT_OMP, FAST_GICP, FAST_VGICP, SMALL_GICP = 0, 1, 2, 3
 DIRECT1, DIRECT7, DIRECT27, KDTREE = 0, 1, 2, 3
+# orc_set_variant ids (oracle/oracle.h): the alternative reading of every version-dependent detail of SURVEY Appendix A
+VARIANTS = {"vgicp_coord_no_half": 0, "ndt_angle_eps_1e5": 1, "ndt_inner_double": 2, "mt_clamp_max_first": 3, "ndt_cov_newer_pcl": 4,
+            "ndt_lookup_mul": 5, "voxelgrid_descending": 6, "radius_nonstrict": 7, "transform_left_to_right": 8, "norm_left_to_right": 9,
+            "euler_no_fixup": 10}
+
+
+class variant:
+    """with variant("ndt_inner_double"): ...  — the oracle follows the alternative upstream reading inside the block."""
+
+    def __init__(self, name, value=1):
+        self.id, self.value = VARIANTS[name], value
+
+    def __enter__(self):
+        lib().orc_set_variant(self.id, self.value)
+
+    def __exit__(self, *a):
+        lib().orc_set_variant(self.id, 0)
 
 
 class Params(ctypes.Structure):
