@@ -26,7 +26,7 @@ CloudView Cloud::view() const {
   v.hx = hx; v.inv_hx = hx > 0 ? 1.0f / hx : 0.f;
   for (int d = 0; d < 3; ++d) v.gd[d] = gd[d];
   v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.cell_tmp = cell_tmp.p; v.spts = spts.p;
-  v.cov = cov.p;
+  v.cov = cov.p; v.nrm = nrm.p;
   v.vres = vres;
   for (int d = 0; d < 3; ++d) { v.vmin[d] = vmin[d]; v.vd[d] = vd[d]; }
   v.vcell = vcell; v.v_start = v_start.p; v.v_cnt = v_cnt.p; v.v_order = v_order.p; v.v_table = v_table.p; v.vrec = vrec.p;
@@ -383,8 +383,10 @@ __global__ void __launch_bounds__(256) vgicp_reduce_kernel(const CloudView* __re
       r.mean[0] = a[0] / nn; r.mean[1] = a[1] / nn; r.mean[2] = a[2] / nn;
 #pragma unroll
       for (int k = 0; k < 6; ++k) r.cov[k] = a[3 + k] / nn;
+      r.w = sqrt(nn);
       r.n = n;
       r.cell = cell;
+      r.pad = 0.0;
       c.vrec[rec] = r;
     }
   }
@@ -508,7 +510,7 @@ struct CovVisitor {
   int32_t* knn_row;
   CovAccum a;
   __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > dk; }
+  __device__ __forceinline__ bool stop(float s) const { return s > dk * kGapSlack; }
   __device__ __forceinline__ void add(const float4& p) {
     const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;
     a.s[0] += dx; a.s[1] += dy; a.s[2] += dz;
@@ -526,7 +528,7 @@ struct TieVisitor {
   float qx, qy, qz, dk;
   int after, found;
   __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > dk; }
+  __device__ __forceinline__ bool stop(float s) const { return s > dk * kGapSlack; }
   __device__ __forceinline__ void test(const float4& p, int j) {
     if (j > after && j < found && dist2_flann(qx, qy, qz, p.x, p.y, p.z) == dk) found = j;
   }
@@ -571,6 +573,10 @@ __device__ __forceinline__ void cov_store(const CloudView& c, int orig, const Co
   double* dst = c.cov + (size_t)orig * 6;
 #pragma unroll
   for (int t = 0; t < 6; ++t) dst[t] = o[t];
+  if (c.nrm) {  // the eigenvector that got 1e-3: o = V V^T - (1 - 1e-3) n n^T
+    double4* dn = reinterpret_cast<double4*>(c.nrm) + orig;
+    *dn = make_double4(V[0], V[3], V[6], 0.0);
+  }
 }
 
 __device__ unsigned long long g_knn_list_overflows = 0;  // queries whose candidate log overflowed (second traversal taken)
@@ -1036,6 +1042,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       cov_k = nd.cov_k;
       cov_mode = nd.cov_mode;
       plan.want(c->cov.p, (size_t)c->n * 6);
+      if (nd.cov_mode == 0) plan.want(c->nrm.p, (size_t)c->n * 4); else c->nrm.p = nullptr;
       c->vres = 0.0;  // a voxel map built from older covariances is stale
       todo_cov.push_back((int)i);
     }
@@ -1211,6 +1218,7 @@ void debug_cov_knn(Ctx& ctx, const b2r_config& cfg, Cloud& c, int k, int32_t* kn
   if (!c.cov.p || c.cov_k == 0) {
     ArenaPlan plan;
     plan.want(c.cov.p, (size_t)c.n * 6);
+    plan.want(c.nrm.p, (size_t)c.n * 4);
     c.mem_cov = plan.commit(ctx);
   }
   CloudView hv = c.view();

@@ -202,12 +202,15 @@ struct DBuf {
 // ------------------------------------------------------------------------------------------------
 // Device-side view of a cloud and of its cached structures.  Kernels that work on many clouds take an
 // array of these and pick views[blockIdx.y].
-struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap)
+struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap); 96 B, the first 80 are what an evaluation reads
   double mean[3];
   double cov[6];     // xx,xy,xz,yy,yz,zz
+  double w;          // sqrt(n), the weight of the voxel's residual
   int n;
   int cell;          // dense cell index inside the table (debug / export)
+  double pad;
 };
+static_assert(sizeof(VoxRec) == 96, "VoxRec layout");
 struct NdtRec {      // NDT leaf (pclomp::VoxelGridCovariance)
   double mean[3];
   float icov[9];     // inverse covariance rounded to float (updateDerivatives casts it on use)
@@ -232,8 +235,10 @@ struct CloudView {
   int* cell_cnt;    // ncell (count, then scatter cursor)
   int2* cell_tmp;   // n: (ordered x bits, point index) grouped by cell in scatter (arbitrary) order, before the in-cell ranking
   float4* spts;
-  // per-point covariances (original order)
+  // per-point covariances (original order) and, for the PLANE-regularised ones, the direction that got the small eigenvalue
+  // (4 doubles per point: unit normal + padding): cov = I - (1 - 1e-3) n n^T up to rounding
   double* cov;
+  double* nrm;
   // VGICP voxel map
   double vres;
   int vmin[3], vd[3];

@@ -74,7 +74,7 @@ struct Cloud {
   // covariances
   int cov_k = 0;  // k the covariances were built with (0 = none)
   int cov_mode = 0;  // Needs::cov_mode they were built with
-  Ref<double> cov;
+  Ref<double> cov, nrm;
   // VGICP voxel map
   double vres = 0.0;  // resolution the map was built with (0 = none)
   int vmin[3] = {0, 0, 0}, vd[3] = {0, 0, 0};

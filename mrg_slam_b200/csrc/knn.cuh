@@ -104,57 +104,195 @@ struct TilePts {
 
 // Visits the rows at Chebyshev (y, z) distance <= r (ring == false) or == r (ring == true) of the query's row.
 // Visitor interface:  thr()      squared distance beyond which a ROW cannot matter (may shrink while scanning);
-//                     stop(dx2)  true when a point at squared x-distance dx2 (and all farther ones) cannot matter;
+//                     stop(s)    true when a point whose squared distance is at least s cannot matter, s = dx^2 + rg2: the
+//                                squared x-distance plus the row's squared (y, z) gap, a lower bound of the distance to
+//                                anything in that row (the strip of a row one cell away is narrower than the bound itself);
 //                     test(p,j)  candidate p = spts[j].
+// s is a bound on the REAL distance while candidates are compared by their float-evaluated distance, which can fall short of
+// it by a few ulps; every visitor therefore compares s with its bound times kGapSlack (the 2e-3-cell margin of the gaps is
+// metres, not ulps, but it vanishes for a gap of zero, where s = fl(dx^2) <= the float distance exactly).
 // The query's own row comes first: a good k-th distance early prunes most of the rest.
-template <typename V, typename S>
-__device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q, float qx, int y, int z, V& v, const S& src) {
+constexpr float kGapSlack = 1.f + 2e-6f;
+// How a row is swept (A/B-measured on the B200):
+//   VISIT_CELL3   the query's x-cell unconditionally (independent loads, unrolled by the compiler), then a sweep towards smaller
+//                 and one towards larger x, each stopped by stop(dx^2 + rg2)
+//   VISIT_MERGED  one loop from the start of the query's x-cell towards larger x (points before the query are skipped, not
+//                 tested, when they cannot matter) and one towards smaller x: fewer candidates, but every load is serialised
+//                 behind the previous test
+//   VISIT_AHEAD   VISIT_CELL3 with the sweeps loading one point ahead of the test
+enum { VISIT_CELL3 = 0, VISIT_MERGED = 1, VISIT_AHEAD = 2, VISIT_SWEEP_MASK = 3, VISIT_LANE_RING = 4 };
+#ifndef B2R_VISIT_DEFAULT
+#define B2R_VISIT_DEFAULT VISIT_MERGED
+#endif
+template <int MODE, typename V, typename S>
+__device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q, float qx, int y, int z, float rg2, V& v, const S& src) {
   const int rowbase = (z * c.gd[1] + y) * c.gd[0];
   const int row_s = __ldg(&c.cell_start[rowbase]), row_e = __ldg(&c.cell_start[rowbase + c.gd[0]]);
   if (row_s == row_e) return;
-  const int cs = __ldg(&c.cell_start[rowbase + q.cx]), ce = __ldg(&c.cell_start[rowbase + q.cx + 1]);
   const typename S::Row sr = src.row(y, z);
-  for (int j = cs; j < ce; ++j) v.test(src.load(c, sr, j), j);
-  for (int j = cs - 1; j >= row_s; --j) {  // towards smaller x
-    const float4 p = src.load(c, sr, j);
-    const float dx = __fsub_rn(qx, p.x);
-    if (v.stop(__fmul_rn(dx, dx))) break;
-    v.test(p, j);
-  }
-  for (int j = ce; j < row_e; ++j) {  // towards larger x
-    const float4 p = src.load(c, sr, j);
-    const float dx = __fsub_rn(qx, p.x);
-    if (v.stop(__fmul_rn(dx, dx))) break;
-    v.test(p, j);
+  if constexpr ((MODE & VISIT_SWEEP_MASK) == VISIT_MERGED) {
+    const int cs = __ldg(&c.cell_start[rowbase + q.cx]);
+    for (int j = cs; j < row_e; ++j) {  // the query's x-cell, then towards larger x
+      const float4 p = src.load(c, sr, j);
+      const float dx = __fsub_rn(qx, p.x);
+      if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) {
+        if (!(dx > 0.f)) break;  // at or beyond the query: everything after it is farther still
+        continue;                // inside the cell, before the query: the following points are closer
+      }
+      v.test(p, j);
+    }
+    for (int j = cs - 1; j >= row_s; --j) {  // towards smaller x
+      const float4 p = src.load(c, sr, j);
+      const float dx = __fsub_rn(qx, p.x);
+      if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
+      v.test(p, j);
+    }
+  } else {
+    const int cs = __ldg(&c.cell_start[rowbase + q.cx]), ce = __ldg(&c.cell_start[rowbase + q.cx + 1]);
+    for (int j = cs; j < ce; ++j) v.test(src.load(c, sr, j), j);
+    if constexpr ((MODE & VISIT_SWEEP_MASK) == VISIT_CELL3) {
+      for (int j = cs - 1; j >= row_s; --j) {  // towards smaller x
+        const float4 p = src.load(c, sr, j);
+        const float dx = __fsub_rn(qx, p.x);
+        if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
+        v.test(p, j);
+      }
+      for (int j = ce; j < row_e; ++j) {  // towards larger x
+        const float4 p = src.load(c, sr, j);
+        const float dx = __fsub_rn(qx, p.x);
+        if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
+        v.test(p, j);
+      }
+    } else {
+      if (cs > row_s) {
+        int j = cs - 1;
+        float4 p = src.load(c, sr, j);
+        for (;;) {
+          const bool more = j > row_s;
+          float4 pn = p;
+          if (more) pn = src.load(c, sr, j - 1);  // in flight while p is tested
+          const float dx = __fsub_rn(qx, p.x);
+          if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
+          v.test(p, j);
+          if (!more) break;
+          p = pn; --j;
+        }
+      }
+      if (ce < row_e) {
+        int j = ce;
+        float4 p = src.load(c, sr, j);
+        for (;;) {
+          const bool more = j + 1 < row_e;
+          float4 pn = p;
+          if (more) pn = src.load(c, sr, j + 1);
+          const float dx = __fsub_rn(qx, p.x);
+          if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
+          v.test(p, j);
+          if (!more) break;
+          p = pn; ++j;
+        }
+      }
+    }
   }
 }
-template <typename V>
-__device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q, float qx, int y, int z, V& v) {
-  visit_row(c, q, qx, y, z, v, GlobalPts{});
+// The rows at Chebyshev distance exactly r.  Every lane walks ITS OWN list of them: a lane keeps stepping along the perimeter
+// until it finds a row that can still matter (inside the grid, gap below the current bound) and only then joins the others in
+// visit_row — which row that is differs from lane to lane.  (A lock-step double loop over (z, y) runs every slot of the ring for
+// the whole warp with the few lanes that need it: ncu showed 7-9 of 32 lanes in the candidate tests.)
+template <int MODE, typename V, typename S>
+__device__ __forceinline__ void visit_ring(const CloudView& c, const QueryCell& q, float qx, int r, V& v, const S& src) {
+  const float h2 = c.h * c.h;
+  const int n = 2 * r;
+  int side = 0, k = 0;
+  for (;;) {
+    int y = 0, z = 0;
+    float rg2 = 0.f;
+    bool found = false;
+    while (side < 4) {
+      int dy, dz;
+      if (side == 0) { dy = k - r; dz = -r; }
+      else if (side == 1) { dy = r; dz = k - r; }
+      else if (side == 2) { dy = r - k; dz = r; }
+      else { dy = -r; dz = r - k; }
+      if (k == 0) {  // a side that lies outside the grid as a whole is skipped at once
+        const bool out = side == 0 ? q.cz - r < 0 : (side == 1 ? q.cy + r >= c.gd[1] : (side == 2 ? q.cz + r >= c.gd[2] : q.cy - r < 0));
+        if (out) { ++side; continue; }
+      }
+      if (++k == n) { k = 0; ++side; }
+      y = q.cy + dy; z = q.cz + dz;
+      if (y < 0 || y >= c.gd[1] || z < 0 || z >= c.gd[2]) continue;
+      const float gy = axis_gap(q.fy, dy), gz = axis_gap(q.fz, dz);
+      rg2 = (gy * gy + gz * gz) * h2;
+      if (rg2 + q.xout2 < v.thr()) { found = true; break; }
+    }
+    if (!found) break;
+    visit_row<MODE>(c, q, qx, y, z, rg2, v, src);
+  }
 }
-template <typename V, typename S>
+template <int MODE, typename V, typename S>
 __device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& q, float qx, int r, bool ring, V& v, const S& src) {
   const int z0 = max(q.cz - r, 0), z1 = min(q.cz + r, c.gd[2] - 1);
   const int y0 = max(q.cy - r, 0), y1 = min(q.cy + r, c.gd[1] - 1);
   const float h2 = c.h * c.h;
-  const bool own_first = !ring && q.cy >= y0 && q.cy <= y1 && q.cz >= z0 && q.cz <= z1;
-  if (own_first) visit_row(c, q, qx, q.cy, q.cz, v, src);
+  if (ring) {
+    if constexpr ((MODE & VISIT_LANE_RING) != 0) {
+      visit_ring<MODE>(c, q, qx, r, v, src);
+    } else {  // the two z edges, then the two y edges without the corners, the warp in lock step
+#pragma unroll 1
+      for (int e = 0; e < 2; ++e) {
+        const int dz = e ? r : -r, z = q.cz + dz;
+        if (z < 0 || z >= c.gd[2]) continue;
+        const float gz = axis_gap(q.fz, dz);
+        for (int y = y0; y <= y1; ++y) {
+          const float gy = axis_gap(q.fy, y - q.cy);
+          const float rg2 = (gy * gy + gz * gz) * h2;
+          if (!(rg2 + q.xout2 < v.thr())) continue;
+          visit_row<MODE>(c, q, qx, y, z, rg2, v, src);
+        }
+      }
+      const int zi0 = max(q.cz - r + 1, 0), zi1 = min(q.cz + r - 1, c.gd[2] - 1);
+#pragma unroll 1
+      for (int e = 0; e < 2; ++e) {
+        const int dy = e ? r : -r, y = q.cy + dy;
+        if (y < 0 || y >= c.gd[1]) continue;
+        const float gy = axis_gap(q.fy, dy);
+        for (int z = zi0; z <= zi1; ++z) {
+          const float gz = axis_gap(q.fz, z - q.cz);
+          const float rg2 = (gy * gy + gz * gz) * h2;
+          if (!(rg2 + q.xout2 < v.thr())) continue;
+          visit_row<MODE>(c, q, qx, y, z, rg2, v, src);
+        }
+      }
+    }
+    return;
+  }
+  if ((MODE & VISIT_LANE_RING) != 0 && r == 1) {  // the common case (query inside the grid): its own row, then the ring around it, lane by lane
+    if (q.cy >= 0 && q.cy < c.gd[1] && q.cz >= 0 && q.cz < c.gd[2]) visit_row<MODE>(c, q, qx, q.cy, q.cz, 0.f, v, src);
+    visit_ring<MODE>(c, q, qx, 1, v, src);
+    return;
+  }
+  const bool own_first = q.cy >= y0 && q.cy <= y1 && q.cz >= z0 && q.cz <= z1;
+  if (own_first) visit_row<MODE>(c, q, qx, q.cy, q.cz, 0.f, v, src);
   for (int z = z0; z <= z1; ++z) {
     const int dz = z - q.cz;
-    const bool zedge = dz == r || dz == -r;
     const float gz = axis_gap(q.fz, dz);
     for (int y = y0; y <= y1; ++y) {
       const int dy = y - q.cy;
-      if (ring ? !(zedge || dy == r || dy == -r) : (own_first && dy == 0 && dz == 0)) continue;
+      if (own_first && dy == 0 && dz == 0) continue;
       const float gy = axis_gap(q.fy, dy);
-      if (!((gy * gy + gz * gz) * h2 + q.xout2 < v.thr())) continue;
-      visit_row(c, q, qx, y, z, v, src);
+      const float rg2 = (gy * gy + gz * gz) * h2;
+      if (!(rg2 + q.xout2 < v.thr())) continue;
+      visit_row<MODE>(c, q, qx, y, z, rg2, v, src);
     }
   }
 }
+template <typename V, typename S>
+__device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& q, float qx, int r, bool ring, V& v, const S& src) {
+  visit_rows<B2R_VISIT_DEFAULT>(c, q, qx, r, ring, v, src);
+}
 template <typename V>
 __device__ __forceinline__ void visit_rows(const CloudView& c, const QueryCell& q, float qx, int r, bool ring, V& v) {
-  visit_rows(c, q, qx, r, ring, v, GlobalPts{});
+  visit_rows<B2R_VISIT_DEFAULT>(c, q, qx, r, ring, v, GlobalPts{});
 }
 
 // ---- K smallest squared distances, ascending, in registers
@@ -178,15 +316,16 @@ template <int K>
 struct TopkVisitor {
   float qx, qy, qz;
   float d[K];
-  __device__ __forceinline__ TopkVisitor(float x, float y, float z) : qx(x), qy(y), qz(z) {
+  float lim;  // d[K - 1] * kGapSlack
+  __device__ __forceinline__ TopkVisitor(float x, float y, float z) : qx(x), qy(y), qz(z), lim(INFINITY) {
 #pragma unroll
     for (int i = 0; i < K; ++i) d[i] = INFINITY;
   }
   __device__ __forceinline__ float thr() const { return d[K - 1]; }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 >= d[K - 1]; }
+  __device__ __forceinline__ bool stop(float s) const { return s > lim; }
   __device__ __forceinline__ void test(const float4& p, int) {
     const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
-    if (d2 < d[K - 1]) topk_insert<K>(d, d2);
+    if (d2 < d[K - 1]) { topk_insert<K>(d, d2); lim = d[K - 1] * kGapSlack; }
   }
 };
 
@@ -204,17 +343,18 @@ struct TopkListVisitor {
   int stride;
   int cnt;
   int* spill;  // SPILL ints of per-thread local memory, kept outside this struct so that d[] stays in registers
+  float lim;   // d[K - 1] * kGapSlack
 #ifdef B2R_KNN_STATS
   int tested = 0;
 #endif
   __device__ __forceinline__ TopkListVisitor(float x, float y, float z, int* l, int s, int* sp)
-      : qx(x), qy(y), qz(z), list(l), stride(s), cnt(0), spill(sp) {
+      : qx(x), qy(y), qz(z), list(l), stride(s), cnt(0), spill(sp), lim(INFINITY) {
 #pragma unroll
     for (int i = 0; i < K; ++i) d[i] = INFINITY;
   }
   // tie-inclusive pruning: a candidate at exactly the K-th distance must still be seen (and logged)
-  __device__ __forceinline__ float thr() const { return d[K - 1] * (1.f + 1e-6f); }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > d[K - 1]; }
+  __device__ __forceinline__ float thr() const { return lim; }
+  __device__ __forceinline__ bool stop(float s) const { return s > lim; }
   __device__ __forceinline__ void test(const float4& p, int j) {
     const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
 #ifdef B2R_KNN_STATS
@@ -222,6 +362,7 @@ struct TopkListVisitor {
 #endif
     if (d2 <= d[K - 1]) {
       topk_insert<K>(d, d2);
+      lim = d[K - 1] * kGapSlack;
       if (cnt < CAP) list[cnt * stride] = j;
       else if (cnt < CAP + SPILL) spill[cnt - CAP] = j;
       ++cnt;
@@ -264,7 +405,7 @@ struct TopkKeyVisitor {
   }
   __device__ __forceinline__ float worst() const { return d[K - 1] == ~0ull ? INFINITY : __uint_as_float((unsigned)(d[K - 1] >> 32)); }
   __device__ __forceinline__ float thr() const { return worst() * (1.f + 1e-6f); }  // equal distances still compete on position
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > worst(); }
+  __device__ __forceinline__ bool stop(float s) const { return s > worst() * kGapSlack; }
   __device__ __forceinline__ void test(const float4& p, int j) {
     const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
     const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
@@ -282,15 +423,17 @@ struct Nn1Visitor {
   float qx, qy, qz, cut;  // points farther than `cut` (squared) cannot matter
   float best;
   int best_pos;
-  __device__ __forceinline__ float thr() const { return fminf(best, cut) * (1.f + 1e-6f); }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > fminf(best, cut); }
+  float lim;  // min(best, cut) * kGapSlack
+  __device__ __forceinline__ float thr() const { return lim; }
+  __device__ __forceinline__ bool stop(float s) const { return s > lim; }
   __device__ __forceinline__ void test(const float4& p, int j) {
     const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
-    if (d2 < best || (d2 == best && j < best_pos)) { best = d2; best_pos = j; }
+    if (d2 < best || (d2 == best && j < best_pos)) { best = d2; best_pos = j; lim = fminf(d2, cut) * kGapSlack; }
   }
 };
+template <int MODE = B2R_VISIT_DEFAULT>
 __device__ __forceinline__ int nn1_search(const CloudView& c, float qx, float qy, float qz, float max_d2, float& best_out) {
-  Nn1Visitor v{qx, qy, qz, max_d2, INFINITY, -1};
+  Nn1Visitor v{qx, qy, qz, max_d2, INFINITY, -1, max_d2 * kGapSlack};
   if (c.n == 0) { best_out = v.best; return -1; }
   const QueryCell q = query_cell(c, qx, qy, qz);
   int r = rows_outside(c, q) + 1;
@@ -299,17 +442,53 @@ __device__ __forceinline__ int nn1_search(const CloudView& c, float qx, float qy
     const float lb = (float)(r - 2) * c.h;
     if ((r >= 3 && lb * lb > max_d2) || q.xout2 > max_d2) { best_out = v.best; return -1; }
   }
-  visit_rows(c, q, qx, r, false, v);
+  visit_rows<MODE>(c, q, qx, r, false, v, GlobalPts{});
   for (;;) {
     const float b2 = ring_safe_d2(r, c.h) + q.xout2;
     if (v.best <= b2) break;     // proven nearest
     if (b2 > max_d2) break;      // anything farther is out of range anyway
     if (ring_covers_grid(c, q, r)) break;
     ++r;
-    visit_rows(c, q, qx, r, true, v);
+    visit_rows<MODE>(c, q, qx, r, true, v, GlobalPts{});
   }
   best_out = v.best;
   return v.best_pos;
+}
+
+// ---- the same search when only the DISTANCE is wanted (getFitnessScore, inlier fraction): no position, no tie rule, a
+// branch-free candidate test.  Returns the squared distance of the nearest point, INFINITY if the cloud is empty or nothing lies
+// within max_d2 of the rows that had to be looked at (a value beyond max_d2 may come back: the caller compares).
+struct Nn1DistVisitor {
+  float qx, qy, qz, cut;
+  float best;
+  float lim;  // min(best, cut) * kGapSlack
+  __device__ __forceinline__ float thr() const { return lim; }
+  __device__ __forceinline__ bool stop(float s) const { return s > lim; }
+  __device__ __forceinline__ void test(const float4& p, int) {
+    best = fminf(best, dist2_flann(qx, qy, qz, p.x, p.y, p.z));
+    lim = fminf(best, cut) * kGapSlack;
+  }
+};
+template <int MODE = B2R_VISIT_DEFAULT>
+__device__ __forceinline__ float nn1_dist(const CloudView& c, float qx, float qy, float qz, float max_d2) {
+  Nn1DistVisitor v{qx, qy, qz, max_d2, INFINITY, max_d2 * kGapSlack};
+  if (c.n == 0) return INFINITY;
+  const QueryCell q = query_cell(c, qx, qy, qz);
+  int r = rows_outside(c, q) + 1;
+  {
+    const float lb = (float)(r - 2) * c.h;
+    if ((r >= 3 && lb * lb > max_d2) || q.xout2 > max_d2) return INFINITY;
+  }
+  visit_rows<MODE>(c, q, qx, r, false, v, GlobalPts{});
+  for (;;) {
+    const float b2 = ring_safe_d2(r, c.h) + q.xout2;
+    if (v.best <= b2) break;
+    if (b2 > max_d2) break;
+    if (ring_covers_grid(c, q, r)) break;
+    ++r;
+    visit_rows<MODE>(c, q, qx, r, true, v, GlobalPts{});
+  }
+  return v.best;
 }
 
 // ---- one thread per query: exact 1-NN of a DOUBLE query under double squared distance, Eigen Vector4d/Packet2d order
@@ -325,7 +504,7 @@ struct Nn1VisitorD {
     return (float)(r * r * (1.0 + 1e-6));
   }
   __device__ __forceinline__ float thr() const { return cutf; }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 > cutf; }
+  __device__ __forceinline__ bool stop(float s) const { return s > cutf; }  // cutf carries a 0.1 mm margin of its own
   __device__ __forceinline__ void test(const float4& p, int j) {
     const double d0 = (double)p.x - qx, d1 = (double)p.y - qy, d2 = (double)p.z - qz;
     const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d2, d2)), __dmul_rn(d1, d1));
@@ -367,7 +546,7 @@ struct RadiusVisitor {
   float qx, qy, qz, r2;
   int cnt, stop_above;
   __device__ __forceinline__ float thr() const { return cnt > stop_above ? 0.f : r2; }
-  __device__ __forceinline__ bool stop(float dx2) const { return dx2 >= r2 || cnt > stop_above; }
+  __device__ __forceinline__ bool stop(float s) const { return s > r2 * kGapSlack || cnt > stop_above; }
   __device__ __forceinline__ void test(const float4& p, int) {
     if (dist2_flann(qx, qy, qz, p.x, p.y, p.z) < r2) ++cnt;
   }

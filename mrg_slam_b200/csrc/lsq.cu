@@ -53,28 +53,23 @@ __device__ __forceinline__ void accumulate(double* acc, const double* M, double 
   const double Me2 = M[2] * e0 + M[4] * e1 + M[5] * e2;
   acc[27] += w * (e0 * Me0 + e1 * Me1 + e2 * Me2);
   if (!lin) return;
-  // J = [S | -I], S = skew(a).  MS = M*S (columns), Hrr = S^T M S = -S*(MS), Hrt = -S^T M = S*M, Htt = M
+  // J = [S | -I], S = skew(a).  Hrt = -S^T M = S M, Htt = M, and Hrr = S^T M S = -S (M S) = S (S M)^T because M S = -(S M)^T
+  // (M symmetric, S skew): the product S M serves both blocks.
   const double Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
-  double MS[9];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    MS[r * 3 + 0] = Mf[r * 3 + 1] * az - Mf[r * 3 + 2] * ay;
-    MS[r * 3 + 1] = -Mf[r * 3 + 0] * az + Mf[r * 3 + 2] * ax;
-    MS[r * 3 + 2] = Mf[r * 3 + 0] * ay - Mf[r * 3 + 1] * ax;
-  }
   // S*X rows: [ -az X1 + ay X2 ; az X0 - ax X2 ; -ay X0 + ax X1 ]
-  double SMS[9], SM[9];
+  double SM[9];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    SMS[0 * 3 + j] = -az * MS[1 * 3 + j] + ay * MS[2 * 3 + j];
-    SMS[1 * 3 + j] = az * MS[0 * 3 + j] - ax * MS[2 * 3 + j];
-    SMS[2 * 3 + j] = -ay * MS[0 * 3 + j] + ax * MS[1 * 3 + j];
     SM[0 * 3 + j] = -az * Mf[1 * 3 + j] + ay * Mf[2 * 3 + j];
     SM[1 * 3 + j] = az * Mf[0 * 3 + j] - ax * Mf[2 * 3 + j];
     SM[2 * 3 + j] = -ay * Mf[0 * 3 + j] + ax * Mf[1 * 3 + j];
   }
-  acc[0] -= w * SMS[0]; acc[1] -= w * SMS[1]; acc[2] -= w * SMS[2];
-  acc[3] -= w * SMS[4]; acc[4] -= w * SMS[5]; acc[5] -= w * SMS[8];
+  acc[0] += w * (-az * SM[0 * 3 + 1] + ay * SM[0 * 3 + 2]);
+  acc[1] += w * (-az * SM[1 * 3 + 1] + ay * SM[1 * 3 + 2]);
+  acc[2] += w * (-az * SM[2 * 3 + 1] + ay * SM[2 * 3 + 2]);
+  acc[3] += w * (az * SM[1 * 3 + 0] - ax * SM[1 * 3 + 2]);
+  acc[4] += w * (az * SM[2 * 3 + 0] - ax * SM[2 * 3 + 2]);
+  acc[5] += w * (-ay * SM[2 * 3 + 0] + ax * SM[2 * 3 + 1]);
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[6 + t] += w * SM[t];
 #pragma unroll
@@ -86,6 +81,41 @@ __device__ __forceinline__ void accumulate(double* acc, const double* M, double 
   acc[24] -= w * Me0;
   acc[25] -= w * Me1;
   acc[26] -= w * Me2;
+}
+
+// FAST_VGICP Mahalanobis matrix M = (C_B + R C_A R^T)^-1 of one source point against one voxel.  fast_gicp's covariances are
+// PLANE-regularised (calculate_covariances: singular values replaced by (1, 1, 1e-3)), so C_A = V V^T - k n n^T with n the
+// direction that got 1e-3, k = 1 - 1e-3 and V V^T = I to the last bit or two, hence R C_A R^T = G - k m m^T with m = R n and
+// G = R R^T — NOT the identity: the pose starts from a float guess whose rotation is orthonormal to 1e-7 only, upstream uses it
+// as it is, and M amplifies that by its condition number (~1e3), so G is formed once per block from the pose actually used.
+// 9 + 6 + 6 multiply-adds instead of the 45 of the triple product, and 24 instead of 48 bytes of source covariance to read; the
+// 3x3 inverse stays explicit.  (Sherman-Morrison on a per-voxel (C_B + I)^-1 would also remove the inverse, but it has to
+// assume G = I: measured 1e-5 off in H and b.)
+__device__ __forceinline__ void rrt(const double* R /*row-major*/, double* G /*xx,xy,xz,yy,yz,zz*/) {
+  G[0] = R[0] * R[0] + R[1] * R[1] + R[2] * R[2];
+  G[1] = R[0] * R[3] + R[1] * R[4] + R[2] * R[5];
+  G[2] = R[0] * R[6] + R[1] * R[7] + R[2] * R[8];
+  G[3] = R[3] * R[3] + R[4] * R[4] + R[5] * R[5];
+  G[4] = R[3] * R[6] + R[4] * R[7] + R[5] * R[8];
+  G[5] = R[6] * R[6] + R[7] * R[7] + R[8] * R[8];
+}
+__device__ __forceinline__ void vgicp_mahalanobis(const double* R /*row-major*/, const double* G, const double* __restrict__ nrm,
+                                                  const double* __restrict__ cov_b, double* M) {
+  const double2 n01 = __ldg(reinterpret_cast<const double2*>(nrm));
+  const double n2 = __ldg(nrm + 2);
+  const double m0 = R[0] * n01.x + R[1] * n01.y + R[2] * n2;
+  const double m1 = R[3] * n01.x + R[4] * n01.y + R[5] * n2;
+  const double m2 = R[6] * n01.x + R[7] * n01.y + R[8] * n2;
+  const double k = 1.0 - 1e-3;
+  const double k0 = k * m0, k1 = k * m1, k2 = k * m2;
+  double S[6];
+  S[0] = (__ldg(&cov_b[0]) + G[0]) - k0 * m0;
+  S[1] = (__ldg(&cov_b[1]) + G[1]) - k0 * m1;
+  S[2] = (__ldg(&cov_b[2]) + G[2]) - k0 * m2;
+  S[3] = (__ldg(&cov_b[3]) + G[3]) - k1 * m1;
+  S[4] = (__ldg(&cov_b[4]) + G[4]) - k1 * m2;
+  S[5] = (__ldg(&cov_b[5]) + G[5]) - k2 * m2;
+  sym3_inverse(S, M);
 }
 
 // grid = (chunks, pairs).  Phase LINEARIZE: correspondences + M at x0, accumulate H, b, err.
@@ -101,10 +131,11 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
   if (phase == PH_DONE) return;
   const CloudView& src = views[pairs[pair].src];
   const CloudView& tgt = views[pairs[pair].tgt];
-  __shared__ double sx0[12], sxi[12], sx0t[9];
+  __shared__ double sx0[12], sxi[12], sx0t[9], sG[6];
   __shared__ double red[kAcc * 8];
   if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
   if (threadIdx.x < 9) sx0t[threadIdx.x] = st.x0[(threadIdx.x % 3) * 3 + threadIdx.x / 3];  // R^T of the linearisation pose
+  if (threadIdx.x == 32) rrt(st.x0, sG);
   __syncthreads();
   const bool lin = phase == PH_LINEARIZE;
   double acc[kAcc];
@@ -124,14 +155,14 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
     const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
     double ax, ay, az;
     apply_pose(sx0, px, py, pz, ax, ay, az);
-    double CA[6];
-    {
+    double RCR[6];
+    if constexpr (METHOD != B2R_FAST_VGICP) {
+      double CA[6];
       const double* pc = src.cov + (size_t)i * 6;
 #pragma unroll
       for (int t = 0; t < 6; ++t) CA[t] = __ldg(&pc[t]);
+      rsrt(sx0, CA, RCR);
     }
-    double RCR[6];
-    rsrt(sx0, CA, RCR);
     if constexpr (METHOD == B2R_FAST_VGICP) {
       const int vx = vgicp_coord_d(ax, tgt.vres), vy = vgicp_coord_d(ay, tgt.vres), vz = vgicp_coord_d(az, tgt.vres);
       bool first = true;
@@ -144,12 +175,10 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
         const int rec = __ldg(&tgt.v_table[(cz * tgt.vd[1] + cy) * tgt.vd[0] + cx]);
         if (rec < 0) continue;
         const VoxRec& v = tgt.vrec[rec];
-        double S[6], M[6];
-#pragma unroll
-        for (int t = 0; t < 6; ++t) S[t] = __ldg(&v.cov[t]) + RCR[t];
-        sym3_inverse(S, M);
+        double M[6];
+        vgicp_mahalanobis(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
         const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
-        const double w = sqrt((double)__ldg(&v.n));
+        const double w = __ldg(&v.w);
         ++ncorr;
         if (lin) {
           accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
@@ -283,26 +312,16 @@ __device__ __forceinline__ int vgicp_probe(const CloudView& tgt, const double* x
 
 // One correspondence of the VGICP cost: source point i of the pair against voxel record rec.
 __device__ __forceinline__ void vgicp_point(double* acc, const CloudView& src, const CloudView& tgt, const double* sx0, const double* sxi,
-                                            int i, int rec, bool lin) {
+                                            const double* sG, int i, int rec, bool lin) {
   const float4 p = __ldg(&src.pts[i]);
   const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
   double ax, ay, az;
   apply_pose(sx0, px, py, pz, ax, ay, az);
-  double CA[6];
-  {
-    const double* pc = src.cov + (size_t)i * 6;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) CA[t] = __ldg(&pc[t]);
-  }
-  double RCR[6];
-  rsrt(sx0, CA, RCR);
   const VoxRec& v = tgt.vrec[rec];
-  double S[6], M[6];
-#pragma unroll
-  for (int t = 0; t < 6; ++t) S[t] = __ldg(&v.cov[t]) + RCR[t];
-  sym3_inverse(S, M);
+  double M[6];
+  vgicp_mahalanobis(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
   const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
-  const double w = sqrt((double)__ldg(&v.n));
+  const double w = __ldg(&v.w);
   if (lin) {
     accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
   } else {
@@ -321,10 +340,11 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
   if (phase == PH_DONE) return;
   const CloudView& src = views[pairs[pair].src];
   const CloudView& tgt = views[pairs[pair].tgt];
-  __shared__ double sx0[12], sxi[12];
+  __shared__ double sx0[12], sxi[12], sG[6];
   __shared__ double red[kAcc * 8];
   __shared__ int2 s_ring[8][kVgRing];  // (source point, voxel record) hits of each warp
   if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
+  if (threadIdx.x == 32) rrt(st.x0, sG);
   __syncthreads();
   const bool lin = phase == PH_LINEARIZE;
   double acc[kAcc];
@@ -351,9 +371,8 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
     if (hit) {
       ring[(tail + __popc(m & ((1u << lane) - 1u))) & (kVgRing - 1)] = make_int2(i, rec1);
       const char* vr = (const char*)&tgt.vrec[rec1];
-      prefetch_l1(vr); prefetch_l1(vr + 32); prefetch_l1(vr + 64); prefetch_l1(vr + sizeof(VoxRec) - 1);
-      const char* pc = (const char*)(src.cov + (size_t)i * 6);
-      prefetch_l1(pc); prefetch_l1(pc + 32); prefetch_l1(pc + 47);
+      prefetch_l1(vr); prefetch_l1(vr + 32); prefetch_l1(vr + 64); prefetch_l1(vr + 79);  // mean, cov, w: the first 80 bytes
+      prefetch_l1(src.nrm + (size_t)i * 4);
     }
     tail += __popc(m);
     __syncwarp();
@@ -363,7 +382,7 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
       const int pos = head + lane;
       if (pos < tail) {
         const int2 it = ring[pos & (kVgRing - 1)];
-        vgicp_point(acc, src, tgt, sx0, sxi, it.x, it.y, lin);
+        vgicp_point(acc, src, tgt, sx0, sxi, sG, it.x, it.y, lin);
         ++ncorr;
       }
       head = min(head + 32, tail);
@@ -908,25 +927,30 @@ void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor,
 // lane: 12.1-20 ms — ncu shows the budgeted first phase alone costs what the plain kernel costs (7.0 G of 7.4 G warp
 // instructions): the time is in the ORDINARY queries' short, divergent sweeps (5-6 of 32 lanes in the distance tests), not in a
 // few expensive ones (profiles/r2/ncu_fitness_batch4096_*.md).
-__global__ void __launch_bounds__(256) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+template <int MODE, bool LEAN>
+__global__ void __launch_bounds__(256, 4) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                        const b2r_result* __restrict__ rows, double max_range, float max_d2, float inlier_d2,
-                                                       double* __restrict__ partials) {
+                                                       int cell_order, double* __restrict__ partials) {
   const int pair = blockIdx.y;
   const CloudView& src = views[pairs[pair].src];
   const CloudView& tgt = views[pairs[pair].tgt];
+  // the queries of a warp should be neighbours in space (same target rows, similar sweep lengths): the source's own cell-sorted
+  // copy gives that whatever the order the cloud came in; the sum is order-independent up to the last bits of a double
+  const float4* __restrict__ qpts = (cell_order && src.spts) ? src.spts : src.pts;
   __shared__ float T[16];
   __shared__ double red[3 * 8];
   if (threadIdx.x < 16) T[threadIdx.x] = rows[pair].T[threadIdx.x];
   __syncthreads();
   double acc[3] = {0.0, 0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(&src.pts[i]);
+    const float4 p = __ldg(&qpts[i]);
     float qx, qy, qz;
     pcl_transform(T, p.x, p.y, p.z, qx, qy, qz);
     float d2;
-    const int pos = nn1_search(tgt, qx, qy, qz, max_d2, d2);
-    if (pos >= 0 && (double)d2 <= max_range) { acc[0] += (double)d2; acc[1] += 1.0; }
-    if (pos >= 0 && d2 < inlier_d2) acc[2] += 1.0;
+    if constexpr (LEAN) d2 = nn1_dist<MODE>(tgt, qx, qy, qz, max_d2);
+    else if (nn1_search<MODE>(tgt, qx, qy, qz, max_d2, d2) < 0) d2 = INFINITY;
+    if (d2 < INFINITY && (double)d2 <= max_range) { acc[0] += (double)d2; acc[1] += 1.0; }
+    if (d2 < inlier_d2) acc[2] += 1.0;
   }
   block_reduce_to<3>(acc, red, partials + ((size_t)pair * gridDim.x + blockIdx.x) * 3);
 }
@@ -954,7 +978,15 @@ void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_
     double pts = 0.0;  // 16 B source point + one gathered 16 B neighbour
     for (int i = 0; i < np; ++i) pts += b.src_sizes[i];
     ProfScope ps(ctx, PROF_FITNESS, 32.0 * pts);
-    B2R_LAUNCH(ctx, fitness_kernel, dim3(chunks, np), 256, 0, b.d_views, b.d_pairs, b.d_rows, max_range, max_d2, inlier_d2, part.p);
+    static const int cell_order = [] { const char* e = getenv("B2R_FIT_CELL_ORDER"); return e ? atoi(e) : 1; }();
+    static const int mode = [] { const char* e = getenv("B2R_FIT_VISIT"); return e ? atoi(e) : (int)VISIT_CELL3; }();
+    static const int lean = [] { const char* e = getenv("B2R_FIT_LEAN"); return e ? atoi(e) : 1; }();
+#define B2R_FIT_LAUNCH(M, L) \
+    B2R_LAUNCH(ctx, (fitness_kernel<M, L>), dim3(chunks, np), 256, 0, b.d_views, b.d_pairs, b.d_rows, max_range, max_d2, inlier_d2, cell_order, part.p)
+    if (mode == VISIT_MERGED) { if (lean) B2R_FIT_LAUNCH(VISIT_MERGED, true); else B2R_FIT_LAUNCH(VISIT_MERGED, false); }
+    else if (mode == (VISIT_CELL3 | VISIT_LANE_RING)) { if (lean) B2R_FIT_LAUNCH(VISIT_CELL3 | VISIT_LANE_RING, true); else B2R_FIT_LAUNCH(VISIT_CELL3 | VISIT_LANE_RING, false); }
+    else { if (lean) B2R_FIT_LAUNCH(VISIT_CELL3, true); else B2R_FIT_LAUNCH(VISIT_CELL3, false); }
+#undef B2R_FIT_LAUNCH
   }
   B2R_LAUNCH(ctx, fitness_finish_kernel, (np + 127) / 128, 128, 0, part.p, np, chunks, b.d_rows, d_inlier_out);
 }
