@@ -421,7 +421,7 @@ def run_b2r(args):
                                 "synchronisations (rank 0's byte counts; max over ranks of the time)"},
             "gpu_launches": int(launches),
             "gpu_launches_note": f"rank 0, timed region: kernels launched by the host + kernels executed inside the {graphs} optimiser-loop CUDA "
-                                 "graphs (2 per round, counted on the device)",
+                                 "graphs (2-3 per round: evaluation kernel(s) + step kernel, counted on the device)",
             "collectives_in_timed_region": int(collectives),
             "comm_nranks": comm.size,
             "clocks": clocks,

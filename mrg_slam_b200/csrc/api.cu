@@ -706,13 +706,13 @@ b2r_status b2r_map_cloud(b2r_handle* hh, const void* const* clouds, const size_t
 uint64_t b2r_kernel_launches(const b2r_handle* hh) {
   if (!hh) return 0;
   const Ctx& c = hh->h.ctx;
-  unsigned long long rounds = 0;
+  unsigned long long in_graphs = 0;  // kernels executed by the optimiser-loop graphs, counted on the device
   if (c.d_graph_rounds) {
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
-    if (cudaMemcpy(&rounds, c.d_graph_rounds, sizeof(rounds), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); rounds = 0; }
+    if (cudaMemcpy(&in_graphs, c.d_graph_rounds, sizeof(in_graphs), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); in_graphs = 0; }
   }
-  return c.launches - c.graph_launches + 2ull * rounds;
+  return c.launches - c.graph_launches + in_graphs;
 }
 uint64_t b2r_graph_launches(const b2r_handle* hh) { return hh ? hh->h.ctx.graph_launches : 0; }
 

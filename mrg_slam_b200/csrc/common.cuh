@@ -89,15 +89,16 @@ struct Ctx {
   std::shared_ptr<StreamOwner> stream_owner;
   uint64_t launches = 0;        // kernel launches + graph launches issued by this handle
   uint64_t graph_launches = 0;  // of which: optimiser loops launched as one CUDA graph
-  unsigned long long* d_graph_rounds = nullptr;  // device counter: {eval, step} rounds executed inside those graphs
+  unsigned long long* d_graph_rounds = nullptr;  // device counter: kernels executed inside those graphs
   // One instantiated loop graph per (eval kernel, step kernel) pair of this handle: later alignments only rewrite the two kernel
   // nodes' parameters (cudaGraphExecKernelNodeSetParams) instead of building and instantiating a new graph (~0.26 ms each).
   struct LoopGraph {
     const void* eval_fn;
+    const void* eval2_fn;
     const void* step_fn;
     cudaGraph_t graph;
     cudaGraphExec_t exec;
-    cudaGraphNode_t eval_node, step_node;
+    cudaGraphNode_t eval_node, eval2_node, step_node;
     cudaGraphConditionalHandle handle;
   };
   std::vector<LoopGraph> loop_graphs;
@@ -202,12 +203,12 @@ struct DBuf {
 // ------------------------------------------------------------------------------------------------
 // Device-side view of a cloud and of its cached structures.  Kernels that work on many clouds take an
 // array of these and pick views[blockIdx.y].
-struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap); 96 B, the first 80 are what an evaluation reads
-  double mean[3];
-  double cov[6];     // xx,xy,xz,yy,yz,zz
-  double w;          // sqrt(n), the weight of the voxel's residual
-  int n;
-  int cell;          // dense cell index inside the table (debug / export)
+struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap); 96 B, the first 80 are what an evaluation reads.
+  double mean[3];    // (Measured and rejected on the 4096-pair batch, where the evaluation kernels run at 95 % of the L1 data pipe's
+  double cov[6];     // wavefront rate: one 128-byte line per record, 21.8 -> 23.8 ms per step — the larger footprint costs more L1 / L2
+  double w;          // hits than the straddling records cost wavefronts; the 80 bytes as five 16-byte loads instead of ten 8-byte
+  int n;             // ones, 21.8 -> 22.4 ms — the linearisation kernel, at its 128-register limit, starts to spill.)
+  int cell;          // w = sqrt(n), the weight of the voxel's residual; cov = xx,xy,xz,yy,yz,zz; cell = dense table index (export)
   double pad;
 };
 static_assert(sizeof(VoxRec) == 96, "VoxRec layout");
@@ -281,8 +282,9 @@ struct LoopArgs {       // passed by value to the step kernels
   int npairs;
   int max_rounds;
   int use_graph;        // 0: the host polls ctl->done between groups of rounds (profiling / fallback path)
+  int kernels_per_round;  // kernel nodes in the loop body (launch accounting)
   cudaGraphConditionalHandle handle;
-  unsigned long long* rounds_total;  // per-handle counter of rounds run inside graphs (kernel-launch accounting), or nullptr
+  unsigned long long* rounds_total;  // per-handle counter of kernels run inside graphs (kernel-launch accounting), or nullptr
 };
 // Called by EVERY thread of a step kernel after its work (no early returns before it).
 __device__ __forceinline__ void loop_tail(const LoopArgs& la) {
@@ -296,7 +298,7 @@ __device__ __forceinline__ void loop_tail(const LoopArgs& la) {
       la.ctl->blocks_finished = 0;
       const int rounds = atomicAdd(&la.ctl->rounds, 1) + 1;
       const int done = atomicAdd(&la.ctl->done, 0);
-      if (la.use_graph && la.rounds_total) atomicAdd(la.rounds_total, 1ull);
+      if (la.use_graph && la.rounds_total) atomicAdd(la.rounds_total, (unsigned long long)la.kernels_per_round);
       if (la.use_graph) cudaGraphSetConditional(la.handle, (done < la.npairs && rounds < la.max_rounds) ? 1u : 0u);
     }
   }

@@ -165,7 +165,8 @@ struct BatchArgs {
 // on or B2R_GRAPH_LOOP=0, as a host-polled loop.  `la` must be the LoopArgs object the step kernel's argument array points at;
 // prof_id < 0: the evaluation launches are not bracketed.  Stream-ordered: returns without synchronising in graph mode.
 void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_block, void** eval_args, const void* step_fn, dim3 step_grid,
-                     dim3 step_block, void** step_args, LoopArgs& la, LoopCtl* d_ctl, int npairs, long max_rounds, int prof_id);
+                     dim3 step_block, void** step_args, LoopArgs& la, LoopCtl* d_ctl, int npairs, long max_rounds, int prof_id,
+                     const void* eval2_fn = nullptr);  // eval2_fn: a second evaluation kernel per round (same grid, block, arguments)
 
 // ---- lsq.cu (FAST_GICP / FAST_VGICP / SMALL_GICP) ----
 void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b);

@@ -28,24 +28,28 @@ static bool graph_loop_enabled() {
   } while (0)
 
 void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_block, void** eval_args, const void* step_fn, dim3 step_grid,
-                     dim3 step_block, void** step_args, LoopArgs& la, LoopCtl* d_ctl, int npairs, long max_rounds, int prof_id) {
+                     dim3 step_block, void** step_args, LoopArgs& la, LoopCtl* d_ctl, int npairs, long max_rounds, int prof_id,
+                     const void* eval2_fn) {
   la.ctl = d_ctl;
   la.npairs = npairs;
   la.max_rounds = (int)std::min<long>(max_rounds, 1l << 30);
   la.handle = 0;
   la.rounds_total = ctx.d_graph_rounds;
+  la.kernels_per_round = eval2_fn ? 3 : 2;
   if (graph_loop_enabled() && !ctx.profile) {
     la.use_graph = 1;
     ctx.reap_graphs(false);
-    cudaKernelNodeParams ke = {}, ks = {};
+    cudaKernelNodeParams ke = {}, ke2 = {}, ks = {};
     ke.func = const_cast<void*>(eval_fn); ke.gridDim = eval_grid; ke.blockDim = eval_block; ke.kernelParams = eval_args;
+    ke2 = ke; ke2.func = const_cast<void*>(eval2_fn);
     ks.func = const_cast<void*>(step_fn); ks.gridDim = step_grid; ks.blockDim = step_block; ks.kernelParams = step_args;
     // ---- a graph of this kernel pair instantiated earlier: rewrite the two nodes' parameters and launch
     if (ctx.loop_graph_cache_ok) {
       for (Ctx::LoopGraph& lg : ctx.loop_graphs) {
-        if (lg.eval_fn != eval_fn || lg.step_fn != step_fn) continue;
+        if (lg.eval_fn != eval_fn || lg.eval2_fn != eval2_fn || lg.step_fn != step_fn) continue;
         la.handle = lg.handle;  // baked into the step kernel's arguments below
         if (cudaGraphExecKernelNodeSetParams(lg.exec, lg.eval_node, &ke) == cudaSuccess &&
+            (!eval2_fn || cudaGraphExecKernelNodeSetParams(lg.exec, lg.eval2_node, &ke2) == cudaSuccess) &&
             cudaGraphExecKernelNodeSetParams(lg.exec, lg.step_node, &ks) == cudaSuccess) {
           B2R_CUDA(cudaGraphLaunch(lg.exec, ctx.stream));
           ctx.launches += 1;
@@ -68,14 +72,19 @@ void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_bl
     cudaGraphNode_t wnode = nullptr;
     B2R_GRAPH(cudaGraphAddNode(&wnode, g, nullptr, 0, &cp), g, ge);
     cudaGraph_t body = cp.conditional.phGraph_out[0];
-    cudaGraphNode_t ne = nullptr, ns = nullptr;
+    cudaGraphNode_t ne = nullptr, ne2 = nullptr, ns = nullptr;
     B2R_GRAPH(cudaGraphAddKernelNode(&ne, body, nullptr, 0, &ke), g, ge);
-    B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, &ne, 1, &ks), g, ge);
+    if (eval2_fn) {
+      B2R_GRAPH(cudaGraphAddKernelNode(&ne2, body, &ne, 1, &ke2), g, ge);
+      B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, &ne2, 1, &ks), g, ge);
+    } else {
+      B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, &ne, 1, &ks), g, ge);
+    }
     B2R_GRAPH(cudaGraphInstantiate(&ge, g, 0), g, ge);
     B2R_GRAPH(cudaGraphLaunch(ge, ctx.stream), g, ge);
     ctx.launches += 1;  // one graph launch; the rounds it ran are counted on the device (LoopArgs::rounds_total)
     ++ctx.graph_launches;
-    if (ctx.loop_graph_cache_ok) ctx.loop_graphs.push_back(Ctx::LoopGraph{eval_fn, step_fn, g, ge, ne, ns, la.handle});
+    if (ctx.loop_graph_cache_ok) ctx.loop_graphs.push_back(Ctx::LoopGraph{eval_fn, eval2_fn, step_fn, g, ge, ne, ne2, ns, la.handle});
     else ctx.graph_graveyard.emplace_back(ge, g);  // released once the stream has drained (destroying it now would wait for the launch)
     return;
   }
@@ -90,6 +99,10 @@ void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_bl
         ProfScope ps(ctx, prof_id >= 0 ? prof_id : 0, 0.0, prof_id >= 0);  // bytes are added by the caller from the work the device did
         B2R_CUDA(cudaLaunchKernel(eval_fn, eval_grid, eval_block, eval_args, 0, ctx.stream));
         ++ctx.launches;
+        if (eval2_fn) {
+          B2R_CUDA(cudaLaunchKernel(eval2_fn, eval_grid, eval_block, eval_args, 0, ctx.stream));
+          ++ctx.launches;
+        }
       }
       B2R_CUDA(cudaLaunchKernel(step_fn, step_grid, step_block, step_args, 0, ctx.stream));
       ++ctx.launches;

@@ -99,6 +99,7 @@ __device__ __forceinline__ void rrt(const double* R /*row-major*/, double* G /*x
   G[4] = R[3] * R[6] + R[4] * R[7] + R[5] * R[8];
   G[5] = R[6] * R[6] + R[7] * R[7] + R[8] * R[8];
 }
+template <bool COV_IN_MEMORY>
 __device__ __forceinline__ void vgicp_mahalanobis(const double* R /*row-major*/, const double* G, const double* __restrict__ nrm,
                                                   const double* __restrict__ cov_b, double* M) {
   const double2 n01 = __ldg(reinterpret_cast<const double2*>(nrm));
@@ -109,12 +110,12 @@ __device__ __forceinline__ void vgicp_mahalanobis(const double* R /*row-major*/,
   const double k = 1.0 - 1e-3;
   const double k0 = k * m0, k1 = k * m1, k2 = k * m2;
   double S[6];
-  S[0] = (__ldg(&cov_b[0]) + G[0]) - k0 * m0;
-  S[1] = (__ldg(&cov_b[1]) + G[1]) - k0 * m1;
-  S[2] = (__ldg(&cov_b[2]) + G[2]) - k0 * m2;
-  S[3] = (__ldg(&cov_b[3]) + G[3]) - k1 * m1;
-  S[4] = (__ldg(&cov_b[4]) + G[4]) - k1 * m2;
-  S[5] = (__ldg(&cov_b[5]) + G[5]) - k2 * m2;
+  S[0] = ((COV_IN_MEMORY ? __ldg(&cov_b[0]) : cov_b[0]) + G[0]) - k0 * m0;
+  S[1] = ((COV_IN_MEMORY ? __ldg(&cov_b[1]) : cov_b[1]) + G[1]) - k0 * m1;
+  S[2] = ((COV_IN_MEMORY ? __ldg(&cov_b[2]) : cov_b[2]) + G[2]) - k0 * m2;
+  S[3] = ((COV_IN_MEMORY ? __ldg(&cov_b[3]) : cov_b[3]) + G[3]) - k1 * m1;
+  S[4] = ((COV_IN_MEMORY ? __ldg(&cov_b[4]) : cov_b[4]) + G[4]) - k1 * m2;
+  S[5] = ((COV_IN_MEMORY ? __ldg(&cov_b[5]) : cov_b[5]) + G[5]) - k2 * m2;
   sym3_inverse(S, M);
 }
 
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
         if (rec < 0) continue;
         const VoxRec& v = tgt.vrec[rec];
         double M[6];
-        vgicp_mahalanobis(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
+        vgicp_mahalanobis<true>(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
         const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
         const double w = __ldg(&v.w);
         ++ncorr;
@@ -311,18 +312,38 @@ __device__ __forceinline__ int vgicp_probe(const CloudView& tgt, const double* x
 }
 
 // One correspondence of the VGICP cost: source point i of the pair against voxel record rec.
+// SEL 0: phase decided at run time (28 accumulators); 1: linearisation only; 2: trial only (acc[0] is the error sum).
+template <int SEL>
 __device__ __forceinline__ void vgicp_point(double* acc, const CloudView& src, const CloudView& tgt, const double* sx0, const double* sxi,
                                             const double* sG, int i, int rec, bool lin) {
   const float4 p = __ldg(&src.pts[i]);
   const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-  double ax, ay, az;
-  apply_pose(sx0, px, py, pz, ax, ay, az);
   const VoxRec& v = tgt.vrec[rec];
   double M[6];
-  vgicp_mahalanobis(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
-  const double m0 = __ldg(&v.mean[0]), m1 = __ldg(&v.mean[1]), m2 = __ldg(&v.mean[2]);
-  const double w = __ldg(&v.w);
-  if (lin) {
+  double m0, m1, m2, w;
+  if constexpr (SEL == 2) {
+    // the trial kernel has registers to spare: the record's 80 bytes as five 16-byte loads (half the wavefronts in the L1 data pipe)
+    const double2* q = reinterpret_cast<const double2*>(&v);
+    const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4);
+    const double cb[6] = {r1.y, r2.x, r2.y, r3.x, r3.y, r4.x};
+    vgicp_mahalanobis<false>(sx0, sG, src.nrm + (size_t)i * 4, cb, M);
+    m0 = r0.x; m1 = r0.y; m2 = r1.x; w = r4.y;
+  } else {
+    vgicp_mahalanobis<true>(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
+    m0 = __ldg(&v.mean[0]); m1 = __ldg(&v.mean[1]); m2 = __ldg(&v.mean[2]);
+    w = __ldg(&v.w);
+  }
+  if constexpr (SEL == 2) {
+    double bx, by, bz;
+    apply_pose(sxi, px, py, pz, bx, by, bz);
+    const double e0 = m0 - bx, e1 = m1 - by, e2 = m2 - bz;
+    const double Me0 = M[0] * e0 + M[1] * e1 + M[2] * e2;
+    const double Me1 = M[1] * e0 + M[3] * e1 + M[4] * e2;
+    const double Me2 = M[2] * e0 + M[4] * e1 + M[5] * e2;
+    acc[0] += w * (e0 * Me0 + e1 * Me1 + e2 * Me2);
+  } else if (SEL == 1 || lin) {
+    double ax, ay, az;
+    apply_pose(sx0, px, py, pz, ax, ay, az);
     accumulate(acc, M, ax, ay, az, m0 - ax, m1 - ay, m2 - az, w, true);
   } else {
     double bx, by, bz;
@@ -332,24 +353,39 @@ __device__ __forceinline__ void vgicp_point(double* acc, const CloudView& src, c
 }
 
 constexpr int kVgRing = 64;  // per warp: <= 31 left over + 32 new
-__global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
-                                                          const LsqState* __restrict__ states, double* __restrict__ partials) {
+// SEL 0: one kernel for both phases (a pair's blocks follow its phase); 1 / 2: only the pairs in the linearisation / trial phase
+// (the other pairs' blocks exit at once).  The trial pass needs one accumulator instead of 28 and runs with four blocks per SM
+// (64 registers) instead of two, so a round launches the two specialisations back to back instead of the common kernel
+// (B2R_VGICP_SPLIT=0 restores that): 22.9 -> 21.8 ms per 4096-pair step.  Three blocks for the linearisation (80 registers, 220 B
+// of spills) lost: 24.3 ms.
+#ifndef B2R_VG_TRIAL_BLOCKS
+#define B2R_VG_TRIAL_BLOCKS 4
+#endif
+#ifndef B2R_VG_LIN_BLOCKS
+#define B2R_VG_LIN_BLOCKS 2
+#endif
+template <int SEL>
+__global__ void __launch_bounds__(256, SEL == 2 ? B2R_VG_TRIAL_BLOCKS : B2R_VG_LIN_BLOCKS) vgicp_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+                                                                          const LsqState* __restrict__ states, double* __restrict__ partials) {
   const int pair = blockIdx.y;
   const LsqState& st = states[pair];
   const int phase = st.phase;
   if (phase == PH_DONE) return;
+  if (SEL == 1 && phase != PH_LINEARIZE) return;
+  if (SEL == 2 && phase != PH_TRIAL) return;
   const CloudView& src = views[pairs[pair].src];
   const CloudView& tgt = views[pairs[pair].tgt];
+  constexpr int NA = SEL == 2 ? 1 : kAcc;
   __shared__ double sx0[12], sxi[12], sG[6];
-  __shared__ double red[kAcc * 8];
+  __shared__ double red[NA * 8];
   __shared__ int2 s_ring[8][kVgRing];  // (source point, voxel record) hits of each warp
   if (threadIdx.x < 12) { sx0[threadIdx.x] = st.x0[threadIdx.x]; sxi[threadIdx.x] = st.xi[threadIdx.x]; }
   if (threadIdx.x == 32) rrt(st.x0, sG);
   __syncthreads();
-  const bool lin = phase == PH_LINEARIZE;
-  double acc[kAcc];
+  const bool lin = SEL == 1 || (SEL == 0 && phase == PH_LINEARIZE);
+  double acc[NA];
 #pragma unroll
-  for (int t = 0; t < kAcc; ++t) acc[t] = 0.0;
+  for (int t = 0; t < NA; ++t) acc[t] = 0.0;
   int ncorr = 0;
   const int n = src.n, s = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -382,7 +418,7 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
       const int pos = head + lane;
       if (pos < tail) {
         const int2 it = ring[pos & (kVgRing - 1)];
-        vgicp_point(acc, src, tgt, sx0, sxi, sG, it.x, it.y, lin);
+        vgicp_point<SEL>(acc, src, tgt, sx0, sxi, sG, it.x, it.y, lin);
         ++ncorr;
       }
       head = min(head + 32, tail);
@@ -392,13 +428,17 @@ __global__ void __launch_bounds__(256, 2) vgicp_eval_kernel(const CloudView* __r
     rec1 = rec2;
   }
   double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * kPart;
-  if (lin) {
-    block_reduce_butterfly<kAcc>(acc, red, out);
-    const int bc = block_sum_int(ncorr, (int*)red);
-    if (threadIdx.x == 0) out[28] = (double)bc;
+  if constexpr (SEL == 2) {
+    block_reduce_to<1>(acc, red, out + 27);
   } else {
-    double e[1] = {acc[27]};
-    block_reduce_to<1>(e, red, out + 27);
+    if (lin) {
+      block_reduce_butterfly<kAcc>(acc, red, out);
+      const int bc = block_sum_int(ncorr, (int*)red);
+      if (threadIdx.x == 0) out[28] = (double)bc;
+    } else {
+      double e[1] = {acc[27]};
+      block_reduce_to<1>(e, red, out + 27);
+    }
   }
 }
 
@@ -713,7 +753,7 @@ static void launch_lsq_eval(Ctx& ctx, int method, dim3 grid, const CloudView* vi
                             uint8_t* corr_valid) {
   static const bool pipelined = [] { const char* e = getenv("B2R_VGICP_PIPE"); return !e || atoi(e) != 0; }();
   if (method == B2R_FAST_VGICP && prm.neighbor_search == B2R_DIRECT1 && !corr_out && pipelined)
-    B2R_LAUNCH(ctx, vgicp_eval_kernel, grid, 256, 0, views, pairs, states, partials);
+    B2R_LAUNCH(ctx, vgicp_eval_kernel<0>, grid, 256, 0, views, pairs, states, partials);
   else if (method == B2R_FAST_VGICP)
     B2R_LAUNCH(ctx, lsq_eval_kernel<B2R_FAST_VGICP>, grid, 256, 0, views, pairs, states, prm, partials, corr_cache, corr_off, corr_out, corr_valid);
   else if (method == B2R_FAST_GICP)
@@ -795,11 +835,13 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
   void* eval_args_pipe[] = {&a_views, &a_pairs, &a_states_c, &a_part};
   void* eval_args_gen[] = {&a_views, &a_pairs, &a_states_c, &prm, &a_part, &a_corr, &a_coff, &a_null_i, &a_null_b};
   void* step_args[] = {&a_states, &prm, &a_part_c, &a_chunks, &a_src_n, &la};
-  const void* eval_fn = pipe ? (const void*)vgicp_eval_kernel
+  static const bool split = [] { const char* e = getenv("B2R_VGICP_SPLIT"); return !e || atoi(e) != 0; }();
+  const void* eval2_fn = (pipe && split) ? (const void*)vgicp_eval_kernel<2> : nullptr;
+  const void* eval_fn = pipe ? (split ? (const void*)vgicp_eval_kernel<1> : (const void*)vgicp_eval_kernel<0>)
                              : (cfg.method == B2R_FAST_VGICP ? (const void*)lsq_eval_kernel<B2R_FAST_VGICP>
                                 : (cfg.method == B2R_FAST_GICP ? (const void*)lsq_eval_kernel<B2R_FAST_GICP> : (const void*)lsq_eval_kernel<B2R_SMALL_GICP>));
   run_device_loop(ctx, eval_fn, dim3(chunks, np), dim3(256), pipe ? eval_args_pipe : eval_args_gen, (const void*)lsq_step_kernel,
-                  dim3((np + 3) / 4), dim3(128), step_args, la, ctl.p, np, max_rounds, PROF_LSQ_EVAL);
+                  dim3((np + 3) / 4), dim3(128), step_args, la, ctl.p, np, max_rounds, PROF_LSQ_EVAL, eval2_fn);
   B2R_LAUNCH(ctx, lsq_rows_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_rows);
   if (ctx.profile) {
     // per evaluation pass 40 B per source point + one 64 B voxel record (VGICP) or 40 B target
