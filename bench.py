@@ -384,6 +384,16 @@ def run_b2r(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     max_ms, max_e2e_ms = float(tt[0]), float(tt[1])
+    # per-rank picture of the last profiled step (untimed): pairs, clouds and the device time of each stage on every rank, so that a
+    # scaling loss can be attributed (imbalance of the partition vs fixed cost per rank)
+    lt = reg.last_timings()
+    mine_t = torch.tensor([float(len(mine)), float(len(needed)), float(sum(len(pool_np[c]) for c in needed)), lt["prep_ms"], lt["optimize_ms"],
+                           lt["fitness_ms"], lt["total_ms"]], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine_t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine_t)
+    else:
+        per_rank = [mine_t]
     if rank == 0:
         value = n_pairs * args.steps / (max_ms / 1000.0)
         e2e = n_pairs * args.steps / (max_e2e_ms / 1000.0)
@@ -435,6 +445,9 @@ def run_b2r(args):
                          "kernels": per_kernel},
             "converged_fraction": conv,
             "rank0_pairs": int(len(mine)), "rank0_clouds": len(needed),
+            "ranks": [{"pairs": int(t[0]), "clouds": int(t[1]), "cloud_points": int(t[2]), "prep_ms": round(float(t[3]), 3),
+                       "optimize_ms": round(float(t[4]), 3), "fitness_ms": round(float(t[5]), 3), "device_ms": round(float(t[6]), 3)}
+                      for t in per_rank],
         }
         if world == 1 and not args.no_extras:
             line["chain"] = run_chain(torch, B, reg, dev, flush, args)

@@ -518,8 +518,9 @@ struct CovVisitor {
     if (knn_row && a.cnt < k) knn_row[a.cnt] = __float_as_int(p.w);
     ++a.cnt;
   }
-  __device__ __forceinline__ void test(const float4& p, int) {
-    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4& p, int, float d2) {
     if (d2 < dk || (ties && d2 == dk)) add(p);
   }
 };
@@ -529,8 +530,10 @@ struct TieVisitor {
   int after, found;
   __device__ __forceinline__ float thr() const { return dk * (1.f + 1e-6f); }
   __device__ __forceinline__ bool stop(float s) const { return s > dk * kGapSlack; }
-  __device__ __forceinline__ void test(const float4& p, int j) {
-    if (j > after && j < found && dist2_flann(qx, qy, qz, p.x, p.y, p.z) == dk) found = j;
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int j, float d2) {
+    if (j > after && j < found && d2 == dk) found = j;
   }
 };
 // more than k points within dk (exact ties at the k-th distance): strictly closer ones, then ties by ascending position.

@@ -388,12 +388,23 @@ __device__ __forceinline__ int block_sum_int(int v, int* smem) {
 }
 
 // FLANN L2_Simple squared distance: float accumulation in dimension order, no FMA contraction.
+// The x and y differences and their squares are formed by Blackwell's packed-pair FP32 instructions (FFMA2 / FMUL2: two IEEE
+// round-to-nearest results per issue slot, sm_100 only): q - p = fma(p, -1, q) is rounded once, exactly like the subtraction,
+// so the value is bit-identical to the scalar chain — 6 instead of 8 issue slots per candidate in kernels that are bound by
+// instruction issue (ncu: knn_cov, fitness).  B2R_NO_F32X2 restores the scalar form.
 __device__ __forceinline__ float dist2_flann(float ax, float ay, float az, float bx, float by, float bz) {
+#if defined(B2R_NO_F32X2)
   float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
   float r = __fmul_rn(dx, dx);
   r = __fadd_rn(r, __fmul_rn(dy, dy));
   r = __fadd_rn(r, __fmul_rn(dz, dz));
   return r;
+#else
+  const float2 d = __ffma2_rn(make_float2(bx, by), make_float2(-1.f, -1.f), make_float2(ax, ay));
+  const float2 sq = __fmul2_rn(d, d);
+  const float dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
+#endif
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -113,6 +113,21 @@ struct TilePts {
 // metres, not ulps, but it vanishes for a gap of zero, where s = fl(dx^2) <= the float distance exactly).
 // The query's own row comes first: a good k-th distance early prunes most of the rest.
 constexpr float kGapSlack = 1.f + 2e-6f;
+// One candidate: FLANN's float squared distance to the query (bit-identical to dist2_flann) and, on the way, fl(dx^2) for the
+// sweep's stop test — the x / y differences and squares come out of one FFMA2 + one FMUL2 (packed-pair FP32, sm_100).
+struct CandD2 { float dx, dx2, d2; };
+__device__ __forceinline__ CandD2 cand_d2(float qx, float qy, float qz, const float4& p) {
+#if defined(B2R_NO_F32X2)
+  const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+  const float dx2 = __fmul_rn(dx, dx);
+  return CandD2{dx, dx2, __fadd_rn(__fadd_rn(dx2, __fmul_rn(dy, dy)), __fmul_rn(dz, dz))};
+#else
+  const float2 d = __ffma2_rn(make_float2(p.x, p.y), make_float2(-1.f, -1.f), make_float2(qx, qy));
+  const float2 sq = __fmul2_rn(d, d);
+  const float dz = __fsub_rn(qz, p.z);
+  return CandD2{d.x, sq.x, __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz))};
+#endif
+}
 // How a row is swept (A/B-measured on the B200):
 //   VISIT_CELL3   the query's x-cell unconditionally (independent loads, unrolled by the compiler), then a sweep towards smaller
 //                 and one towards larger x, each stopped by stop(dx^2 + rg2)
@@ -130,38 +145,42 @@ __device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q
   const int row_s = __ldg(&c.cell_start[rowbase]), row_e = __ldg(&c.cell_start[rowbase + c.gd[0]]);
   if (row_s == row_e) return;
   const typename S::Row sr = src.row(y, z);
+  const float qy = v.qy_f(), qz = v.qz_f();
   if constexpr ((MODE & VISIT_SWEEP_MASK) == VISIT_MERGED) {
     const int cs = __ldg(&c.cell_start[rowbase + q.cx]);
     for (int j = cs; j < row_e; ++j) {  // the query's x-cell, then towards larger x
       const float4 p = src.load(c, sr, j);
-      const float dx = __fsub_rn(qx, p.x);
-      if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) {
-        if (!(dx > 0.f)) break;  // at or beyond the query: everything after it is farther still
-        continue;                // inside the cell, before the query: the following points are closer
+      const CandD2 d = cand_d2(qx, qy, qz, p);
+      if (v.stop(__fadd_rn(d.dx2, rg2))) {
+        if (!(d.dx > 0.f)) break;  // at or beyond the query: everything after it is farther still
+        continue;                  // inside the cell, before the query: the following points are closer
       }
-      v.test(p, j);
+      v.test(p, j, d.d2);
     }
     for (int j = cs - 1; j >= row_s; --j) {  // towards smaller x
       const float4 p = src.load(c, sr, j);
-      const float dx = __fsub_rn(qx, p.x);
-      if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
-      v.test(p, j);
+      const CandD2 d = cand_d2(qx, qy, qz, p);
+      if (v.stop(__fadd_rn(d.dx2, rg2))) break;
+      v.test(p, j, d.d2);
     }
   } else {
     const int cs = __ldg(&c.cell_start[rowbase + q.cx]), ce = __ldg(&c.cell_start[rowbase + q.cx + 1]);
-    for (int j = cs; j < ce; ++j) v.test(src.load(c, sr, j), j);
+    for (int j = cs; j < ce; ++j) {
+      const float4 p = src.load(c, sr, j);
+      v.test(p, j, cand_d2(qx, qy, qz, p).d2);
+    }
     if constexpr ((MODE & VISIT_SWEEP_MASK) == VISIT_CELL3) {
       for (int j = cs - 1; j >= row_s; --j) {  // towards smaller x
         const float4 p = src.load(c, sr, j);
-        const float dx = __fsub_rn(qx, p.x);
-        if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
-        v.test(p, j);
+        const CandD2 d = cand_d2(qx, qy, qz, p);
+        if (v.stop(__fadd_rn(d.dx2, rg2))) break;
+        v.test(p, j, d.d2);
       }
       for (int j = ce; j < row_e; ++j) {  // towards larger x
         const float4 p = src.load(c, sr, j);
-        const float dx = __fsub_rn(qx, p.x);
-        if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
-        v.test(p, j);
+        const CandD2 d = cand_d2(qx, qy, qz, p);
+        if (v.stop(__fadd_rn(d.dx2, rg2))) break;
+        v.test(p, j, d.d2);
       }
     } else {
       if (cs > row_s) {
@@ -171,9 +190,9 @@ __device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q
           const bool more = j > row_s;
           float4 pn = p;
           if (more) pn = src.load(c, sr, j - 1);  // in flight while p is tested
-          const float dx = __fsub_rn(qx, p.x);
-          if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
-          v.test(p, j);
+          const CandD2 d = cand_d2(qx, qy, qz, p);
+          if (v.stop(__fadd_rn(d.dx2, rg2))) break;
+          v.test(p, j, d.d2);
           if (!more) break;
           p = pn; --j;
         }
@@ -185,9 +204,9 @@ __device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q
           const bool more = j + 1 < row_e;
           float4 pn = p;
           if (more) pn = src.load(c, sr, j + 1);
-          const float dx = __fsub_rn(qx, p.x);
-          if (v.stop(__fadd_rn(__fmul_rn(dx, dx), rg2))) break;
-          v.test(p, j);
+          const CandD2 d = cand_d2(qx, qy, qz, p);
+          if (v.stop(__fadd_rn(d.dx2, rg2))) break;
+          v.test(p, j, d.d2);
           if (!more) break;
           p = pn; ++j;
         }
@@ -323,8 +342,9 @@ struct TopkVisitor {
   }
   __device__ __forceinline__ float thr() const { return d[K - 1]; }
   __device__ __forceinline__ bool stop(float s) const { return s > lim; }
-  __device__ __forceinline__ void test(const float4& p, int) {
-    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int, float d2) {
     if (d2 < d[K - 1]) { topk_insert<K>(d, d2); lim = d[K - 1] * kGapSlack; }
   }
 };
@@ -355,8 +375,9 @@ struct TopkListVisitor {
   // tie-inclusive pruning: a candidate at exactly the K-th distance must still be seen (and logged)
   __device__ __forceinline__ float thr() const { return lim; }
   __device__ __forceinline__ bool stop(float s) const { return s > lim; }
-  __device__ __forceinline__ void test(const float4& p, int j) {
-    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int j, float d2) {
 #ifdef B2R_KNN_STATS
     ++tested;
 #endif
@@ -406,8 +427,9 @@ struct TopkKeyVisitor {
   __device__ __forceinline__ float worst() const { return d[K - 1] == ~0ull ? INFINITY : __uint_as_float((unsigned)(d[K - 1] >> 32)); }
   __device__ __forceinline__ float thr() const { return worst() * (1.f + 1e-6f); }  // equal distances still compete on position
   __device__ __forceinline__ bool stop(float s) const { return s > worst() * kGapSlack; }
-  __device__ __forceinline__ void test(const float4& p, int j) {
-    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int j, float d2) {
     const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
     if (key < d[K - 1]) {
 #pragma unroll
@@ -426,8 +448,9 @@ struct Nn1Visitor {
   float lim;  // min(best, cut) * kGapSlack
   __device__ __forceinline__ float thr() const { return lim; }
   __device__ __forceinline__ bool stop(float s) const { return s > lim; }
-  __device__ __forceinline__ void test(const float4& p, int j) {
-    const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int j, float d2) {
     if (d2 < best || (d2 == best && j < best_pos)) { best = d2; best_pos = j; lim = fminf(d2, cut) * kGapSlack; }
   }
 };
@@ -464,8 +487,10 @@ struct Nn1DistVisitor {
   float lim;  // min(best, cut) * kGapSlack
   __device__ __forceinline__ float thr() const { return lim; }
   __device__ __forceinline__ bool stop(float s) const { return s > lim; }
-  __device__ __forceinline__ void test(const float4& p, int) {
-    best = fminf(best, dist2_flann(qx, qy, qz, p.x, p.y, p.z));
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int, float d2) {
+    best = fminf(best, d2);
     lim = fminf(best, cut) * kGapSlack;
   }
 };
@@ -505,7 +530,9 @@ struct Nn1VisitorD {
   }
   __device__ __forceinline__ float thr() const { return cutf; }
   __device__ __forceinline__ bool stop(float s) const { return s > cutf; }  // cutf carries a 0.1 mm margin of its own
-  __device__ __forceinline__ void test(const float4& p, int j) {
+  __device__ __forceinline__ float qy_f() const { return fy; }
+  __device__ __forceinline__ float qz_f() const { return fz; }
+  __device__ __forceinline__ void test(const float4& p, int j, float) {
     const double d0 = (double)p.x - qx, d1 = (double)p.y - qy, d2 = (double)p.z - qz;
     const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d2, d2)), __dmul_rn(d1, d1));
     if (d < best || (d == best && j < best_pos)) {
@@ -547,8 +574,10 @@ struct RadiusVisitor {
   int cnt, stop_above;
   __device__ __forceinline__ float thr() const { return cnt > stop_above ? 0.f : r2; }
   __device__ __forceinline__ bool stop(float s) const { return s > r2 * kGapSlack || cnt > stop_above; }
-  __device__ __forceinline__ void test(const float4& p, int) {
-    if (dist2_flann(qx, qy, qz, p.x, p.y, p.z) < r2) ++cnt;
+  __device__ __forceinline__ float qy_f() const { return qy; }
+  __device__ __forceinline__ float qz_f() const { return qz; }
+  __device__ __forceinline__ void test(const float4&, int, float d2) {
+    if (d2 < r2) ++cnt;
   }
 };
 __device__ __forceinline__ int radius_count(const CloudView& c, float qx, float qy, float qz, float r2, int stop_above) {
