@@ -151,8 +151,14 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
 #pragma unroll
     for (int t = 0; t < 12; ++t) Tf[t] = (float)sx0[t];
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < src.n; i += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(&src.pts[i]);
+  // FAST_GICP / SMALL_GICP walk the source in ITS cell order (spts) when it has one: a warp's 32 nearest-neighbour queries are
+  // then neighbours in space (same target rows, similar sweep lengths), whatever order the cloud came in — the same measure that
+  // took the fitness kernel from 10.1 to 7.7 ms.  `i` stays the original index (covariance, debug export); the correspondence
+  // cache is indexed by the walk position, consistently in both phases.
+  const bool cell_walk = METHOD != B2R_FAST_VGICP && src.spts != nullptr;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < src.n; j += gridDim.x * blockDim.x) {
+    const float4 p = cell_walk ? __ldg(&src.spts[j]) : __ldg(&src.pts[j]);
+    const int i = cell_walk ? __float_as_int(p.w) : j;
     const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
     double ax, ay, az;
     apply_pose(sx0, px, py, pz, ax, ay, az);
@@ -201,11 +207,11 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
       // r' = R^T r this is the same accumulation as above on [skew(p) | -I].
       int pos;
       if (!lin && cc) {
-        pos = cc[i];
+        pos = cc[j];
       } else {
         double d2;
         pos = nn1_search_d(tgt, ax, ay, az, prm.corr_thr2, d2);
-        if (cc) cc[i] = pos;
+        if (cc) cc[j] = pos;
       }
       if (corr_out) corr_out[i] = pos >= 0 ? __float_as_int(tgt.spts[pos].w) : -1;
       if (pos >= 0) {
@@ -244,13 +250,13 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
       int pos;
       bool ok;
       if (!lin && cc) {
-        pos = cc[i];
+        pos = cc[j];
         ok = pos >= 0;
       } else {
         float d2;
         pos = nn1_search(tgt, q[0], q[1], q[2], prm.corr_max_d2, d2);
         ok = pos >= 0 && (double)d2 < prm.corr_thr2;
-        if (cc) cc[i] = ok ? pos : -1;
+        if (cc) cc[j] = ok ? pos : -1;
       }
       if (corr_out) corr_out[i] = ok ? __float_as_int(tgt.spts[pos].w) : -1;
       if (ok) {
