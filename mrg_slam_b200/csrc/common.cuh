@@ -203,13 +203,13 @@ struct DBuf {
 // ------------------------------------------------------------------------------------------------
 // Device-side view of a cloud and of its cached structures.  Kernels that work on many clouds take an
 // array of these and pick views[blockIdx.y].
-struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap); 96 B, the first 80 are what an evaluation reads.
-  double mean[3];    // (Measured and rejected on the 4096-pair batch, where the evaluation kernels run at 95 % of the L1 data pipe's
-  double cov[6];     // wavefront rate: one 128-byte line per record, 21.8 -> 23.8 ms per step — the larger footprint costs more L1 / L2
-  double w;          // hits than the straddling records cost wavefronts; the 80 bytes as five 16-byte loads instead of ten 8-byte
-  int n;             // ones, 21.8 -> 22.4 ms — the linearisation kernel, at its 128-register limit, starts to spill.)
-  int cell;          // w = sqrt(n), the weight of the voxel's residual; cov = xx,xy,xz,yy,yz,zz; cell = dense table index (export)
-  double pad;
+struct VoxRec {      // VGICP Gaussian voxel (fast_gicp GaussianVoxelMap); 96 B, the first 80 are what an evaluation reads,
+  double cov[6];     // as five 16-byte loads in the order it uses them: covariance (xx,xy,xz,yy,yz,zz) for the Mahalanobis matrix,
+  double mean[3];    // then mean and weight for the residual.
+  double w;          // w = sqrt(n), the weight of the voxel's residual
+  int n;             // (Measured and rejected on the 4096-pair batch, where the evaluation kernels run at 82-95 % of the L1 data
+  int cell;          // pipe's wavefront rate: one 128-byte line per record, 21.8 -> 23.8 ms per step — the larger footprint costs more
+  double pad;        // L1 / L2 hits than the straddling records cost wavefronts.)  cell = dense table index (export)
 };
 static_assert(sizeof(VoxRec) == 96, "VoxRec layout");
 struct NdtRec {      // NDT leaf (pclomp::VoxelGridCovariance)

@@ -327,17 +327,16 @@ __device__ __forceinline__ void vgicp_point(double* acc, const CloudView& src, c
   const VoxRec& v = tgt.vrec[rec];
   double M[6];
   double m0, m1, m2, w;
-  if constexpr (SEL == 2) {
-    // the trial kernel has registers to spare: the record's 80 bytes as five 16-byte loads (half the wavefronts in the L1 data pipe)
+  {
+    // the record's 80 hot bytes as five 16-byte loads (half the requests of ten 8-byte ones in the L1 data pipe), in two stages so
+    // that the linearisation kernel, at its 128-register limit, does not hold all twenty registers at once
     const double2* q = reinterpret_cast<const double2*>(&v);
-    const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4);
-    const double cb[6] = {r1.y, r2.x, r2.y, r3.x, r3.y, r4.x};
+    const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+    const double cb[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
     vgicp_mahalanobis<false>(sx0, sG, src.nrm + (size_t)i * 4, cb, M);
-    m0 = r0.x; m1 = r0.y; m2 = r1.x; w = r4.y;
-  } else {
-    vgicp_mahalanobis<true>(sx0, sG, src.nrm + (size_t)i * 4, v.cov, M);
-    m0 = __ldg(&v.mean[0]); m1 = __ldg(&v.mean[1]); m2 = __ldg(&v.mean[2]);
-    w = __ldg(&v.w);
+    if (SEL != 2) asm volatile("" ::: "memory");
+    const double2 r3 = __ldg(q + 3), r4 = __ldg(q + 4);
+    m0 = r3.x; m1 = r3.y; m2 = r4.x; w = r4.y;
   }
   if constexpr (SEL == 2) {
     double bx, by, bz;
@@ -413,8 +412,16 @@ __global__ void __launch_bounds__(256, SEL == 2 ? B2R_VG_TRIAL_BLOCKS : B2R_VG_L
     if (hit) {
       ring[(tail + __popc(m & ((1u << lane) - 1u))) & (kVgRing - 1)] = make_int2(i, rec1);
       const char* vr = (const char*)&tgt.vrec[rec1];
-      prefetch_l1(vr); prefetch_l1(vr + 32); prefetch_l1(vr + 64); prefetch_l1(vr + 79);  // mean, cov, w: the first 80 bytes
-      prefetch_l1(src.nrm + (size_t)i * 4);
+#ifndef B2R_VG_PREFETCH_LIN
+#define B2R_VG_PREFETCH_LIN 0
+#endif
+      // Prefetching the hit's voxel record and normal into L1 (CCTL.PF1) paid when one kernel served both phases at two blocks
+      // per SM; with the split kernels it costs more L1 requests than it hides latency (measured per 4096-pair step: 20.83 ms
+      // with the prefetches, 20.54 without).
+      if (SEL != 2 && B2R_VG_PREFETCH_LIN) {
+        prefetch_l1(vr); prefetch_l1(vr + 32); prefetch_l1(vr + 64); prefetch_l1(vr + 79);  // mean, cov, w: the first 80 bytes
+        prefetch_l1(src.nrm + (size_t)i * 4);
+      }
     }
     tail += __popc(m);
     __syncwarp();

@@ -24,7 +24,7 @@ def run(factor,xf,nwarps=200):
     Bt=((T[:3,:3]@B[so].T).T+T[:3,3])
     rng=np.random.default_rng(1)
     starts=rng.choice(len(Bt)//32-1,nwarps,replace=False)*32
-    tot_cand=0; costA=0; costB=0; costC=0; nq=0; rows_tot=0
+    tot_cand=0; costA=0; costB=0; costC=0; costD=0; nq=0; rows_tot=0
     for s0 in starts:
         lanes=[]
         for q in Bt[s0:s0+32]:
@@ -72,6 +72,10 @@ def run(factor,xf,nwarps=200):
             for v in l:
                 s=slots[v[0]]; s[0]=max(s[0],v[1]); s[1]=max(s[1],v[2]); s[2]=max(s[2],v[3])
         costC+=sum(sum(s) for s in slots.values())
-    print(f'factor {factor} xf {xf}: cands/query {tot_cand/nq:.1f} rows/query {rows_tot/nq:.2f}  per-warp candidate-steps: flattened {costA/nwarps:.1f}  per-lane-rows {costB/nwarps:.1f}  lockstep {costC/nwarps:.1f}   ideal {tot_cand/nq:.1f}')
-for f,xf in [(2.5,0.34),(2.5,0.17),(1.8,0.34),(1.3,0.34),(3.5,0.34)]:
+        slotsD=collections.defaultdict(int)
+        for l in lanes:
+            for v in l: slotsD[v[0]]=max(slotsD[v[0]], v[1]+v[2]+v[3])
+        costD+=sum(slotsD.values())
+    print(f'factor {factor} xf {xf}: cands/query {tot_cand/nq:.1f} rows/query {rows_tot/nq:.2f}  per-warp candidate-steps: flattened {costA/nwarps:.1f}  per-lane-rows {costB/nwarps:.1f}  lockstep {costC/nwarps:.1f}  lockstep-rows+merged-row-loop {costD/nwarps:.1f}   ideal {tot_cand/nq:.1f}')
+for f,xf in [(2.5,0.34),(2.5,0.17)]:
     run(f,xf)
