@@ -204,8 +204,11 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vect
     // dv, dblk and the optimisers' buffers are released stream-ordered: after everything enqueued above
     if (all_live) {
       if (out_all) {
-        B2R_CUDA(cudaMemcpyAsync(out_all, d_rows, sizeof(b2r_result) * np, cudaMemcpyDeviceToHost, ctx.stream));
+        const size_t tot = sizeof(b2r_result) * np;
+        void* stage = ctx.pinned_buf(tot);
+        B2R_CUDA(cudaMemcpyAsync(stage ? stage : (void*)out_all, d_rows, tot, cudaMemcpyDeviceToHost, ctx.stream));
         B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+        if (stage) memcpy(out_all, stage, tot);
         tr.mark("rows_d2h+sync");
       }
       tr.print("run_align (host ms; device work is asynchronous)");
@@ -322,6 +325,7 @@ void b2r_destroy(b2r_handle* hh) {
     if (h.user_ev[i]) cudaEventDestroy(h.user_ev[i]);
   h.ctx.prof_resolve();
   h.ctx.reap_graphs(true);
+  if (h.ctx.pinned) { cudaFreeHost(h.ctx.pinned); h.ctx.pinned = nullptr; h.ctx.pinned_bytes = 0; }
   if (h.ctx.d_graph_rounds) cudaFree(h.ctx.d_graph_rounds);
   for (cudaEvent_t e : h.ctx.ev_pool) cudaEventDestroy(e);
   h.ctx.ev_pool.clear();
@@ -641,8 +645,11 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
   return guarded(hh, [&](Handle& h) {
     if (!cfg) throw Error(B2R_ERR_INVALID_ARG, "null config");
     DevCloud cur;
+    HostTrace tr;  // B2R_TRACE=1: stage times with a synchronisation after each stage (attribution only)
+    auto mark = [&](const char* name) { if (tr.on) { cudaStreamSynchronize(h.ctx.stream); tr.mark(name); } };
     load_points(h.ctx, in, n, stride_bytes, memspace, cur.pts);
     cur.n = (int)n;
+    mark("load");
     // cloud_callback order (apps/prefiltering_component.cpp:149-151): distance_filter, downsample, outlier_removal.
     // When VoxelGrid follows the distance filter, the filter is folded into VoxelGrid's own passes (no compaction,
     // no count read-back in between); the result is identical.
@@ -659,6 +666,7 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
       filter_voxelgrid(h.ctx, cur.pts.p, cur.n, cfg->downsample_resolution, cfg->downsample_min_points_per_voxel, nxt, ovf,
                        fold ? range : nullptr);
       cur = std::move(nxt);
+      mark("voxelgrid");
     }
     if (cfg->outlier_removal_method == 1) {
       DevCloud nxt;
@@ -669,7 +677,10 @@ b2r_status b2r_prefilter(b2r_handle* hh, const b2r_prefilter_config* cfg, const 
       filter_radius(h.ctx, h.cfg, cur.pts.p, cur.n, cfg->radius_radius, cfg->radius_min_neighbors, nxt, &cur);
       cur = std::move(nxt);
     }
+    mark("outlier");
     finish_filter(h, cur, out, m, memspace);
+    mark("store");
+    tr.print("prefilter");
   });
 }
 

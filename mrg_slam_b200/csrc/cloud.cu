@@ -25,7 +25,7 @@ CloudView Cloud::view() const {
   v.h = h; v.inv_h = h > 0 ? 1.0f / h : 0.f;
   v.hx = hx; v.inv_hx = hx > 0 ? 1.0f / hx : 0.f;
   for (int d = 0; d < 3; ++d) v.gd[d] = gd[d];
-  v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.cell_tmp = cell_tmp.p; v.spts = spts.p;
+  v.ncell = ncell; v.cell_start = cell_start.p; v.cell_cnt = cell_cnt.p; v.cell_tmp = cell_tmp.p; v.spts = spts.p; v.spair = spair.p;
   v.cov = cov.p; v.nrm = nrm.p;
   v.vres = vres;
   for (int d = 0; d < 3; ++d) { v.vmin[d] = vmin[d]; v.vd[d] = vd[d]; }
@@ -341,7 +341,14 @@ __global__ void grid_rank_kernel(const CloudView* __restrict__ views) {
         const int2 o = c.cell_tmp[t];
         rank += (o.x < me.x || (o.x == me.x && o.y < me.y)) ? 1 : 0;
       }
-      c.spts[s + rank] = make_float4(p.x, p.y, p.z, __int_as_float(me.y));
+      const int pos = s + rank;
+      c.spts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(me.y));
+      float* pr = reinterpret_cast<float*>(c.spair) + (size_t)(pos >> 1) * 8 + (pos & 1);
+      pr[0] = p.x; pr[2] = p.y; pr[4] = p.z; pr[6] = __int_as_float(me.y);
+      if (j == 0 && (c.n & 1)) {  // the odd cloud's last record: its second point lies at +inf
+        float* pe = reinterpret_cast<float*>(c.spair) + (size_t)(c.n >> 1) * 8 + 1;
+        pe[0] = INFINITY; pe[2] = INFINITY; pe[4] = INFINITY; pe[6] = __int_as_float(-1);
+      }
     } else {
       int* order = MODE == GRID_VGICP ? c.v_order : c.n_order;
       const int* tmp = order + c.n;
@@ -1034,6 +1041,7 @@ void clouds_prepare(Ctx& ctx, const b2r_config& cfg, const std::vector<Cloud*>& 
       plan.want_zeroed(c->cell_cnt.p, (size_t)c->ncell);
       plan.want(c->cell_tmp.p, (size_t)c->n);
       plan.want(c->spts.p, (size_t)c->n);
+      plan.want(c->spair.p, ((size_t)c->n + 1) / 2 * 2);
       todo_grid.push_back((int)i);
     }
     const bool new_cov = nd.cov_k > 0 && (c->cov_k != nd.cov_k || c->cov_mode != nd.cov_mode);

@@ -118,6 +118,21 @@ struct Ctx {
     }
   }
   int num_sms = 148;
+  // pinned host staging for small device->host results (result tables, counters): a copy into pageable memory goes through the
+  // driver's own bounce buffer and costs several times the transfer
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* pinned_buf(size_t bytes) {
+    if (bytes > pinned_bytes) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      pinned_bytes = 0;
+      const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+      if (cudaHostAlloc(&pinned, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); pinned = nullptr; return nullptr; }
+      pinned_bytes = want;
+    }
+    return pinned;
+  }
   bool profile = false;
   std::vector<ProfRec> prof_pending;
   std::vector<cudaEvent_t> ev_pool;
@@ -236,6 +251,10 @@ struct CloudView {
   int* cell_cnt;    // ncell (count, then scatter cursor)
   int2* cell_tmp;   // n: (ordered x bits, point index) grouped by cell in scatter (arbitrary) order, before the in-cell ranking
   float4* spts;
+  // the same points, two per record, component-wise: record m = {x[2m] x[2m+1] y[2m] y[2m+1]} {z[2m] z[2m+1] w[2m] w[2m+1]}, so that
+  // ONE packed-pair FP32 instruction (FFMA2 / FMUL2 / FADD2, sm_100) serves two neighbouring candidates of a row; an odd cloud
+  // ends with a point at +inf (never nearest)
+  float4* spair;
   // per-point covariances (original order) and, for the PLANE-regularised ones, the direction that got the small eigenvalue
   // (4 doubles per point: unit normal + padding): cov = I - (1 - 1e-3) n n^T up to rounding
   double* cov;
@@ -385,6 +404,36 @@ __device__ __forceinline__ int block_sum_int(int v, int* smem) {
   for (int w = 0; w < nwarp; ++w) s += smem[w];
   __syncthreads();
   return s;
+}
+
+// Packed-pair FP32 (sm_100: FFMA2 / FMUL2 and the add as FFMA2 with a unit factor): two IEEE round-to-nearest results per issue
+// slot.  Written as PTX with explicit .rn: the CUDA intrinsics (__fmul2_rn / __fadd2_rn) are contracted by the compiler into fused
+// multiply-adds like ordinary float arithmetic (seen in SASS, and as a last-bit difference from FLANN's distance), the .rn PTX
+// forms are not.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {  // a - b
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 // FLANN L2_Simple squared distance: float accumulation in dimension order, no FMA contraction.

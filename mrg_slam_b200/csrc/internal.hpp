@@ -70,7 +70,7 @@ struct Cloud {
   int ncell = 0;
   Ref<int> cell_start, cell_cnt;
   Ref<int2> cell_tmp;
-  Ref<float4> spts;
+  Ref<float4> spts, spair;
   // covariances
   int cov_k = 0;  // k the covariances were built with (0 = none)
   int cov_mode = 0;  // Needs::cov_mode they were built with

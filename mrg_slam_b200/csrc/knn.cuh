@@ -135,7 +135,12 @@ __device__ __forceinline__ CandD2 cand_d2(float qx, float qy, float qz, const fl
 //                 tested, when they cannot matter) and one towards smaller x: fewer candidates, but every load is serialised
 //                 behind the previous test
 //   VISIT_AHEAD   VISIT_CELL3 with the sweeps loading one point ahead of the test
-enum { VISIT_CELL3 = 0, VISIT_MERGED = 1, VISIT_AHEAD = 2, VISIT_SWEEP_MASK = 3, VISIT_LANE_RING = 4 };
+//   VISIT_PAIRS   (1-NN visitors only) candidates two at a time from the pair-interleaved copy `spair`: the three differences, their
+//                 squares and the two sums are packed-pair FP32 instructions (8 issue slots for two candidates instead of 12), and
+//                 the loop overhead halves.  A pair may reach one position beyond the row's ends: that is another real point of the
+//                 cloud (or the +inf pad), harmless for a minimum — which is why k-NN / radius visitors, where a point must not be
+//                 counted twice, keep the single-candidate sweeps.
+enum { VISIT_CELL3 = 0, VISIT_MERGED = 1, VISIT_AHEAD = 2, VISIT_SWEEP_MASK = 3, VISIT_LANE_RING = 4, VISIT_PAIRS = 8 };
 #ifndef B2R_VISIT_DEFAULT
 #define B2R_VISIT_DEFAULT VISIT_MERGED
 #endif
@@ -146,7 +151,43 @@ __device__ __forceinline__ void visit_row(const CloudView& c, const QueryCell& q
   if (row_s == row_e) return;
   const typename S::Row sr = src.row(y, z);
   const float qy = v.qy_f(), qz = v.qz_f();
-  if constexpr ((MODE & VISIT_SWEEP_MASK) == VISIT_MERGED) {
+  if constexpr ((MODE & VISIT_PAIRS) != 0) {
+    const int cs = __ldg(&c.cell_start[rowbase + q.cx]), ce = __ldg(&c.cell_start[rowbase + q.cx + 1]);
+    const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
+    const float4* __restrict__ sp = c.spair;
+    // FLANN's ((dx^2 + dy^2) + dz^2) for the two points of record m, every operation rounded like its scalar form
+#define B2R_PAIR_D2(m)                                                                          \
+    const float4 pa = __ldg(&sp[2 * (size_t)(m)]), pb = __ldg(&sp[2 * (size_t)(m) + 1]);          \
+    const unsigned long long dxp = f2_sub(qx2, f2_pack(pa.x, pa.y));                             \
+    const unsigned long long dyp = f2_sub(qy2, f2_pack(pa.z, pa.w));                             \
+    const unsigned long long dzp = f2_sub(qz2, f2_pack(pb.x, pb.y));                             \
+    const float2 sx = f2_unpack(f2_mul(dxp, dxp)), sy = f2_unpack(f2_mul(dyp, dyp)), sz = f2_unpack(f2_mul(dzp, dzp)); \
+    /* the sums stay scalar: ptxas contracts a packed multiply feeding a packed add into FFMA2 even when both carry .rn */      \
+    const float2 d2 = make_float2(__fadd_rn(__fadd_rn(sx.x, sy.x), sz.x), __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y));
+    const int mc0 = cs >> 1;
+    int mu = mc0;  // first record of the sweep towards larger x
+    if (ce > cs) {
+      const int mc1 = (ce - 1) >> 1;
+      for (int m = mc0; m <= mc1; ++m) {  // the query's x-cell: unconditional, independent loads
+        B2R_PAIR_D2(m)
+        v.test2(d2.x, d2.y, 2 * m);
+      }
+      mu = mc1 + 1;
+    }
+    for (int m = mu; 2 * m < row_e; ++m) {  // towards larger x
+      B2R_PAIR_D2(m)
+      // the record's first point decides: it is the nearer one in x, provided it lies beyond the query's x-cell (the first
+      // record after an EMPTY cell may begin one position earlier — in a lower cell, or in the previous row)
+      if (2 * m >= cs && v.stop(__fadd_rn(sx.x, rg2))) break;
+      v.test2(d2.x, d2.y, 2 * m);
+    }
+    for (int m = mc0 - 1; m >= 0 && 2 * m + 1 >= row_s; --m) {  // towards smaller x: the record's second point is the nearer one
+      B2R_PAIR_D2(m)
+      if (v.stop(__fadd_rn(sx.y, rg2))) break;
+      v.test2(d2.x, d2.y, 2 * m);
+    }
+#undef B2R_PAIR_D2
+  } else if constexpr ((MODE & VISIT_SWEEP_MASK) == VISIT_MERGED) {
     const int cs = __ldg(&c.cell_start[rowbase + q.cx]);
     for (int j = cs; j < row_e; ++j) {  // the query's x-cell, then towards larger x
       const float4 p = src.load(c, sr, j);
@@ -453,6 +494,11 @@ struct Nn1Visitor {
   __device__ __forceinline__ void test(const float4&, int j, float d2) {
     if (d2 < best || (d2 == best && j < best_pos)) { best = d2; best_pos = j; lim = fminf(d2, cut) * kGapSlack; }
   }
+  __device__ __forceinline__ void test2(float da, float db, int j) {
+    if (da < best || (da == best && j < best_pos)) { best = da; best_pos = j; }
+    if (db < best || (db == best && j + 1 < best_pos)) { best = db; best_pos = j + 1; }
+    lim = fminf(best, cut) * kGapSlack;
+  }
 };
 template <int MODE = B2R_VISIT_DEFAULT>
 __device__ __forceinline__ int nn1_search(const CloudView& c, float qx, float qy, float qz, float max_d2, float& best_out) {
@@ -491,6 +537,10 @@ struct Nn1DistVisitor {
   __device__ __forceinline__ float qz_f() const { return qz; }
   __device__ __forceinline__ void test(const float4&, int, float d2) {
     best = fminf(best, d2);
+    lim = fminf(best, cut) * kGapSlack;
+  }
+  __device__ __forceinline__ void test2(float da, float db, int) {
+    best = fminf(best, fminf(da, db));
     lim = fminf(best, cut) * kGapSlack;
   }
 };

@@ -14,6 +14,9 @@
 
 namespace b2r {
 
+#ifndef B2R_NN1_MODE
+#define B2R_NN1_MODE VISIT_PAIRS
+#endif
 enum { PH_LINEARIZE = 0, PH_TRIAL = 1, PH_DONE = 2 };
 constexpr int kAcc = 28;   // Hrr(6) Hrt(9) Htt(6) b(6) err(1)
 constexpr int kPart = 29;  // per-block partials: the kAcc sums + the number of correspondences (measurement only)
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(256, 2) lsq_eval_kernel(const CloudView* __res
         ok = pos >= 0;
       } else {
         float d2;
-        pos = nn1_search(tgt, q[0], q[1], q[2], prm.corr_max_d2, d2);
+        pos = nn1_search<B2R_NN1_MODE>(tgt, q[0], q[1], q[2], prm.corr_max_d2, d2);
         ok = pos >= 0 && (double)d2 < prm.corr_thr2;
         if (cc) cc[j] = ok ? pos : -1;
       }
@@ -952,7 +955,7 @@ __global__ void nn_export_kernel(const CloudView* __restrict__ views, Mat16 T, i
   float qx, qy, qz;
   pcl_transform(T.m, p.x, p.y, p.z, qx, qy, qz);
   float d2;
-  const int pos = nn1_search(tgt, qx, qy, qz, INFINITY, d2);
+  const int pos = nn1_search<B2R_NN1_MODE>(tgt, qx, qy, qz, INFINITY, d2);
   idx[i] = pos >= 0 ? __float_as_int(tgt.spts[pos].w) : -1;
   d2o[i] = d2;
   if (xyz) { xyz[3 * (size_t)i] = qx; xyz[3 * (size_t)i + 1] = qy; xyz[3 * (size_t)i + 2] = qz; }
@@ -1034,11 +1037,12 @@ void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_
     for (int i = 0; i < np; ++i) pts += b.src_sizes[i];
     ProfScope ps(ctx, PROF_FITNESS, 32.0 * pts);
     static const int cell_order = [] { const char* e = getenv("B2R_FIT_CELL_ORDER"); return e ? atoi(e) : 1; }();
-    static const int mode = [] { const char* e = getenv("B2R_FIT_VISIT"); return e ? atoi(e) : (int)VISIT_CELL3; }();
+    static const int mode = [] { const char* e = getenv("B2R_FIT_VISIT"); return e ? atoi(e) : (int)VISIT_PAIRS; }();
     static const int lean = [] { const char* e = getenv("B2R_FIT_LEAN"); return e ? atoi(e) : 1; }();
 #define B2R_FIT_LAUNCH(M, L) \
     B2R_LAUNCH(ctx, (fitness_kernel<M, L>), dim3(chunks, np), 256, 0, b.d_views, b.d_pairs, b.d_rows, max_range, max_d2, inlier_d2, cell_order, part.p)
-    if (mode == VISIT_MERGED) { if (lean) B2R_FIT_LAUNCH(VISIT_MERGED, true); else B2R_FIT_LAUNCH(VISIT_MERGED, false); }
+    if (mode == VISIT_PAIRS) { if (lean) B2R_FIT_LAUNCH(VISIT_PAIRS, true); else B2R_FIT_LAUNCH(VISIT_PAIRS, false); }
+    else if (mode == VISIT_MERGED) { if (lean) B2R_FIT_LAUNCH(VISIT_MERGED, true); else B2R_FIT_LAUNCH(VISIT_MERGED, false); }
     else if (mode == (VISIT_CELL3 | VISIT_LANE_RING)) { if (lean) B2R_FIT_LAUNCH(VISIT_CELL3 | VISIT_LANE_RING, true); else B2R_FIT_LAUNCH(VISIT_CELL3 | VISIT_LANE_RING, false); }
     else { if (lean) B2R_FIT_LAUNCH(VISIT_CELL3, true); else B2R_FIT_LAUNCH(VISIT_CELL3, false); }
 #undef B2R_FIT_LAUNCH

@@ -129,8 +129,11 @@ void gather_rows(Handle* h, b2r_comm* comm, const b2r_result* d_send, const b2r_
     Ctx& ctx = h->ctx;
     DBuf<b2r_result> recv; recv.alloc(all.size(), ctx.stream);
     nccl_check(nccl().AllGather(d_send, recv.p, bytes, ncclChar, comm->nccl, ctx.stream), "ncclAllGather");
-    B2R_CUDA(cudaMemcpyAsync(all.data(), recv.p, all.size() * sizeof(b2r_result), cudaMemcpyDeviceToHost, ctx.stream));
+    const size_t tot = all.size() * sizeof(b2r_result);
+    void* stage = ctx.pinned_buf(tot);  // pinned: the table arrives by DMA, then one host memcpy
+    B2R_CUDA(cudaMemcpyAsync(stage ? stage : (void*)all.data(), recv.p, tot, cudaMemcpyDeviceToHost, ctx.stream));
     B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (stage) memcpy(all.data(), stage, tot);
   } else {
     if (comm->host_fn(comm->host_user, h_send, all.data(), bytes) != 0) throw Error(B2R_ERR_COMM, "host all-gather callback failed");
   }
