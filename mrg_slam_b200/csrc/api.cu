@@ -61,7 +61,9 @@ Needs needs_for(const b2r_config& cfg, bool is_target, bool want_fitness) {
       if (is_target) { nd.leaf = (float)cfg.resolution; nd.leaf_centroids = cfg.neighbor_search == B2R_KDTREE; }
       break;
   }
-  if (is_target && want_fitness) nd.grid = true;
+  // getFitnessScore: the target's NN grid is searched; the SOURCE's grid only provides the order its points are queried in (cell
+  // order: a warp's queries are neighbours in space) — 0.3 ms of grid builds against 4 ms of fitness on the 4096-pair NDT batch
+  if (want_fitness) nd.grid = true;
   return nd;
 }
 

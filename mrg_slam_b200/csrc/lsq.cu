@@ -1028,7 +1028,8 @@ __global__ void fitness_finish_kernel(const double* __restrict__ partials, int n
 void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_d2, int* d_inlier_out) {
   const int np = b.np;
   if (np == 0) return;
-  const int chunks = pick_chunks(ctx, np, b.maxn);
+  static const int fit_chunk_mul = [] { const char* e = getenv("B2R_FIT_CHUNK_MUL"); return e ? atoi(e) : 1; }();
+  const int chunks = pick_chunks(ctx, np, b.maxn) * fit_chunk_mul;
   DBuf<double> part; part.alloc((size_t)np * chunks * 3, ctx.stream);
   float max_d2 = max_range >= (double)FLT_MAX ? INFINITY : (float)(max_range * 1.0001);
   if (inlier_d2 > 0.f) max_d2 = fmaxf(max_d2, inlier_d2 * 1.0001f);
@@ -1039,8 +1040,9 @@ void fitness_batch(Ctx& ctx, const BatchArgs& b, double max_range, float inlier_
     static const int cell_order = [] { const char* e = getenv("B2R_FIT_CELL_ORDER"); return e ? atoi(e) : 1; }();
     static const int mode = [] { const char* e = getenv("B2R_FIT_VISIT"); return e ? atoi(e) : (int)VISIT_PAIRS; }();
     static const int lean = [] { const char* e = getenv("B2R_FIT_LEAN"); return e ? atoi(e) : 1; }();
+    static const int fit_threads = [] { const char* e = getenv("B2R_FIT_THREADS"); return e ? atoi(e) : 256; }();
 #define B2R_FIT_LAUNCH(M, L) \
-    B2R_LAUNCH(ctx, (fitness_kernel<M, L>), dim3(chunks, np), 256, 0, b.d_views, b.d_pairs, b.d_rows, max_range, max_d2, inlier_d2, cell_order, part.p)
+    B2R_LAUNCH(ctx, (fitness_kernel<M, L>), dim3(chunks, np), fit_threads, 0, b.d_views, b.d_pairs, b.d_rows, max_range, max_d2, inlier_d2, cell_order, part.p)
     if (mode == VISIT_PAIRS) { if (lean) B2R_FIT_LAUNCH(VISIT_PAIRS, true); else B2R_FIT_LAUNCH(VISIT_PAIRS, false); }
     else if (mode == VISIT_MERGED) { if (lean) B2R_FIT_LAUNCH(VISIT_MERGED, true); else B2R_FIT_LAUNCH(VISIT_MERGED, false); }
     else if (mode == (VISIT_CELL3 | VISIT_LANE_RING)) { if (lean) B2R_FIT_LAUNCH(VISIT_CELL3 | VISIT_LANE_RING, true); else B2R_FIT_LAUNCH(VISIT_CELL3 | VISIT_LANE_RING, false); }
