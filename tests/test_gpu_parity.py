@@ -378,6 +378,43 @@ def test_information_matrix_fitness(reg, vlp16_pair):
         c.close()
 
 
+def test_nearest_neighbor_search_small_and_odd_clouds(reg):
+    """The 1-NN sweeps read the target two points at a time from a pair-interleaved copy (knn.cuh VISIT_PAIRS): clouds of 1, 2, 3 ...
+    points, odd sizes (the +inf pad), duplicate points, points on one line (a single grid row) and queries far outside the target's
+    box must give the brute-force answer, bit for bit (FLANN's float association)."""
+    rng = np.random.default_rng(20261017)
+
+    def brute(tgt, q):
+        d = q[:, None, :3].astype(np.float32) - tgt[None, :, :3].astype(np.float32)
+        d2 = ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32)
+        return (d2 + (d[..., 2] * d[..., 2]).astype(np.float32)).astype(np.float32).min(axis=1)
+
+    def cloud(n, kind):
+        c = np.zeros((n, 4), dtype=np.float32)
+        if kind == "box":
+            c[:, :3] = rng.uniform(-5, 5, (n, 3))
+        elif kind == "line":  # one row of the grid: everything along x
+            c[:, 0] = rng.uniform(-20, 20, n)
+        elif kind == "dup":   # many exact duplicates
+            c[:, :3] = rng.integers(-2, 3, (n, 3)).astype(np.float32)
+        else:                 # flat, like a ground plane
+            c[:, :2] = rng.uniform(-8, 8, (n, 2))
+        return c
+
+    g = reg
+    for kind in ("box", "line", "dup", "plane"):
+        for n in (1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 257, 1001):
+            tgt = cloud(n, kind)
+            q = cloud(97, kind)
+            q[:8, :3] += 40.0          # far outside the target's box
+            q[8:16, :3] = tgt[rng.integers(0, n, 8), :3]  # exactly on target points
+            ct, cq = B.Cloud(g, tgt), B.Cloud(g, q)
+            want = brute(tgt, q)
+            f = g.fitness_pair(ct, cq, np.eye(4))
+            assert abs(f - float(want.astype(np.float64).mean())) <= 1e-12 * max(1.0, abs(f)), (kind, n)
+            ct.close(); cq.close()
+
+
 # ------------------------------------------------------------------------------------------------ size-independent properties
 def test_properties_full_size_hdl64(reg):
     """KITTI-shape clouds (BASELINE config 2): properties that need no oracle."""
