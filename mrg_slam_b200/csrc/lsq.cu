@@ -372,8 +372,10 @@ constexpr int kVgRing = 64;  // per warp: <= 31 left over + 32 new
 #ifndef B2R_VG_LIN_BLOCKS
 #define B2R_VG_LIN_BLOCKS 2
 #endif
-template <int SEL>
-__global__ void __launch_bounds__(256, SEL == 2 ? B2R_VG_TRIAL_BLOCKS : B2R_VG_LIN_BLOCKS) vgicp_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+// THREADS: 256 for large batches; 128 (the same registers per thread, twice the blocks per SM) when a launch has few blocks — smaller
+// blocks leave shorter tails: 3.28 -> 3.20 ms per 512-pair step, but 19.8 -> 20.0 ms at 4096 pairs.
+template <int SEL, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, (SEL == 2 ? B2R_VG_TRIAL_BLOCKS : B2R_VG_LIN_BLOCKS) * (256 / THREADS)) vgicp_eval_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                                           const LsqState* __restrict__ states, double* __restrict__ partials) {
   const int pair = blockIdx.y;
   const LsqState& st = states[pair];
@@ -852,11 +854,13 @@ void lsq_align_batch(Ctx& ctx, const b2r_config& cfg, const BatchArgs& b) {
   void* eval_args_gen[] = {&a_views, &a_pairs, &a_states_c, &prm, &a_part, &a_corr, &a_coff, &a_null_i, &a_null_b};
   void* step_args[] = {&a_states, &prm, &a_part_c, &a_chunks, &a_src_n, &la};
   static const bool split = [] { const char* e = getenv("B2R_VGICP_SPLIT"); return !e || atoi(e) != 0; }();
-  const void* eval2_fn = (pipe && split) ? (const void*)vgicp_eval_kernel<2> : nullptr;
-  const void* eval_fn = pipe ? (split ? (const void*)vgicp_eval_kernel<1> : (const void*)vgicp_eval_kernel<0>)
+  static const int small_batch = [] { const char* e = getenv("B2R_VG_SMALL_BATCH"); return e ? atoi(e) : 640; }();  // pairs per launch up to which 128-thread blocks are used (measured: better at 512, worse from 1024 on)
+  const bool small = pipe && split && np <= small_batch;
+  const void* eval2_fn = (pipe && split) ? (small ? (const void*)vgicp_eval_kernel<2, 128> : (const void*)vgicp_eval_kernel<2>) : nullptr;
+  const void* eval_fn = pipe ? (split ? (small ? (const void*)vgicp_eval_kernel<1, 128> : (const void*)vgicp_eval_kernel<1>) : (const void*)vgicp_eval_kernel<0>)
                              : (cfg.method == B2R_FAST_VGICP ? (const void*)lsq_eval_kernel<B2R_FAST_VGICP>
                                 : (cfg.method == B2R_FAST_GICP ? (const void*)lsq_eval_kernel<B2R_FAST_GICP> : (const void*)lsq_eval_kernel<B2R_SMALL_GICP>));
-  run_device_loop(ctx, eval_fn, dim3(chunks, np), dim3(256), pipe ? eval_args_pipe : eval_args_gen, (const void*)lsq_step_kernel,
+  run_device_loop(ctx, eval_fn, dim3(chunks, np), dim3(small ? 128 : 256), pipe ? eval_args_pipe : eval_args_gen, (const void*)lsq_step_kernel,
                   dim3((np + 3) / 4), dim3(128), step_args, la, ctl.p, np, max_rounds, PROF_LSQ_EVAL, eval2_fn);
   B2R_LAUNCH(ctx, lsq_rows_kernel, (np + 127) / 128, 128, 0, ds.p, np, b.d_rows);
   if (ctx.profile) {
