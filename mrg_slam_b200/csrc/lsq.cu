@@ -989,8 +989,11 @@ void transform_cloud(Ctx& ctx, const float4* in, int n, const float* T_colmajor,
 // lane: 12.1-20 ms — ncu shows the budgeted first phase alone costs what the plain kernel costs (7.0 G of 7.4 G warp
 // instructions): the time is in the ORDINARY queries' short, divergent sweeps (5-6 of 32 lanes in the distance tests), not in a
 // few expensive ones (profiles/r2/ncu_fitness_batch4096_*.md).
+#ifndef B2R_FIT_BLOCKS
+#define B2R_FIT_BLOCKS 4
+#endif
 template <int MODE, bool LEAN>
-__global__ void __launch_bounds__(256, 4) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
+__global__ void __launch_bounds__(256, B2R_FIT_BLOCKS) fitness_kernel(const CloudView* __restrict__ views, const PairDesc* __restrict__ pairs,
                                                        const b2r_result* __restrict__ rows, double max_range, float max_d2, float inlier_d2,
                                                        int cell_order, double* __restrict__ partials) {
   const int pair = blockIdx.y;
