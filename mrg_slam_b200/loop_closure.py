@@ -411,3 +411,28 @@ def match_keyframes(reg, clouds, pairs, guesses, estimates, links, fitness_score
             continue  # :162-166
         accepted.append(lp)
     return accepted, loops, details, table
+
+
+# ------------------------------------------------------------------------------------------------ information matrix of an edge
+def information_weight(a, max_x, min_y, max_y, x):
+    """InformationMatrixCalculator::weight (information_matrix_calculator.cpp:83-88)."""
+    y = (1.0 - np.exp(-a * x)) / (1.0 - np.exp(-a * max_x))
+    return min_y + (max_y - min_y) * y
+
+
+def calc_information_matrix(reg, cloud1, cloud2, relpose, use_const_inf_matrix=False, const_stddev_x=0.5, const_stddev_q=0.1, var_gain_a=2.0,
+                            min_stddev_x=0.1, max_stddev_x=0.75, min_stddev_q=0.05, max_stddev_q=0.2, fitness_score_thresh=1.25):
+    """InformationMatrixCalculator::calc_information_matrix (information_matrix_calculator.cpp:14-44; defaults = config/mrg_slam.yaml:216-223,
+    :173): the 6x6 information matrix of an odometry / loop edge from the fitness score of cloud2 (moved by relpose) against cloud1.
+    `reg` is anything with fitness_pair(target, source, T) — the GPU engine (one b2r_fitness_pair call on retained clouds) or the oracle."""
+    inf = np.eye(6)
+    if use_const_inf_matrix:
+        inf[:3, :3] /= const_stddev_x
+        inf[3:, 3:] /= const_stddev_q
+        return inf
+    fitness = reg.fitness_pair(cloud1, cloud2, np.asarray(relpose, dtype=np.float64))
+    w_x = information_weight(var_gain_a, fitness_score_thresh, min_stddev_x ** 2, max_stddev_x ** 2, fitness)
+    w_q = information_weight(var_gain_a, fitness_score_thresh, min_stddev_q ** 2, max_stddev_q ** 2, fitness)
+    inf[:3, :3] /= w_x
+    inf[3:, 3:] /= w_q
+    return inf

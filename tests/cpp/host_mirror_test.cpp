@@ -12,6 +12,7 @@
 #include <mutex>
 #include <thread>
 
+#include <b2r/information_matrix.hpp>
 #include <b2r/loop_matcher.hpp>
 #include <b2r/pcl_adapter.hpp>
 #include <b2r/registration.hpp>
@@ -331,6 +332,25 @@ int main(int argc, char** argv) {
       CHECK(m.status == B2R_OK && m.best >= 0 && m.best_score < 1.25);
       CHECK(m.loop_found && m.consistency_passed && m.aligns == 3);  // two candidates + the prev check
       CHECK(m.delta_trans[0] >= 0.f && m.delta_trans[0] < 0.3f && m.delta_trans[1] < 0.f);
+      // ---- InformationMatrixCalculator::calc_information_matrix (information_matrix_calculator.cpp:14-44) of the loop edge
+      {
+        double inf[36], fit = -1.0;
+        b2r::Mat4d relpose;
+        for (int i = 0; i < 16; ++i) relpose[i] = (double)m.rel_pose_new_to_best[i];
+        b2r::InformationMatrixParams ip;
+        CHECK(b2r::calc_information_matrix(h, k4.cloud, cands[m.best]->cloud, relpose.data(), ip, inf, &fit) == B2R_OK);
+        double want_fit = 0.0;
+        CHECK(b2r_fitness_pair(h, k4.cloud, cands[m.best]->cloud, m.rel_pose_new_to_best.data(), DBL_MAX, &want_fit) == B2R_OK);
+        CHECK(fit == want_fit && fit > 0.0 && fit < 1.25);
+        const double y = (1.0 - std::exp(-2.0 * fit)) / (1.0 - std::exp(-2.0 * 1.25));
+        const double wx = 0.1 * 0.1 + (0.75 * 0.75 - 0.1 * 0.1) * y, wq = 0.05 * 0.05 + (0.2 * 0.2 - 0.05 * 0.05) * y;
+        for (int r = 0; r < 6; ++r)
+          for (int c2 = 0; c2 < 6; ++c2)
+            CHECK(std::fabs(inf[r * 6 + c2] - (r != c2 ? 0.0 : (r < 3 ? 1.0 / wx : 1.0 / wq))) <= 1e-12 / (r < 3 ? wx : wq));
+        ip.use_const_inf_matrix = true;
+        CHECK(b2r::calc_information_matrix(h, k4.cloud, cands[m.best]->cloud, relpose.data(), ip, inf) == B2R_OK);
+        CHECK(inf[0] == 1.0 / 0.5 && inf[21] == 1.0 / 0.1 && inf[1] == 0.0);
+      }
       // the best candidate's pose is the single-pair result, bit for bit
       b2r_result r1;
       const b2r::Mat4f g = b2r::registration_guess(k4.estimate, cands[m.best]->estimate);
