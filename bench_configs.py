@@ -195,23 +195,32 @@ def run_prefilter(args):
     out = {}
     for name, sensor in (("hdl64_121600", synth.HDL64), ("os1_128_1M", synth.OS1_128_1M)):
         raw = synth.scan(sensor, 7)
+        import torch
+        raw_pinned = torch.from_numpy(raw).pin_memory().numpy()
         cases = {}
         for oname, method in (("radius_0.5_2", 2), ("statistical_30_1.2", 1), ("voxelgrid_only", 0)):
             cfg = B.PrefilterConfig()
             reg._lib.b2r_default_prefilter_config(__import__("ctypes").byref(cfg))
             cfg.outlier_removal_method = method
-            e2e, dev, f = [], [], None
-            for it in range(args.warmup + args.steps):
-                t0 = time.perf_counter()
-                reg.event_record(0)
-                f = reg.prefilter(raw, cfg)
-                reg.event_record(1)
-                reg.synchronize()
-                if it >= args.warmup:
-                    e2e.append(1e3 * (time.perf_counter() - t0)); dev.append(reg.event_elapsed_ms(0, 1))
+            def timed(buf):
+                e2e, dev, f = [], [], None
+                for it in range(args.warmup + args.steps):
+                    t0 = time.perf_counter()
+                    reg.event_record(0)
+                    f = reg.prefilter(buf, cfg)
+                    reg.event_record(1)
+                    reg.synchronize()
+                    if it >= args.warmup:
+                        e2e.append(1e3 * (time.perf_counter() - t0)); dev.append(reg.event_elapsed_ms(0, 1))
+                return e2e, dev, f
+            e2e, dev, f = timed(raw)               # pageable host input (a ROS message buffer)
+            e2e_pin, dev_pin, f_pin = timed(raw_pinned)  # the same scan in pinned host memory (the bench contract's e2e input)
+            assert np.array_equal(f.view(np.uint32), f_pin.view(np.uint32))
             cases[oname] = {"points_in": len(raw), "points_out": len(f), "device_ms_median": float(np.median(dev)),
                             "e2e_ms_median": float(np.median(e2e)), "Mpts_per_s_e2e": len(raw) / np.median(e2e) / 1e3,
-                            "Mpts_per_s_device": len(raw) / np.median(dev) / 1e3}
+                            "Mpts_per_s_device": len(raw) / np.median(dev) / 1e3,
+                            "pinned_input": {"e2e_ms_median": float(np.median(e2e_pin)), "device_ms_median": float(np.median(dev_pin)),
+                                             "Mpts_per_s_e2e": len(raw) / np.median(e2e_pin) / 1e3}}
             if args.cpu:
                 from tests import oraclelib as O
                 O.set_num_threads(0)
