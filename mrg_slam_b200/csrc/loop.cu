@@ -75,8 +75,12 @@ void run_device_loop(Ctx& ctx, const void* eval_fn, dim3 eval_grid, dim3 eval_bl
     cudaGraphNode_t ne = nullptr, ne2 = nullptr, ns = nullptr;
     B2R_GRAPH(cudaGraphAddKernelNode(&ne, body, nullptr, 0, &ke), g, ge);
     if (eval2_fn) {
-      B2R_GRAPH(cudaGraphAddKernelNode(&ne2, body, &ne, 1, &ke2), g, ge);
-      B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, &ne2, 1, &ks), g, ge);
+      // the two evaluation kernels touch disjoint pairs (each serves the pairs of one phase), so they are independent nodes: in
+      // the lock-step early rounds one of them has nothing to do and its launch hides behind the other instead of preceding it
+      static const bool parallel = [] { const char* e = getenv("B2R_LOOP_PARALLEL_EVAL"); return !e || atoi(e) != 0; }();
+      B2R_GRAPH(cudaGraphAddKernelNode(&ne2, body, parallel ? nullptr : &ne, parallel ? 0 : 1, &ke2), g, ge);
+      cudaGraphNode_t deps[2] = {ne, ne2};
+      B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, deps, 2, &ks), g, ge);
     } else {
       B2R_GRAPH(cudaGraphAddKernelNode(&ns, body, &ne, 1, &ks), g, ge);
     }
