@@ -313,14 +313,24 @@ def run_b2r(args):
     own = rank_of == rank
     guesses32 = np.ascontiguousarray(guesses.transpose(0, 2, 1).reshape(n_pairs, 16).astype(np.float32))  # column-major
 
+    host_ms = {"create_clouds": 0.0, "pair_arrays": 0.0, "align_batch_sharded": 0.0, "close": 0.0, "steps": 0}
+
     def step(bufs, memspace):
+        t0 = time.perf_counter()
         cl = B.CloudBatch(reg, ptrs[id(bufs)], sizes, memspace)
+        t1 = time.perf_counter()
         handle_of = np.zeros(len(pool_np), dtype=np.uint64)
         handle_of[needed_a] = cl.handles[:len(needed)]
         src = np.where(own, handle_of[pair_s], 0).astype(np.uint64)
         tgt = np.where(own, handle_of[pair_t], 0).astype(np.uint64)
+        t2 = time.perf_counter()
         table = reg.align_batch_sharded(comm, src, tgt, ids, guesses32, weights=weights, with_fitness=True)
+        t3 = time.perf_counter()
         cl.close()
+        t4 = time.perf_counter()
+        for k, v in zip(("create_clouds", "pair_arrays", "align_batch_sharded", "close"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            host_ms[k] += 1e3 * v
+        host_ms["steps"] += 1
         return table
 
     def barrier():
@@ -340,6 +350,8 @@ def run_b2r(args):
     if rank == 0:
         sampler.start()
     total_ms = 0.0
+    for k in host_ms:
+        host_ms[k] = 0
     barrier()
     torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed steps (no effect otherwise)
     for _ in range(args.steps):
@@ -351,6 +363,7 @@ def run_b2r(args):
         total_ms += reg.event_elapsed_ms(0, 1)
     barrier()
     torch.cuda.profiler.stop()
+    host_value = {k: round(v / max(host_ms["steps"], 1), 4) for k, v in host_ms.items() if k != "steps"}  # rank 0's wall clock per timed step
     launches = reg.kernel_launches() - l0
     graphs = reg.graph_launches() - g0
     collectives = comm.collectives() - c0
@@ -445,6 +458,9 @@ def run_b2r(args):
                          "note": "rank 0; algorithmic bytes per launch (SURVEY 8d conventions) / CUDA-event duration of the dominant kernel "
                                  f"family, measured in a separate pass of {prof_steps} of the same steps with per-kernel events",
                          "kernels": per_kernel},
+            "host_ms_per_step": {**host_value, "note": "rank 0, wall clock of the public calls of one timed step (clouds resident in HBM): batch cloud "
+                                 "creation (copy + bounding boxes + their read-back), the pair table, b2r_align_batch_sharded (returns with the "
+                                 "gathered table), release"},
             "converged_fraction": conv,
             "rank0_pairs": int(len(mine)), "rank0_clouds": len(needed),
             "ranks": [{"pairs": int(t[0]), "clouds": int(t[1]), "cloud_points": int(t[2]), "prep_ms": round(float(t[3]), 3),

@@ -100,44 +100,64 @@ b2r_status comm_guarded(b2r_comm* c, F&& f) {
 // every rank gets a contiguous block of targets whose summed weight is as close to total / nranks as whole targets allow (a
 // target goes where most of it falls), never starving the later ranks.  Every rank computes the same answer.
 void partition_pairs(const int64_t* target_ids, const double* weights, size_t n, int nranks, int32_t* rank_of_pair) {
-  std::vector<int64_t> order;
-  std::map<int64_t, std::vector<size_t>> groups;
-  for (size_t i = 0; i < n; ++i) {
-    auto it = groups.find(target_ids[i]);
-    if (it == groups.end()) { order.push_back(target_ids[i]); groups[target_ids[i]] = {i}; }
-    else it->second.push_back(i);
-  }
+  // targets in order of first appearance, each with its summed weight (one pass, no per-target lists)
+  std::map<int64_t, int> slot;
+  std::vector<double> gw;
+  std::vector<int> slot_of(n);
   double total = 0.0;
-  for (size_t i = 0; i < n; ++i) total += weights ? weights[i] : 1.0;
+  int last_slot = -1;
+  int64_t last_id = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double w = weights ? weights[i] : 1.0;
+    int k;
+    if (last_slot >= 0 && target_ids[i] == last_id) {
+      k = last_slot;  // the candidates of a target are usually consecutive
+    } else {
+      auto it = slot.find(target_ids[i]);
+      if (it == slot.end()) { k = (int)gw.size(); slot[target_ids[i]] = k; gw.push_back(0.0); }
+      else k = it->second;
+      last_slot = k; last_id = target_ids[i];
+    }
+    gw[k] += w;
+    slot_of[i] = k;
+    total += w;
+  }
+  std::vector<int32_t> rank_of_slot(gw.size());
   int rank = 0;
   double acc = 0.0;
-  for (int64_t t : order) {
-    const std::vector<size_t>& g = groups[t];
-    double gw = 0.0;
-    for (size_t i : g) gw += weights ? weights[i] : 1.0;
-    while (rank < nranks - 1 && acc + 0.5 * gw >= (rank + 1) * total / nranks) ++rank;
-    for (size_t i : g) rank_of_pair[i] = rank;
-    acc += gw;
+  for (size_t k = 0; k < gw.size(); ++k) {
+    while (rank < nranks - 1 && acc + 0.5 * gw[k] >= (rank + 1) * total / nranks) ++rank;
+    rank_of_slot[k] = rank;
+    acc += gw[k];
   }
+  for (size_t i = 0; i < n; ++i) rank_of_pair[i] = rank_of_slot[slot_of[i]];
 }
 
-// All-gathers `cnt_max` rows per rank.  send: this rank's rows (device for NCCL, host for the callback transport).
-void gather_rows(Handle* h, b2r_comm* comm, const b2r_result* d_send, const b2r_result* h_send, size_t cnt_max, std::vector<b2r_result>& all) {
+// All-gathers `cnt_max` rows per rank.  send: this rank's rows (device for NCCL, host for the callback transport).  Returns the
+// gathered table [rank][cnt_max]: the handle's pinned staging buffer when the table arrived there by DMA (valid until the
+// handle's next call), `all` otherwise.
+const b2r_result* gather_rows(Handle* h, b2r_comm* comm, const b2r_result* d_send, const b2r_result* h_send, size_t cnt_max,
+                              std::vector<b2r_result>& all) {
   const size_t bytes = cnt_max * sizeof(b2r_result);
-  all.resize(cnt_max * (size_t)comm->nranks);
+  const size_t rows = cnt_max * (size_t)comm->nranks;
+  const b2r_result* table = nullptr;
   if (comm->nccl) {
     Ctx& ctx = h->ctx;
-    DBuf<b2r_result> recv; recv.alloc(all.size(), ctx.stream);
+    DBuf<b2r_result> recv; recv.alloc(rows, ctx.stream);
     nccl_check(nccl().AllGather(d_send, recv.p, bytes, ncclChar, comm->nccl, ctx.stream), "ncclAllGather");
-    const size_t tot = all.size() * sizeof(b2r_result);
-    void* stage = ctx.pinned_buf(tot);  // pinned: the table arrives by DMA, then one host memcpy
-    B2R_CUDA(cudaMemcpyAsync(stage ? stage : (void*)all.data(), recv.p, tot, cudaMemcpyDeviceToHost, ctx.stream));
+    const size_t tot = rows * sizeof(b2r_result);
+    void* stage = ctx.pinned_buf(tot);
+    if (!stage) { all.resize(rows); stage = all.data(); }
+    B2R_CUDA(cudaMemcpyAsync(stage, recv.p, tot, cudaMemcpyDeviceToHost, ctx.stream));
     B2R_CUDA(cudaStreamSynchronize(ctx.stream));
-    if (stage) memcpy(all.data(), stage, tot);
+    table = static_cast<const b2r_result*>(stage);
   } else {
+    all.resize(rows);
     if (comm->host_fn(comm->host_user, h_send, all.data(), bytes) != 0) throw Error(B2R_ERR_COMM, "host all-gather callback failed");
+    table = all.data();
   }
   ++comm->collectives;
+  return table;
 }
 
 }  // namespace
@@ -228,21 +248,21 @@ b2r_status b2r_gather_results(b2r_handle* hh, b2r_comm* comm, const int32_t* ran
     std::vector<b2r_result> send(cnt_max), all;
     memset(send.data(), 0, sizeof(b2r_result) * cnt_max);
     if (cnt[comm->rank]) memcpy(send.data(), local, sizeof(b2r_result) * cnt[comm->rank]);
+    const b2r_result* table = send.data();
     if (comm->nranks == 1 && !comm->nccl) {
-      all = send;
     } else if (comm->nccl) {
       Handle& h = *b2r_handle_impl(hh);
       B2R_CUDA(cudaSetDevice(h.ctx.device));
       DBuf<b2r_result> dsend; dsend.alloc(cnt_max, h.ctx.stream);
       B2R_CUDA(cudaMemcpyAsync(dsend.p, send.data(), sizeof(b2r_result) * cnt_max, cudaMemcpyHostToDevice, h.ctx.stream));
-      gather_rows(&h, comm, dsend.p, nullptr, cnt_max, all);
+      table = gather_rows(&h, comm, dsend.p, nullptr, cnt_max, all);
     } else {
-      gather_rows(nullptr, comm, nullptr, send.data(), cnt_max, all);
+      table = gather_rows(nullptr, comm, nullptr, send.data(), cnt_max, all);
     }
     std::vector<size_t> cur(comm->nranks, 0);
     for (size_t i = 0; i < n_pairs; ++i) {
       const int r = rank_of_pair[i];
-      out[i] = all[(size_t)r * cnt_max + cur[r]++];
+      out[i] = table[(size_t)r * cnt_max + cur[r]++];
     }
   });
 }
@@ -319,13 +339,13 @@ b2r_status b2r_align_batch_sharded(b2r_handle* hh, b2r_comm* comm, b2r_cloud* co
     tr.mark("run_align");
     // ---- one all-gather of fixed-size rows; every rank ends up with the whole table in pair order
     std::vector<b2r_result> all;
-    if (comm->nranks == 1 && host_transport) all = host_rows;
-    else gather_rows(&h, comm, send.p, host_rows.data(), cnt_max, all);
+    const b2r_result* table = host_rows.data();
+    if (!(comm->nranks == 1 && host_transport)) table = gather_rows(&h, comm, send.p, host_rows.data(), cnt_max, all);
     tr.mark("allgather+d2h+sync");
     std::vector<size_t> cur(comm->nranks, 0);
     for (size_t i = 0; i < n_pairs; ++i) {
       const int r = rank_of[i];
-      out[i] = all[(size_t)r * cnt_max + cur[r]++];
+      out[i] = table[(size_t)r * cnt_max + cur[r]++];
     }
     tr.mark("scatter");
     tr.print("align_batch_sharded");
