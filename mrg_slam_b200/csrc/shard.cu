@@ -144,12 +144,22 @@ const b2r_result* gather_rows(Handle* h, b2r_comm* comm, const b2r_result* d_sen
   if (comm->nccl) {
     Ctx& ctx = h->ctx;
     DBuf<b2r_result> recv; recv.alloc(rows, ctx.stream);
+    HostTrace tr;  // B2R_TRACE=1: device time of the collective itself (includes waiting for the slowest rank)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (tr.on) { e0 = ctx.get_event(); e1 = ctx.get_event(); cudaEventRecord(e0, ctx.stream); }
     nccl_check(nccl().AllGather(d_send, recv.p, bytes, ncclChar, comm->nccl, ctx.stream), "ncclAllGather");
+    if (tr.on) cudaEventRecord(e1, ctx.stream);
     const size_t tot = rows * sizeof(b2r_result);
     void* stage = ctx.pinned_buf(tot);
     if (!stage) { all.resize(rows); stage = all.data(); }
     B2R_CUDA(cudaMemcpyAsync(stage, recv.p, tot, cudaMemcpyDeviceToHost, ctx.stream));
     B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (tr.on) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      fprintf(stderr, "[b2r trace] rank %d ncclAllGather (device, incl. waiting for the other ranks): %.3f ms, %zu B per rank\n", comm->rank, ms, bytes);
+      ctx.ev_pool.push_back(e0); ctx.ev_pool.push_back(e1);
+    }
     table = static_cast<const b2r_result*>(stage);
   } else {
     all.resize(rows);
