@@ -456,7 +456,10 @@ def run_b2r(args):
                          "kernel_us_per_launch": 1e3 * d["ms"] / nl,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "rank 0; algorithmic bytes per launch (SURVEY 8d conventions) / CUDA-event duration of the dominant kernel "
-                                 f"family, measured in a separate pass of {prof_steps} of the same steps with per-kernel events",
+                                 f"family, measured in a separate pass of {prof_steps} of the same steps with per-kernel events; for lsq_eval a 'launch' is one round "
+                                 "of the optimiser loop = the linearisation kernel + the trial kernel launched back to back (a pair is served by one "
+                                 "of them); traffic is the DRAM traffic of one full linearisation launch under ncu — far below the algorithmic "
+                                 "bytes because the batch's working set is L2-resident",
                          "kernels": per_kernel},
             "host_ms_per_step": {**host_value, "note": "rank 0, wall clock of the public calls of one timed step (clouds resident in HBM): batch cloud "
                                  "creation (copy + bounding boxes + their read-back), the pair table, b2r_align_batch_sharded (returns with the "
