@@ -186,3 +186,29 @@ def test_partition_by_target_balances_weights():
         assert max(loads) <= 1.02 * sum(w) / ws  # within one target group of the ideal share
         for s in shards:  # targets never split
             assert len({targets[i] for i in s}) * 16 == len(s)
+
+
+def test_partition_by_target_matches_the_stated_rule_on_interleaved_ids():
+    """b2r_partition_by_target against a direct restatement of its rule (targets in order of first appearance, contiguous blocks,
+    a target goes where most of its weight falls), with target ids that repeat non-consecutively and arbitrary weights."""
+    from mrg_slam_b200 import lib as B
+    rng = np.random.default_rng(7)
+    for trial in range(30):
+        n = int(rng.integers(1, 400))
+        ids = rng.integers(-5, 40, n).astype(np.int64) * 1000003
+        w = rng.uniform(0.5, 3.0, n) if trial % 2 else None
+        ws = int(rng.integers(1, 9))
+        got = B.partition_by_target(ids, ws, w)
+        order, gw, total = [], {}, 0.0
+        for i, t in enumerate(ids):
+            if t not in gw:
+                order.append(t); gw[t] = 0.0
+            gw[t] += 1.0 if w is None else w[i]
+            total += 1.0 if w is None else w[i]  # the same summation order as the library
+        rank, acc, rank_of_target = 0, 0.0, {}
+        for t in order:
+            while rank < ws - 1 and acc + 0.5 * gw[t] >= (rank + 1) * total / ws:
+                rank += 1
+            rank_of_target[t] = rank
+            acc += gw[t]
+        assert list(got) == [rank_of_target[t] for t in ids]
