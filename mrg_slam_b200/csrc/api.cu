@@ -182,6 +182,22 @@ void run_align(Handle& h, const std::vector<Cloud*>& sources_in, const std::vect
     if (rows_dev && all_live) d_rows = rows_dev;
     else { rows_tmp.alloc(np, ctx.stream); d_rows = rows_tmp.p; }
     DBuf<CloudView> dv;
+    {
+      // clouds of a split upload (cloud.cu): the search structures of those that have arrived are built (enqueued) first, while
+      // the copy of the others is still running on the copy stream; the second call then waits for them and builds the rest
+      std::vector<Cloud*> ready;
+      std::vector<Needs> ready_needs;
+      bool waiting = false;
+      for (size_t i = 0; i < uniq.size(); ++i) {
+        if (uniq[i]->pending && !uniq[i]->pending->resolved) waiting = true;
+        else { ready.push_back(uniq[i]); ready_needs.push_back(needs[i]); }
+      }
+      if (waiting && !ready.empty()) {
+        DBuf<CloudView> first;
+        clouds_prepare(ctx, h.cfg, ready, ready_needs, first);
+        tr.mark("prepare(arrived)");
+      }
+    }
     clouds_prepare(ctx, h.cfg, uniq, needs, dv);
     tr.mark("prepare");
     B2R_CUDA(cudaEventRecord(h.ev[1], ctx.stream));
@@ -327,6 +343,9 @@ void b2r_destroy(b2r_handle* hh) {
     if (h.user_ev[i]) cudaEventDestroy(h.user_ev[i]);
   h.ctx.prof_resolve();
   h.ctx.reap_graphs(true);
+  if (auto pb = h.ctx.pending_boxes.lock()) pb->resolve();  // an upload still in flight uses the copy stream and the pinned area
+  if (h.ctx.copy_stream) { cudaStreamSynchronize(h.ctx.copy_stream); cudaStreamDestroy(h.ctx.copy_stream); h.ctx.copy_stream = nullptr; }
+  if (h.ctx.pinned_boxes) { cudaFreeHost(h.ctx.pinned_boxes); h.ctx.pinned_boxes = nullptr; h.ctx.pinned_boxes_cap = 0; }
   if (h.ctx.pinned) { cudaFreeHost(h.ctx.pinned); h.ctx.pinned = nullptr; h.ctx.pinned_bytes = 0; }
   if (h.ctx.d_graph_rounds) cudaFree(h.ctx.d_graph_rounds);
   for (cudaEvent_t e : h.ctx.ev_pool) cudaEventDestroy(e);

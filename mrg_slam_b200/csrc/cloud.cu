@@ -892,7 +892,21 @@ static void launch_knn_cov(Ctx& ctx, const CloudView* dviews, const std::vector<
 
 // bounding boxes of the clouds that lack one: one kernel over all of them, one D2H, one synchronisation.
 // device_srcs (optional, one per cloud, same order): packed device buffers the points are copied from in the same pass.
+// a cloud whose box is still on its way (split upload): wait for its group and take the box
+static void cloud_resolve_box(Cloud& c) {
+  if (!c.pending) return;
+  c.pending->resolve();
+  const int* v = c.pending->vals.data() + (size_t)6 * c.pending_idx;
+  for (int d = 0; d < 3; ++d) {
+    c.bmin[d] = c.n ? ordered_to_float(v[d]) : 0.f;
+    c.bmax[d] = c.n ? ordered_to_float(v[3 + d]) : 0.f;
+  }
+  c.has_bbox = true;
+  c.pending.reset();
+}
+
 void clouds_compute_bbox(Ctx& ctx, const std::vector<Cloud*>& clouds, const void* const* device_srcs = nullptr) {
+  for (Cloud* c : clouds) cloud_resolve_box(*c);
   std::vector<Cloud*> todo;
   std::vector<const float4*> srcs;
   for (size_t i = 0; i < clouds.size(); ++i) {
@@ -986,7 +1000,87 @@ void clouds_upload(Ctx& ctx, Cloud* const* clouds, const void* const* points, co
       B2R_LAUNCH(ctx, repack32_kernel, (unsigned)((n[i] + 255) / 256), 256, 0, src, (int)n[i], c.pts.p);
     }
   }
-  clouds_compute_bbox(ctx, all, fused_copy ? points : nullptr);  // synchronises
+  // Pinned host clouds, large batch: the batch is copied in two halves.  The first half goes as before (kernel on the handle's
+  // stream, boxes read back, one synchronisation); the second half's copy + box kernel runs on a second stream and is NOT waited
+  // for: its clouds carry a PendingBoxes, and the batch path prepares the first half's structures (grid, covariances, voxel maps)
+  // while the second half is still coming over PCIe (api.cu: run_align).  B2R_SPLIT_UPLOAD=0 restores the single kernel.
+  static const bool split_on = [] { const char* e = getenv("B2R_SPLIT_UPLOAD"); return !e || atoi(e) != 0; }();
+  if (!(fused_copy && memspace != B2R_DEVICE && split_on && count >= 16)) {
+    clouds_compute_bbox(ctx, all, fused_copy ? points : nullptr);  // synchronises
+    return;
+  }
+  if (auto old = ctx.pending_boxes.lock()) old->resolve();  // the pinned area is about to be reused
+  const int nc = (int)count;
+  size_t tot_pts = 0, acc_pts = 0;
+  for (size_t i = 0; i < count; ++i) tot_pts += n[i];
+  int k = 0;  // first cloud of the second half
+  while (k < nc - 1 && acc_pts + n[k] <= tot_pts / 2) acc_pts += n[k++];
+  k = std::max(k, 1);
+  if (!ctx.copy_stream) B2R_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+  if (ctx.pinned_boxes_cap < (size_t)nc * 6) {
+    if (ctx.pinned_boxes) cudaFreeHost(ctx.pinned_boxes);
+    ctx.pinned_boxes = nullptr;
+    ctx.pinned_boxes_cap = 0;
+    B2R_CUDA(cudaHostAlloc((void**)&ctx.pinned_boxes, sizeof(int) * 6 * (size_t)nc * 2, cudaHostAllocDefault));
+    ctx.pinned_boxes_cap = (size_t)nc * 6 * 2;
+  }
+  std::vector<CloudView> hv(nc);
+  std::vector<const float4*> srcs(nc);
+  int maxn_a = 1, maxn_b = 1;
+  for (int i = 0; i < nc; ++i) {
+    hv[i] = all[i]->view();
+    srcs[i] = (const float4*)points[i];
+    (i < k ? maxn_a : maxn_b) = std::max(i < k ? maxn_a : maxn_b, all[i]->n);
+  }
+  DBuf<CloudView> dv; dv.alloc(nc, ctx.stream);
+  DBuf<const float4*> dsrc; dsrc.alloc(nc, ctx.stream);
+  DBuf<int> db; db.alloc((size_t)nc * 6, ctx.stream);
+  B2R_CUDA(cudaMemcpyAsync(dv.p, hv.data(), sizeof(CloudView) * nc, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_CUDA(cudaMemcpyAsync(dsrc.p, srcs.data(), sizeof(const float4*) * nc, cudaMemcpyHostToDevice, ctx.stream));
+  B2R_LAUNCH(ctx, bbox_init_kernel, (nc * 6 + 255) / 256, 256, 0, db.p, nc);
+  auto pb = std::make_shared<PendingBoxes>();
+  pb->device = ctx.device;
+  pb->count = nc - k;
+  pb->pinned = ctx.pinned_boxes + (size_t)6 * k;
+  // ---- first half on the handle's stream
+  {
+    dim3 g(blocks_for(maxn_a, 256 * 8, std::max(1, 4 * ctx.num_sms / k)), k);
+    B2R_LAUNCH(ctx, bbox_kernel<true>, g, 256, 0, dv.p, db.p, dsrc.p);
+  }
+  // ---- second half on the copy stream, behind the first half's kernel (the two would only share the PCIe link otherwise, and
+  // the first half would arrive later); not waited for here
+  cudaEvent_t first_done = ctx.get_event();
+  B2R_CUDA(cudaEventRecord(first_done, ctx.stream));
+  B2R_CUDA(cudaStreamWaitEvent(ctx.copy_stream, first_done, 0));
+  ctx.ev_pool.push_back(first_done);
+  {
+    dim3 g(blocks_for(maxn_b, 256 * 8, std::max(1, 4 * ctx.num_sms / (nc - k))), nc - k);
+    bbox_kernel<true><<<g, 256, 0, ctx.copy_stream>>>(dv.p + k, db.p + (size_t)6 * k, dsrc.p + k);
+    ++ctx.launches;
+    B2R_CUDA(cudaGetLastError());
+    B2R_CUDA(cudaMemcpyAsync(ctx.pinned_boxes + (size_t)6 * k, db.p + (size_t)6 * k, sizeof(int) * 6 * (nc - k), cudaMemcpyDeviceToHost, ctx.copy_stream));
+    B2R_CUDA(cudaEventCreateWithFlags(&pb->ev, cudaEventDisableTiming));
+    B2R_CUDA(cudaEventRecord(pb->ev, ctx.copy_stream));
+  }
+  // ---- the first half's boxes: one synchronisation of the handle's stream
+  {
+    B2R_CUDA(cudaMemcpyAsync(ctx.pinned_boxes, db.p, sizeof(int) * 6 * k, cudaMemcpyDeviceToHost, ctx.stream));
+    B2R_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (int i = 0; i < k; ++i) {
+      Cloud* c = all[i];
+      for (int d = 0; d < 3; ++d) {
+        c->bmin[d] = c->n ? ordered_to_float(ctx.pinned_boxes[i * 6 + d]) : 0.f;
+        c->bmax[d] = c->n ? ordered_to_float(ctx.pinned_boxes[i * 6 + 3 + d]) : 0.f;
+      }
+      c->has_bbox = true;
+    }
+  }
+  // the kernel on the copy stream still reads dv / dsrc and writes db: they are released when its event has passed
+  pb->scratch.push_back({dv.p, ctx.stream}); dv.p = nullptr;
+  pb->scratch.push_back({dsrc.p, ctx.stream}); dsrc.p = nullptr;
+  pb->scratch.push_back({db.p, ctx.stream}); db.p = nullptr;
+  for (int i = k; i < nc; ++i) { all[i]->pending = pb; all[i]->pending_idx = i - k; }
+  ctx.pending_boxes = pb;
 }
 
 template <int MODE>

@@ -53,6 +53,32 @@ struct StreamOwner {
   }
 };
 
+// Bounding boxes of a group of clouds whose upload is still running on the handle's copy stream (clouds_upload, split upload of
+// pinned host clouds: the second half of a batch is pulled over PCIe while the first half's search structures are being built).
+// Shared by the clouds of the group; whoever needs a box first waits for the event and reads them all.
+struct PendingBoxes {
+  int device = 0;
+  cudaEvent_t ev = nullptr;     // after the group's copy + box kernel and the read-back of the boxes
+  const int* pinned = nullptr;  // where the boxes arrive (the Ctx's pinned area; valid until resolved)
+  int count = 0;                // clouds in the group
+  std::vector<int> vals;        // 6 ordered ints per cloud, once resolved
+  bool resolved = false;
+  std::vector<std::pair<void*, cudaStream_t>> scratch;  // device scratch of the group's kernel, released after the event
+  void resolve() {
+    if (resolved) return;
+    cudaSetDevice(device);
+    if (ev) cudaEventSynchronize(ev);
+    if (pinned) vals.assign(pinned, pinned + (size_t)6 * count);
+    for (auto& sc : scratch) cudaFreeAsync(sc.first, sc.second);
+    scratch.clear();
+    resolved = true;
+  }
+  ~PendingBoxes() {
+    resolve();  // the copy must have finished before the clouds' storage can be released
+    if (ev) cudaEventDestroy(ev);
+  }
+};
+
 // Host-side stage timer (B2R_TRACE=1): wall-clock milliseconds between marks, printed to stderr by the caller.
 struct HostTrace {
   bool on;
@@ -118,6 +144,12 @@ struct Ctx {
     }
   }
   int num_sms = 148;
+  // split upload (cloud.cu): a second stream for the copy of a batch's second half, a pinned area its boxes arrive in, and the
+  // group that may still be in flight (resolved before the area is reused and when the handle goes away)
+  cudaStream_t copy_stream = nullptr;
+  int* pinned_boxes = nullptr;
+  size_t pinned_boxes_cap = 0;
+  std::weak_ptr<PendingBoxes> pending_boxes;
   // pinned host staging for small device->host results (result tables, counters): a copy into pageable memory goes through the
   // driver's own bounce buffer and costs several times the transfer
   void* pinned = nullptr;

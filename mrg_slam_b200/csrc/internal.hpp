@@ -60,6 +60,9 @@ struct Cloud {
   // step).  Rebuilding a structure with other parameters (k, covariance mode, resolution, leaf) replaces its entry, so the
   // superseded allocation is released as soon as no other structure uses it: device memory does not grow with alternating use.
   std::shared_ptr<Arena> mem_pts, mem_grid, mem_cov, mem_vox, mem_ndt;
+  // declared after the arenas: released first, and its destructor waits for an upload that may still be writing into mem_pts
+  std::shared_ptr<PendingBoxes> pending;
+  int pending_idx = 0;
   Ref<float4> pts;
   bool has_bbox = false;
   float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};

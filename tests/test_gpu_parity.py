@@ -415,6 +415,38 @@ def test_nearest_neighbor_search_small_and_odd_clouds(reg):
             ct.close(); cq.close()
 
 
+def test_split_upload_of_pinned_batches_gives_identical_results():
+    """A batch of >= 16 pinned host clouds is uploaded in two halves, the second one on a copy stream while the first half's search
+    structures are built (cloud.cu: clouds_upload / api.cu: run_align).  The rows must be bit-identical to the same batch from
+    pageable host memory (single synchronous path), also when the clouds are released without ever being aligned."""
+    torch = pytest.importorskip("torch")
+    g = B.Registration(B.default_config(B.FAST_VGICP))
+    scans = [oracle_prefilter(synth.scan(synth.VLP16, 40 + i)) for i in range(18)]
+    poses = [synth.pose(40 + i) for i in range(18)]
+    pairs = [(t, s) for t in range(2, 16) for s in (t - 2, t + 1, t + 2)]
+    guesses = []
+    for t, s in pairs:
+        gt = np.linalg.inv(poses[t]) @ poses[s]
+        gt[0, 3] += 0.2
+        guesses.append(gt)
+    pinned = [torch.from_numpy(c).pin_memory() for c in scans]
+    # never aligned, released at once: the pending half must not be freed under the running copy
+    for c in B.create_clouds(g, [p.data_ptr() for p in pinned], [p.shape[0] for p in pinned], B.HOST):
+        c.close()
+    rows = []
+    for bufs, memspace in ((pinned, B.HOST), (None, None), (pinned, B.HOST)):
+        if bufs is None:
+            cl = [B.Cloud(g, c) for c in scans]  # pageable numpy arrays, one by one
+        else:
+            cl = B.create_clouds(g, [p.data_ptr() for p in bufs], [p.shape[0] for p in bufs], memspace)
+        res = g.align_batch([cl[s] for _, s in pairs], [cl[t] for t, _ in pairs], guesses, with_fitness=True)
+        rows.append([(list(r.T), r.iterations, r.converged, r.fitness) for r in res])
+        for c in cl:
+            c.close()
+    assert rows[0] == rows[1] == rows[2]
+    g.close()
+
+
 # ------------------------------------------------------------------------------------------------ size-independent properties
 def test_properties_full_size_hdl64(reg):
     """KITTI-shape clouds (BASELINE config 2): properties that need no oracle."""
