@@ -11,18 +11,22 @@
 //
 // Search: ONE THREAD PER QUERY.  For every row within Chebyshev distance r (in y, z cells of size h) of the query's
 // row, the thread scans the x-cell the query falls into and then SWEEPS the sorted row outwards in both directions,
-// stopping a direction as soon as (dx)^2 alone reaches the current bound (k-th distance, search radius ...): since
-// fl(dx^2) <= fl(d^2) and |dx| only grows, nothing beyond can qualify.  So the candidates of a row are just the strip
-// |dx| < bound, at point granularity, whatever the cell size.  Rows whose (y, z) distance lower bound already exceeds
-// the bound are skipped.  r grows ring by ring (whole rows, so a ring is just the rows with max(|dy|,|dz|) == r) until
-// the k-th distance is proven: <= the distance to the nearest unvisited row.
-// Queries are issued in cell order where possible, so the lanes of a warp walk nearly the same rows and runs
-// (L1-resident, partly broadcast loads).
+// stopping a direction as soon as dx^2 + gap^2 exceeds the current bound (k-th distance, search radius ...), gap being the
+// row's (y, z) distance lower bound: |dx| only grows along a sweep, so nothing beyond can qualify, and the strip of a row
+// one cell away is narrower than the bound itself.  So the candidates of a row are just that strip, at point granularity,
+// whatever the cell size.  Rows whose gap already exceeds the bound are skipped.  r grows ring by ring (whole rows, so a ring
+// is just the rows with max(|dy|,|dz|) == r) until the k-th distance is proven: <= the distance to the nearest unvisited row.
+// Queries are issued in cell order (also the SOURCE points of a fitness / FAST_GICP pass: in their own cloud's cell order),
+// so the lanes of a warp walk nearly the same rows and runs (L1-resident, partly broadcast loads).
+//
+// Candidate arithmetic: FLANN's float squared distance, formed by Blackwell's packed-pair FP32 instructions — per candidate
+// (x, y) together (cand_d2), or, in the 1-NN searches, TWO neighbouring points of a row per instruction from the
+// pair-interleaved copy `spair` (VISIT_PAIRS) — every element rounded exactly like the scalar chain, so distances stay
+// bit-identical.
 //
 // topk<K>: the K smallest squared distances, ascending, in registers; insertion is a 2-instruction-per-slot
-// min/max chain and is skipped when the candidate does not beat the current K-th value.  Callers that need the
-// neighbours themselves (covariances) make a second pass over the same rows with the proven k-th distance as the
-// acceptance radius: no index list is kept, which keeps the register footprint at K floats.
+// min/max chain and is skipped when the candidate does not beat the current K-th value.  The covariance kernel logs every
+// candidate that entered the top-k (TopkListVisitor) and re-reads only those in its second pass.
 #pragma once
 #include <climits>
 
